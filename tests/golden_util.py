@@ -1,0 +1,115 @@
+"""Load and replay the golden trajectories of ``tests/golden`` through any stepper.
+
+A *stepper* is anything with
+
+* ``set_state(state_dict)``  -- oracle state-dict layout (see ``oracle.np_oracle.NpOracle``)
+* ``step(actions[R,N], od_noise[R], perlin[R] | None, interp_ids[R,k] | None) -> rewards[R,N]``
+* ``get_state() -> dict`` with at least ``t_air,t_mass,on,lockout,sso,power,signal,od_temp,
+  solar,base_power,epoch``
+* ``obs_vectors(table) -> [R,N,D]``
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def case_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class GoldenCase:
+    def __init__(self, name: str):
+        self.name = name
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.z = {k: z[k] for k in z.files}
+        self.meta = json.loads(bytes(self.z["meta_json"]).decode())
+        self.env_prop = self.meta["env_prop"]
+        self.T = self.meta["T"]
+        self.N = self.env_prop["cluster_prop"]["nb_agents"]
+        self.obs_stride = self.meta.get("obs_stride", 1)
+
+    @property
+    def state0(self) -> dict:
+        return {k[len("state0_"):]: v for k, v in self.z.items() if k.startswith("state0_")}
+
+    def table(self):
+        if self.meta.get("table_seed") is None:
+            return None
+        from oracle.config import synthetic_table
+
+        return synthetic_table(self.meta["table_seed"])
+
+    def comm(self, t: int):
+        """Neighbour table valid for the observation after step ``t`` (t = 0: reset obs)."""
+        if "comm_per_step" in self.z:
+            return self.z["comm_per_step"][t]
+        return self.z["comm_table"]
+
+    def last_obs_house0(self) -> dict:
+        return json.loads(bytes(self.z["last_obs_house0_json"]).decode())
+
+
+def _close(a, b, rtol, atol, what):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    if not np.all(err <= tol):
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError(f"{what}: |{a[i]} - {b[i]}| = {err[i]:.3e} > tol {tol[i]:.3e} at {i}")
+    return float(err.max()) if err.size else 0.0
+
+
+def replay(case: GoldenCase, stepper, rtol: float, scales: dict | None = None,
+           reinject_every: int | None = None, check_obs: bool = True):
+    """Replay ``case`` through ``stepper``; discrete state must match bit-exactly, continuous
+    quantities within ``rtol`` relative to their natural scale (``atol = rtol * scale``).
+
+    Returns the dict of worst absolute errors per quantity."""
+    z = case.z
+    sc = {"t_air": 20.0, "t_mass": 20.0, "od_temp": 20.0, "solar": 1000.0,
+          "power": 6000.0 * case.N, "signal": 6000.0 * case.N, "base_power": 6000.0 * case.N,
+          "rewards": 1.0, "obs": 1.0}
+    if scales:
+        sc.update(scales)
+    worst = {}
+
+    def chk(name, got, want):
+        e = _close(got, want, rtol, rtol * sc[name], f"{case.name}:{name}")
+        worst[name] = max(worst.get(name, 0.0), e)
+
+    stepper.set_state(case.state0)
+    if check_obs:
+        chk("obs", stepper.obs_vectors(case.comm(0))[0], z["obs"][0])
+    uses_perlin = case.env_prop["power_grid_prop"]["signal_properties"]["mode"] == "perlin"
+    for t in range(case.T):
+        perlin = [z["perlin"][t]] if uses_perlin else None
+        ids = z["interp_ids"][t][None] if z["interp_ids"][t][0] >= 0 else None
+        rew = stepper.step(z["actions"][t][None], [z["od_noise"][t]], perlin, ids)
+        st = stepper.get_state()
+        for k in ("on", "lockout", "sso"):
+            got = np.asarray(st[k])[0].astype(np.int64)
+            if not np.array_equal(got, z[k][t].astype(np.int64)):
+                bad = np.nonzero(got != z[k][t])[0]
+                raise AssertionError(f"{case.name}: discrete state '{k}' differs at step {t}, houses {bad[:8]}")
+        assert int(np.asarray(st["epoch"])[0]) == int(z["epoch"][t]), f"{case.name}: epoch at step {t}"
+        for k in ("t_air", "t_mass"):
+            chk(k, np.asarray(st[k])[0], z[k][t])
+        for k in ("power", "signal", "od_temp", "solar", "base_power"):
+            chk(k, np.asarray(st[k])[0], z[k][t])
+        chk("rewards", np.asarray(rew)[0], z["rewards"][t])
+        if check_obs and (t + 1) % case.obs_stride == 0:
+            chk("obs", stepper.obs_vectors(case.comm(t + 1))[0], z["obs"][(t + 1) // case.obs_stride])
+        if reinject_every and (t + 1) % reinject_every == 0:
+            # re-anchor the continuous state on the golden trajectory (per-step error test)
+            s = dict(st)
+            s["t_air"] = z["t_air"][t][None]
+            s["t_mass"] = z["t_mass"][t][None]
+            stepper.reinject(s)
+    return worst
