@@ -1,0 +1,246 @@
+/*
+ * drsim.h -- C ABI of the B200-native demand-response environment step (libdrsim.so).
+ *
+ * The reference (ALLabMTL/marl-demandresponse) is pure Python and has no FFI for this path:
+ * callers construct `Environment(env_props)` directly and call `reset()` / `step(action_dict)`
+ * (server/app/core/environment/environment.py:39,49,72; call sites
+ * server/app/services/controller_manager.py:109,172 and training_manager.py:161,231).  This
+ * header is therefore the boundary a maintainer would bind with `ctypes` from a replacement
+ * `Environment` class; every entry point names the reference code it
+ * replaces.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative DRSIM_E_* code,
+ *     the message is available from drsim_last_error() (thread-local);
+ *   - the library owns all device buffers of a handle (one cudaMalloc slab); callers own the
+ *     action / injected-noise buffers they pass in;
+ *   - one handle is bound to one CUDA device; calls on a handle are not re-entrant and are
+ *     ordered by the `stream` argument (a cudaStream_t passed as void*, NULL = default stream);
+ *   - there is NO CPU fallback: drsim_create fails unless the device is compute capability 10.x.
+ *
+ * Layout: per-house planes are structure-of-arrays [n_rep][house_stride] with
+ * house_stride = n_house rounded up to a multiple of 4 (16-byte vector accesses); per-replica
+ * ("env") scalars are [n_rep] doubles.
+ */
+#ifndef DRSIM_H_
+#define DRSIM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRSIM_ABI_VERSION 1
+#define DRSIM_MAX_SIGNAL_TERMS 8
+#define DRSIM_INTERP_SUBTABLES 162      /* 3*3*3*3*2 nearest-neighbour cells            */
+#define DRSIM_INTERP_SUBTABLE_LEN 25920 /* 9*5*8*12*6 values of the 5-D multilinear part */
+
+enum { DRSIM_OK = 0, DRSIM_E_ARG = -1, DRSIM_E_CUDA = -2, DRSIM_E_DEVICE = -3, DRSIM_E_STATE = -4 };
+
+enum { DRSIM_F32 = 0, DRSIM_F64 = 1 };
+/* rewards_calculator.py:46-133 */
+enum { DRSIM_PEN_INDIVIDUAL_L2 = 0, DRSIM_PEN_COMMON_L2 = 1, DRSIM_PEN_COMMON_MAX = 2, DRSIM_PEN_MIXTURE = 3 };
+/* power_grid.py:144-161 */
+enum { DRSIM_BASE_CONSTANT = 0, DRSIM_BASE_INTERPOLATION = 1 };
+/* signal_calculator.py:33-115 */
+enum { DRSIM_SIG_FLAT = 0, DRSIM_SIG_SINUSOIDALS = 1, DRSIM_SIG_REGULAR_STEPS = 2, DRSIM_SIG_PERLIN = 3 };
+/* observation layouts: none, utils/norm.py:178-218 (hand-engineered, with neighbour messages),
+ * "TarMAC" = own-state features only + static neighbour index tensor */
+enum { DRSIM_OBS_NONE = 0, DRSIM_OBS_HAND_ENGINEERED = 1, DRSIM_OBS_TARMAC = 2 };
+/* neighbour source: arithmetic ring (agent_communication_builder.py:63-85) or explicit table */
+enum { DRSIM_COMM_RING = 0, DRSIM_COMM_TABLE = 1 };
+/* where per-step noise comes from when the matching pointer of drsim_step_args is NULL */
+enum { DRSIM_NOISE_ZERO = 0, DRSIM_NOISE_PHILOX = 1 };
+/* action source: caller-provided, or restated controllers
+ * (controllers/bangbang_controllers.py:18-89, greedy_myopic_controller.py:67-104) */
+enum {
+  DRSIM_POLICY_EXTERNAL = 0,
+  DRSIM_POLICY_DEADBAND_BANGBANG = 1,
+  DRSIM_POLICY_BANGBANG = 2,
+  DRSIM_POLICY_ALWAYS_ON = 3,
+  DRSIM_POLICY_GREEDY_MYOPIC = 4
+};
+/* kernel path: auto, force the fused single-kernel tile path, force the general 3-kernel path */
+enum { DRSIM_PATH_AUTO = 0, DRSIM_PATH_FUSED = 1, DRSIM_PATH_SPLIT = 2 };
+
+/* Flattened EnvironmentProperties (environment_properties.py:339-371 and the classes it nests). */
+typedef struct drsim_config {
+  int32_t abi_version; /* must be DRSIM_ABI_VERSION */
+  int32_t n_rep;       /* R independent replicas of the cluster                           */
+  int32_t n_house;     /* N = cluster_prop.nb_agents (houses owned by THIS handle)        */
+  int32_t precision;   /* DRSIM_F32 | DRSIM_F64                                           */
+  int32_t dt;          /* time_step.seconds (hvac.py:46)                                  */
+  int32_t path;        /* DRSIM_PATH_*                                                    */
+
+  /* single very large cluster split across devices: this handle owns houses
+   * [house_offset, house_offset + n_house) of a cluster of n_house_global houses; 0/0 = whole */
+  int64_t house_offset;
+  int64_t n_house_global;
+  int64_t rep_offset; /* global index of local replica 0 (keys the Philox streams)          */
+
+  /* BuildingProperties / HvacProperties defaults (environment_properties.py:70-205) */
+  double deadband;
+  double cop;
+  double latent_cooling_fraction;
+  int32_t lockout_duration;
+  int32_t solar_gain; /* bool */
+  double window_area;
+  double shading_coeff;
+  double default_target_temp;
+  double default_Ua, default_Ca, default_Cm, default_Hm;
+  double default_cooling_capacity;
+
+  /* TemperatureProperties (cluster_properties.py:9-28) */
+  double day_temp, night_temp, temp_std, phase;
+
+  /* RewardProperties (environment_properties.py:221-258) */
+  double alpha_temp, alpha_sig, norm_reg_sig;
+  int32_t penalty_mode;
+  int32_t pad0_;
+  double alpha_ind_l2, alpha_common_l2, alpha_common_max;
+
+  /* PowerGridProperties (power_grid_properties.py:6-70) */
+  int32_t base_power_mode;
+  int32_t interp_update_period;
+  int32_t interp_nb_agents;
+  int32_t signal_mode;
+  double avg_power_per_hvac;
+  int32_t n_signal_terms; /* len(amplitude_ratios) == len(periods) for sinusoidals */
+  int32_t nb_octaves;
+  double amplitude_ratios[DRSIM_MAX_SIGNAL_TERMS];
+  double periods[DRSIM_MAX_SIGNAL_TERMS];
+  double amplitude_per_hvac;
+  int32_t octaves_step;
+  int32_t period;
+
+  /* observation layout (utils/norm.py, StateProperties / MessageProperties) */
+  int32_t obs_layout;
+  int32_t nb_comm;   /* min(max_nb_agents_communication, N-1), agent_communication_builder.py:49-52 */
+  int32_t comm_mode; /* DRSIM_COMM_* */
+  int32_t state_solar_gain, state_thermal, state_hvac;
+  int32_t message_thermal, message_hvac;
+
+  int32_t noise_mode; /* DRSIM_NOISE_* */
+  int32_t policy;     /* DRSIM_POLICY_* */
+  uint64_t seed;      /* Philox key */
+} drsim_config;
+
+/* Host-side full state, fp64, row-major [n_rep][n_house] / [n_rep]; NULL members are skipped by
+ * drsim_set_state and left untouched by drsim_get_state.  The four thermal parameters are turned
+ * into the per-house update coefficients inside drsim_set_state (building.py:160-201). */
+typedef struct drsim_host_state {
+  double *t_air, *t_mass;          /* Building.indoor_temp / current_mass_temp            */
+  double *target;                  /* init_props.target_temp                              */
+  double *Ua, *Ca, *Cm, *Hm;       /* init_props thermal parameters                       */
+  double *cap;                     /* hvac.init_props.cooling_capacity                    */
+  uint8_t *on, *lockout;           /* HVAC.turned_on / lockout                            */
+  int32_t *sso;                    /* HVAC.seconds_since_off                              */
+  int64_t *epoch;                  /* Environment.date_time as naive seconds since 1970   */
+  double *od_temp;                 /* Environment.current_od_temp                         */
+  double *signal;                  /* PowerGrid.current_signal                            */
+  double *base_power;              /* PowerGrid.base_power                                */
+  double *power;                   /* Cluster.current_power_consumption                   */
+  double *solar;                   /* Building.current_solar_gain (cluster-wide)          */
+  double *artificial_ratio;        /* PowerGridProperties.artificial_ratio (post-draw)    */
+  double *max_power;               /* Cluster.max_power                                   */
+  int32_t *t_since_interp;         /* PowerGrid.time_since_last_interp                    */
+} drsim_host_state;
+
+/* Device pointers of a handle (zero-copy views for torch / cupy).  `real` planes are float
+ * (DRSIM_F32) or double (DRSIM_F64). */
+typedef struct drsim_ptrs {
+  int32_t n_rep, n_house, house_stride, obs_dim, real_bytes, nb_comm;
+  void *t_air, *t_mass;        /* real  [R][stride] */
+  int32_t *sso;                /* i32   [R][stride] */
+  uint8_t *flags;              /* u8    [R][stride]  bit0 = turned_on, bit1 = lockout */
+  void *target, *cap;          /* real  [R][stride] */
+  void *reward;                /* real  [R][stride] */
+  void *obs;                   /* real  [R][stride][obs_dim] */
+  uint8_t *actions;            /* u8    [R][stride]  internal action plane (policies / host API) */
+  int64_t *epoch;              /* i64   [R] */
+  double *od_temp, *signal, *base_power, *power, *solar, *pen_sum, *pen_max; /* f64 [R] */
+  int32_t *comm_table;         /* i32   [N][nb_comm] (or [R][N][nb_comm] if per-replica) or NULL */
+  double *metrics;             /* f64   [R][DRSIM_N_METRICS] running rollout accumulators */
+  double *acc;                 /* f64   [R][DRSIM_N_ACC] per-rank partial sums of drsim_step_begin */
+  double *rew_sig;             /* f64   [R] alpha_sig * signal penalty / norm of the last step */
+} drsim_ptrs;
+
+#define DRSIM_N_ACC 6 /* P, sum pen/N, max pen, sum dT, sum dT^2, interpolated base-power sum */
+
+#define DRSIM_N_METRICS 6 /* steps, sum reward/N, sum |Ta-target|/N, sum (Ta-target)^2/N, sum |P-S|, sum (P-S)^2 */
+
+/* Per-step inputs, all DEVICE pointers; NULL selects the handle's own source. */
+typedef struct drsim_step_args {
+  const uint8_t *actions;     /* u8 [R][house_stride]; NULL = internal plane / on-device policy      */
+  const double *od_noise;     /* [R]  the random.gauss(0, temp_std) draw of environment.py:158       */
+  const double *perlin;       /* [R]  value of Perlin.calculate_noise (perlin.py:41-56)              */
+  const int32_t *interp_ids;  /* [R][interp_nb_agents] ids of random.choices (interpolation.py:223)  */
+} drsim_step_args;
+
+typedef struct drsim_handle drsim_t;
+
+/* Environment.__init__ (environment.py:39-47): allocate a simulator for R x N houses on `device`. */
+int drsim_create(const drsim_config *cfg, int device, drsim_t **out);
+int drsim_destroy(drsim_t *h);
+/* copy.deepcopy(env) (training_manager.py:269): clone all device state into a new handle. */
+int drsim_clone(const drsim_t *h, drsim_t **out);
+int drsim_buffers(drsim_t *h, drsim_ptrs *out);
+
+/* State injection / extraction (replaces poking Building/HVAC attributes, building.py:49-61,
+ * hvac.py:36-41).  Synchronous with respect to `stream`. */
+int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *stream);
+int drsim_get_state(drsim_t *h, drsim_host_state *st, void *stream);
+
+/* Cluster.agent_communicators (cluster.py:66-70): explicit neighbour table, host int32
+ * [n_house][nb_comm] (per_replica = 0) or [n_rep][n_house][nb_comm] (per_replica = 1). */
+int drsim_set_comm_table(drsim_t *h, const int32_t *table, int per_replica, void *stream);
+
+/* PowerInterpolator.values (interpolation.py:88-90) re-ordered to
+ * [162][9][5][8][12][6], host fp64. */
+int drsim_set_interp_table(drsim_t *h, const double *sub_tables, void *stream);
+
+/* Environment.step (environment.py:72-108): one step of every replica on `stream`. */
+int drsim_step(drsim_t *h, const drsim_step_args *args, void *stream);
+
+/* PowerGrid.step at reset + get_obs (environment.py:66-70): recompute signal (optional) and the
+ * observation / message gather from the current state without advancing time. */
+int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal, void *stream);
+
+/* Environment.step for ONE cluster whose houses are split across several handles / GPUs
+ * (SURVEY 8e): drsim_step_begin updates the local houses and leaves this rank's partial sums in
+ * drsim_ptrs.acc ([R][DRSIM_N_ACC]); the caller combines them across ranks (sum, except column 2 =
+ * max) with its collective of choice and hands the combined device array to drsim_step_finish,
+ * which runs the env epilogue, rewards and observations. */
+int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream);
+int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_combined, void *stream);
+
+/* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out
+ * ([R][4] doubles: power, signal, od_temp, mean reward); copies are inside the call and ordered on
+ * `stream`; the call returns after the results have landed (stream synchronised). */
+int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                    const int32_t *interp_ids, double *env_out, void *stream);
+
+/* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
+int64_t drsim_launch_count(const drsim_t *h);
+
+/* Host-side restatements of the env-level scalars, exported for CPU tests of the shared
+ * __host__ __device__ code (utils/utils.py:42-117, environment.py:132-159). */
+double drsim_host_solar_gain(int64_t epoch, double window_area, double shading_coeff);
+double drsim_host_od_temp(int64_t epoch, double day_temp, double night_temp, double phase, double noise);
+void drsim_host_civil(int64_t epoch, int32_t out7[7]); /* year, month, day, hour, minute, second, yday */
+/* per-house update coefficients from (Ua, Ca, Cm, Hm, dt): out[0..5] = difference-form f32-path
+ * coefficients (fp64), out[6..11] = r1, r2, A3, A4, e1, e2 of building.py:196-206 */
+void drsim_host_thermal_coefs(double Ua, double Ca, double Cm, double Hm, int32_t dt, double out12[12]);
+/* Philox4x32-10 block, for cross-checking the NumPy restatement */
+void drsim_host_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out4[4]);
+
+const char *drsim_last_error(void);
+int drsim_abi_version(void);
+/* sizeof(drsim_config / drsim_host_state / drsim_ptrs / drsim_step_args), for binding sanity checks */
+int drsim_sizeof(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRSIM_H_ */

@@ -1,0 +1,331 @@
+"""Thin Python owner of a ``drsim_t`` handle: config flattening, state I/O, zero-copy views.
+
+PyTorch is used only as plumbing (device tensors aliasing the library's buffers, the current
+CUDA stream); all arithmetic of the step happens in ``libdrsim.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import datetime as _dt
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .properties import EnvironmentProperties, as_props
+
+EPOCH0 = _dt.datetime(1970, 1, 1)
+
+
+def to_epoch(dt: _dt.datetime) -> int:
+    d = dt - EPOCH0
+    return d.days * 86400 + d.seconds
+
+
+def from_epoch(sec: int) -> _dt.datetime:
+    return EPOCH0 + _dt.timedelta(seconds=int(sec))
+
+
+def nb_comm_of(props: EnvironmentProperties) -> int:
+    """agent_communication_builder.py:49-52."""
+    cp = props.cluster_prop
+    return int(min(cp.agents_comm_prop.max_nb_agents_communication, cp.nb_agents - 1))
+
+
+def flatten_config(props: Any, n_rep: int = 1, precision: str = "f32", obs_layout: str = "hand_engineered",
+                   policy: str = "external", noise: str = "zero", seed: int = 0, path: str = "auto",
+                   comm_table: bool | None = None, house_offset: int = 0, n_house_local: int | None = None,
+                   rep_offset: int = 0) -> _lib.Config:
+    """``EnvironmentProperties`` -> ``drsim_config`` (include/drsim.h)."""
+    p = as_props(props)
+    hp, hv = p.cluster_prop.house_prop, p.cluster_prop.house_prop.hvac_prop
+    gp, rp = p.power_grid_prop, p.reward_prop
+    sp, bp = gp.signal_properties, gp.base_power_props
+    c = _lib.Config()
+    c.abi_version = _lib.ABI_VERSION
+    c.n_rep = int(n_rep)
+    n_glob = int(p.cluster_prop.nb_agents)
+    c.n_house = int(n_house_local) if n_house_local is not None else n_glob
+    c.house_offset = int(house_offset)
+    c.n_house_global = n_glob
+    c.rep_offset = int(rep_offset)
+    c.precision = {"f32": _lib.F32, "f64": _lib.F64}[precision]
+    c.dt = int(p.time_step.seconds)  # hvac.py:46 reads time_step.seconds
+    c.path = _lib.PATH[path]
+    c.deadband = hp.deadband
+    c.cop = hv.cop
+    c.latent_cooling_fraction = hv.latent_cooling_fraction
+    c.lockout_duration = hv.lockout_duration
+    c.solar_gain = int(hp.solar_gain)
+    c.window_area = hp.window_area
+    c.shading_coeff = hp.shading_coeff
+    c.default_target_temp = hp.target_temp
+    c.default_Ua, c.default_Ca, c.default_Cm, c.default_Hm = hp.Ua, hp.Ca, hp.Cm, hp.Hm
+    c.default_cooling_capacity = hv.cooling_capacity
+    tp = p.temp_prop
+    c.day_temp, c.night_temp, c.temp_std, c.phase = tp.day_temp, tp.night_temp, tp.temp_std, tp.phase
+    c.alpha_temp, c.alpha_sig, c.norm_reg_sig = rp.alpha_temp, rp.alpha_sig, float(rp.norm_reg_sig)
+    c.penalty_mode = _lib.PEN[rp.penalty_props.mode]
+    c.alpha_ind_l2 = rp.penalty_props.alpha_ind_l2
+    c.alpha_common_l2 = rp.penalty_props.alpha_common_l2
+    c.alpha_common_max = rp.penalty_props.alpha_common_max
+    if rp.sig_penalty_mode != "common_L2":  # rewards_calculator.py:197-201
+        raise ValueError(f"Unknown signal penalty mode: {rp.sig_penalty_mode}")
+    c.base_power_mode = _lib.BASE[bp.mode]
+    c.interp_update_period = bp.interp_update_period
+    c.interp_nb_agents = bp.interp_nb_agents
+    c.avg_power_per_hvac = float(bp.avg_power_per_hvac)
+    c.signal_mode = _lib.SIG[sp.mode]
+    if sp.mode == "sinusoidals" and len(sp.periods) != len(sp.amplitude_ratios):
+        raise ValueError(  # signal_calculator.py:61-66
+            "Power grid signal parameters: periods and amplitude_ratios lists should have the same length.")
+    n_terms = min(len(sp.amplitude_ratios), _lib.MAX_SIGNAL_TERMS)
+    c.n_signal_terms = n_terms
+    for k in range(n_terms):
+        c.amplitude_ratios[k] = sp.amplitude_ratios[k]
+        if k < len(sp.periods):
+            c.periods[k] = float(sp.periods[k])
+    c.amplitude_per_hvac = float(sp.amplitude_per_hvac)
+    c.nb_octaves, c.octaves_step, c.period = sp.nb_octaves, sp.octaves_step, sp.period
+    c.obs_layout = _lib.OBS[obs_layout]
+    c.nb_comm = nb_comm_of(p)
+    mode = p.cluster_prop.agents_comm_prop.mode
+    if comm_table is None:
+        comm_table = mode != "neighbours"
+    c.comm_mode = _lib.COMM_TABLE if comm_table else _lib.COMM_RING
+    st, mp = p.state_prop, p.cluster_prop.message_prop
+    c.state_solar_gain, c.state_thermal, c.state_hvac = int(st.solar_gain), int(st.thermal), int(st.hvac)
+    c.message_thermal, c.message_hvac = int(mp.thermal), int(mp.hvac)
+    c.noise_mode = _lib.NOISE[noise]
+    c.policy = _lib.POLICY[policy]
+    c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return c
+
+
+_HOUSE_F64 = ("t_air", "t_mass", "target", "Ua", "Ca", "Cm", "Hm", "cap")
+_ENV_F64 = ("od_temp", "signal", "base_power", "power", "solar", "artificial_ratio", "max_power")
+
+
+class _DevArray:
+    """Minimal ``__cuda_array_interface__`` carrier for zero-copy torch views."""
+
+    def __init__(self, ptr: int, shape, typestr: str, strides=None):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False),
+            "version": 3, "strides": None if strides is None else tuple(int(s) for s in strides),
+        }
+
+
+class DrSim:
+    """Owns one ``drsim_t``: R replicas x N houses on one CUDA device."""
+
+    def __init__(self, cfg: _lib.Config, device: int = 0):
+        self._L = _lib.lib()
+        self.cfg = cfg
+        self.device = int(device)
+        self._h = C.c_void_p()
+        _lib.check(self._L.drsim_create(C.byref(cfg), self.device, C.byref(self._h)))
+        self._bind()
+
+    def _bind(self):
+        ptrs = _lib.Ptrs()
+        _lib.check(self._L.drsim_buffers(self._h, C.byref(ptrs)))
+        self.ptrs = ptrs
+        self.R, self.N, self.Ns, self.D = ptrs.n_rep, ptrs.n_house, ptrs.house_stride, ptrs.obs_dim
+        self.real = np.float64 if ptrs.real_bytes == 8 else np.float32
+        self._views: Optional[Dict[str, Any]] = None
+
+    # ---- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.drsim_destroy(self._h)
+            self._h = C.c_void_p()
+            self._views = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def clone(self) -> "DrSim":
+        other = object.__new__(DrSim)
+        other._L, other.cfg, other.device = self._L, self.cfg, self.device
+        other._h = C.c_void_p()
+        _lib.check(self._L.drsim_clone(self._h, C.byref(other._h)))
+        other._bind()
+        return other
+
+    # ---- stream plumbing ------------------------------------------------------------------
+    def _stream(self, stream=None) -> C.c_void_p:
+        if stream is not None:
+            return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- state I/O (host fp64 arrays) -----------------------------------------------------
+    def set_state(self, st: Dict[str, Any], stream=None) -> None:
+        R, N = self.R, self.N
+        hs = _lib.HostState()
+        keep = []
+
+        def put(name, arr, dtype, shape, ptype):
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(arr).astype(dtype, copy=False), shape))
+            keep.append(a)
+            setattr(hs, name, a.ctypes.data_as(ptype))
+
+        for k in _HOUSE_F64:
+            if k in st:
+                put(k, st[k], np.float64, (R, N), _lib._pd)
+        for k in ("on", "lockout"):
+            if k in st:
+                put(k, np.asarray(st[k]).astype(bool), np.uint8, (R, N), _lib._pu8)
+        if "sso" in st:
+            put("sso", st["sso"], np.int32, (R, N), _lib._pi32)
+        if "epoch" in st:
+            put("epoch", st["epoch"], np.int64, (R,), _lib._pi64)
+        for k in _ENV_F64:
+            if k in st:
+                put(k, st[k], np.float64, (R,), _lib._pd)
+        if "t_since_interp" in st:
+            put("t_since_interp", st["t_since_interp"], np.int32, (R,), _lib._pi32)
+        _lib.check(self._L.drsim_set_state(self._h, C.byref(hs), self._stream(stream)))
+
+    def get_state(self, keys=None, stream=None) -> Dict[str, np.ndarray]:
+        R, N = self.R, self.N
+        hs = _lib.HostState()
+        out: Dict[str, np.ndarray] = {}
+        want = set(keys) if keys else {"t_air", "t_mass", "target", "cap", "on", "lockout", "sso", "epoch",
+                                       "od_temp", "signal", "base_power", "power", "solar", "artificial_ratio",
+                                       "max_power", "t_since_interp"}
+
+        def get(name, dtype, shape, ptype):
+            a = np.zeros(shape, dtype=dtype)
+            out[name] = a
+            setattr(hs, name, a.ctypes.data_as(ptype))
+
+        for k in ("t_air", "t_mass", "target", "cap"):
+            if k in want:
+                get(k, np.float64, (R, N), _lib._pd)
+        for k in ("on", "lockout"):
+            if k in want:
+                get(k, np.uint8, (R, N), _lib._pu8)
+        if "sso" in want:
+            get("sso", np.int32, (R, N), _lib._pi32)
+        if "epoch" in want:
+            get("epoch", np.int64, (R,), _lib._pi64)
+        for k in _ENV_F64:
+            if k in want:
+                get(k, np.float64, (R,), _lib._pd)
+        if "t_since_interp" in want:
+            get("t_since_interp", np.int32, (R,), _lib._pi32)
+        _lib.check(self._L.drsim_get_state(self._h, C.byref(hs), self._stream(stream)))
+        return out
+
+    def set_comm_table(self, table: np.ndarray, stream=None) -> None:
+        t = np.ascontiguousarray(np.asarray(table, dtype=np.int32))
+        per_rep = 1 if t.ndim == 3 else 0
+        want = ((self.R,) if per_rep else ()) + (self.N, self.ptrs.nb_comm)
+        if t.shape != want:
+            raise ValueError(f"neighbour table shape {t.shape}, expected {want}")
+        _lib.check(self._L.drsim_set_comm_table(self._h, t.ctypes.data_as(C.c_void_p), per_rep, self._stream(stream)))
+
+    def set_interp_table(self, table10d: np.ndarray, stream=None) -> None:
+        """``table10d``: the flat / 10-D table in the reference's key order
+        (``interp_dict_keys.csv``); it is re-ordered here to [162][9][5][8][12][6]."""
+        t = np.asarray(table10d, dtype=np.float64).reshape(3, 3, 3, 3, 9, 5, 8, 2, 12, 6)
+        t = np.ascontiguousarray(np.moveaxis(t, 7, 4)).reshape(-1)
+        _lib.check(self._L.drsim_set_interp_table(self._h, t.ctypes.data_as(C.c_void_p), self._stream(stream)))
+
+    # ---- stepping -------------------------------------------------------------------------
+    @staticmethod
+    def _ptr(x) -> Optional[int]:
+        if x is None:
+            return None
+        return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+    def _args(self, actions=None, od_noise=None, perlin=None, interp_ids=None) -> _lib.StepArgs:
+        a = _lib.StepArgs()
+        a.actions, a.od_noise = self._ptr(actions), self._ptr(od_noise)
+        a.perlin, a.interp_ids = self._ptr(perlin), self._ptr(interp_ids)
+        return a
+
+    def step(self, actions=None, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
+        """All arguments are device tensors / pointers laid out as ``drsim_step_args`` wants
+        (``actions`` u8 with row stride ``Ns``; fp64 noise; int32 ids)."""
+        a = self._args(actions, od_noise, perlin, interp_ids)
+        _lib.check(self._L.drsim_step(self._h, C.byref(a), self._stream(stream)))
+
+    def refresh(self, recompute_signal: bool, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
+        a = self._args(None, od_noise, perlin, interp_ids)
+        _lib.check(self._L.drsim_refresh(self._h, C.byref(a), int(recompute_signal), self._stream(stream)))
+
+    def step_begin(self, actions=None, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
+        a = self._args(actions, od_noise, perlin, interp_ids)
+        _lib.check(self._L.drsim_step_begin(self._h, C.byref(a), self._stream(stream)))
+
+    def step_finish(self, acc, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
+        a = self._args(None, od_noise, perlin, interp_ids)
+        _lib.check(self._L.drsim_step_finish(self._h, C.byref(a), self._ptr(acc), self._stream(stream)))
+
+    def step_host(self, actions: Optional[np.ndarray], od_noise=None, perlin=None, interp_ids=None,
+                  env_out: Optional[np.ndarray] = None, stream=None) -> Optional[np.ndarray]:
+        """Host-buffer step (``drsim_step_host``): numpy (or pinned torch CPU) buffers in and out."""
+        def hp(x, dtype):
+            if x is None:
+                return None
+            if hasattr(x, "data_ptr"):
+                return C.c_void_p(x.data_ptr())
+            x = np.ascontiguousarray(x, dtype=dtype)
+            keep.append(x)
+            return x.ctypes.data_as(C.c_void_p)
+
+        keep: list = []
+        if env_out is None:
+            env_out = np.zeros((self.R, 4), dtype=np.float64)
+        _lib.check(self._L.drsim_step_host(
+            self._h, hp(actions, np.uint8), hp(od_noise, np.float64), hp(perlin, np.float64),
+            hp(interp_ids, np.int32), hp(env_out, np.float64), self._stream(stream)))
+        return env_out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.drsim_launch_count(self._h))
+
+    # ---- zero-copy torch views ------------------------------------------------------------
+    def views(self) -> Dict[str, Any]:
+        """Torch CUDA tensors aliasing the library's buffers (no copies).  House planes are
+        ``[R, N]`` views of ``[R, Ns]`` storage; ``obs`` is ``[R, N, D]``."""
+        if self._views is not None:
+            return self._views
+        import torch
+
+        p, R, N, Ns, D = self.ptrs, self.R, self.N, self.Ns, self.D
+        rt = "<f8" if p.real_bytes == 8 else "<f4"
+        dev = torch.device("cuda", self.device)
+
+        def t(ptr, shape, typestr):
+            if not ptr:
+                return None
+            x = torch.as_tensor(_DevArray(ptr, shape, typestr), device=dev)
+            x._drsim_owner = self  # keep the handle alive as long as a view exists
+            return x
+
+        v: Dict[str, Any] = {}
+        for k in ("t_air", "t_mass", "target", "cap", "reward"):
+            v[k] = t(getattr(p, k), (R, Ns), rt)[:, :N]
+        v["sso"] = t(p.sso, (R, Ns), "<i4")[:, :N]
+        v["flags"] = t(p.flags, (R, Ns), "|u1")[:, :N]
+        v["actions"] = t(p.actions, (R, Ns), "|u1")[:, :N]
+        v["actions_padded"] = t(p.actions, (R, Ns), "|u1")
+        v["obs"] = t(p.obs, (R, Ns, D), rt)[:, :N, :] if D else None
+        v["epoch"] = t(p.epoch, (R,), "<i8")
+        for k in ("od_temp", "signal", "base_power", "power", "solar", "pen_sum", "pen_max", "rew_sig"):
+            v[k] = t(getattr(p, k), (R,), "<f8")
+        v["metrics"] = t(p.metrics, (R, _lib.N_METRICS), "<f8")
+        v["acc"] = t(p.acc, (R, _lib.N_ACC), "<f8")
+        if p.comm_table:
+            v["comm_table"] = t(p.comm_table, (N, p.nb_comm), "<i4")
+        self._views = v
+        return v

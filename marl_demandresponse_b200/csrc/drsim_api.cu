@@ -1,0 +1,752 @@
+// drsim_api.cu -- C ABI of libdrsim.so (see include/drsim.h).  Host-side orchestration only:
+// buffer carving, state injection / extraction, per-step path selection and kernel launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "drsim_kernels.cuh"
+
+using namespace drsim;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail(DRSIM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+namespace {
+
+constexpr size_t kAlign = 256;
+
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + kAlign - 1) / kAlign * kAlign;
+    return o;
+  }
+};
+
+}  // namespace
+
+struct drsim_handle {
+  drsim_config cfg;
+  SimParams p;
+  int device = 0;
+  int sm_count = 148;
+  int real_bytes = 4;
+  unsigned char *slab = nullptr;
+  size_t slab_bytes = 0;
+  // offsets inside the slab
+  size_t o_t_air, o_t_mass, o_sso, o_flags, o_target, o_cap, o_coef[9], o_ratio[4], o_sub, o_reward, o_obs,
+      o_actions, o_epoch, o_od, o_solar_next, o_solar_cur, o_signal, o_base, o_power, o_art, o_maxp, o_pen_sum,
+      o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids;
+  bool has_ratio = false, has_interp = false, has_comm = false;
+  int chunks = 1;       // CTAs per cluster in the general path
+  int obs_chunks = 1;   // k_obs CTAs per cluster
+  bool fused_ok = false;
+  FusedGeom geom{};
+  int fused_grid = 0;
+  int64_t step = 0;
+  int t_since_interp = 0;  // host mirror of PowerGrid.time_since_last_interp (common to all replicas)
+  int64_t launches = 0;
+  int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
+  // pinned staging for drsim_step_host
+  double *h_env = nullptr;
+
+  template <typename T>
+  T *at(size_t off) const {
+    return reinterpret_cast<T *>(slab + off);
+  }
+};
+
+
+template <typename real>
+static Planes<real> make_planes(const drsim_handle *h) {
+  Planes<real> pl{};
+  pl.t_air = h->at<real>(h->o_t_air);
+  pl.t_mass = h->at<real>(h->o_t_mass);
+  pl.sso = h->at<int32_t>(h->o_sso);
+  pl.flags = h->at<uint8_t>(h->o_flags);
+  pl.target = h->at<real>(h->o_target);
+  pl.cap = h->at<real>(h->o_cap);
+  for (int k = 0; k < NCoef<real>::n; ++k) pl.coef[k] = h->at<real>(h->o_coef[k]);
+  for (int k = 0; k < 4; ++k) pl.ratio[k] = h->has_ratio ? h->at<float>(h->o_ratio[k]) : nullptr;
+  pl.interp_sub = h->has_interp ? h->at<uint8_t>(h->o_sub) : nullptr;
+  pl.reward = h->at<real>(h->o_reward);
+  pl.obs = h->p.obs_dim ? h->at<real>(h->o_obs) : nullptr;
+  pl.actions = h->at<uint8_t>(h->o_actions);
+  pl.epoch = h->at<int64_t>(h->o_epoch);
+  pl.od_temp = h->at<double>(h->o_od);
+  pl.solar_next = h->at<double>(h->o_solar_next);
+  pl.solar_cur = h->at<double>(h->o_solar_cur);
+  pl.signal = h->at<double>(h->o_signal);
+  pl.base_power = h->at<double>(h->o_base);
+  pl.power = h->at<double>(h->o_power);
+  pl.artificial_ratio = h->at<double>(h->o_art);
+  pl.max_power = h->at<double>(h->o_maxp);
+  pl.pen_sum = h->at<double>(h->o_pen_sum);
+  pl.pen_max = h->at<double>(h->o_pen_max);
+  pl.rew_sig = h->at<double>(h->o_rew_sig);
+  pl.t_since_interp = h->at<int32_t>(h->o_tsi);
+  pl.metrics = h->at<double>(h->o_metrics);
+  pl.partials = h->at<double>(h->o_partials);
+  pl.acc = h->at<double>(h->o_acc);
+  pl.comm_table = h->has_comm ? h->at<int32_t>(h->o_comm) : nullptr;
+  pl.interp_table = h->has_interp ? h->at<real>(h->o_interp) : nullptr;
+  return pl;
+}
+
+static int fill_params(const drsim_config &c, SimParams &p, std::string &why) {
+  if (c.abi_version != DRSIM_ABI_VERSION) { why = "abi_version mismatch"; return -1; }
+  if (c.n_rep < 1 || c.n_house < 1) { why = "n_rep and n_house must be >= 1"; return -1; }
+  if (c.precision != DRSIM_F32 && c.precision != DRSIM_F64) { why = "precision"; return -1; }
+  if (c.dt < 1) { why = "dt must be >= 1 s"; return -1; }
+  if (c.cop <= 0 || c.lockout_duration < 0) { why = "hvac properties"; return -1; }
+  if (c.n_signal_terms < 0 || c.n_signal_terms > DRSIM_MAX_SIGNAL_TERMS) { why = "n_signal_terms"; return -1; }
+  if (c.signal_mode == DRSIM_SIG_PERLIN && c.n_signal_terms < 1) { why = "perlin needs amplitude_ratios[0]"; return -1; }
+  if (c.signal_mode == DRSIM_SIG_REGULAR_STEPS && c.period < 1) { why = "regular_steps needs period"; return -1; }
+  if (c.nb_comm < 0) { why = "nb_comm"; return -1; }
+  memset(&p, 0, sizeof(p));
+  p.R = c.n_rep;
+  p.N = c.n_house;
+  p.Ns = (c.n_house + 3) / 4 * 4;
+  p.dt = c.dt;
+  p.house_offset = c.house_offset;
+  p.n_global = c.n_house_global > 0 ? c.n_house_global : c.n_house;
+  p.rep_offset = c.rep_offset;
+  if (p.house_offset < 0 || p.house_offset + p.N > p.n_global) { why = "house_offset / n_house_global"; return -1; }
+  p.deadband = c.deadband; p.cop = c.cop; p.latent = c.latent_cooling_fraction;
+  p.window_area = c.window_area; p.shading = c.shading_coeff;
+  p.lockout_duration = c.lockout_duration; p.solar_on = c.solar_gain;
+  p.default_target = c.default_target_temp;
+  p.dUa = c.default_Ua; p.dCa = c.default_Ca; p.dCm = c.default_Cm; p.dHm = c.default_Hm;
+  p.dcap = c.default_cooling_capacity;
+  p.day_temp = c.day_temp; p.night_temp = c.night_temp; p.temp_std = c.temp_std; p.phase = c.phase;
+  p.alpha_temp = c.alpha_temp; p.alpha_sig = c.alpha_sig; p.nrs = c.norm_reg_sig;
+  {  // rewards_calculator.py:155-165 via utils.py:4-23
+    const double t0 = c.default_target_temp;
+    const double v = t0 + 1, hi = t0 + 0.0 / 2;
+    p.norm_temp = (v - hi) * (v - hi);
+    const double lo = c.norm_reg_sig - 0.0 / 2, vs = 0.75 * c.norm_reg_sig;
+    p.norm_sig = (lo - vs) * (lo - vs);
+  }
+  p.penalty_mode = c.penalty_mode;
+  p.a_ind = c.alpha_ind_l2; p.a_cl2 = c.alpha_common_l2; p.a_cmax = c.alpha_common_max;
+  p.base_mode = c.base_power_mode; p.interp_period = c.interp_update_period; p.interp_k = c.interp_nb_agents;
+  p.signal_mode = c.signal_mode; p.n_terms = c.n_signal_terms; p.nb_octaves = c.nb_octaves;
+  p.octaves_step = c.octaves_step; p.period = c.period;
+  p.avg_power = c.avg_power_per_hvac; p.amp_per_hvac = c.amplitude_per_hvac;
+  for (int k = 0; k < DRSIM_MAX_SIGNAL_TERMS; ++k) { p.amp[k] = c.amplitude_ratios[k]; p.periods[k] = c.periods[k]; }
+  p.obs_layout = c.obs_layout; p.nb_comm = c.nb_comm; p.comm_mode = c.comm_mode; p.comm_per_rep = 0;
+  p.st_solar = c.state_solar_gain; p.st_thermal = c.state_thermal; p.st_hvac = c.state_hvac;
+  p.msg_thermal = c.message_thermal; p.msg_hvac = c.message_hvac;
+  p.own_dim = 10 + (p.st_hvac ? 2 : 0) + (p.st_solar ? 1 : 0) + (p.st_thermal ? 5 : 0);
+  p.msg_dim = 4 + (p.msg_thermal ? 4 : 0) + (p.msg_hvac ? 3 : 0);
+  if (p.obs_layout == DRSIM_OBS_NONE) p.obs_dim = 0;
+  else if (p.obs_layout == DRSIM_OBS_TARMAC) p.obs_dim = p.own_dim;
+  else if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) p.obs_dim = p.own_dim + p.nb_comm * p.msg_dim;
+  else { why = "obs_layout"; return -1; }
+  if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0 && p.N != p.n_global) {
+    why = "hand-engineered neighbour messages are not supported on a house-sharded cluster yet";
+    return -1;
+  }
+  if (p.base_mode == DRSIM_BASE_INTERPOLATION && (p.interp_k < 1 || p.interp_period < 1)) { why = "interp props"; return -1; }
+  p.noise_mode = c.noise_mode; p.policy = c.policy; p.seed = c.seed;
+  return 0;
+}
+
+static void plan_fused(drsim_handle *h) {
+  const SimParams &p = h->p;
+  h->fused_ok = false;
+  if (h->cfg.path == DRSIM_PATH_SPLIT) return;
+  if (p.Ns > kTileSlots || p.N != p.n_global) return;
+  FusedGeom g{};
+  g.envs_per_tile = std::min(p.R, kTileSlots / p.Ns);
+  g.n_tiles = (p.R + g.envs_per_tile - 1) / g.envs_per_tile;
+  g.max_segs = p.Ns >= 128 ? 2 : (128 + p.Ns - 1) / p.Ns + 1;
+  const int rb = h->real_bytes;
+  const int slots = g.envs_per_tile * p.Ns;
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
+  g.off_msg = take((size_t)slots * 4 * rb);
+  g.off_own = take((size_t)slots * 4 * rb);
+  g.off_env = take((size_t)g.envs_per_tile * 8 * rb);
+  g.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double));
+  g.off_tile = (int)off;
+  const size_t fixed = off;
+  const size_t row = (size_t)p.obs_dim * rb;
+  int chunk = 0;
+  if (row > 0) {
+    // aim for >= 2 resident CTAs per SM (<= ~110 KB each); fall back to one big CTA
+    const size_t budgets[2] = {110 * 1024, 220 * 1024};
+    for (size_t b : budgets) {
+      if (fixed + 32 * row > b) continue;
+      chunk = (int)std::min<size_t>((b - fixed) / row, (size_t)slots);
+      chunk = chunk / 4 * 4;
+      if (chunk >= 32 || chunk == slots) break;
+    }
+    if (chunk < 4) return;  // does not fit: general path
+  }
+  g.chunk_rows = chunk;
+  g.smem_bytes = (int)(fixed + (size_t)chunk * row);
+  h->geom = g;
+  h->fused_ok = true;
+}
+
+template <typename real>
+static int configure_kernels(drsim_handle *h) {
+  if (h->fused_ok) {
+    CU_TRY(cudaFuncSetAttribute(k_fused<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real>, kThreads, h->geom.smem_bytes));
+    if (per_sm < 1) { h->fused_ok = false; }
+    else h->fused_grid = std::min(h->geom.n_tiles, per_sm * h->sm_count);
+  }
+  const size_t obs_smem = (size_t)kObsChunk * h->p.obs_dim * sizeof(real);
+  if (obs_smem > 48 * 1024)
+    CU_TRY(cudaFuncSetAttribute(k_obs<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)obs_smem));
+  if (h->p.policy == DRSIM_POLICY_GREEDY_MYOPIC) {
+    int n2 = 1;
+    while (n2 < h->p.N) n2 <<= 1;
+    const size_t sm = (size_t)n2 * 12;
+    if (sm > 200 * 1024) return fail(DRSIM_E_ARG, "greedy-myopic: cluster too large for the shared-memory sort");
+    if (sm > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_greedy<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  }
+  return 0;
+}
+
+extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) {
+  if (!cfg || !out) return fail(DRSIM_E_ARG, "null argument");
+  *out = nullptr;
+  SimParams p;
+  std::string why;
+  if (fill_params(*cfg, p, why)) return fail(DRSIM_E_ARG, "drsim_create: " + why);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(DRSIM_E_DEVICE, std::string("drsim requires an sm_100 (B200) device, found ") + prop.name +
+                                    " (cc " + std::to_string(prop.major) + "." + std::to_string(prop.minor) +
+                                    "); there is no CPU or other-arch fallback");
+  CU_TRY(cudaSetDevice(device));
+  auto *h = new drsim_handle();
+  h->cfg = *cfg;
+  h->p = p;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->real_bytes = cfg->precision == DRSIM_F64 ? 8 : 4;
+  const int rb = h->real_bytes;
+  h->has_ratio = p.st_thermal || p.msg_thermal;
+  h->has_interp = p.base_mode == DRSIM_BASE_INTERPOLATION;
+  h->has_comm = p.comm_mode == DRSIM_COMM_TABLE && p.nb_comm > 0;
+  h->chunks = (p.Ns / 4 + kThreads - 1) / kThreads;
+  h->obs_chunks = (p.Ns + kObsChunk - 1) / kObsChunk;
+  h->t_since_interp = p.interp_period + 1;  // power_grid.py:64-66
+
+  Carver cv;
+  const size_t HP = (size_t)p.R * p.Ns;
+  h->o_t_air = cv.take(HP * rb); h->o_t_mass = cv.take(HP * rb);
+  h->o_sso = cv.take(HP * 4); h->o_flags = cv.take(HP);
+  h->o_target = cv.take(HP * rb); h->o_cap = cv.take(HP * rb);
+  const int nc = cfg->precision == DRSIM_F64 ? 9 : 6;
+  for (int k = 0; k < nc; ++k) h->o_coef[k] = cv.take(HP * rb);
+  if (h->has_ratio) for (int k = 0; k < 4; ++k) h->o_ratio[k] = cv.take(HP * 4);
+  if (h->has_interp) { h->o_sub = cv.take(HP); h->o_interp = cv.take((size_t)DRSIM_INTERP_SUBTABLES * DRSIM_INTERP_SUBTABLE_LEN * rb); }
+  h->o_reward = cv.take(HP * rb);
+  h->o_obs = cv.take(HP * p.obs_dim * rb + 16);
+  h->o_actions = cv.take(HP);
+  const size_t E8 = (size_t)p.R * 8;
+  h->o_epoch = cv.take(E8);
+  // contiguous env-output block (one D2H copy in drsim_step_host): power, signal, od, pen_sum, pen_max, rew_sig
+  const size_t blk = cv.take(E8 * 6);
+  h->o_power = blk; h->o_signal = blk + E8; h->o_od = blk + 2 * E8;
+  h->o_pen_sum = blk + 3 * E8; h->o_pen_max = blk + 4 * E8; h->o_rew_sig = blk + 5 * E8;
+  h->o_solar_next = cv.take(E8); h->o_solar_cur = cv.take(E8); h->o_base = cv.take(E8);
+  h->o_art = cv.take(E8); h->o_maxp = cv.take(E8); h->o_tsi = cv.take((size_t)p.R * 4);
+  h->o_metrics = cv.take(E8 * DRSIM_N_METRICS);
+  h->o_partials = cv.take(E8 * h->chunks * kRed);
+  h->o_acc = cv.take(E8 * DRSIM_N_ACC);
+  if (h->has_comm) h->o_comm = cv.take((size_t)p.R * p.N * p.nb_comm * 4);  // room for per-replica tables
+  h->o_in_od = cv.take(E8); h->o_in_perlin = cv.take(E8);
+  h->o_in_ids = cv.take((size_t)p.R * std::max(1, p.interp_k) * 4);
+  h->slab_bytes = cv.off;
+  cudaError_t e = cudaMalloc(&h->slab, h->slab_bytes);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(DRSIM_E_CUDA, std::string("cudaMalloc of ") + std::to_string(cv.off) + " bytes: " + cudaGetErrorString(e));
+  }
+  cudaMemset(h->slab, 0, h->slab_bytes);
+  cudaMallocHost(&h->h_env, E8 * 6);
+  plan_fused(h);
+  int rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
+  if (rc) { drsim_destroy(h); return rc; }
+  if (cfg->path == DRSIM_PATH_FUSED && !h->fused_ok) {
+    drsim_destroy(h);
+    return fail(DRSIM_E_ARG, "path=FUSED requested but the cluster does not fit a tile (N > 1024, sharded, or obs row too large)");
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int drsim_destroy(drsim_t *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->slab) cudaFree(h->slab);
+  if (h->h_env) cudaFreeHost(h->h_env);
+  delete h;
+  return 0;
+}
+
+extern "C" int drsim_clone(const drsim_t *src, drsim_t **out) {
+  if (!src || !out) return fail(DRSIM_E_ARG, "null argument");
+  drsim_t *h = nullptr;
+  int rc = drsim_create(&src->cfg, src->device, &h);
+  if (rc) return rc;
+  CU_TRY(cudaMemcpy(h->slab, src->slab, src->slab_bytes, cudaMemcpyDeviceToDevice));
+  h->p = src->p;
+  h->step = src->step;
+  h->t_since_interp = src->t_since_interp;
+  *out = h;
+  return 0;
+}
+
+extern "C" int drsim_buffers(drsim_t *h, drsim_ptrs *o) {
+  if (!h || !o) return fail(DRSIM_E_ARG, "null argument");
+  memset(o, 0, sizeof(*o));
+  o->n_rep = h->p.R; o->n_house = h->p.N; o->house_stride = h->p.Ns; o->obs_dim = h->p.obs_dim;
+  o->real_bytes = h->real_bytes; o->nb_comm = h->p.nb_comm;
+  o->t_air = h->slab + h->o_t_air; o->t_mass = h->slab + h->o_t_mass;
+  o->sso = h->at<int32_t>(h->o_sso); o->flags = h->at<uint8_t>(h->o_flags);
+  o->target = h->slab + h->o_target; o->cap = h->slab + h->o_cap;
+  o->reward = h->slab + h->o_reward; o->obs = h->p.obs_dim ? h->slab + h->o_obs : nullptr;
+  o->actions = h->at<uint8_t>(h->o_actions);
+  o->epoch = h->at<int64_t>(h->o_epoch);
+  o->od_temp = h->at<double>(h->o_od); o->signal = h->at<double>(h->o_signal);
+  o->base_power = h->at<double>(h->o_base); o->power = h->at<double>(h->o_power);
+  o->solar = h->at<double>(h->o_solar_cur); o->pen_sum = h->at<double>(h->o_pen_sum);
+  o->pen_max = h->at<double>(h->o_pen_max);
+  o->comm_table = h->has_comm ? h->at<int32_t>(h->o_comm) : nullptr;
+  o->metrics = h->at<double>(h->o_metrics);
+  o->acc = h->at<double>(h->o_acc);
+  o->rew_sig = h->at<double>(h->o_rew_sig);
+  return 0;
+}
+
+// ---- state injection -----------------------------------------------------------------------
+template <typename T, typename F>
+static int upload_house(drsim_handle *h, size_t off, cudaStream_t s, F &&value) {
+  const SimParams &p = h->p;
+  std::vector<T> buf((size_t)p.R * p.Ns);
+  for (int r = 0; r < p.R; ++r)
+    for (int n = 0; n < p.Ns; ++n) buf[(size_t)r * p.Ns + n] = n < p.N ? (T)value((size_t)r * p.N + n) : (T)0;
+  CU_TRY(cudaMemcpyAsync(h->slab + off, buf.data(), buf.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+template <typename T, typename SRC>
+static int upload_env(drsim_handle *h, size_t off, cudaStream_t s, const SRC *src) {
+  std::vector<T> buf(h->p.R);
+  for (int r = 0; r < h->p.R; ++r) buf[r] = (T)src[r];
+  CU_TRY(cudaMemcpyAsync(h->slab + off, buf.data(), buf.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return 0;
+}
+
+static int nearest3(double v) {  // grid {0.9, 1, 1.1}, np.argmin(|grid - v|) after clipping
+  v = std::min(1.1, std::max(0.9, v));
+  const double g[3] = {0.9, 1, 1.1};
+  int best = 0;
+  double bd = std::fabs(g[0] - v);
+  for (int i = 1; i < 3; ++i) {
+    const double d = std::fabs(g[i] - v);
+    if (d < bd) { bd = d; best = i; }
+  }
+  return best;
+}
+
+template <typename real>
+static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t s) {
+  const SimParams &p = h->p;
+  int rc;
+#define UP_HOUSE(field, T, off)                                                           \
+  if (st->field) {                                                                        \
+    auto *src = st->field;                                                                \
+    if ((rc = upload_house<T>(h, off, s, [src](size_t i) { return src[i]; }))) return rc; \
+  }
+  UP_HOUSE(t_air, real, h->o_t_air)
+  UP_HOUSE(t_mass, real, h->o_t_mass)
+  UP_HOUSE(target, real, h->o_target)
+  UP_HOUSE(cap, real, h->o_cap)
+  UP_HOUSE(sso, int32_t, h->o_sso)
+#undef UP_HOUSE
+  if (st->on || st->lockout) {
+    if (!(st->on && st->lockout)) return fail(DRSIM_E_ARG, "set_state: on and lockout must be given together");
+    auto *on = st->on;
+    auto *lk = st->lockout;
+    if ((rc = upload_house<uint8_t>(h, h->o_flags, s, [on, lk](size_t i) { return (on[i] ? 1 : 0) | (lk[i] ? 2 : 0); })))
+      return rc;
+  }
+  if (st->Ua || st->Ca || st->Cm || st->Hm) {
+    if (!(st->Ua && st->Ca && st->Cm && st->Hm)) return fail(DRSIM_E_ARG, "set_state: Ua, Ca, Cm, Hm must be given together");
+    const size_t n = (size_t)p.R * p.N;
+    std::vector<double> co(n * 12);
+    for (size_t i = 0; i < n; ++i) thermal_coefs(st->Ua[i], st->Ca[i], st->Cm[i], st->Hm[i], p.dt, &co[i * 12]);
+    if (sizeof(real) == 4) {
+      for (int k = 0; k < 6; ++k)
+        if ((rc = upload_house<real>(h, h->o_coef[k], s, [&co, k](size_t i) { return co[i * 12 + k]; }))) return rc;
+    } else {
+      const double *src[3] = {st->Ua, st->Ca, st->Hm};
+      for (int k = 0; k < 3; ++k) {
+        const double *a = src[k];
+        if ((rc = upload_house<real>(h, h->o_coef[k], s, [a](size_t i) { return a[i]; }))) return rc;
+      }
+      for (int k = 0; k < 6; ++k)
+        if ((rc = upload_house<real>(h, h->o_coef[3 + k], s, [&co, k](size_t i) { return co[i * 12 + 6 + k]; }))) return rc;
+    }
+    if (h->has_ratio) {
+      const double *src[4] = {st->Ua, st->Ca, st->Cm, st->Hm};
+      const double dflt[4] = {p.dUa, p.dCa, p.dCm, p.dHm};
+      for (int k = 0; k < 4; ++k) {
+        const double *a = src[k];
+        const double d = dflt[k];
+        if ((rc = upload_house<float>(h, h->o_ratio[k], s, [a, d](size_t i) { return a[i] / d; }))) return rc;
+      }
+    }
+    if (h->has_interp) {
+      if (!st->cap) return fail(DRSIM_E_ARG, "set_state: interpolation needs cap together with the thermal parameters");
+      auto *Ua = st->Ua; auto *Ca = st->Ca; auto *Cm = st->Cm; auto *Hm = st->Hm; auto *cap = st->cap;
+      const SimParams pp = p;
+      if ((rc = upload_house<uint8_t>(h, h->o_sub, s, [=](size_t i) {
+             // interpolation.py:148-162, :227-235, :245-264 (key order Ua, Cm, Ca, Hm, then HVAC_power)
+             const int iu = nearest3(Ua[i] / pp.dUa), icm = nearest3(Cm[i] / pp.dCm);
+             const int ica = nearest3(Ca[i] / pp.dCa), ihm = nearest3(Hm[i] / pp.dHm);
+             const double c = std::min(15000.0, std::max(10000.0, cap[i]));
+             const int ihv = std::fabs(10000.0 - c) <= std::fabs(15000.0 - c) ? 0 : 1;
+             return (((iu * 3 + icm) * 3 + ica) * 3 + ihm) * 2 + ihv;
+           })))
+        return rc;
+    }
+  }
+#define UP_ENV(field, T, off) \
+  if (st->field && (rc = upload_env<T>(h, off, s, st->field))) return rc;
+  UP_ENV(epoch, int64_t, h->o_epoch)
+  UP_ENV(od_temp, double, h->o_od)
+  UP_ENV(signal, double, h->o_signal)
+  UP_ENV(base_power, double, h->o_base)
+  UP_ENV(power, double, h->o_power)
+  UP_ENV(solar, double, h->o_solar_cur)
+  UP_ENV(artificial_ratio, double, h->o_art)
+  UP_ENV(max_power, double, h->o_maxp)
+  UP_ENV(t_since_interp, int32_t, h->o_tsi)
+#undef UP_ENV
+  if (st->t_since_interp) h->t_since_interp = st->t_since_interp[0];
+  if (st->epoch) {
+    // solar gain of the NEXT step's datetime (building.py:176-181 uses the already-advanced time)
+    std::vector<double> sn(p.R);
+    for (int r = 0; r < p.R; ++r)
+      sn[r] = p.solar_on ? solar_gain(civil_from_epoch(st->epoch[r] + p.dt), p.window_area, p.shading) : 0.0;
+    if ((rc = upload_env<double>(h, h->o_solar_next, s, sn.data()))) return rc;
+  }
+  return 0;
+}
+
+extern "C" int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *stream) {
+  if (!h || !st) return fail(DRSIM_E_ARG, "null argument");
+  CU_TRY(cudaSetDevice(h->device));
+  auto s = (cudaStream_t)stream;
+  return h->real_bytes == 8 ? set_state_t<double>(h, st, s) : set_state_t<float>(h, st, s);
+}
+
+template <typename T, typename DST>
+static int download_house(drsim_handle *h, size_t off, cudaStream_t s, DST *dst, int shift = 0, int mask = -1) {
+  const SimParams &p = h->p;
+  std::vector<T> buf((size_t)p.R * p.Ns);
+  CU_TRY(cudaMemcpyAsync(buf.data(), h->slab + off, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  for (int r = 0; r < p.R; ++r)
+    for (int n = 0; n < p.N; ++n) {
+      const T v = buf[(size_t)r * p.Ns + n];
+      dst[(size_t)r * p.N + n] = mask == -1 ? (DST)v : (DST)(((int)v >> shift) & mask);
+    }
+  return 0;
+}
+
+template <typename T, typename DST>
+static int download_env(drsim_handle *h, size_t off, cudaStream_t s, DST *dst) {
+  std::vector<T> buf(h->p.R);
+  CU_TRY(cudaMemcpyAsync(buf.data(), h->slab + off, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  for (int r = 0; r < h->p.R; ++r) dst[r] = (DST)buf[r];
+  return 0;
+}
+
+template <typename real>
+static int get_state_t(drsim_handle *h, drsim_host_state *st, cudaStream_t s) {
+  int rc;
+  if (st->t_air && (rc = download_house<real>(h, h->o_t_air, s, st->t_air))) return rc;
+  if (st->t_mass && (rc = download_house<real>(h, h->o_t_mass, s, st->t_mass))) return rc;
+  if (st->target && (rc = download_house<real>(h, h->o_target, s, st->target))) return rc;
+  if (st->cap && (rc = download_house<real>(h, h->o_cap, s, st->cap))) return rc;
+  if (st->sso && (rc = download_house<int32_t>(h, h->o_sso, s, st->sso))) return rc;
+  if (st->on && (rc = download_house<uint8_t>(h, h->o_flags, s, st->on, 0, 1))) return rc;
+  if (st->lockout && (rc = download_house<uint8_t>(h, h->o_flags, s, st->lockout, 1, 1))) return rc;
+  if (st->epoch && (rc = download_env<int64_t>(h, h->o_epoch, s, st->epoch))) return rc;
+  if (st->od_temp && (rc = download_env<double>(h, h->o_od, s, st->od_temp))) return rc;
+  if (st->signal && (rc = download_env<double>(h, h->o_signal, s, st->signal))) return rc;
+  if (st->base_power && (rc = download_env<double>(h, h->o_base, s, st->base_power))) return rc;
+  if (st->power && (rc = download_env<double>(h, h->o_power, s, st->power))) return rc;
+  if (st->solar && (rc = download_env<double>(h, h->o_solar_cur, s, st->solar))) return rc;
+  if (st->artificial_ratio && (rc = download_env<double>(h, h->o_art, s, st->artificial_ratio))) return rc;
+  if (st->max_power && (rc = download_env<double>(h, h->o_maxp, s, st->max_power))) return rc;
+  if (st->t_since_interp && (rc = download_env<int32_t>(h, h->o_tsi, s, st->t_since_interp))) return rc;
+  return 0;
+}
+
+extern "C" int drsim_get_state(drsim_t *h, drsim_host_state *st, void *stream) {
+  if (!h || !st) return fail(DRSIM_E_ARG, "null argument");
+  CU_TRY(cudaSetDevice(h->device));
+  auto s = (cudaStream_t)stream;
+  return h->real_bytes == 8 ? get_state_t<double>(h, st, s) : get_state_t<float>(h, st, s);
+}
+
+extern "C" int drsim_set_comm_table(drsim_t *h, const int32_t *table, int per_replica, void *stream) {
+  if (!h || !table) return fail(DRSIM_E_ARG, "null argument");
+  if (!h->has_comm) return fail(DRSIM_E_STATE, "handle was not created with comm_mode = DRSIM_COMM_TABLE and nb_comm > 0");
+  CU_TRY(cudaSetDevice(h->device));
+  const SimParams &p = h->p;
+  const size_t n = (size_t)(per_replica ? p.R : 1) * p.N * p.nb_comm;
+  for (size_t i = 0; i < n; ++i)
+    if (table[i] < 0 || table[i] >= p.n_global) return fail(DRSIM_E_ARG, "neighbour id out of range");
+  auto s = (cudaStream_t)stream;
+  CU_TRY(cudaMemcpyAsync(h->slab + h->o_comm, table, n * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  h->p.comm_per_rep = per_replica ? 1 : 0;
+  return 0;
+}
+
+extern "C" int drsim_set_interp_table(drsim_t *h, const double *sub, void *stream) {
+  if (!h || !sub) return fail(DRSIM_E_ARG, "null argument");
+  if (!h->has_interp) return fail(DRSIM_E_STATE, "handle was not created with base_power_mode = interpolation");
+  CU_TRY(cudaSetDevice(h->device));
+  const size_t n = (size_t)DRSIM_INTERP_SUBTABLES * DRSIM_INTERP_SUBTABLE_LEN;
+  auto s = (cudaStream_t)stream;
+  if (h->real_bytes == 8) {
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_interp, sub, n * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
+  } else {
+    std::vector<float> f(n);
+    for (size_t i = 0; i < n; ++i) f[i] = (float)sub[i];
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_interp, f.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+// ---- stepping ------------------------------------------------------------------------------
+template <typename real>
+static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const SimParams &p = h->p;
+  if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
+    int n2 = 1;
+    while (n2 < p.N) n2 <<= 1;
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
+    h->launches++;
+  }
+  k_house<real><<<p.R * h->chunks, kThreads, 0, s>>>(pl, p, in, h->chunks);
+  k_reduce<real><<<p.R, 128, 0, s>>>(pl, p, in, h->chunks);
+  h->launches += 2;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <typename real>
+static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const SimParams &p = h->p;
+  k_env<real><<<(p.R + 127) / 128, 128, 0, s>>>(pl, p, in, acc ? acc : pl.acc);
+  k_obs<real><<<p.R * h->obs_chunks, kObsChunk, (size_t)kObsChunk * p.obs_dim * sizeof(real), s>>>(pl, p, in, h->obs_chunks);
+  h->launches += 2;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <typename real>
+static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const SimParams &p = h->p;
+  if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
+    int n2 = 1;
+    while (n2 < p.N) n2 <<= 1;
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
+    h->launches++;
+  }
+  k_fused<real><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
+  h->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp) {
+  StepIn in{};
+  if (a) { in.actions = a->actions; in.od_noise = a->od_noise; in.perlin = a->perlin; in.interp_ids = a->interp_ids; }
+  in.step = h->step;
+  in.advance = advance;
+  in.do_interp = do_interp;
+  return in;
+}
+
+// decides whether the interpolator fires on this power-grid step (power_grid.py:150-161) and
+// advances the host mirror of the counter
+static int interp_decision(drsim_handle *h) {
+  if (h->p.base_mode != DRSIM_BASE_INTERPOLATION) return 0;
+  h->t_since_interp += h->p.dt;
+  if (h->t_since_interp >= h->p.interp_period) { h->t_since_interp = 0; return 1; }
+  return 0;
+}
+
+static int run_step(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp, cudaStream_t s) {
+  const StepIn in = make_in(h, a, advance, do_interp);
+  const bool dbl = h->real_bytes == 8;
+  int rc;
+  if (h->fused_ok && do_interp <= 0) {
+    rc = dbl ? launch_fused<double>(h, in, s) : launch_fused<float>(h, in, s);
+  } else {
+    if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "house-sharded cluster: use drsim_step_begin / drsim_step_finish");
+    rc = dbl ? launch_house_phase<double>(h, in, s) : launch_house_phase<float>(h, in, s);
+    if (rc) return rc;
+    rc = dbl ? launch_env_phase<double>(h, in, nullptr, s) : launch_env_phase<float>(h, in, nullptr, s);
+  }
+  return rc;
+}
+
+extern "C" int drsim_step(drsim_t *h, const drsim_step_args *args, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  CU_TRY(cudaSetDevice(h->device));
+  const int di = interp_decision(h);
+  int rc = run_step(h, args, 1, di, (cudaStream_t)stream);
+  if (!rc) h->step++;
+  return rc;
+}
+
+extern "C" int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  CU_TRY(cudaSetDevice(h->device));
+  if (h->p.N != h->p.n_global)
+    return fail(DRSIM_E_STATE, "drsim_refresh is not available on a house-sharded cluster");
+  int di = -1;
+  if (recompute_signal) di = interp_decision(h);
+  return run_step(h, args, 0, di, (cudaStream_t)stream);
+}
+
+extern "C" int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  CU_TRY(cudaSetDevice(h->device));
+  h->pending_interp = interp_decision(h);
+  const StepIn in = make_in(h, args, 1, h->pending_interp);
+  return h->real_bytes == 8 ? launch_house_phase<double>(h, in, (cudaStream_t)stream)
+                            : launch_house_phase<float>(h, in, (cudaStream_t)stream);
+}
+
+extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  CU_TRY(cudaSetDevice(h->device));
+  const StepIn in = make_in(h, args, 1, h->pending_interp);
+  int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, (cudaStream_t)stream)
+                              : launch_env_phase<float>(h, in, acc, (cudaStream_t)stream);
+  if (!rc) h->step++;
+  return rc;
+}
+
+extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                               const int32_t *interp_ids, double *env_out, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  CU_TRY(cudaSetDevice(h->device));
+  auto s = (cudaStream_t)stream;
+  const SimParams &p = h->p;
+  drsim_step_args a{};
+  if (actions) {
+    CU_TRY(cudaMemcpy2DAsync(h->slab + h->o_actions, p.Ns, actions, p.N, p.N, p.R, cudaMemcpyHostToDevice, s));
+    a.actions = h->at<uint8_t>(h->o_actions);
+  }
+  if (od_noise) {
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_od, od_noise, (size_t)p.R * 8, cudaMemcpyHostToDevice, s));
+    a.od_noise = h->at<double>(h->o_in_od);
+  }
+  if (perlin) {
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_perlin, perlin, (size_t)p.R * 8, cudaMemcpyHostToDevice, s));
+    a.perlin = h->at<double>(h->o_in_perlin);
+  }
+  if (interp_ids) {
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_ids, interp_ids, (size_t)p.R * p.interp_k * 4, cudaMemcpyHostToDevice, s));
+    a.interp_ids = h->at<int32_t>(h->o_in_ids);
+  }
+  int rc = drsim_step(h, &a, stream);
+  if (rc) return rc;
+  if (env_out) {
+    const size_t E8 = (size_t)p.R * 8;
+    CU_TRY(cudaMemcpyAsync(h->h_env, h->slab + h->o_power, E8 * 6, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const double *pw = h->h_env, *sg = pw + p.R, *od = sg + p.R, *ps = od + p.R, *pm = ps + p.R, *rs = pm + p.R;
+    for (int r = 0; r < p.R; ++r) {
+      double pen = ps[r];  // mean individual penalty == common_L2 value
+      if (p.penalty_mode == DRSIM_PEN_COMMON_MAX) pen = pm[r];
+      else if (p.penalty_mode == DRSIM_PEN_MIXTURE)
+        pen = (p.a_ind * ps[r] + p.a_cl2 * ps[r] + p.a_cmax * pm[r]) / (p.a_ind + p.a_cl2 + p.a_cmax);
+      env_out[r * 4 + 0] = pw[r];
+      env_out[r * 4 + 1] = sg[r];
+      env_out[r * 4 + 2] = od[r];
+      env_out[r * 4 + 3] = -(p.alpha_temp * pen / p.norm_temp + rs[r]);
+    }
+  } else {
+    CU_TRY(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+extern "C" int64_t drsim_launch_count(const drsim_t *h) { return h ? h->launches : 0; }
+
+// ---- host-side debug entry points ----------------------------------------------------------
+extern "C" double drsim_host_solar_gain(int64_t epoch, double window_area, double shading_coeff) {
+  return solar_gain(civil_from_epoch(epoch), window_area, shading_coeff);
+}
+extern "C" double drsim_host_od_temp(int64_t epoch, double day_temp, double night_temp, double phase, double noise) {
+  return od_temp_model(civil_from_epoch(epoch), day_temp, night_temp, phase, noise);
+}
+extern "C" void drsim_host_civil(int64_t epoch, int32_t out7[7]) {
+  const Civil c = civil_from_epoch(epoch);
+  out7[0] = c.year; out7[1] = c.month; out7[2] = c.day; out7[3] = c.hour; out7[4] = c.minute; out7[5] = c.second;
+  out7[6] = c.yday;
+}
+extern "C" void drsim_host_thermal_coefs(double Ua, double Ca, double Cm, double Hm, int32_t dt, double out12[12]) {
+  thermal_coefs(Ua, Ca, Cm, Hm, dt, out12);
+}
+extern "C" void drsim_host_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out4[4]) {
+  const U4 r = philox4x32_10(seed, c0, c1, c2, c3);
+  out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+
+extern "C" const char *drsim_last_error(void) { return g_err.c_str(); }
+extern "C" int drsim_abi_version(void) { return DRSIM_ABI_VERSION; }
+extern "C" int drsim_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(drsim_config);
+    case 1: return (int)sizeof(drsim_host_state);
+    case 2: return (int)sizeof(drsim_ptrs);
+    case 3: return (int)sizeof(drsim_step_args);
+    default: return -1;
+  }
+}

@@ -1,0 +1,812 @@
+// drsim_kernels.cuh -- sm_100a kernels of the demand-response environment step.
+//
+// Two execution paths over the same device functions (drsim_device.cuh):
+//
+//  * k_fused   one persistent kernel per step.  A CTA owns a *tile* of E whole clusters that
+//              are contiguous in every SoA plane; house state is read with 128-bit loads, kept in
+//              registers across the per-cluster power reduction (segmented warp shuffles + one
+//              shared-memory pass), the env-level epilogue (time, outdoor temperature, signal) runs
+//              on E threads, then rewards are written from registers and the observation rows are
+//              assembled in shared memory and leave through TMA bulk stores
+//              (cp.async.bulk.global.shared::cta).  Algorithmic bytes = every plane touched once.
+//  * k_house / k_reduce / k_env / k_obs   general path for clusters larger than a tile, for the
+//              steps on which the interpolated base power is re-evaluated, and for a single
+//              cluster split across GPUs (the all-gather of the per-rank partial sums sits between
+//              k_reduce and k_env).
+//
+// Reference citations are relative to /root/reference/server/app.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "drsim_device.cuh"
+
+namespace drsim {
+
+constexpr int kThreads = 256;       // CTA size of the house kernels
+constexpr int kHousesPerThread = 4; // one 128-bit access per fp32 plane
+constexpr int kTileSlots = kThreads * kHousesPerThread;
+constexpr int kRed = 5;             // reduced per cluster: P, sum pen/N, max pen, sum dT, sum dT^2
+constexpr int kObsChunk = 128;      // houses per k_obs CTA (general path)
+
+template <typename real>
+struct Planes {
+  // per-house state [R][Ns]
+  real *t_air, *t_mass;
+  int32_t *sso;
+  uint8_t *flags;
+  // per-house static [R][Ns]
+  const real *target, *cap;
+  const real *coef[9];       // fp32: c0..c5 ; fp64: Ua, Ca, Hm, r1, r2, A3, A4, e1, e2
+  const float *ratio[4];     // Ua, Ca, Cm, Hm over the defaults (only if an obs flag needs them)
+  const uint8_t *interp_sub; // nearest-neighbour cell of the interpolation table
+  // per-house outputs
+  real *reward;
+  real *obs;
+  uint8_t *actions;
+  // per-env [R]
+  int64_t *epoch;
+  double *od_temp, *solar_next, *solar_cur, *signal, *base_power, *power, *artificial_ratio, *max_power;
+  double *pen_sum, *pen_max, *rew_sig;
+  int32_t *t_since_interp;
+  double *metrics;   // [R][DRSIM_N_METRICS]
+  double *partials;  // [R][chunks][kRed]  (general path)
+  double *acc;       // [R][kRed + 1]      (general path: reduced values + interpolated sum)
+  const int32_t *comm_table;
+  const real *interp_table;  // [162][9][5][8][12][6]
+};
+
+struct StepIn {
+  const uint8_t *actions;
+  const double *od_noise;
+  const double *perlin;
+  const int32_t *interp_ids;
+  int64_t step;
+  int do_interp;
+  int advance;  // 1 = real step, 0 = refresh (recompute signal / obs without advancing time)
+};
+
+// ------------------------------------------------------------------------------------------
+// vector access helpers: 4 consecutive houses per thread
+// ------------------------------------------------------------------------------------------
+DRSIM_D void load4(const float *p, float v[4]) {
+  const float4 t = *reinterpret_cast<const float4 *>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+DRSIM_D void load4(const double *p, double v[4]) {
+  const double2 a = reinterpret_cast<const double2 *>(p)[0];
+  const double2 b = reinterpret_cast<const double2 *>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+DRSIM_D void load4_ro(const float *p, float v[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+DRSIM_D void load4_ro(const double *p, double v[4]) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+  const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+DRSIM_D void store4(float *p, const float v[4]) {
+  *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+DRSIM_D void store4(double *p, const double v[4]) {
+  reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+}
+DRSIM_D void load4i(const int32_t *p, int v[4]) {
+  const int4 t = *reinterpret_cast<const int4 *>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+DRSIM_D void store4i(int32_t *p, const int v[4]) {
+  *reinterpret_cast<int4 *>(p) = make_int4(v[0], v[1], v[2], v[3]);
+}
+DRSIM_D uint32_t load4b(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
+DRSIM_D void store4b(uint8_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
+
+template <typename real> struct NCoef;
+template <> struct NCoef<float> { static constexpr int n = 6; };
+template <> struct NCoef<double> { static constexpr int n = 9; };
+
+DRSIM_D void thermal_step(float &ta, float &tm, const float *c, float od, float Qa) {
+  thermal_step_f32(ta, tm, c, od, Qa);
+}
+DRSIM_D void thermal_step(double &ta, double &tm, const double *c, double od, double Qa) {
+  thermal_step_f64(ta, tm, c, od, Qa);
+}
+DRSIM_D float hvac_heat(float cap, float one_plus_latent) { return -cap / one_plus_latent; }
+DRSIM_D double hvac_heat(double cap, double one_plus_latent) { return DR_DIV(DR_MUL(-1.0, cap), one_plus_latent); }
+
+// ------------------------------------------------------------------------------------------
+// the per-thread house work: 4 houses, loaded with vector accesses, updated in registers
+// ------------------------------------------------------------------------------------------
+template <typename real>
+struct House4 {
+  real ta[4], tm[4], target[4], cap[4];
+  int sso[4];
+  uint32_t flags;  // 4 x u8
+  int valid;       // number of real houses among the 4 slots
+};
+
+// Loads state + static planes of 4 houses at plane offset `off`, applies the policy / action,
+// hvac.py:43-64, building.py:141-222, writes the state back and returns the per-thread partial
+// sums in red[kRed].
+template <typename real>
+DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const StepIn &in, size_t off,
+                         int valid, real od_prev, real solar, House4<real> &h, double red[kRed]) {
+  constexpr int NC = NCoef<real>::n;
+  real coef[NC][4];
+  load4(pl.t_air + off, h.ta);
+  load4(pl.t_mass + off, h.tm);
+  load4i(pl.sso + off, h.sso);
+  h.flags = load4b(pl.flags + off);
+  load4_ro(pl.target + off, h.target);
+  load4_ro(pl.cap + off, h.cap);
+#pragma unroll
+  for (int k = 0; k < NC; ++k) load4_ro(pl.coef[k] + off, coef[k]);
+  uint32_t act = 0;
+  if (p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC)
+    act = load4b((in.actions ? in.actions : pl.actions) + off);
+  h.valid = valid;
+  const real one_plus_latent = (real)(1.0 + p.latent);
+  const real cop = (real)p.cop;
+  const real db = (real)p.deadband;
+  real P = 0, ps = 0, pm = 0, ds = 0, d2 = 0;
+  uint32_t nf = h.flags;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < valid) {
+      uint32_t f = (h.flags >> (8 * j)) & 0xffu;
+      const bool ext = (act >> (8 * j)) & 0xffu;
+      const bool a = policy_action<real>(p.policy, h.ta[j], h.target[j], db, f & 1u, ext);
+      if (in.advance) {
+        hvac_fsm(f, h.sso[j], a, p.dt, p.lockout_duration);
+        const real q = (f & 1u) ? hvac_heat(h.cap[j], one_plus_latent) : (real)0;
+        real c[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) c[k] = coef[k][j];
+        thermal_step(h.ta[j], h.tm[j], c, od_prev, q + solar);
+      }
+      nf = (nf & ~(0xffu << (8 * j))) | (f << (8 * j));
+      if (f & 1u) P += h.cap[j] / cop;
+      const real pen = deadband_l2<real>(h.target[j], db, h.ta[j]);
+      ps += pen / (real)p.n_global;
+      pm = pen > pm ? pen : pm;
+      const real dT = h.ta[j] - h.target[j];
+      ds += dT;
+      d2 += dT * dT;
+    }
+  }
+  h.flags = nf;
+  if (in.advance) {
+    store4(pl.t_air + off, h.ta);
+    store4(pl.t_mass + off, h.tm);
+    store4i(pl.sso + off, h.sso);
+    store4b(pl.flags + off, h.flags);
+  }
+  red[0] = (double)P; red[1] = (double)ps; red[2] = (double)pm; red[3] = (double)ds; red[4] = (double)d2;
+}
+
+DRSIM_D void red_combine(double a[kRed], const double b[kRed]) {
+  a[0] += b[0]; a[1] += b[1]; a[2] = fmax(a[2], b[2]); a[3] += b[3]; a[4] += b[4];
+}
+
+// ------------------------------------------------------------------------------------------
+// env-level epilogue (one thread per cluster): environment.py:87-106
+// ------------------------------------------------------------------------------------------
+struct EnvRegs {
+  int64_t epoch;
+  double od_temp, solar_next, signal, base_power, artificial_ratio, max_power;
+  int t_since_interp;
+};
+
+template <typename real>
+DRSIM_D EnvRegs env_load(const Planes<real> &pl, int r) {
+  EnvRegs e;
+  e.epoch = pl.epoch[r];
+  e.od_temp = pl.od_temp[r];
+  e.solar_next = pl.solar_next[r];
+  e.signal = pl.signal[r];
+  e.base_power = pl.base_power[r];
+  e.artificial_ratio = pl.artificial_ratio[r];
+  e.max_power = pl.max_power[r];
+  e.t_since_interp = pl.t_since_interp[r];
+  return e;
+}
+
+// values the house/obs phases need from the env epilogue
+template <typename real>
+struct EnvBroadcast {
+  real power_n, signal_n, solar_n, od_n, rew_sig, pen_common, pen_max;
+};
+
+template <typename real>
+DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams &p, const StepIn &in,
+                                        int r, EnvRegs e, const double red[kRed], double interp_sum) {
+  const uint32_t env_global = (uint32_t)(p.rep_offset + r);
+  double solar_cur = pl.solar_cur[r];
+  double rew_sig = 0.0;
+  if (in.advance) {
+    e.epoch += p.dt;                                               // environment.py:87
+    solar_cur = e.solar_next;                                      // gain used by this step's update
+  }
+  const Civil now = civil_from_epoch(e.epoch);
+  if (in.advance) {
+    e.solar_next = p.solar_on ? solar_gain(civil_from_epoch(e.epoch + p.dt), p.window_area, p.shading) : 0.0;
+    double noise = 0.0;                                            // environment.py:158
+    if (in.od_noise) noise = in.od_noise[r];
+    else if (p.noise_mode == DRSIM_NOISE_PHILOX)
+      noise = p.temp_std * philox_normal(p.seed, env_global, 0u, (uint32_t)in.step, PURPOSE_OD);
+    e.od_temp = od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise);
+    const double dev = (red[0] - e.signal) / (double)p.n_global;   // rewards_calculator.py:198 (old signal, Q6)
+    rew_sig = p.alpha_sig * (dev * dev) / p.norm_sig;
+    // running rollout metrics (metrics_service.py:108-157 restated as per-cluster sums)
+    double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
+    m[0] += 1.0;
+    m[2] += fabs(red[3]) / (double)p.n_global;
+    m[3] += red[4] / (double)p.n_global;
+    m[4] += fabs(red[0] - e.signal);
+    m[5] += (red[0] - e.signal) * (red[0] - e.signal);
+  }
+  if (in.advance || in.do_interp >= 0) {
+    // power_grid.py:130-161
+    if (p.base_mode == DRSIM_BASE_CONSTANT) {
+      e.base_power = p.avg_power * (double)p.n_global;
+    } else if (in.do_interp > 0) {
+      const double factor = p.n_global <= p.interp_k ? 1.0 : (double)p.n_global / (double)p.interp_k;
+      e.base_power = interp_sum * factor;
+      e.t_since_interp = 0;
+    } else if (in.advance) {
+      e.t_since_interp += p.dt;
+    }
+    double perlin = 0.0;
+    if (p.signal_mode == DRSIM_SIG_PERLIN) {
+      if (in.perlin) perlin = in.perlin[r];
+      else if (p.noise_mode == DRSIM_NOISE_PHILOX) {
+        const double x = (double)(now.hour * 3600 + now.minute * 60 + now.second);
+        perlin = philox_perlin(p.seed, env_global, x / (double)p.period, p.nb_octaves, p.octaves_step);
+      }
+    }
+    e.signal = grid_signal(p, e.base_power, now, perlin, e.artificial_ratio, e.max_power);
+  }
+  pl.epoch[r] = e.epoch;
+  pl.od_temp[r] = e.od_temp;
+  pl.solar_next[r] = e.solar_next;
+  pl.solar_cur[r] = solar_cur;
+  pl.signal[r] = e.signal;
+  pl.base_power[r] = e.base_power;
+  pl.power[r] = red[0];
+  pl.pen_sum[r] = red[1];
+  pl.pen_max[r] = red[2];
+  pl.rew_sig[r] = rew_sig;
+  pl.t_since_interp[r] = e.t_since_interp;
+  EnvBroadcast<real> b;
+  b.power_n = (real)(red[0] / p.nrs);                              // norm.py:144-146
+  b.signal_n = (real)(e.signal / (p.nrs * (double)p.n_global));    // norm.py:132-135
+  b.solar_n = (real)(solar_cur / 1000.0);                          // norm.py:113-114
+  b.od_n = (real)((e.od_temp - 20.0) / 5.0);                       // norm.py:164-165
+  b.rew_sig = (real)rew_sig;
+  b.pen_common = (real)red[1];
+  b.pen_max = (real)red[2];
+  return b;
+}
+
+// rewards_calculator.py:135-181 for one house
+template <typename real>
+DRSIM_D real house_reward(const SimParams &p, real ta, real target, const EnvBroadcast<real> &e) {
+  const real ind = deadband_l2<real>(target, (real)p.deadband, ta);
+  real pen;
+  switch (p.penalty_mode) {
+    case DRSIM_PEN_COMMON_L2: pen = e.pen_common; break;
+    case DRSIM_PEN_COMMON_MAX: pen = e.pen_max; break;
+    case DRSIM_PEN_MIXTURE:
+      pen = ((real)p.a_ind * ind + (real)p.a_cl2 * e.pen_common + (real)p.a_cmax * e.pen_max) /
+            (real)(p.a_ind + p.a_cl2 + p.a_cmax);
+      break;
+    default: pen = ind;
+  }
+  return (real)-1 * ((real)p.alpha_temp * pen / (real)p.norm_temp + e.rew_sig);
+}
+
+// neighbour k of house n: ring (agent_communication_builder.py:63-85) or explicit table
+DRSIM_D int neighbour_of(const SimParams &p, const int32_t *table, int r, int n, int k) {
+  if (p.comm_mode == DRSIM_COMM_RING) {
+    const int N = (int)p.n_global, lo = p.nb_comm / 2;
+    int v = k < lo ? n - lo + k : n + 1 + (k - lo);
+    v %= N;
+    return v < 0 ? v + N : v;
+  }
+  const size_t base = p.comm_per_rep ? (size_t)r * p.N * p.nb_comm : 0;
+  return __ldg(table + base + (size_t)n * p.nb_comm + k);
+}
+
+// own-state part of the observation row (utils/norm.py:71-146)
+template <typename real>
+DRSIM_D int obs_own(real *row, const SimParams &p, uint32_t f, real sso_n, real ta, real tm, real target,
+                    const EnvBroadcast<real> &e, const float ratio[4]) {
+  int i = 0;
+  row[i++] = (real)(f & 1u);
+  row[i++] = (real)((f >> 1) & 1u);
+  row[i++] = sso_n;
+  row[i++] = (real)1;
+  if (p.st_hvac) { row[i++] = (real)1; row[i++] = (real)1; }
+  row[i++] = e.power_n;
+  row[i++] = e.signal_n;
+  row[i++] = (real)p.deadband;
+  row[i++] = (ta - (real)20) / (real)5;
+  row[i++] = (tm - (real)20) / (real)5;
+  row[i++] = (target - (real)20) / (real)5;
+  if (p.st_solar) row[i++] = e.solar_n;
+  if (p.st_thermal) {
+    row[i++] = (real)ratio[0]; row[i++] = (real)ratio[1]; row[i++] = (real)ratio[2]; row[i++] = (real)ratio[3];
+    row[i++] = e.od_n;
+  }
+  return i;
+}
+
+// ------------------------------------------------------------------------------------------
+// General path, kernel 1: house update + per-CTA partial sums.  grid = R * chunks CTAs.
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_house(Planes<real> pl, SimParams p, StepIn in, int chunks) {
+  const int r = blockIdx.x / chunks, c = blockIdx.x % chunks;
+  const int n0 = (c * kThreads + threadIdx.x) * kHousesPerThread;
+  double red[kRed] = {0, 0, 0, 0, 0};
+  if (n0 < p.N) {
+    House4<real> h;
+    const int valid = min(4, p.N - n0);
+    house4_step<real>(pl, p, in, (size_t)r * p.Ns + n0, valid, (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
+  }
+  // deterministic block reduction: warp shuffles, then warp 0 over the 8 warp partials
+  __shared__ double wp[kThreads / 32][kRed];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double t[kRed];
+#pragma unroll
+    for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+    red_combine(red, t);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < kRed; ++k) wp[w][k] = red[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a[kRed] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < kThreads / 32; ++i) red_combine(a, wp[i]);
+    double *dst = pl.partials + ((size_t)r * chunks + c) * kRed;
+    for (int k = 0; k < kRed; ++k) dst[k] = a[k];
+  }
+}
+
+// 5-D multilinear of scipy.interpolate.interpn as used by interpolation.py:137-178
+template <typename real>
+DRSIM_D real interp5(const real *sub, const real x[5]) {
+  const real g_air[9] = {-4, -2, -1, (real)-0.3, 0, (real)0.3, 1, 2, 4};
+  const real g_mass[5] = {-4, -2, 0, 2, 4};
+  const real g_od[8] = {1, 3, 5, 7, 9, 11, 13, 15};
+  const real g_hour[12] = {0, 10800, 21600, 25200, 27000, 39600, 46800, 57600, 61200, 63000, 75600, 86399};
+  const real g_date[6] = {0, 79, 171, 263, 354, 364};
+  const real *grids[5] = {g_air, g_mass, g_od, g_hour, g_date};
+  const int len[5] = {9, 5, 8, 12, 6};
+  const int stride[5] = {5 * 8 * 12 * 6, 8 * 12 * 6, 12 * 6, 6, 1};
+  int idx[5];
+  real y[5];
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    const real *g = grids[d];
+    real v = x[d];
+    v = v > g[len[d] - 1] ? g[len[d] - 1] : (v < g[0] ? g[0] : v);  // interpolation.py:245-264
+    int i = 0;
+    for (int k = 1; k < len[d] - 1; ++k) i += (g[k] <= v) ? 1 : 0;  // g[i] <= v < g[i+1], clipped to [0, n-2]
+    idx[d] = i;
+    y[d] = (v - g[i]) / (g[i + 1] - g[i]);
+  }
+  real value = 0;
+  for (int corner = 0; corner < 32; ++corner) {  // last dimension fastest (itertools.product order)
+    real w = 1;
+    int o = 0;
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      const int up = (corner >> (4 - d)) & 1;
+      w = w * (up ? y[d] : ((real)1 - y[d]));
+      o += (idx[d] + up) * stride[d];
+    }
+    value = value + __ldg(sub + o) * w;
+  }
+  return value;
+}
+
+// ------------------------------------------------------------------------------------------
+// General path, kernel 2: per-cluster reduction of the CTA partials (+ the interpolated base
+// power of the sampled houses this handle owns).  One CTA per cluster.
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, StepIn in, int chunks) {
+  const int r = blockIdx.x;
+  double red[kRed] = {0, 0, 0, 0, 0};
+  // fixed assignment + fixed combine order => deterministic
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x) red_combine(red, pl.partials + ((size_t)r * chunks + c) * kRed);
+  double isum = 0.0;
+  if (in.do_interp > 0) {
+    const int k_all = p.n_global <= p.interp_k ? (int)p.n_global : p.interp_k;
+    const Civil now = civil_from_epoch(pl.epoch[r] + (in.advance ? p.dt : 0));
+    // outdoor temperature the interpolator sees is the NEW one (environment.py:94,104-106);
+    // it is recomputed here exactly as the epilogue will (same noise source)
+    double noise = 0.0;
+    if (in.advance) {
+      if (in.od_noise) noise = in.od_noise[r];
+      else if (p.noise_mode == DRSIM_NOISE_PHILOX)
+        noise = p.temp_std * philox_normal(p.seed, (uint32_t)(p.rep_offset + r), 0u, (uint32_t)in.step, PURPOSE_OD);
+    }
+    const double od_new = in.advance ? od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise) : pl.od_temp[r];
+    for (int k = threadIdx.x; k < k_all; k += blockDim.x) {
+      int64_t id;
+      if (p.n_global <= p.interp_k) id = k;                       // interpolation.py:220-222
+      else if (in.interp_ids) id = in.interp_ids[(size_t)r * p.interp_k + k];
+      else {                                                       // random.choices, :223
+        const U4 u = philox4x32_10(p.seed, (uint32_t)(p.rep_offset + r), (uint32_t)k, (uint32_t)in.step, PURPOSE_INTERP);
+        id = (int64_t)(((uint64_t)u.x * (uint64_t)p.n_global) >> 32);
+      }
+      id -= p.house_offset;
+      if (id < 0 || id >= p.N) continue;                           // owned by another rank
+      const size_t o = (size_t)r * p.Ns + id;
+      const real tgt = pl.target[o];
+      real x[5];
+      x[0] = pl.t_air[o] - tgt;
+      x[1] = pl.t_mass[o] - tgt;
+      x[2] = (real)od_new - tgt;
+      if (p.solar_on) {
+        x[3] = (real)(now.hour * 3600 + now.minute * 60 + now.second);
+        x[4] = (real)now.yday;                                     // quirk Q12
+      } else {
+        x[3] = 0; x[4] = 0;
+      }
+      isum += (double)interp5<real>(pl.interp_table + (size_t)pl.interp_sub[o] * DRSIM_INTERP_SUBTABLE_LEN, x);
+    }
+  }
+  __shared__ double wp[4][kRed + 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double t[kRed];
+#pragma unroll
+    for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+    red_combine(red, t);
+    isum += __shfl_down_sync(0xffffffffu, isum, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    for (int k = 0; k < kRed; ++k) wp[w][k] = red[k];
+    wp[w][kRed] = isum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a[kRed] = {0, 0, 0, 0, 0};
+    double s = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { red_combine(a, wp[i]); s += wp[i][kRed]; }
+    double *dst = pl.acc + (size_t)r * (kRed + 1);
+    for (int k = 0; k < kRed; ++k) dst[k] = a[k];
+    dst[kRed] = s;
+  }
+}
+
+// General path, kernel 3: env epilogue, one thread per cluster.  `acc` holds the (possibly
+// cross-rank combined) reduced values.
+template <typename real>
+__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.R) return;
+  const double *a = acc + (size_t)r * (kRed + 1);
+  double red[kRed];
+  for (int k = 0; k < kRed; ++k) red[k] = a[k];
+  env_epilogue<real>(pl, p, in, r, env_load(pl, r), red, a[kRed]);
+}
+
+// General path, kernel 4: rewards + observation rows for a chunk of kObsChunk houses.
+// Neighbour messages are gathered from global memory (any table); rows are assembled in shared
+// memory and written back with coalesced 128-bit stores.
+template <typename real>
+__global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p, StepIn in, int chunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  real *tile = reinterpret_cast<real *>(smem_raw);
+  const int r = blockIdx.x / chunks, c = blockIdx.x % chunks;
+  const int n = c * kObsChunk + threadIdx.x;
+  const int D = p.obs_dim;
+  EnvBroadcast<real> e;
+  e.power_n = (real)(pl.power[r] / p.nrs);
+  e.signal_n = (real)(pl.signal[r] / (p.nrs * (double)p.n_global));
+  e.solar_n = (real)(pl.solar_cur[r] / 1000.0);
+  e.od_n = (real)((pl.od_temp[r] - 20.0) / 5.0);
+  e.rew_sig = (real)pl.rew_sig[r];
+  e.pen_common = (real)pl.pen_sum[r];
+  e.pen_max = (real)pl.pen_max[r];
+  const real nrs = (real)p.nrs, cop = (real)p.cop;
+  const int dur = p.lockout_duration;
+  const size_t rb = (size_t)r * p.Ns;
+  if (n < p.Ns) {
+    real *row = tile + (size_t)threadIdx.x * D;
+    if (n < p.N) {
+      const size_t o = rb + n;
+      const real ta = pl.t_air[o], tm = pl.t_mass[o], tgt = pl.target[o];
+      if (in.advance) pl.reward[o] = house_reward<real>(p, ta, tgt, e);
+      if (D > 0) {
+        float ratio[4] = {0, 0, 0, 0};
+        if (p.st_thermal)
+          for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][o];
+        const uint32_t f = pl.flags[o];
+        int i = obs_own<real>(row, p, f, (real)(pl.sso[o] / dur), ta, tm, tgt, e, ratio);
+        if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
+          const int n_glob = n + (int)p.house_offset;
+          for (int k = 0; k < p.nb_comm; ++k) {
+            const int nb = neighbour_of(p, pl.comm_table, r, n_glob, k) - (int)p.house_offset;
+            // a neighbour owned by another rank is served from the halo planes appended after
+            // the local houses (see drsim_api.cu); nb is then remapped by the host-built table
+            const size_t q = rb + nb;
+            const real cap_k = pl.cap[q];
+            row[i++] = (pl.t_air[q] - pl.target[q]) / (real)5;     // norm.py:39
+            row[i++] = (real)(pl.sso[q] / dur);                    // norm.py:40-43
+            row[i++] = ((pl.flags[q] & 1u) ? cap_k / cop : (real)0) / nrs;
+            row[i++] = (cap_k / cop) / nrs;
+            if (p.msg_thermal)
+              for (int m = 0; m < 4; ++m) row[i++] = (real)pl.ratio[m][q];
+            if (p.msg_hvac) {                                      // constants, quirk Q11
+              row[i++] = (real)p.cop; row[i++] = (real)p.latent; row[i++] = (real)p.dcap;
+            }
+          }
+        }
+      }
+    } else {
+      for (int i = 0; i < D; ++i) row[i] = (real)0;  // padding slot
+    }
+  }
+  if (D == 0) return;
+  __syncthreads();
+  const int rows = min(kObsChunk, p.Ns - c * kObsChunk);
+  const size_t bytes = (size_t)rows * D * sizeof(real);  // rows % 4 == 0 -> multiple of 16
+  const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+  uint4 *dst = reinterpret_cast<uint4 *>(pl.obs + (rb + (size_t)c * kObsChunk) * D);
+  for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk store helpers (shared::cta -> global), PTX ISA cp.async.bulk
+// ------------------------------------------------------------------------------------------
+DRSIM_D void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+DRSIM_D void bulk_store_wait_read() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+DRSIM_D void fence_proxy_async_smem() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// geometry of the fused tile kernel, computed on the host
+struct FusedGeom {
+  int envs_per_tile;   // E: whole clusters per tile (E * Ns <= kTileSlots)
+  int n_tiles;         // ceil(R / E)
+  int chunk_rows;      // observation rows staged per TMA store (multiple of 4)
+  int max_segs;        // max clusters overlapping one warp (+1)
+  // dynamic shared memory offsets (bytes)
+  int off_msg, off_own, off_env, off_wp, off_tile, smem_bytes;
+};
+
+template <typename real>
+struct alignas(16) Msg4 {
+  real dT, sso_n, p_n, pmax_n;
+};
+template <typename real>
+struct alignas(16) Own4 {
+  real ta, tm, target, flags;
+};
+
+// ------------------------------------------------------------------------------------------
+// Fused path: one persistent kernel per step.
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p, StepIn in, FusedGeom g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Msg4<real> *s_msg = reinterpret_cast<Msg4<real> *>(smem_raw + g.off_msg);
+  Own4<real> *s_own = reinterpret_cast<Own4<real> *>(smem_raw + g.off_own);
+  EnvBroadcast<real> *s_env = reinterpret_cast<EnvBroadcast<real> *>(smem_raw + g.off_env);
+  double *s_wp = reinterpret_cast<double *>(smem_raw + g.off_wp);  // [warps][max_segs][kRed]
+  real *s_tile = reinterpret_cast<real *>(smem_raw + g.off_tile);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ns = p.Ns, D = p.obs_dim;
+  const real nrs = (real)p.nrs, cop = (real)p.cop;
+  const int dur = p.lockout_duration;
+  bool store_pending = false;
+
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+    const int r0 = tile * g.envs_per_tile;
+    const int E = min(g.envs_per_tile, p.R - r0);
+    const int slots = E * Ns;
+    const size_t base = (size_t)r0 * Ns;
+
+    // env state of the tile's clusters is fetched early by the threads that will run the epilogue
+    EnvRegs er;
+    if (threadIdx.x < E) er = env_load(pl, r0 + threadIdx.x);
+
+    // ---- phase 1: house update in registers --------------------------------------------
+    const int s0 = threadIdx.x * kHousesPerThread;
+    const int e_loc = s0 < slots ? s0 / Ns : -1 - warp;  // inactive threads never match a segment
+    House4<real> h;
+    double red[kRed] = {0, 0, 0, 0, 0};
+    if (s0 < slots) {
+      const int r = r0 + e_loc;
+      const int n0 = s0 - e_loc * Ns;
+      const int valid = min(4, p.N - n0);  // <= 0 only for pure padding slots (Ns - N < 4)
+      house4_step<real>(pl, p, in, base + s0, valid < 0 ? 0 : valid, (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
+        const real pmax = h.cap[j] / cop;
+        Msg4<real> m;
+        m.dT = (h.ta[j] - h.target[j]) / (real)5;                  // norm.py:39
+        m.sso_n = (real)(h.sso[j] / dur);                          // norm.py:40-43
+        m.p_n = ((f & 1u) ? pmax : (real)0) / nrs;
+        m.pmax_n = pmax / nrs;
+        Own4<real> o;
+        o.ta = h.ta[j]; o.tm = h.tm[j]; o.target = h.target[j]; o.flags = (real)f;
+        if (j >= h.valid) { m.dT = m.sso_n = m.p_n = m.pmax_n = 0; o.ta = o.tm = o.target = o.flags = 0; }
+        s_msg[s0 + j] = m;
+        s_own[s0 + j] = o;
+      }
+    }
+    // segmented warp reduction over clusters (lanes of one cluster are contiguous)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double t[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+      const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
+      if (lane + o < 32 && eo == e_loc) red_combine(red, t);
+    }
+    const int e_prev = __shfl_up_sync(0xffffffffu, e_loc, 1);
+    const bool head = (lane == 0) || (e_prev != e_loc);
+    const int e_first = __shfl_sync(0xffffffffu, e_loc, 0);
+    if (head && e_loc >= 0) {
+      double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) dst[k] = red[k];
+    }
+    // the previous tile's bulk store must have finished READING the staging tile before any
+    // thread overwrites it in phase 3 of this tile
+    if (store_pending && threadIdx.x == 0) bulk_store_wait_read();
+    __syncthreads();
+
+    // ---- phase 2: env epilogue on E threads ---------------------------------------------
+    if (threadIdx.x < E) {
+      const int e = threadIdx.x;
+      const int w_lo = (e * Ns) / 128, w_hi = ((e + 1) * Ns - 1) / 128;
+      double a[kRed] = {0, 0, 0, 0, 0};
+      for (int w = w_lo; w <= w_hi; ++w) {
+        const int ef = (w * 128) / Ns;  // first cluster seen by warp w
+        red_combine(a, s_wp + ((size_t)w * g.max_segs + (e - ef)) * kRed);
+      }
+      s_env[e] = env_epilogue<real>(pl, p, in, r0 + e, er, a, 0.0);
+    }
+    __syncthreads();
+
+    // ---- phase 3: rewards from registers, observation rows through shared memory --------
+    if (s0 < slots && in.advance) {
+      const EnvBroadcast<real> e = s_env[e_loc];
+      real rw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rw[j] = j < h.valid ? house_reward<real>(p, h.ta[j], h.target[j], e) : (real)0;
+      store4(pl.reward + base + s0, rw);
+    }
+    if (D > 0) {
+      for (int cb = 0; cb < slots; cb += g.chunk_rows) {
+        const int rows = min(g.chunk_rows, slots - cb);
+        if (cb > 0) {
+          if (threadIdx.x == 0) bulk_store_wait_read();
+          __syncthreads();
+        }
+        for (int i = threadIdx.x; i < rows; i += kThreads) {
+          const int s = cb + i;
+          const int e = s / Ns, n = s - e * Ns;
+          real *row = s_tile + (size_t)i * D;
+          if (n < p.N) {
+            const Own4<real> o = s_own[s];
+            const Msg4<real> m = s_msg[s];
+            float ratio[4] = {0, 0, 0, 0};
+            if (p.st_thermal)
+              for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s];
+            int q = obs_own<real>(row, p, (uint32_t)o.flags, m.sso_n, o.ta, o.tm, o.target, s_env[e], ratio);
+            if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
+              for (int k = 0; k < p.nb_comm; ++k) {
+                const int nb = neighbour_of(p, pl.comm_table, r0 + e, n, k);
+                const Msg4<real> mk = s_msg[e * Ns + nb];
+                row[q++] = mk.dT; row[q++] = mk.sso_n; row[q++] = mk.p_n; row[q++] = mk.pmax_n;
+                if (p.msg_thermal)
+                  for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][base + e * Ns + nb];
+                if (p.msg_hvac) { row[q++] = (real)p.cop; row[q++] = (real)p.latent; row[q++] = (real)p.dcap; }
+              }
+            }
+          } else {
+            for (int q = 0; q < D; ++q) row[q] = (real)0;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          bulk_store_s2g(pl.obs + (base + cb) * D, s_tile, (uint32_t)((size_t)rows * D * sizeof(real)));
+          store_pending = true;
+        }
+      }
+    }
+    // s_msg / s_own / s_env / s_wp are rewritten by the next tile's phase 1: all readers are done
+    // after this barrier (the staging tile itself is protected by wait_group.read above)
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && store_pending) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Greedy-myopic controller on device (greedy_myopic_controller.py:67-104): one CTA per cluster,
+// bitonic sort of (key, id) in shared memory, then the inherently sequential knapsack scan.
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, int n_pow2) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *key = reinterpret_cast<double *>(smem_raw);
+  int *idx = reinterpret_cast<int *>(key + n_pow2);
+  const int r = blockIdx.x;
+  const size_t rb = (size_t)r * p.Ns;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    if (i < p.N) {
+      key[i] = -(double)(pl.t_air[rb + i] - pl.target[rb + i]);
+      idx[i] = i;
+    } else {
+      key[i] = INFINITY;
+      idx[i] = 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const double ki = key[i], kl = key[l];
+          const int ii = idx[i], il = idx[l];
+          const bool gt = (ki > kl) || (ki == kl && ii > il);  // (key, id) order == stable sort
+          if (gt == up) { key[i] = kl; key[l] = ki; idx[i] = il; idx[l] = ii; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < p.Ns; i += blockDim.x) pl.actions[rb + i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double target = pl.signal[r];
+    double total = 0.0;
+    for (int i = 0; i < p.N; ++i) {
+      const int hh = idx[i];
+      const double pw = (double)pl.cap[rb + hh] / p.cop;
+      const bool lock = (pl.flags[rb + hh] >> 1) & 1u;
+      if (pw + total < target || (fabs(pw + total - target) < fabs(total - target) && !lock)) {
+        total += pw;
+        pl.actions[rb + hh] = 1;
+      }
+    }
+  }
+}
+
+}  // namespace drsim
