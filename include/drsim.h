@@ -145,12 +145,20 @@ typedef struct drsim_host_state {
   double *artificial_ratio;        /* PowerGridProperties.artificial_ratio (post-draw)    */
   double *max_power;               /* Cluster.max_power                                   */
   int32_t *t_since_interp;         /* PowerGrid.time_since_last_interp                    */
+  /* optional [n_rep][n_house][12]: precomputed output of drsim_host_thermal_coefs for each house
+   * (set_state only).  When NULL the library derives it from Ua, Ca, Cm, Hm with libm; a caller
+   * that wants the constants of building.py:196-206 bit-identical to NumPy's passes its own. */
+  double *thermal_coefs;
 } drsim_host_state;
 
 /* Device pointers of a handle (zero-copy views for torch / cupy).  `real` planes are float
  * (DRSIM_F32) or double (DRSIM_F64). */
 typedef struct drsim_ptrs {
   int32_t n_rep, n_house, house_stride, obs_dim, real_bytes, nb_comm;
+  /* 1 (DRSIM_F32): the t_air / t_mass planes hold the DEVIATION from the house set-point,
+   * Ta - target and Tm - target (what reward, messages, controllers and the interpolator consume;
+   * it also keeps fp32 rounding at the 1e-7 degC level); 0 (DRSIM_F64): absolute degC. */
+  int32_t temp_is_deviation, pad_;
   void *t_air, *t_mass;        /* real  [R][stride] */
   int32_t *sso;                /* i32   [R][stride] */
   uint8_t *flags;              /* u8    [R][stride]  bit0 = turned_on, bit1 = lockout */

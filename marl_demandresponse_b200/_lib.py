@@ -68,13 +68,14 @@ class HostState(C.Structure):
         ("on", _pu8), ("lockout", _pu8), ("sso", _pi32), ("epoch", _pi64),
         ("od_temp", _pd), ("signal", _pd), ("base_power", _pd), ("power", _pd), ("solar", _pd),
         ("artificial_ratio", _pd), ("max_power", _pd), ("t_since_interp", _pi32),
+        ("thermal_coefs", _pd),
     ]
 
 
 class Ptrs(C.Structure):
     _fields_ = [
         ("n_rep", _i32), ("n_house", _i32), ("house_stride", _i32), ("obs_dim", _i32), ("real_bytes", _i32),
-        ("nb_comm", _i32),
+        ("nb_comm", _i32), ("temp_is_deviation", _i32), ("pad_", _i32),
         ("t_air", C.c_void_p), ("t_mass", C.c_void_p), ("sso", C.c_void_p), ("flags", C.c_void_p),
         ("target", C.c_void_p), ("cap", C.c_void_p), ("reward", C.c_void_p), ("obs", C.c_void_p),
         ("actions", C.c_void_p), ("epoch", C.c_void_p),

@@ -32,6 +32,22 @@ def nb_comm_of(props: EnvironmentProperties) -> int:
     return int(min(cp.agents_comm_prop.max_nb_agents_communication, cp.nb_agents - 1))
 
 
+def comm_width(props: EnvironmentProperties) -> int:
+    """Number of neighbour messages per agent = width of the table the reference builds:
+    ``neighbours`` / ``random_*``: nb_comm; ``closed_groups``: the un-clamped
+    ``max_nb_agents_communication`` when the first group is complete
+    (agent_communication_builder.py:94-101); ``neighbours_2D``: 2 d (d + 1) cells of the
+    Manhattan ball (:152-166), independent of nb_comm."""
+    cp = props.cluster_prop.agents_comm_prop
+    c = nb_comm_of(props)
+    if cp.mode == "neighbours_2D":
+        d = cp.max_communication_distance
+        return 2 * d * (d + 1)
+    if cp.mode == "closed_groups" and c <= props.cluster_prop.nb_agents:
+        return cp.max_nb_agents_communication if c == cp.max_nb_agents_communication else c
+    return c
+
+
 def flatten_config(props: Any, n_rep: int = 1, precision: str = "f32", obs_layout: str = "hand_engineered",
                    policy: str = "external", noise: str = "zero", seed: int = 0, path: str = "auto",
                    comm_table: bool | None = None, house_offset: int = 0, n_house_local: int | None = None,
@@ -88,7 +104,7 @@ def flatten_config(props: Any, n_rep: int = 1, precision: str = "f32", obs_layou
     c.amplitude_per_hvac = float(sp.amplitude_per_hvac)
     c.nb_octaves, c.octaves_step, c.period = sp.nb_octaves, sp.octaves_step, sp.period
     c.obs_layout = _lib.OBS[obs_layout]
-    c.nb_comm = nb_comm_of(p)
+    c.nb_comm = comm_width(p)
     mode = p.cluster_prop.agents_comm_prop.mode
     if comm_table is None:
         comm_table = mode != "neighbours"
@@ -100,6 +116,40 @@ def flatten_config(props: Any, n_rep: int = 1, precision: str = "f32", obs_layou
     c.policy = _lib.POLICY[policy]
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     return c
+
+
+def thermal_coefs(Ua, Ca, Cm, Hm, dt: int) -> np.ndarray:
+    """Vectorised fp64 derivation of the per-house update constants (building.py:186-206), laid
+    out as ``drsim_host_thermal_coefs`` does: [..., 0:6] difference-form coefficients of the fp32
+    path, [..., 6:12] = r1, r2, A3, A4, e1, e2 of the fp64 literal replay.  Computed with NumPy so
+    the fp64 constants are the very numbers the reference's ``np.sqrt`` / ``np.exp`` produce."""
+    Ua, Ca, Cm, Hm = (np.asarray(x, dtype=np.float64) for x in (Ua, Ca, Cm, Hm))
+    a = Cm * Ca / Hm
+    b = Cm * (Ua + Hm) / Hm + Ca
+    c = Ua
+    root = np.sqrt(b * b - 4 * a * c)
+    r1 = (-b + root) / (2 * a)
+    r2 = (-b - root) / (2 * a)
+    A3 = r1 * Ca / Hm + (Ua + Hm) / Hm
+    A4 = r2 * Ca / Hm + (Ua + Hm) / Hm
+    e1 = np.exp(r1 * dt)
+    e2 = np.exp(r2 * dt)
+
+    def F(ta, tm, od, Qa):  # the linear map (Ta, Tm, Tod, Qa) -> (Ta', Tm') on a basis vector
+        d = Qa + Ua * od
+        dT = Hm * tm / Ca - (Ua + Hm) * ta / Ca + Ua * od / Ca + Qa / Ca
+        A1 = (r2 * ta - dT - r2 * d / c) / (r2 - r1)
+        A2 = ta - d / c - A1
+        return A1 * e1 + A2 * e2 + d / c, A1 * A3 * e1 + A2 * A4 * e2 + d / c
+
+    out = np.empty(Ua.shape + (12,), dtype=np.float64)
+    out[..., 0], _ = F(0.0, 1.0, 0.0, 0.0)
+    out[..., 1], out[..., 4] = F(0.0, 0.0, 1.0, 0.0)
+    out[..., 2], out[..., 5] = F(0.0, 0.0, 0.0, 1.0)
+    _, out[..., 3] = F(1.0, 0.0, 0.0, 0.0)
+    for k, v in enumerate((r1, r2, A3, A4, e1, e2)):
+        out[..., 6 + k] = v
+    return out
 
 
 _HOUSE_F64 = ("t_air", "t_mass", "target", "Ua", "Ca", "Cm", "Hm", "cap")
@@ -190,6 +240,10 @@ class DrSim:
                 put(k, st[k], np.float64, (R,), _lib._pd)
         if "t_since_interp" in st:
             put("t_since_interp", st["t_since_interp"], np.int32, (R,), _lib._pi32)
+        if all(k in st for k in ("Ua", "Ca", "Cm", "Hm")):
+            bc = lambda k: np.broadcast_to(np.asarray(st[k], dtype=np.float64), (R, N))
+            co = thermal_coefs(bc("Ua"), bc("Ca"), bc("Cm"), bc("Hm"), int(self.cfg.dt))
+            put("thermal_coefs", co, np.float64, (R, N, 12), _lib._pd)
         _lib.check(self._L.drsim_set_state(self._h, C.byref(hs), self._stream(stream)))
 
     def get_state(self, keys=None, stream=None) -> Dict[str, np.ndarray]:
@@ -313,8 +367,15 @@ class DrSim:
             return x
 
         v: Dict[str, Any] = {}
-        for k in ("t_air", "t_mass", "target", "cap", "reward"):
+        for k in ("target", "cap", "reward"):
             v[k] = t(getattr(p, k), (R, Ns), rt)[:, :N]
+        # fp32 build: the planes hold Ta - target / Tm - target; fp64 build: absolute degC
+        ta, tm = t(p.t_air, (R, Ns), rt)[:, :N], t(p.t_mass, (R, Ns), rt)[:, :N]
+        v["temp_is_deviation"] = bool(p.temp_is_deviation)
+        if p.temp_is_deviation:
+            v["dt_air"], v["dt_mass"] = ta, tm
+        else:
+            v["t_air"], v["t_mass"] = ta, tm
         v["sso"] = t(p.sso, (R, Ns), "<i4")[:, :N]
         v["flags"] = t(p.flags, (R, Ns), "|u1")[:, :N]
         v["actions"] = t(p.actions, (R, Ns), "|u1")[:, :N]

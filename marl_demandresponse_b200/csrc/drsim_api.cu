@@ -83,7 +83,7 @@ static Planes<real> make_planes(const drsim_handle *h) {
   pl.target = h->at<real>(h->o_target);
   pl.cap = h->at<real>(h->o_cap);
   for (int k = 0; k < NCoef<real>::n; ++k) pl.coef[k] = h->at<real>(h->o_coef[k]);
-  for (int k = 0; k < 4; ++k) pl.ratio[k] = h->has_ratio ? h->at<float>(h->o_ratio[k]) : nullptr;
+  for (int k = 0; k < 4; ++k) pl.ratio[k] = h->has_ratio ? h->at<real>(h->o_ratio[k]) : nullptr;
   pl.interp_sub = h->has_interp ? h->at<uint8_t>(h->o_sub) : nullptr;
   pl.reward = h->at<real>(h->o_reward);
   pl.obs = h->p.obs_dim ? h->at<real>(h->o_obs) : nullptr;
@@ -262,7 +262,7 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   h->o_target = cv.take(HP * rb); h->o_cap = cv.take(HP * rb);
   const int nc = cfg->precision == DRSIM_F64 ? 9 : 6;
   for (int k = 0; k < nc; ++k) h->o_coef[k] = cv.take(HP * rb);
-  if (h->has_ratio) for (int k = 0; k < 4; ++k) h->o_ratio[k] = cv.take(HP * 4);
+  if (h->has_ratio) for (int k = 0; k < 4; ++k) h->o_ratio[k] = cv.take(HP * rb);
   if (h->has_interp) { h->o_sub = cv.take(HP); h->o_interp = cv.take((size_t)DRSIM_INTERP_SUBTABLES * DRSIM_INTERP_SUBTABLE_LEN * rb); }
   h->o_reward = cv.take(HP * rb);
   h->o_obs = cv.take(HP * p.obs_dim * rb + 16);
@@ -327,6 +327,7 @@ extern "C" int drsim_buffers(drsim_t *h, drsim_ptrs *o) {
   memset(o, 0, sizeof(*o));
   o->n_rep = h->p.R; o->n_house = h->p.N; o->house_stride = h->p.Ns; o->obs_dim = h->p.obs_dim;
   o->real_bytes = h->real_bytes; o->nb_comm = h->p.nb_comm;
+  o->temp_is_deviation = h->real_bytes == 4 ? 1 : 0;
   o->t_air = h->slab + h->o_t_air; o->t_mass = h->slab + h->o_t_mass;
   o->sso = h->at<int32_t>(h->o_sso); o->flags = h->at<uint8_t>(h->o_flags);
   o->target = h->slab + h->o_target; o->cap = h->slab + h->o_cap;
@@ -365,6 +366,29 @@ static int upload_env(drsim_handle *h, size_t off, cudaStream_t s, const SRC *sr
   return 0;
 }
 
+template <typename T, typename DST>
+static int download_house(drsim_handle *h, size_t off, cudaStream_t s, DST *dst, int shift = 0, int mask = -1) {
+  const SimParams &p = h->p;
+  std::vector<T> buf((size_t)p.R * p.Ns);
+  CU_TRY(cudaMemcpyAsync(buf.data(), h->slab + off, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  for (int r = 0; r < p.R; ++r)
+    for (int n = 0; n < p.N; ++n) {
+      const T v = buf[(size_t)r * p.Ns + n];
+      dst[(size_t)r * p.N + n] = mask == -1 ? (DST)v : (DST)(((int)v >> shift) & mask);
+    }
+  return 0;
+}
+
+template <typename T, typename DST>
+static int download_env(drsim_handle *h, size_t off, cudaStream_t s, DST *dst) {
+  std::vector<T> buf(h->p.R);
+  CU_TRY(cudaMemcpyAsync(buf.data(), h->slab + off, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  for (int r = 0; r < h->p.R; ++r) dst[r] = (DST)buf[r];
+  return 0;
+}
+
 static int nearest3(double v) {  // grid {0.9, 1, 1.1}, np.argmin(|grid - v|) after clipping
   v = std::min(1.1, std::max(0.9, v));
   const double g[3] = {0.9, 1, 1.1};
@@ -386,9 +410,26 @@ static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t
     auto *src = st->field;                                                                \
     if ((rc = upload_house<T>(h, off, s, [src](size_t i) { return src[i]; }))) return rc; \
   }
-  UP_HOUSE(t_air, real, h->o_t_air)
-  UP_HOUSE(t_mass, real, h->o_t_mass)
   UP_HOUSE(target, real, h->o_target)
+  if (st->t_air || st->t_mass) {
+    // fp32 planes carry Ta - target / Tm - target (formed in fp64, then rounded once)
+    std::vector<double> tgt;
+    const double *tg = st->target;
+    if (sizeof(real) == 4 && !tg) {
+      tgt.resize((size_t)p.R * p.N);
+      if ((rc = download_house<real>(h, h->o_target, s, tgt.data()))) return rc;
+      tg = tgt.data();
+    }
+    const bool devi = sizeof(real) == 4;
+    if (st->t_air) {
+      auto *src = st->t_air;
+      if ((rc = upload_house<real>(h, h->o_t_air, s, [=](size_t i) { return devi ? src[i] - tg[i] : src[i]; }))) return rc;
+    }
+    if (st->t_mass) {
+      auto *src = st->t_mass;
+      if ((rc = upload_house<real>(h, h->o_t_mass, s, [=](size_t i) { return devi ? src[i] - tg[i] : src[i]; }))) return rc;
+    }
+  }
   UP_HOUSE(cap, real, h->o_cap)
   UP_HOUSE(sso, int32_t, h->o_sso)
 #undef UP_HOUSE
@@ -402,11 +443,16 @@ static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t
   if (st->Ua || st->Ca || st->Cm || st->Hm) {
     if (!(st->Ua && st->Ca && st->Cm && st->Hm)) return fail(DRSIM_E_ARG, "set_state: Ua, Ca, Cm, Hm must be given together");
     const size_t n = (size_t)p.R * p.N;
-    std::vector<double> co(n * 12);
-    for (size_t i = 0; i < n; ++i) thermal_coefs(st->Ua[i], st->Ca[i], st->Cm[i], st->Hm[i], p.dt, &co[i * 12]);
+    std::vector<double> co_own;
+    const double *co = st->thermal_coefs;
+    if (!co) {
+      co_own.resize(n * 12);
+      for (size_t i = 0; i < n; ++i) thermal_coefs(st->Ua[i], st->Ca[i], st->Cm[i], st->Hm[i], p.dt, &co_own[i * 12]);
+      co = co_own.data();
+    }
     if (sizeof(real) == 4) {
       for (int k = 0; k < 6; ++k)
-        if ((rc = upload_house<real>(h, h->o_coef[k], s, [&co, k](size_t i) { return co[i * 12 + k]; }))) return rc;
+        if ((rc = upload_house<real>(h, h->o_coef[k], s, [co, k](size_t i) { return co[i * 12 + k]; }))) return rc;
     } else {
       const double *src[3] = {st->Ua, st->Ca, st->Hm};
       for (int k = 0; k < 3; ++k) {
@@ -414,7 +460,7 @@ static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t
         if ((rc = upload_house<real>(h, h->o_coef[k], s, [a](size_t i) { return a[i]; }))) return rc;
       }
       for (int k = 0; k < 6; ++k)
-        if ((rc = upload_house<real>(h, h->o_coef[3 + k], s, [&co, k](size_t i) { return co[i * 12 + 6 + k]; }))) return rc;
+        if ((rc = upload_house<real>(h, h->o_coef[3 + k], s, [co, k](size_t i) { return co[i * 12 + 6 + k]; }))) return rc;
     }
     if (h->has_ratio) {
       const double *src[4] = {st->Ua, st->Ca, st->Cm, st->Hm};
@@ -422,7 +468,7 @@ static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t
       for (int k = 0; k < 4; ++k) {
         const double *a = src[k];
         const double d = dflt[k];
-        if ((rc = upload_house<float>(h, h->o_ratio[k], s, [a, d](size_t i) { return a[i] / d; }))) return rc;
+        if ((rc = upload_house<real>(h, h->o_ratio[k], s, [a, d](size_t i) { return a[i] / d; }))) return rc;
       }
     }
     if (h->has_interp) {
@@ -470,34 +516,18 @@ extern "C" int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *str
   return h->real_bytes == 8 ? set_state_t<double>(h, st, s) : set_state_t<float>(h, st, s);
 }
 
-template <typename T, typename DST>
-static int download_house(drsim_handle *h, size_t off, cudaStream_t s, DST *dst, int shift = 0, int mask = -1) {
-  const SimParams &p = h->p;
-  std::vector<T> buf((size_t)p.R * p.Ns);
-  CU_TRY(cudaMemcpyAsync(buf.data(), h->slab + off, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaStreamSynchronize(s));
-  for (int r = 0; r < p.R; ++r)
-    for (int n = 0; n < p.N; ++n) {
-      const T v = buf[(size_t)r * p.Ns + n];
-      dst[(size_t)r * p.N + n] = mask == -1 ? (DST)v : (DST)(((int)v >> shift) & mask);
-    }
-  return 0;
-}
-
-template <typename T, typename DST>
-static int download_env(drsim_handle *h, size_t off, cudaStream_t s, DST *dst) {
-  std::vector<T> buf(h->p.R);
-  CU_TRY(cudaMemcpyAsync(buf.data(), h->slab + off, buf.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
-  CU_TRY(cudaStreamSynchronize(s));
-  for (int r = 0; r < h->p.R; ++r) dst[r] = (DST)buf[r];
-  return 0;
-}
-
 template <typename real>
 static int get_state_t(drsim_handle *h, drsim_host_state *st, cudaStream_t s) {
   int rc;
   if (st->t_air && (rc = download_house<real>(h, h->o_t_air, s, st->t_air))) return rc;
   if (st->t_mass && (rc = download_house<real>(h, h->o_t_mass, s, st->t_mass))) return rc;
+  if (sizeof(real) == 4 && (st->t_air || st->t_mass)) {
+    const size_t n = (size_t)h->p.R * h->p.N;
+    std::vector<double> tgt(n);
+    if ((rc = download_house<real>(h, h->o_target, s, tgt.data()))) return rc;
+    if (st->t_air) for (size_t i = 0; i < n; ++i) st->t_air[i] += tgt[i];
+    if (st->t_mass) for (size_t i = 0; i < n; ++i) st->t_mass[i] += tgt[i];
+  }
   if (st->target && (rc = download_house<real>(h, h->o_target, s, st->target))) return rc;
   if (st->cap && (rc = download_house<real>(h, h->o_cap, s, st->cap))) return rc;
   if (st->sso && (rc = download_house<int32_t>(h, h->o_sso, s, st->sso))) return rc;

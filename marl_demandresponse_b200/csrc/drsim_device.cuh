@@ -248,12 +248,15 @@ DRSIM_HD bool policy_action(int policy, real t_air, real target, real deadband, 
 // ------------------------------------------------------------------------------------------
 // fp32 production path: the update is exactly affine with unit row sums, so it is applied in
 // difference form with six per-house coefficients precomputed in fp64 (thermal_coefs below):
-//   Ta' = Ta + c0 (Tm - Ta) + c1 (Tod - Ta) + c2 Qa ;  Tm' = Tm + c3 (Ta - Tm) + c4 (Tod - Tm) + c5 Qa
-DRSIM_HD void thermal_step_f32(float &ta, float &tm, const float c[6], float od, float Qa) {
-  const float na = fmaf(c[2], Qa, fmaf(c[1], od - ta, fmaf(c[0], tm - ta, ta)));
-  const float nm = fmaf(c[5], Qa, fmaf(c[4], od - tm, fmaf(c[3], ta - tm, tm)));
-  ta = na;
-  tm = nm;
+//   Ta' = Ta + [c0 (Tm - Ta) + c1 (Tod - Ta) + c2 Qa] ;  Tm' = Tm + [c3 (Ta - Tm) + c4 (Tod - Tm) + c5 Qa]
+// Unit row sums make the map shift-invariant, so the fp32 planes carry the deviations
+// xa = Ta - target, xm = Tm - target (|x| ~ 1 => ulp ~ 1e-7 instead of 2e-6 at 20 degC) and
+// `od` is Tod - target.  The small increment is formed first and added once (one rounding).
+DRSIM_HD void thermal_step_f32(float &xa, float &xm, const float c[6], float od, float Qa) {
+  const float ia = fmaf(c[2], Qa, fmaf(c[1], od - xa, c[0] * (xm - xa)));
+  const float im = fmaf(c[5], Qa, fmaf(c[4], od - xm, c[3] * (xa - xm)));
+  xa += ia;
+  xm += im;
 }
 
 #if defined(__CUDA_ARCH__)

@@ -38,7 +38,7 @@ struct Planes {
   // per-house static [R][Ns]
   const real *target, *cap;
   const real *coef[9];       // fp32: c0..c5 ; fp64: Ua, Ca, Hm, r1, r2, A3, A4, e1, e2
-  const float *ratio[4];     // Ua, Ca, Cm, Hm over the defaults (only if an obs flag needs them)
+  const real *ratio[4];      // Ua, Ca, Cm, Hm over the defaults (only if an obs flag needs them)
   const uint8_t *interp_sub; // nearest-neighbour cell of the interpolation table
   // per-house outputs
   real *reward;
@@ -117,6 +117,28 @@ DRSIM_D void thermal_step(double &ta, double &tm, const double *c, double od, do
 DRSIM_D float hvac_heat(float cap, float one_plus_latent) { return -cap / one_plus_latent; }
 DRSIM_D double hvac_heat(double cap, double one_plus_latent) { return DR_DIV(DR_MUL(-1.0, cap), one_plus_latent); }
 
+// Temperature representation of the t_air / t_mass planes (see drsim_ptrs.temp_is_deviation):
+// fp32 stores the deviation from the set-point, fp64 the absolute temperature (literal replay).
+template <typename real> struct Rep;
+template <> struct Rep<float> {
+  static DRSIM_D float dev(float x, float) { return x; }                                // Ta - target
+  static DRSIM_D float minus20(float x, float target) { return x + (target - 20.f); }   // Ta - 20
+  static DRSIM_D float od_in(float od, float target) { return od - target; }
+  static DRSIM_D float pen(float target, float db, float x) { return deadband_l2<float>(0.f, db, x); }
+  static DRSIM_D bool act(int policy, float x, float, float db, bool on, bool ext) {
+    return policy_action<float>(policy, x, 0.f, db, on, ext);
+  }
+};
+template <> struct Rep<double> {
+  static DRSIM_D double dev(double t, double target) { return t - target; }
+  static DRSIM_D double minus20(double t, double) { return t - 20.0; }
+  static DRSIM_D double od_in(double od, double) { return od; }
+  static DRSIM_D double pen(double target, double db, double t) { return deadband_l2<double>(target, db, t); }
+  static DRSIM_D bool act(int policy, double t, double target, double db, bool on, bool ext) {
+    return policy_action<double>(policy, t, target, db, on, ext);
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // the per-thread house work: 4 houses, loaded with vector accesses, updated in registers
 // ------------------------------------------------------------------------------------------
@@ -158,21 +180,21 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const StepI
     if (j < valid) {
       uint32_t f = (h.flags >> (8 * j)) & 0xffu;
       const bool ext = (act >> (8 * j)) & 0xffu;
-      const bool a = policy_action<real>(p.policy, h.ta[j], h.target[j], db, f & 1u, ext);
+      const bool a = Rep<real>::act(p.policy, h.ta[j], h.target[j], db, f & 1u, ext);
       if (in.advance) {
         hvac_fsm(f, h.sso[j], a, p.dt, p.lockout_duration);
         const real q = (f & 1u) ? hvac_heat(h.cap[j], one_plus_latent) : (real)0;
         real c[NC];
 #pragma unroll
         for (int k = 0; k < NC; ++k) c[k] = coef[k][j];
-        thermal_step(h.ta[j], h.tm[j], c, od_prev, q + solar);
+        thermal_step(h.ta[j], h.tm[j], c, Rep<real>::od_in(od_prev, h.target[j]), q + solar);
       }
       nf = (nf & ~(0xffu << (8 * j))) | (f << (8 * j));
       if (f & 1u) P += h.cap[j] / cop;
-      const real pen = deadband_l2<real>(h.target[j], db, h.ta[j]);
+      const real pen = Rep<real>::pen(h.target[j], db, h.ta[j]);
       ps += pen / (real)p.n_global;
       pm = pen > pm ? pen : pm;
-      const real dT = h.ta[j] - h.target[j];
+      const real dT = Rep<real>::dev(h.ta[j], h.target[j]);
       ds += dT;
       d2 += dT * dT;
     }
@@ -275,13 +297,16 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
   pl.solar_cur[r] = solar_cur;
   pl.signal[r] = e.signal;
   pl.base_power[r] = e.base_power;
-  pl.power[r] = red[0];
+  // a refresh keeps the injected cluster power: the reference's reset observation carries the
+  // power cached BEFORE the property noise was applied (cluster.py:61-65 vs environment.py:58)
+  const double P = in.advance ? red[0] : pl.power[r];
+  if (in.advance) pl.power[r] = P;
   pl.pen_sum[r] = red[1];
   pl.pen_max[r] = red[2];
   pl.rew_sig[r] = rew_sig;
   pl.t_since_interp[r] = e.t_since_interp;
   EnvBroadcast<real> b;
-  b.power_n = (real)(red[0] / p.nrs);                              // norm.py:144-146
+  b.power_n = (real)(P / p.nrs);                                   // norm.py:144-146
   b.signal_n = (real)(e.signal / (p.nrs * (double)p.n_global));    // norm.py:132-135
   b.solar_n = (real)(solar_cur / 1000.0);                          // norm.py:113-114
   b.od_n = (real)((e.od_temp - 20.0) / 5.0);                       // norm.py:164-165
@@ -294,7 +319,7 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
 // rewards_calculator.py:135-181 for one house
 template <typename real>
 DRSIM_D real house_reward(const SimParams &p, real ta, real target, const EnvBroadcast<real> &e) {
-  const real ind = deadband_l2<real>(target, (real)p.deadband, ta);
+  const real ind = Rep<real>::pen(target, (real)p.deadband, ta);
   real pen;
   switch (p.penalty_mode) {
     case DRSIM_PEN_COMMON_L2: pen = e.pen_common; break;
@@ -322,8 +347,8 @@ DRSIM_D int neighbour_of(const SimParams &p, const int32_t *table, int r, int n,
 
 // own-state part of the observation row (utils/norm.py:71-146)
 template <typename real>
-DRSIM_D int obs_own(real *row, const SimParams &p, uint32_t f, real sso_n, real ta, real tm, real target,
-                    const EnvBroadcast<real> &e, const float ratio[4]) {
+DRSIM_D int obs_own(real *row, const SimParams &p, uint32_t f, real sso_n, real ta20, real tm20, real tg20,
+                    const EnvBroadcast<real> &e, const real ratio[4]) {
   int i = 0;
   row[i++] = (real)(f & 1u);
   row[i++] = (real)((f >> 1) & 1u);
@@ -333,9 +358,9 @@ DRSIM_D int obs_own(real *row, const SimParams &p, uint32_t f, real sso_n, real 
   row[i++] = e.power_n;
   row[i++] = e.signal_n;
   row[i++] = (real)p.deadband;
-  row[i++] = (ta - (real)20) / (real)5;
-  row[i++] = (tm - (real)20) / (real)5;
-  row[i++] = (target - (real)20) / (real)5;
+  row[i++] = ta20 / (real)5;
+  row[i++] = tm20 / (real)5;
+  row[i++] = tg20 / (real)5;
   if (p.st_solar) row[i++] = e.solar_n;
   if (p.st_thermal) {
     row[i++] = (real)ratio[0]; row[i++] = (real)ratio[1]; row[i++] = (real)ratio[2]; row[i++] = (real)ratio[3];
@@ -452,8 +477,8 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
       const size_t o = (size_t)r * p.Ns + id;
       const real tgt = pl.target[o];
       real x[5];
-      x[0] = pl.t_air[o] - tgt;
-      x[1] = pl.t_mass[o] - tgt;
+      x[0] = Rep<real>::dev(pl.t_air[o], tgt);
+      x[1] = Rep<real>::dev(pl.t_mass[o], tgt);
       x[2] = (real)od_new - tgt;
       if (p.solar_on) {
         x[3] = (real)(now.hour * 3600 + now.minute * 60 + now.second);
@@ -529,11 +554,12 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
       const real ta = pl.t_air[o], tm = pl.t_mass[o], tgt = pl.target[o];
       if (in.advance) pl.reward[o] = house_reward<real>(p, ta, tgt, e);
       if (D > 0) {
-        float ratio[4] = {0, 0, 0, 0};
+        real ratio[4] = {0, 0, 0, 0};
         if (p.st_thermal)
           for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][o];
         const uint32_t f = pl.flags[o];
-        int i = obs_own<real>(row, p, f, (real)(pl.sso[o] / dur), ta, tm, tgt, e, ratio);
+        int i = obs_own<real>(row, p, f, (real)(pl.sso[o] / dur), Rep<real>::minus20(ta, tgt),
+                              Rep<real>::minus20(tm, tgt), tgt - (real)20, e, ratio);
         if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
           const int n_glob = n + (int)p.house_offset;
           for (int k = 0; k < p.nb_comm; ++k) {
@@ -542,7 +568,7 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
             // the local houses (see drsim_api.cu); nb is then remapped by the host-built table
             const size_t q = rb + nb;
             const real cap_k = pl.cap[q];
-            row[i++] = (pl.t_air[q] - pl.target[q]) / (real)5;     // norm.py:39
+            row[i++] = Rep<real>::dev(pl.t_air[q], pl.target[q]) / (real)5;  // norm.py:39
             row[i++] = (real)(pl.sso[q] / dur);                    // norm.py:40-43
             row[i++] = ((pl.flags[q] & 1u) ? cap_k / cop : (real)0) / nrs;
             row[i++] = (cap_k / cop) / nrs;
@@ -651,7 +677,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
         const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
         const real pmax = h.cap[j] / cop;
         Msg4<real> m;
-        m.dT = (h.ta[j] - h.target[j]) / (real)5;                  // norm.py:39
+        m.dT = Rep<real>::dev(h.ta[j], h.target[j]) / (real)5;     // norm.py:39
         m.sso_n = (real)(h.sso[j] / dur);                          // norm.py:40-43
         m.p_n = ((f & 1u) ? pmax : (real)0) / nrs;
         m.pmax_n = pmax / nrs;
@@ -719,10 +745,11 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
           if (n < p.N) {
             const Own4<real> o = s_own[s];
             const Msg4<real> m = s_msg[s];
-            float ratio[4] = {0, 0, 0, 0};
+            real ratio[4] = {0, 0, 0, 0};
             if (p.st_thermal)
               for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s];
-            int q = obs_own<real>(row, p, (uint32_t)o.flags, m.sso_n, o.ta, o.tm, o.target, s_env[e], ratio);
+            int q = obs_own<real>(row, p, (uint32_t)o.flags, m.sso_n, Rep<real>::minus20(o.ta, o.target),
+                                  Rep<real>::minus20(o.tm, o.target), o.target - (real)20, s_env[e], ratio);
             if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
               for (int k = 0; k < p.nb_comm; ++k) {
                 const int nb = neighbour_of(p, pl.comm_table, r0 + e, n, k);
@@ -769,7 +796,7 @@ __global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, i
   const size_t rb = (size_t)r * p.Ns;
   for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
     if (i < p.N) {
-      key[i] = -(double)(pl.t_air[rb + i] - pl.target[rb + i]);
+      key[i] = -(double)Rep<real>::dev(pl.t_air[rb + i], pl.target[rb + i]);
       idx[i] = i;
     } else {
       key[i] = INFINITY;

@@ -29,7 +29,7 @@ def _stepper(case, precision, path, **kw):
 def test_golden_trajectory(name, precision, path):
     case = GoldenCase(name)
     st = _stepper(case, precision, path)
-    worst = replay(case, st, rtol=RTOL[precision])
+    worst = replay(case, st, rtol=RTOL[precision], precision=precision)
     print(name, precision, path, {k: f"{v:.2e}" for k, v in worst.items()})
 
 

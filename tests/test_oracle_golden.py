@@ -10,7 +10,7 @@ from oracle.np_oracle import NpOracle
 def test_np_oracle_matches_reference_golden(name):
     case = GoldenCase(name)
     orc = NpOracle(case.env_prop, 1, table=case.table())
-    worst = replay(case, orc, rtol=1e-12)
+    worst = replay(case, orc, rtol=1e-12, precision="f64")
     # fp64 literal restatement: agreement is at rounding level, far inside 1e-12
     assert worst["t_air"] < 1e-11 and worst["rewards"] < 1e-11
 
