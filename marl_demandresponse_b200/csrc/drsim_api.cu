@@ -52,17 +52,22 @@ struct drsim_handle {
   // offsets inside the slab
   size_t o_t_air, o_t_mass, o_sso, o_flags, o_target, o_cap, o_coef[9], o_ratio[4], o_sub, o_reward, o_obs,
       o_actions, o_epoch, o_od, o_solar_next, o_solar_cur, o_signal, o_base, o_power, o_art, o_maxp, o_pen_sum,
-      o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids;
+      o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids,
+      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec;
+  static constexpr int kSched = 64;  // steps pre-generated per k_schedule launch
+  bool sched_valid = false;
+  int64_t sched_base = 0;
   bool has_ratio = false, has_interp = false, has_comm = false;
   int chunks = 1;       // CTAs per cluster in the general path
   int obs_chunks = 1;   // k_obs CTAs per cluster
-  bool fused_ok = false;
+  bool fused_ok = false, fused_direct = false;
   FusedGeom geom{};
   int fused_grid = 0;
   int64_t step = 0;
   int t_since_interp = 0;  // host mirror of PowerGrid.time_since_last_interp (common to all replicas)
   int64_t launches = 0;
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
+  StepIn pending_in{};
   // pinned staging for drsim_step_host
   double *h_env = nullptr;
 
@@ -165,6 +170,11 @@ static int fill_params(const drsim_config &c, SimParams &p, std::string &why) {
   }
   if (p.base_mode == DRSIM_BASE_INTERPOLATION && (p.interp_k < 1 || p.interp_period < 1)) { why = "interp props"; return -1; }
   p.noise_mode = c.noise_mode; p.policy = c.policy; p.seed = c.seed;
+  p.fd_dur = make_fastdiv((uint32_t)std::max(1, c.lockout_duration));
+  p.fd_ns = make_fastdiv((uint32_t)p.Ns);
+  p.inv_cop = 1.0 / p.cop; p.inv_nrs = 1.0 / p.nrs; p.inv_norm_temp = 1.0 / p.norm_temp;
+  p.inv_n_global = 1.0 / (double)p.n_global;
+  if (c.lockout_duration < 1) { why = "lockout_duration must be >= 1 s"; return -1; }
   return 0;
 }
 
@@ -177,31 +187,37 @@ static void plan_fused(drsim_handle *h) {
   g.envs_per_tile = std::min(p.R, kTileSlots / p.Ns);
   g.n_tiles = (p.R + g.envs_per_tile - 1) / g.envs_per_tile;
   g.max_segs = p.Ns >= 128 ? 2 : (128 + p.Ns - 1) / p.Ns + 1;
+  g.need_msg = (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0) ? 1 : 0;
   const int rb = h->real_bytes;
   const int slots = g.envs_per_tile * p.Ns;
-  size_t off = 0;
-  auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
-  g.off_msg = take((size_t)slots * 4 * rb);
-  g.off_own = take((size_t)slots * 4 * rb);
-  g.off_env = take((size_t)g.envs_per_tile * 8 * rb);
-  g.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double));
-  g.off_tile = (int)off;
-  const size_t fixed = off;
   const size_t row = (size_t)p.obs_dim * rb;
-  int chunk = 0;
-  if (row > 0) {
-    // aim for >= 2 resident CTAs per SM (<= ~110 KB each); fall back to one big CTA
+  auto layout = [&](bool direct, int chunk) {
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
+    g.off_msg = take((g.need_msg || !direct) ? (size_t)slots * 4 * rb : 0);
+    g.off_own = take(!direct ? (size_t)slots * 4 * rb : 0);
+    g.off_env = take((size_t)g.envs_per_tile * 8 * rb);
+    g.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double));
+    g.off_tile = (int)off;
+    g.chunk_rows = chunk;
+    g.smem_bytes = (int)(off + (size_t)chunk * row);
+    return off;
+  };
+  // direct: the whole tile's rows staged at once (one TMA store per tile, rows from registers)
+  layout(true, row ? slots : 0);
+  if (g.smem_bytes > 100 * 1024) {
+    // chunked staging; aim for >= 2 resident CTAs per SM, fall back to one big CTA
+    const size_t fixed = layout(false, 0);
+    int chunk = 0;
     const size_t budgets[2] = {110 * 1024, 220 * 1024};
     for (size_t b : budgets) {
       if (fixed + 32 * row > b) continue;
-      chunk = (int)std::min<size_t>((b - fixed) / row, (size_t)slots);
-      chunk = chunk / 4 * 4;
-      if (chunk >= 32 || chunk == slots) break;
+      chunk = (int)std::min<size_t>((b - fixed) / row, (size_t)slots) / 4 * 4;
+      if (chunk >= 32) break;
     }
     if (chunk < 4) return;  // does not fit: general path
+    layout(false, chunk);
   }
-  g.chunk_rows = chunk;
-  g.smem_bytes = (int)(fixed + (size_t)chunk * row);
   h->geom = g;
   h->fused_ok = true;
 }
@@ -209,9 +225,16 @@ static void plan_fused(drsim_handle *h) {
 template <typename real>
 static int configure_kernels(drsim_handle *h) {
   if (h->fused_ok) {
-    CU_TRY(cudaFuncSetAttribute(k_fused<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+    const bool direct = h->geom.chunk_rows == h->geom.envs_per_tile * h->p.Ns || h->p.obs_dim == 0;
+    h->fused_direct = direct;
     int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real>, kThreads, h->geom.smem_bytes));
+    if (direct) {
+      CU_TRY(cudaFuncSetAttribute(k_fused<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real, true>, kThreads, h->geom.smem_bytes));
+    } else {
+      CU_TRY(cudaFuncSetAttribute(k_fused<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real, false>, kThreads, h->geom.smem_bytes));
+    }
     if (per_sm < 1) { h->fused_ok = false; }
     else h->fused_grid = std::min(h->geom.n_tiles, per_sm * h->sm_count);
   }
@@ -281,6 +304,8 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   if (h->has_comm) h->o_comm = cv.take((size_t)p.R * p.N * p.nb_comm * 4);  // room for per-replica tables
   h->o_in_od = cv.take(E8); h->o_in_perlin = cv.take(E8);
   h->o_in_ids = cv.take((size_t)p.R * std::max(1, p.interp_k) * 4);
+  h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
+  h->o_sched_aux = cv.take(E8 * drsim_handle::kSched); h->o_sched_tsec = cv.take((size_t)p.R * 4 * drsim_handle::kSched);
   h->slab_bytes = cv.off;
   cudaError_t e = cudaMalloc(&h->slab, h->slab_bytes);
   if (e != cudaSuccess) {
@@ -318,6 +343,8 @@ extern "C" int drsim_clone(const drsim_t *src, drsim_t **out) {
   h->p = src->p;
   h->step = src->step;
   h->t_since_interp = src->t_since_interp;
+  h->sched_valid = src->sched_valid;
+  h->sched_base = src->sched_base;
   *out = h;
   return 0;
 }
@@ -512,6 +539,7 @@ static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t
 extern "C" int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *stream) {
   if (!h || !st) return fail(DRSIM_E_ARG, "null argument");
   CU_TRY(cudaSetDevice(h->device));
+  h->sched_valid = false;
   auto s = (cudaStream_t)stream;
   return h->real_bytes == 8 ? set_state_t<double>(h, st, s) : set_state_t<float>(h, st, s);
 }
@@ -624,18 +652,43 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
     k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
     h->launches++;
   }
-  k_fused<real><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
+  if (h->fused_direct) k_fused<real, true><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
+  else k_fused<real, false><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   h->launches++;
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
-static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp) {
+template <typename real>
+static void launch_schedule(drsim_handle *h, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const int n = drsim_handle::kSched * h->p.R;
+  k_schedule<real><<<(n + 127) / 128, 128, 0, s>>>(pl, h->p, h->step, drsim_handle::kSched, h->at<double>(h->o_sched_od),
+                                                    h->at<double>(h->o_sched_solar), h->at<double>(h->o_sched_aux),
+                                                    h->at<int32_t>(h->o_sched_tsec));
+  h->launches++;
+}
+
+// When no noise is injected for this step the env-level time series comes from the pre-generated
+// schedule (regenerated every kSched steps, off the per-step critical path).
+static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp, cudaStream_t s) {
   StepIn in{};
   if (a) { in.actions = a->actions; in.od_noise = a->od_noise; in.perlin = a->perlin; in.interp_ids = a->interp_ids; }
   in.step = h->step;
   in.advance = advance;
   in.do_interp = do_interp;
+  if (advance && !in.od_noise && !in.perlin) {
+    if (!h->sched_valid || h->step < h->sched_base || h->step >= h->sched_base + drsim_handle::kSched) {
+      if (h->real_bytes == 8) launch_schedule<double>(h, s); else launch_schedule<float>(h, s);
+      h->sched_base = h->step;
+      h->sched_valid = true;
+    }
+    const size_t slot = (size_t)(h->step - h->sched_base) * h->p.R;
+    in.sched_od = h->at<double>(h->o_sched_od) + slot;
+    in.sched_solar = h->at<double>(h->o_sched_solar) + slot;
+    in.sched_aux = h->at<double>(h->o_sched_aux) + slot;
+    in.sched_tsec = h->at<int32_t>(h->o_sched_tsec) + slot;
+  }
   return in;
 }
 
@@ -649,10 +702,10 @@ static int interp_decision(drsim_handle *h) {
 }
 
 static int run_step(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp, cudaStream_t s) {
-  const StepIn in = make_in(h, a, advance, do_interp);
+  const StepIn in = make_in(h, a, advance, do_interp, s);
   const bool dbl = h->real_bytes == 8;
   int rc;
-  if (h->fused_ok && do_interp <= 0) {
+  if (h->fused_ok && do_interp <= 0 && advance) {
     rc = dbl ? launch_fused<double>(h, in, s) : launch_fused<float>(h, in, s);
   } else {
     if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "house-sharded cluster: use drsim_step_begin / drsim_step_finish");
@@ -686,7 +739,8 @@ extern "C" int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *s
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   CU_TRY(cudaSetDevice(h->device));
   h->pending_interp = interp_decision(h);
-  const StepIn in = make_in(h, args, 1, h->pending_interp);
+  const StepIn in = make_in(h, args, 1, h->pending_interp, (cudaStream_t)stream);
+  h->pending_in = in;
   return h->real_bytes == 8 ? launch_house_phase<double>(h, in, (cudaStream_t)stream)
                             : launch_house_phase<float>(h, in, (cudaStream_t)stream);
 }
@@ -694,7 +748,8 @@ extern "C" int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *s
 extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   CU_TRY(cudaSetDevice(h->device));
-  const StepIn in = make_in(h, args, 1, h->pending_interp);
+  (void)args;
+  const StepIn in = h->pending_in;
   int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, (cudaStream_t)stream)
                               : launch_env_phase<float>(h, in, acc, (cudaStream_t)stream);
   if (!rc) h->step++;

@@ -169,8 +169,34 @@ DRSIM_HD double philox_perlin(uint64_t key, uint32_t env, double x_over_period, 
 // ------------------------------------------------------------------------------------------
 // flattened, kernel-side view of drsim_config (doubles; converted to `real` where used)
 // ------------------------------------------------------------------------------------------
+// exact unsigned division by a launch-invariant divisor (Granlund & Montgomery, PLDI'94):
+// q = (t + ((n - t) >> s1)) >> s2 with t = mulhi(m, n)
+struct FastDiv {
+  uint32_t m, s1, s2, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l > 1 ? l - 1 : 0;
+  f.d = d;
+  return f;
+}
+DRSIM_HD uint32_t fast_div(uint32_t n, const FastDiv &f) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t t = __umulhi(f.m, n);
+#else
+  const uint32_t t = (uint32_t)(((uint64_t)f.m * n) >> 32);
+#endif
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 struct SimParams {
   int R, N, Ns;  // replicas, houses, house stride (N rounded up to 4)
+  FastDiv fd_dur, fd_ns;  // seconds_since_off / lockout_duration ; slot / Ns
+  double inv_cop, inv_nrs, inv_norm_temp, inv_n_global;  // fp32 build multiplies by reciprocals
   int dt;
   int64_t house_offset, n_global, rep_offset;
   double deadband, cop, latent, window_area, shading;
@@ -189,6 +215,26 @@ struct SimParams {
   int noise_mode, policy;
   uint64_t seed;
 };
+
+// Same signal from pre-generated time-dependent parts (k_schedule): `aux` = sum_k ratio_k sin(2 pi t/T_k)
+// (sinusoidals) or the noise value (perlin); t_sec = seconds since midnight.
+DRSIM_HD double grid_signal_sched(const SimParams &p, double base, int t_sec, double aux,
+                                  double artificial_ratio, double max_power) {
+  double v = base;
+  if (p.signal_mode == DRSIM_SIG_SINUSOIDALS) {
+    v = base + base * aux;
+  } else if (p.signal_mode == DRSIM_SIG_REGULAR_STEPS) {
+    const double amplitude = p.amp_per_hvac * (double)p.n_global;
+    const double ratio = base / amplitude;
+    const double arg = (double)(t_sec % p.period) - (1 - ratio) * p.period;
+    v = amplitude * (arg < 0 ? 0.0 : 1.0);
+  } else if (p.signal_mode == DRSIM_SIG_PERLIN) {
+    v = base + (base * p.amp[0] * aux);
+    v = v > 0 ? v : 0.0;
+  }
+  v = v * artificial_ratio;
+  return v < max_power ? v : max_power;
+}
 
 // signal_calculator.py:33-129 + power_grid.py:97-100
 DRSIM_HD double grid_signal(const SimParams &p, double base, const Civil &t, double perlin,

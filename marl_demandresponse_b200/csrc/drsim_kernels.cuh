@@ -61,10 +61,31 @@ struct StepIn {
   const double *od_noise;
   const double *perlin;
   const int32_t *interp_ids;
+  // pre-generated env-level time series for this step (k_schedule), or NULL: inline evaluation
+  const double *sched_od, *sched_solar, *sched_aux;
+  const int32_t *sched_tsec;
   int64_t step;
   int do_interp;
   int advance;  // 1 = real step, 0 = refresh (recompute signal / obs without advancing time)
 };
+
+// Launch-invariant constants in registers.  The fp32 build multiplies by reciprocals (<= 1 ulp
+// from the true quotient, far inside the 1e-5 budget); the fp64 build divides like the reference.
+template <typename real>
+struct KC {
+  real cop, nrs, db, one_plus_latent, norm_temp, n_glob;
+  real inv_cop, inv_nrs, inv_norm_temp, inv_n;
+  DRSIM_D explicit KC(const SimParams &p) {
+    cop = (real)p.cop; nrs = (real)p.nrs; db = (real)p.deadband; one_plus_latent = (real)(1.0 + p.latent);
+    norm_temp = (real)p.norm_temp; n_glob = (real)p.n_global;
+    inv_cop = (real)p.inv_cop; inv_nrs = (real)p.inv_nrs; inv_norm_temp = (real)p.inv_norm_temp;
+    inv_n = (real)p.inv_n_global;
+  }
+};
+DRSIM_D float qdiv(float x, float, float inv) { return x * inv; }
+DRSIM_D double qdiv(double x, double d, double) { return x / d; }
+DRSIM_D float div5(float x) { return x * 0.2f; }
+DRSIM_D double div5(double x) { return x / 5.0; }
 
 // ------------------------------------------------------------------------------------------
 // vector access helpers: 4 consecutive houses per thread
@@ -153,9 +174,10 @@ struct House4 {
 // Loads state + static planes of 4 houses at plane offset `off`, applies the policy / action,
 // hvac.py:43-64, building.py:141-222, writes the state back and returns the per-thread partial
 // sums in red[kRed].
-template <typename real>
-DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const StepIn &in, size_t off,
-                         int valid, real od_prev, real solar, House4<real> &h, double red[kRed]) {
+template <typename real, bool ALWAYS_ADVANCE = false>
+DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const KC<real> &kc, const StepIn &in,
+                         size_t off, int valid, real od_prev, real solar, House4<real> &h, real red[kRed]) {
+  const bool advance = ALWAYS_ADVANCE || in.advance;
   constexpr int NC = NCoef<real>::n;
   real coef[NC][4];
   load4(pl.t_air + off, h.ta);
@@ -170,9 +192,7 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const StepI
   if (p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC)
     act = load4b((in.actions ? in.actions : pl.actions) + off);
   h.valid = valid;
-  const real one_plus_latent = (real)(1.0 + p.latent);
-  const real cop = (real)p.cop;
-  const real db = (real)p.deadband;
+  const real db = kc.db;
   real P = 0, ps = 0, pm = 0, ds = 0, d2 = 0;
   uint32_t nf = h.flags;
 #pragma unroll
@@ -181,18 +201,18 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const StepI
       uint32_t f = (h.flags >> (8 * j)) & 0xffu;
       const bool ext = (act >> (8 * j)) & 0xffu;
       const bool a = Rep<real>::act(p.policy, h.ta[j], h.target[j], db, f & 1u, ext);
-      if (in.advance) {
+      if (advance) {
         hvac_fsm(f, h.sso[j], a, p.dt, p.lockout_duration);
-        const real q = (f & 1u) ? hvac_heat(h.cap[j], one_plus_latent) : (real)0;
+        const real q = (f & 1u) ? hvac_heat(h.cap[j], kc.one_plus_latent) : (real)0;
         real c[NC];
 #pragma unroll
         for (int k = 0; k < NC; ++k) c[k] = coef[k][j];
         thermal_step(h.ta[j], h.tm[j], c, Rep<real>::od_in(od_prev, h.target[j]), q + solar);
       }
       nf = (nf & ~(0xffu << (8 * j))) | (f << (8 * j));
-      if (f & 1u) P += h.cap[j] / cop;
+      if (f & 1u) P += qdiv(h.cap[j], kc.cop, kc.inv_cop);
       const real pen = Rep<real>::pen(h.target[j], db, h.ta[j]);
-      ps += pen / (real)p.n_global;
+      ps += qdiv(pen, kc.n_glob, kc.inv_n);
       pm = pen > pm ? pen : pm;
       const real dT = Rep<real>::dev(h.ta[j], h.target[j]);
       ds += dT;
@@ -200,17 +220,18 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const StepI
     }
   }
   h.flags = nf;
-  if (in.advance) {
+  if (advance) {
     store4(pl.t_air + off, h.ta);
     store4(pl.t_mass + off, h.tm);
     store4i(pl.sso + off, h.sso);
     store4b(pl.flags + off, h.flags);
   }
-  red[0] = (double)P; red[1] = (double)ps; red[2] = (double)pm; red[3] = (double)ds; red[4] = (double)d2;
+  red[0] = P; red[1] = ps; red[2] = pm; red[3] = ds; red[4] = d2;
 }
 
-DRSIM_D void red_combine(double a[kRed], const double b[kRed]) {
-  a[0] += b[0]; a[1] += b[1]; a[2] = fmax(a[2], b[2]); a[3] += b[3]; a[4] += b[4];
+template <typename T, typename U>
+DRSIM_D void red_combine(T a[kRed], const U b[kRed]) {
+  a[0] += (T)b[0]; a[1] += (T)b[1]; a[2] = a[2] > (T)b[2] ? a[2] : (T)b[2]; a[3] += (T)b[3]; a[4] += (T)b[4];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -220,10 +241,13 @@ struct EnvRegs {
   int64_t epoch;
   double od_temp, solar_next, signal, base_power, artificial_ratio, max_power;
   int t_since_interp;
+  // this step's pre-generated values (k_schedule), valid when StepIn::sched_od != NULL
+  double s_od, s_solar, s_aux;
+  int s_tsec;
 };
 
 template <typename real>
-DRSIM_D EnvRegs env_load(const Planes<real> &pl, int r) {
+DRSIM_D EnvRegs env_load(const Planes<real> &pl, const StepIn &in, int r) {
   EnvRegs e;
   e.epoch = pl.epoch[r];
   e.od_temp = pl.od_temp[r];
@@ -233,6 +257,9 @@ DRSIM_D EnvRegs env_load(const Planes<real> &pl, int r) {
   e.artificial_ratio = pl.artificial_ratio[r];
   e.max_power = pl.max_power[r];
   e.t_since_interp = pl.t_since_interp[r];
+  if (in.sched_od) {
+    e.s_od = in.sched_od[r]; e.s_solar = in.sched_solar[r]; e.s_aux = in.sched_aux[r]; e.s_tsec = in.sched_tsec[r];
+  }
   return e;
 }
 
@@ -242,36 +269,44 @@ struct EnvBroadcast {
   real power_n, signal_n, solar_n, od_n, rew_sig, pen_common, pen_max;
 };
 
+// mean over the cluster of the per-agent reward (rewards_calculator.py:174-179), from the reduced
+// penalties: mean individual penalty == the common_L2 value
+DRSIM_D double mean_reward(const SimParams &p, double pen_mean, double pen_max, double rew_sig) {
+  double pen = pen_mean;
+  if (p.penalty_mode == DRSIM_PEN_COMMON_MAX) pen = pen_max;
+  else if (p.penalty_mode == DRSIM_PEN_MIXTURE)
+    pen = (p.a_ind * pen_mean + p.a_cl2 * pen_mean + p.a_cmax * pen_max) / (p.a_ind + p.a_cl2 + p.a_cmax);
+  return -(p.alpha_temp * pen / p.norm_temp + rew_sig);
+}
+
 template <typename real>
 DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams &p, const StepIn &in,
                                         int r, EnvRegs e, const double red[kRed], double interp_sum) {
   const uint32_t env_global = (uint32_t)(p.rep_offset + r);
-  double solar_cur = pl.solar_cur[r];
-  double rew_sig = 0.0;
+  double solar_cur, rew_sig = 0.0, P;
+  const bool sched = in.advance && in.sched_od != nullptr;
   if (in.advance) {
     e.epoch += p.dt;                                               // environment.py:87
     solar_cur = e.solar_next;                                      // gain used by this step's update
-  }
-  const Civil now = civil_from_epoch(e.epoch);
-  if (in.advance) {
-    e.solar_next = p.solar_on ? solar_gain(civil_from_epoch(e.epoch + p.dt), p.window_area, p.shading) : 0.0;
-    double noise = 0.0;                                            // environment.py:158
-    if (in.od_noise) noise = in.od_noise[r];
-    else if (p.noise_mode == DRSIM_NOISE_PHILOX)
-      noise = p.temp_std * philox_normal(p.seed, env_global, 0u, (uint32_t)in.step, PURPOSE_OD);
-    e.od_temp = od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise);
-    const double dev = (red[0] - e.signal) / (double)p.n_global;   // rewards_calculator.py:198 (old signal, Q6)
+    P = red[0];
+    const double dev = (P - e.signal) / (double)p.n_global;        // rewards_calculator.py:198 (old signal, Q6)
     rew_sig = p.alpha_sig * (dev * dev) / p.norm_sig;
     // running rollout metrics (metrics_service.py:108-157 restated as per-cluster sums)
     double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
     m[0] += 1.0;
+    m[1] += mean_reward(p, red[1], red[2], rew_sig);
     m[2] += fabs(red[3]) / (double)p.n_global;
     m[3] += red[4] / (double)p.n_global;
-    m[4] += fabs(red[0] - e.signal);
-    m[5] += (red[0] - e.signal) * (red[0] - e.signal);
+    m[4] += fabs(P - e.signal);
+    m[5] += (P - e.signal) * (P - e.signal);
+  } else {
+    solar_cur = pl.solar_cur[r];
+    // a refresh keeps the injected cluster power: the reference's reset observation carries the
+    // power cached BEFORE the property noise was applied (cluster.py:61-65 vs environment.py:58)
+    P = pl.power[r];
   }
-  if (in.advance || in.do_interp >= 0) {
-    // power_grid.py:130-161
+  const bool grid = in.advance || in.do_interp >= 0;
+  if (grid) {                                                      // power_grid.py:130-161
     if (p.base_mode == DRSIM_BASE_CONSTANT) {
       e.base_power = p.avg_power * (double)p.n_global;
     } else if (in.do_interp > 0) {
@@ -281,15 +316,33 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
     } else if (in.advance) {
       e.t_since_interp += p.dt;
     }
-    double perlin = 0.0;
-    if (p.signal_mode == DRSIM_SIG_PERLIN) {
-      if (in.perlin) perlin = in.perlin[r];
-      else if (p.noise_mode == DRSIM_NOISE_PHILOX) {
-        const double x = (double)(now.hour * 3600 + now.minute * 60 + now.second);
-        perlin = philox_perlin(p.seed, env_global, x / (double)p.period, p.nb_octaves, p.octaves_step);
-      }
+  }
+  if (sched) {
+    // fast path: every time-dependent scalar of this step was pre-generated by k_schedule
+    e.solar_next = e.s_solar;
+    e.od_temp = e.s_od;
+    e.signal = grid_signal_sched(p, e.base_power, e.s_tsec, e.s_aux, e.artificial_ratio, e.max_power);
+  } else {
+    const Civil now = civil_from_epoch(e.epoch);
+    if (in.advance) {
+      e.solar_next = p.solar_on ? solar_gain(civil_from_epoch(e.epoch + p.dt), p.window_area, p.shading) : 0.0;
+      double noise = 0.0;                                          // environment.py:158
+      if (in.od_noise) noise = in.od_noise[r];
+      else if (p.noise_mode == DRSIM_NOISE_PHILOX)
+        noise = p.temp_std * philox_normal(p.seed, env_global, 0u, (uint32_t)in.step, PURPOSE_OD);
+      e.od_temp = od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise);
     }
-    e.signal = grid_signal(p, e.base_power, now, perlin, e.artificial_ratio, e.max_power);
+    if (grid) {
+      double perlin = 0.0;
+      if (p.signal_mode == DRSIM_SIG_PERLIN) {
+        if (in.perlin) perlin = in.perlin[r];
+        else if (p.noise_mode == DRSIM_NOISE_PHILOX) {
+          const double x = (double)(now.hour * 3600 + now.minute * 60 + now.second);
+          perlin = philox_perlin(p.seed, env_global, x / (double)p.period, p.nb_octaves, p.octaves_step);
+        }
+      }
+      e.signal = grid_signal(p, e.base_power, now, perlin, e.artificial_ratio, e.max_power);
+    }
   }
   pl.epoch[r] = e.epoch;
   pl.od_temp[r] = e.od_temp;
@@ -297,9 +350,6 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
   pl.solar_cur[r] = solar_cur;
   pl.signal[r] = e.signal;
   pl.base_power[r] = e.base_power;
-  // a refresh keeps the injected cluster power: the reference's reset observation carries the
-  // power cached BEFORE the property noise was applied (cluster.py:61-65 vs environment.py:58)
-  const double P = in.advance ? red[0] : pl.power[r];
   if (in.advance) pl.power[r] = P;
   pl.pen_sum[r] = red[1];
   pl.pen_max[r] = red[2];
@@ -316,10 +366,40 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
   return b;
 }
 
+// Pre-generation of the env-level time series: thread (k, r) evaluates, for step `step0 + k` of
+// replica r, the outdoor temperature (environment.py:132-159 with the Philox gauss draw), the
+// solar gain of the following step (utils.py:42-117), seconds since midnight and the
+// time-dependent factor of the signal (signal_calculator.py:46-115).  Counter-based noise makes
+// this exact: the values are the ones the inline epilogue would compute.
+template <typename real>
+__global__ void k_schedule(Planes<real> pl, SimParams p, int64_t step0, int K, double *od, double *solar,
+                           double *aux, int32_t *tsec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * p.R) return;
+  const int k = i / p.R, r = i - k * p.R;
+  const uint32_t env_global = (uint32_t)(p.rep_offset + r);
+  const int64_t epoch = pl.epoch[r] + (int64_t)(k + 1) * p.dt;
+  const Civil now = civil_from_epoch(epoch);
+  double noise = 0.0;
+  if (p.noise_mode == DRSIM_NOISE_PHILOX)
+    noise = p.temp_std * philox_normal(p.seed, env_global, 0u, (uint32_t)(step0 + k), PURPOSE_OD);
+  od[i] = od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise);
+  solar[i] = p.solar_on ? solar_gain(civil_from_epoch(epoch + p.dt), p.window_area, p.shading) : 0.0;
+  const int t_sec = now.hour * 3600 + now.minute * 60 + now.second;
+  tsec[i] = t_sec;
+  double a = 0.0;
+  if (p.signal_mode == DRSIM_SIG_SINUSOIDALS) {
+    for (int t = 0; t < p.n_terms; ++t) a += p.amp[t] * sin(2 * 3.141592653589793 * t_sec / p.periods[t]);
+  } else if (p.signal_mode == DRSIM_SIG_PERLIN && p.noise_mode == DRSIM_NOISE_PHILOX) {
+    a = philox_perlin(p.seed, env_global, (double)t_sec / (double)p.period, p.nb_octaves, p.octaves_step);
+  }
+  aux[i] = a;
+}
+
 // rewards_calculator.py:135-181 for one house
 template <typename real>
-DRSIM_D real house_reward(const SimParams &p, real ta, real target, const EnvBroadcast<real> &e) {
-  const real ind = Rep<real>::pen(target, (real)p.deadband, ta);
+DRSIM_D real house_reward(const SimParams &p, const KC<real> &kc, real ta, real target, const EnvBroadcast<real> &e) {
+  const real ind = Rep<real>::pen(target, kc.db, ta);
   real pen;
   switch (p.penalty_mode) {
     case DRSIM_PEN_COMMON_L2: pen = e.pen_common; break;
@@ -330,7 +410,7 @@ DRSIM_D real house_reward(const SimParams &p, real ta, real target, const EnvBro
       break;
     default: pen = ind;
   }
-  return (real)-1 * ((real)p.alpha_temp * pen / (real)p.norm_temp + e.rew_sig);
+  return (real)-1 * (qdiv((real)p.alpha_temp * pen, kc.norm_temp, kc.inv_norm_temp) + e.rew_sig);
 }
 
 // neighbour k of house n: ring (agent_communication_builder.py:63-85) or explicit table
@@ -358,15 +438,36 @@ DRSIM_D int obs_own(real *row, const SimParams &p, uint32_t f, real sso_n, real 
   row[i++] = e.power_n;
   row[i++] = e.signal_n;
   row[i++] = (real)p.deadband;
-  row[i++] = ta20 / (real)5;
-  row[i++] = tm20 / (real)5;
-  row[i++] = tg20 / (real)5;
+  row[i++] = div5(ta20);
+  row[i++] = div5(tm20);
+  row[i++] = div5(tg20);
   if (p.st_solar) row[i++] = e.solar_n;
   if (p.st_thermal) {
     row[i++] = (real)ratio[0]; row[i++] = (real)ratio[1]; row[i++] = (real)ratio[2]; row[i++] = (real)ratio[3];
     row[i++] = e.od_n;
   }
   return i;
+}
+
+// deterministic reduction of per-thread partials over a CTA: warp shuffles, then a fixed-order
+// pass over the warp partials by thread 0
+template <typename real, int WARPS>
+DRSIM_D void block_reduce(real red[kRed], double out[kRed], double (*wp)[kRed]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    real t[kRed];
+#pragma unroll
+    for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+    red_combine(red, t);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < kRed; ++k) wp[w][k] = (double)red[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kRed; ++k) out[k] = 0.0;
+    for (int i = 0; i < WARPS; ++i) red_combine(out, wp[i]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -376,30 +477,19 @@ template <typename real>
 __global__ void __launch_bounds__(kThreads) k_house(Planes<real> pl, SimParams p, StepIn in, int chunks) {
   const int r = blockIdx.x / chunks, c = blockIdx.x % chunks;
   const int n0 = (c * kThreads + threadIdx.x) * kHousesPerThread;
-  double red[kRed] = {0, 0, 0, 0, 0};
+  const KC<real> kc(p);
+  real red[kRed] = {0, 0, 0, 0, 0};
   if (n0 < p.N) {
     House4<real> h;
     const int valid = min(4, p.N - n0);
-    house4_step<real>(pl, p, in, (size_t)r * p.Ns + n0, valid, (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
+    house4_step<real>(pl, p, kc, in, (size_t)r * p.Ns + n0, valid, (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
   }
-  // deterministic block reduction: warp shuffles, then warp 0 over the 8 warp partials
   __shared__ double wp[kThreads / 32][kRed];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double t[kRed];
-#pragma unroll
-    for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
-    red_combine(red, t);
-  }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0)
-    for (int k = 0; k < kRed; ++k) wp[w][k] = red[k];
-  __syncthreads();
+  double out[kRed];
+  block_reduce<real, kThreads / 32>(red, out, wp);
   if (threadIdx.x == 0) {
-    double a[kRed] = {0, 0, 0, 0, 0};
-    for (int i = 0; i < kThreads / 32; ++i) red_combine(a, wp[i]);
     double *dst = pl.partials + ((size_t)r * chunks + c) * kRed;
-    for (int k = 0; k < kRed; ++k) dst[k] = a[k];
+    for (int k = 0; k < kRed; ++k) dst[k] = out[k];
   }
 }
 
@@ -454,16 +544,21 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
   double isum = 0.0;
   if (in.do_interp > 0) {
     const int k_all = p.n_global <= p.interp_k ? (int)p.n_global : p.interp_k;
-    const Civil now = civil_from_epoch(pl.epoch[r] + (in.advance ? p.dt : 0));
-    // outdoor temperature the interpolator sees is the NEW one (environment.py:94,104-106);
-    // it is recomputed here exactly as the epilogue will (same noise source)
-    double noise = 0.0;
+    // the interpolator sees the NEW outdoor temperature and datetime (environment.py:94,104-106);
+    // both are re-derived here exactly as the epilogue will derive them
+    const int64_t epoch_new = pl.epoch[r] + (in.advance ? p.dt : 0);
+    const Civil now = civil_from_epoch(epoch_new);
+    double od_new = pl.od_temp[r];
     if (in.advance) {
-      if (in.od_noise) noise = in.od_noise[r];
-      else if (p.noise_mode == DRSIM_NOISE_PHILOX)
-        noise = p.temp_std * philox_normal(p.seed, (uint32_t)(p.rep_offset + r), 0u, (uint32_t)in.step, PURPOSE_OD);
+      if (in.sched_od) od_new = in.sched_od[r];
+      else {
+        double noise = 0.0;
+        if (in.od_noise) noise = in.od_noise[r];
+        else if (p.noise_mode == DRSIM_NOISE_PHILOX)
+          noise = p.temp_std * philox_normal(p.seed, (uint32_t)(p.rep_offset + r), 0u, (uint32_t)in.step, PURPOSE_OD);
+        od_new = od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise);
+      }
     }
-    const double od_new = in.advance ? od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise) : pl.od_temp[r];
     for (int k = threadIdx.x; k < k_all; k += blockDim.x) {
       int64_t id;
       if (p.n_global <= p.interp_k) id = k;                       // interpolation.py:220-222
@@ -523,7 +618,7 @@ __global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc
   const double *a = acc + (size_t)r * (kRed + 1);
   double red[kRed];
   for (int k = 0; k < kRed; ++k) red[k] = a[k];
-  env_epilogue<real>(pl, p, in, r, env_load(pl, r), red, a[kRed]);
+  env_epilogue<real>(pl, p, in, r, env_load(pl, in, r), red, a[kRed]);
 }
 
 // General path, kernel 4: rewards + observation rows for a chunk of kObsChunk houses.
@@ -536,6 +631,7 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
   const int r = blockIdx.x / chunks, c = blockIdx.x % chunks;
   const int n = c * kObsChunk + threadIdx.x;
   const int D = p.obs_dim;
+  const KC<real> kc(p);
   EnvBroadcast<real> e;
   e.power_n = (real)(pl.power[r] / p.nrs);
   e.signal_n = (real)(pl.signal[r] / (p.nrs * (double)p.n_global));
@@ -544,37 +640,32 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
   e.rew_sig = (real)pl.rew_sig[r];
   e.pen_common = (real)pl.pen_sum[r];
   e.pen_max = (real)pl.pen_max[r];
-  const real nrs = (real)p.nrs, cop = (real)p.cop;
-  const int dur = p.lockout_duration;
   const size_t rb = (size_t)r * p.Ns;
   if (n < p.Ns) {
     real *row = tile + (size_t)threadIdx.x * D;
     if (n < p.N) {
       const size_t o = rb + n;
       const real ta = pl.t_air[o], tm = pl.t_mass[o], tgt = pl.target[o];
-      if (in.advance) pl.reward[o] = house_reward<real>(p, ta, tgt, e);
+      if (in.advance) pl.reward[o] = house_reward<real>(p, kc, ta, tgt, e);
       if (D > 0) {
         real ratio[4] = {0, 0, 0, 0};
         if (p.st_thermal)
           for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][o];
         const uint32_t f = pl.flags[o];
-        int i = obs_own<real>(row, p, f, (real)(pl.sso[o] / dur), Rep<real>::minus20(ta, tgt),
+        int i = obs_own<real>(row, p, f, (real)fast_div((uint32_t)pl.sso[o], p.fd_dur), Rep<real>::minus20(ta, tgt),
                               Rep<real>::minus20(tm, tgt), tgt - (real)20, e, ratio);
         if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
-          const int n_glob = n + (int)p.house_offset;
           for (int k = 0; k < p.nb_comm; ++k) {
-            const int nb = neighbour_of(p, pl.comm_table, r, n_glob, k) - (int)p.house_offset;
-            // a neighbour owned by another rank is served from the halo planes appended after
-            // the local houses (see drsim_api.cu); nb is then remapped by the host-built table
+            const int nb = neighbour_of(p, pl.comm_table, r, n, k);
             const size_t q = rb + nb;
-            const real cap_k = pl.cap[q];
-            row[i++] = Rep<real>::dev(pl.t_air[q], pl.target[q]) / (real)5;  // norm.py:39
-            row[i++] = (real)(pl.sso[q] / dur);                    // norm.py:40-43
-            row[i++] = ((pl.flags[q] & 1u) ? cap_k / cop : (real)0) / nrs;
-            row[i++] = (cap_k / cop) / nrs;
+            const real pmax = qdiv(pl.cap[q], kc.cop, kc.inv_cop);
+            row[i++] = div5(Rep<real>::dev(pl.t_air[q], pl.target[q]));        // norm.py:39
+            row[i++] = (real)fast_div((uint32_t)pl.sso[q], p.fd_dur);          // norm.py:40-43
+            row[i++] = qdiv((pl.flags[q] & 1u) ? pmax : (real)0, kc.nrs, kc.inv_nrs);
+            row[i++] = qdiv(pmax, kc.nrs, kc.inv_nrs);
             if (p.msg_thermal)
               for (int m = 0; m < 4; ++m) row[i++] = (real)pl.ratio[m][q];
-            if (p.msg_hvac) {                                      // constants, quirk Q11
+            if (p.msg_hvac) {                                                  // constants, quirk Q11
               row[i++] = (real)p.cop; row[i++] = (real)p.latent; row[i++] = (real)p.dcap;
             }
           }
@@ -619,8 +710,9 @@ DRSIM_D void fence_proxy_async_smem() {
 struct FusedGeom {
   int envs_per_tile;   // E: whole clusters per tile (E * Ns <= kTileSlots)
   int n_tiles;         // ceil(R / E)
-  int chunk_rows;      // observation rows staged per TMA store (multiple of 4)
+  int chunk_rows;      // observation rows staged per TMA store (multiple of 4); == E * Ns: "direct"
   int max_segs;        // max clusters overlapping one warp (+1)
+  int need_msg;        // neighbour messages are gathered (hand-engineered layout with nb_comm > 0)
   // dynamic shared memory offsets (bytes)
   int off_msg, off_own, off_env, off_wp, off_tile, smem_bytes;
 };
@@ -634,11 +726,17 @@ struct alignas(16) Own4 {
   real ta, tm, target, flags;
 };
 
+template <typename real> struct FusedOcc { static constexpr int min_ctas = 1; };
+template <> struct FusedOcc<float> { static constexpr int min_ctas = 3; };
+
 // ------------------------------------------------------------------------------------------
-// Fused path: one persistent kernel per step.
+// Fused path: one persistent kernel per step (always a real step: refreshes use the general path).
+// DIRECT: the whole tile's observation rows fit the staging buffer; each thread writes the rows of
+// its own 4 houses straight from registers and one TMA bulk store per tile ships them.
 // ------------------------------------------------------------------------------------------
-template <typename real>
-__global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p, StepIn in, FusedGeom g) {
+template <typename real, bool DIRECT>
+__global__ void __launch_bounds__(kThreads, FusedOcc<real>::min_ctas)
+k_fused(Planes<real> pl, SimParams p, StepIn in, FusedGeom g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Msg4<real> *s_msg = reinterpret_cast<Msg4<real> *>(smem_raw + g.off_msg);
   Own4<real> *s_own = reinterpret_cast<Own4<real> *>(smem_raw + g.off_own);
@@ -648,8 +746,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Ns = p.Ns, D = p.obs_dim;
-  const real nrs = (real)p.nrs, cop = (real)p.cop;
-  const int dur = p.lockout_duration;
+  const KC<real> kc(p);
   bool store_pending = false;
 
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
@@ -660,38 +757,43 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
 
     // env state of the tile's clusters is fetched early by the threads that will run the epilogue
     EnvRegs er;
-    if (threadIdx.x < E) er = env_load(pl, r0 + threadIdx.x);
+    if (threadIdx.x < E) er = env_load(pl, in, r0 + threadIdx.x);
 
     // ---- phase 1: house update in registers --------------------------------------------
     const int s0 = threadIdx.x * kHousesPerThread;
-    const int e_loc = s0 < slots ? s0 / Ns : -1 - warp;  // inactive threads never match a segment
+    const bool active = s0 < slots;
+    const int e_loc = active ? (int)fast_div((uint32_t)s0, p.fd_ns) : -1 - warp;  // inactive: never a segment
     House4<real> h;
-    double red[kRed] = {0, 0, 0, 0, 0};
-    if (s0 < slots) {
+    real red[kRed] = {0, 0, 0, 0, 0};
+    if (active) {
       const int r = r0 + e_loc;
       const int n0 = s0 - e_loc * Ns;
-      const int valid = min(4, p.N - n0);  // <= 0 only for pure padding slots (Ns - N < 4)
-      house4_step<real>(pl, p, in, base + s0, valid < 0 ? 0 : valid, (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
+      house4_step<real, true>(pl, p, kc, in, base + s0, min(4, p.N - n0), (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
+      if (g.need_msg || !DIRECT) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
-        const real pmax = h.cap[j] / cop;
-        Msg4<real> m;
-        m.dT = Rep<real>::dev(h.ta[j], h.target[j]) / (real)5;     // norm.py:39
-        m.sso_n = (real)(h.sso[j] / dur);                          // norm.py:40-43
-        m.p_n = ((f & 1u) ? pmax : (real)0) / nrs;
-        m.pmax_n = pmax / nrs;
-        Own4<real> o;
-        o.ta = h.ta[j]; o.tm = h.tm[j]; o.target = h.target[j]; o.flags = (real)f;
-        if (j >= h.valid) { m.dT = m.sso_n = m.p_n = m.pmax_n = 0; o.ta = o.tm = o.target = o.flags = 0; }
-        s_msg[s0 + j] = m;
-        s_own[s0 + j] = o;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
+          const real pmax = qdiv(h.cap[j], kc.cop, kc.inv_cop);
+          Msg4<real> m;
+          m.dT = div5(Rep<real>::dev(h.ta[j], h.target[j]));                  // norm.py:39
+          m.sso_n = (real)fast_div((uint32_t)h.sso[j], p.fd_dur);             // norm.py:40-43
+          m.p_n = qdiv((f & 1u) ? pmax : (real)0, kc.nrs, kc.inv_nrs);
+          m.pmax_n = qdiv(pmax, kc.nrs, kc.inv_nrs);
+          if (j >= h.valid) { m.dT = m.sso_n = m.p_n = m.pmax_n = 0; }
+          s_msg[s0 + j] = m;
+          if (!DIRECT) {
+            Own4<real> o;
+            o.ta = h.ta[j]; o.tm = h.tm[j]; o.target = h.target[j]; o.flags = (real)f;
+            if (j >= h.valid) { o.ta = o.tm = o.target = o.flags = 0; }
+            s_own[s0 + j] = o;
+          }
+        }
       }
     }
     // segmented warp reduction over clusters (lanes of one cluster are contiguous)
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      double t[kRed];
+      real t[kRed];
 #pragma unroll
       for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
       const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
@@ -703,7 +805,7 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
     if (head && e_loc >= 0) {
       double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
 #pragma unroll
-      for (int k = 0; k < kRed; ++k) dst[k] = red[k];
+      for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
     }
     // the previous tile's bulk store must have finished READING the staging tile before any
     // thread overwrites it in phase 3 of this tile
@@ -724,39 +826,32 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
     __syncthreads();
 
     // ---- phase 3: rewards from registers, observation rows through shared memory --------
-    if (s0 < slots && in.advance) {
+    if (active) {
       const EnvBroadcast<real> e = s_env[e_loc];
       real rw[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rw[j] = j < h.valid ? house_reward<real>(p, h.ta[j], h.target[j], e) : (real)0;
+      for (int j = 0; j < 4; ++j) rw[j] = j < h.valid ? house_reward<real>(p, kc, h.ta[j], h.target[j], e) : (real)0;
       store4(pl.reward + base + s0, rw);
-    }
-    if (D > 0) {
-      for (int cb = 0; cb < slots; cb += g.chunk_rows) {
-        const int rows = min(g.chunk_rows, slots - cb);
-        if (cb > 0) {
-          if (threadIdx.x == 0) bulk_store_wait_read();
-          __syncthreads();
-        }
-        for (int i = threadIdx.x; i < rows; i += kThreads) {
-          const int s = cb + i;
-          const int e = s / Ns, n = s - e * Ns;
-          real *row = s_tile + (size_t)i * D;
-          if (n < p.N) {
-            const Own4<real> o = s_own[s];
-            const Msg4<real> m = s_msg[s];
+      if (DIRECT && D > 0) {
+        const int n0 = s0 - e_loc * Ns;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          real *row = s_tile + (size_t)(s0 + j) * D;
+          if (j < h.valid) {
+            const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
             real ratio[4] = {0, 0, 0, 0};
             if (p.st_thermal)
-              for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s];
-            int q = obs_own<real>(row, p, (uint32_t)o.flags, m.sso_n, Rep<real>::minus20(o.ta, o.target),
-                                  Rep<real>::minus20(o.tm, o.target), o.target - (real)20, s_env[e], ratio);
-            if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
+              for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s0 + j];
+            int q = obs_own<real>(row, p, f, (real)fast_div((uint32_t)h.sso[j], p.fd_dur),
+                                  Rep<real>::minus20(h.ta[j], h.target[j]), Rep<real>::minus20(h.tm[j], h.target[j]),
+                                  h.target[j] - (real)20, e, ratio);
+            if (g.need_msg) {
               for (int k = 0; k < p.nb_comm; ++k) {
-                const int nb = neighbour_of(p, pl.comm_table, r0 + e, n, k);
-                const Msg4<real> mk = s_msg[e * Ns + nb];
+                const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
+                const Msg4<real> mk = s_msg[e_loc * Ns + nb];
                 row[q++] = mk.dT; row[q++] = mk.sso_n; row[q++] = mk.p_n; row[q++] = mk.pmax_n;
                 if (p.msg_thermal)
-                  for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][base + e * Ns + nb];
+                  for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][base + e_loc * Ns + nb];
                 if (p.msg_hvac) { row[q++] = (real)p.cop; row[q++] = (real)p.latent; row[q++] = (real)p.dcap; }
               }
             }
@@ -764,11 +859,55 @@ __global__ void __launch_bounds__(kThreads) k_fused(Planes<real> pl, SimParams p
             for (int q = 0; q < D; ++q) row[q] = (real)0;
           }
         }
+      }
+    }
+    if (D > 0) {
+      if (DIRECT) {
         fence_proxy_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
-          bulk_store_s2g(pl.obs + (base + cb) * D, s_tile, (uint32_t)((size_t)rows * D * sizeof(real)));
+          bulk_store_s2g(pl.obs + base * D, s_tile, (uint32_t)((size_t)slots * D * sizeof(real)));
           store_pending = true;
+        }
+      } else {
+        for (int cb = 0; cb < slots; cb += g.chunk_rows) {
+          const int rows = min(g.chunk_rows, slots - cb);
+          if (cb > 0) {
+            if (threadIdx.x == 0) bulk_store_wait_read();
+            __syncthreads();
+          }
+          for (int i = threadIdx.x; i < rows; i += kThreads) {
+            const int s = cb + i;
+            const int e = (int)fast_div((uint32_t)s, p.fd_ns), n = s - e * Ns;
+            real *row = s_tile + (size_t)i * D;
+            if (n < p.N) {
+              const Own4<real> o = s_own[s];
+              const Msg4<real> m = s_msg[s];
+              real ratio[4] = {0, 0, 0, 0};
+              if (p.st_thermal)
+                for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s];
+              int q = obs_own<real>(row, p, (uint32_t)o.flags, m.sso_n, Rep<real>::minus20(o.ta, o.target),
+                                    Rep<real>::minus20(o.tm, o.target), o.target - (real)20, s_env[e], ratio);
+              if (g.need_msg) {
+                for (int k = 0; k < p.nb_comm; ++k) {
+                  const int nb = neighbour_of(p, pl.comm_table, r0 + e, n, k);
+                  const Msg4<real> mk = s_msg[e * Ns + nb];
+                  row[q++] = mk.dT; row[q++] = mk.sso_n; row[q++] = mk.p_n; row[q++] = mk.pmax_n;
+                  if (p.msg_thermal)
+                    for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][base + e * Ns + nb];
+                  if (p.msg_hvac) { row[q++] = (real)p.cop; row[q++] = (real)p.latent; row[q++] = (real)p.dcap; }
+                }
+              }
+            } else {
+              for (int q = 0; q < D; ++q) row[q] = (real)0;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            bulk_store_s2g(pl.obs + (base + cb) * D, s_tile, (uint32_t)((size_t)rows * D * sizeof(real)));
+            store_pending = true;
+          }
         }
       }
     }

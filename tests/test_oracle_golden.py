@@ -48,3 +48,42 @@ def test_controllers_reproduce_golden_actions():
                 a = greedy_myopic(t_air, st["target"][0], st["cap"][0], hv["cop"], lock, sig)
             assert np.array_equal(a.astype(np.uint8), z["actions"][t]), (name, t)
             t_air, on, lock, sig = z["t_air"][t], z["on"][t], z["lockout"][t], z["signal"][t]
+
+
+@pytest.mark.parametrize("name", [n for n in case_names() if "allflags" not in n])
+def test_scalar_port_matches_reference_golden(name):
+    """The per-house pure-Python port (the timed CPU baseline) against the same fixtures."""
+    from oracle.scalar_port import ScalarEnv
+
+    case = GoldenCase(name)
+    env = ScalarEnv(case.env_prop, table=case.table())
+
+    class Adapter:
+        def set_state(self, st):
+            env.set_state(st)
+
+        def get_state(self):
+            return env.get_state()
+
+        def step(self, a, od, perlin, ids):
+            t = self.t
+            self.t += 1
+            return env.step(a, od, perlin, ids, comm=case.comm(t + 1))
+
+    ad = Adapter()
+    ad.t = 0
+    replay(case, ad, rtol=1e-12, check_obs=False, precision="f64")
+    # dict observation of house 0 after the last step equals the reference's (keys, order, values)
+    got, want = env.last_obs[0], case.last_obs_house0()
+    assert list(got.keys()) == list(want.keys())
+    for k, v in want.items():
+        if k == "datetime":
+            assert got[k].isoformat() == v
+        elif k == "message":
+            assert len(got[k]) == len(v)
+            for mg, mw in zip(got[k], v):
+                assert set(mw.keys()) <= set(mg.keys()) | {"cop", "latent_cooling_fraction", "cooling_capacity", "Ua", "Ca", "Cm", "Hm"}
+                for kk in ("seconds_since_off", "curr_consumption", "max_consumption", "current_temp_diff_to_target"):
+                    assert abs(float(mg[kk]) - float(mw[kk])) <= 1e-9 * max(1.0, abs(float(mw[kk])))
+        else:
+            assert abs(float(got[k]) - float(v)) <= 1e-9 * max(1.0, abs(float(v))), k
