@@ -173,7 +173,10 @@ static int fill_params(const drsim_config &c, SimParams &p, std::string &why) {
   p.fd_dur = make_fastdiv((uint32_t)std::max(1, c.lockout_duration));
   p.fd_ns = make_fastdiv((uint32_t)p.Ns);
   p.inv_cop = 1.0 / p.cop; p.inv_nrs = 1.0 / p.nrs; p.inv_norm_temp = 1.0 / p.norm_temp;
-  p.inv_n_global = 1.0 / (double)p.n_global;
+  p.inv_n_global = 1.0 / (double)p.n_global; p.inv_norm_sig = 1.0 / p.norm_sig;
+  p.hf.db = (float)p.deadband; p.hf.half_db = (float)(p.deadband / 2); p.hf.deadband = (float)p.deadband;
+  p.hf.inv_cop = (float)p.inv_cop; p.hf.inv_nrs = (float)p.inv_nrs; p.hf.inv_n = (float)p.inv_n_global;
+  p.hf.neg_inv_opl = (float)(-1.0 / (1.0 + p.latent)); p.hf.rew_scale = (float)(p.alpha_temp / p.norm_temp);
   if (c.lockout_duration < 1) { why = "lockout_duration must be >= 1 s"; return -1; }
   return 0;
 }
@@ -194,7 +197,7 @@ static void plan_fused(drsim_handle *h) {
   auto layout = [&](bool direct, int chunk) {
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
-    g.off_msg = take((g.need_msg || !direct) ? (size_t)slots * 4 * rb : 0);
+    g.off_msg = take((g.need_msg || !direct) ? (size_t)slots * 4 * rb * (direct ? 2 : 1) : 0);
     g.off_own = take(!direct ? (size_t)slots * 4 * rb : 0);
     g.off_env = take((size_t)g.envs_per_tile * 8 * rb);
     g.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double));
@@ -229,8 +232,8 @@ static int configure_kernels(drsim_handle *h) {
     h->fused_direct = direct;
     int per_sm = 0;
     if (direct) {
-      CU_TRY(cudaFuncSetAttribute(k_fused<real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
-      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real, true>, kThreads, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_direct<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_direct<real>, kThreads, h->geom.smem_bytes));
     } else {
       CU_TRY(cudaFuncSetAttribute(k_fused<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real, false>, kThreads, h->geom.smem_bytes));
@@ -652,7 +655,7 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
     k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
     h->launches++;
   }
-  if (h->fused_direct) k_fused<real, true><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
+  if (h->fused_direct) k_fused_direct<real><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   else k_fused<real, false><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   h->launches++;
   CU_TRY(cudaGetLastError());

@@ -193,10 +193,17 @@ DRSIM_HD uint32_t fast_div(uint32_t n, const FastDiv &f) {
   return (t + ((n - t) >> f.s1)) >> f.s2;
 }
 
+// fp32 hot-path constants, filled on the host so the kernels read them straight from the constant
+// bank (no per-thread fp64 -> fp32 conversions, no divisions)
+struct HotF {
+  float db, half_db, inv_cop, inv_nrs, inv_n, neg_inv_opl, rew_scale, deadband;
+};
+
 struct SimParams {
   int R, N, Ns;  // replicas, houses, house stride (N rounded up to 4)
+  HotF hf;
   FastDiv fd_dur, fd_ns;  // seconds_since_off / lockout_duration ; slot / Ns
-  double inv_cop, inv_nrs, inv_norm_temp, inv_n_global;  // fp32 build multiplies by reciprocals
+  double inv_cop, inv_nrs, inv_norm_temp, inv_n_global, inv_norm_sig;  // reciprocals (fp32 build, fast epilogue)
   int dt;
   int64_t house_offset, n_global, rep_offset;
   double deadband, cop, latent, window_area, shading;

@@ -229,6 +229,86 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const KC<re
   red[0] = P; red[1] = ps; red[2] = pm; red[3] = ds; red[4] = d2;
 }
 
+// Lean fp32 specialisation of house4_step for the fused production kernel: branch-free lock-out
+// FSM (hvac.py:43-64), deviation-form thermal update, constants straight from the constant bank.
+// Padding slots (N % 4 != 0) carry zero state / zero coefficients and are masked out of the sums.
+DRSIM_D void house4_step_f32(const Planes<float> &pl, const SimParams &p, const StepIn &in, size_t off, int valid,
+                             float od_prev, float solar, House4<float> &h, float red[kRed]) {
+  float c[6][4];
+  load4(pl.t_air + off, h.ta);
+  load4(pl.t_mass + off, h.tm);
+  load4i(pl.sso + off, h.sso);
+  h.flags = load4b(pl.flags + off);
+  load4_ro(pl.target + off, h.target);
+  load4_ro(pl.cap + off, h.cap);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) load4_ro(pl.coef[k] + off, c[k]);
+  uint32_t act = 0;
+  const int policy = p.policy;
+  if (policy == DRSIM_POLICY_EXTERNAL || policy == DRSIM_POLICY_GREEDY_MYOPIC)
+    act = load4b((in.actions ? in.actions : pl.actions) + off);
+  h.valid = valid;
+  const int dt = p.dt, dur = p.lockout_duration;
+  const float half_db = p.hf.half_db;
+  float P = 0, ps = 0, pm = 0, ds = 0, d2 = 0;
+  uint32_t nf = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t f0 = (h.flags >> (8 * j)) & 0xffu;
+    const bool on = f0 & 1u;
+    bool a = (act >> (8 * j)) & 0xffu;
+    if (policy == DRSIM_POLICY_DEADBAND_BANGBANG) a = h.ta[j] < -half_db ? false : (h.ta[j] > half_db ? true : on);
+    else if (policy == DRSIM_POLICY_BANGBANG) a = h.ta[j] > 0.f;
+    else if (policy == DRSIM_POLICY_ALWAYS_ON) a = true;
+    int sso = h.sso[j] + (on ? 0 : dt);
+    bool lock = !on && sso < dur;
+    const bool on_n = !lock && a;
+    sso = on_n ? 0 : sso;
+    lock = lock || (!on_n && sso + dt < dur);
+    h.sso[j] = sso;
+    nf |= ((on_n ? 1u : 0u) | (lock ? 2u : 0u)) << (8 * j);
+    const float Qa = (on_n ? h.cap[j] * p.hf.neg_inv_opl : 0.f) + solar;
+    const float odr = od_prev - h.target[j];
+    const float xa = h.ta[j], xm = h.tm[j];
+    const float ia = fmaf(c[2][j], Qa, fmaf(c[1][j], odr - xa, c[0][j] * (xm - xa)));
+    const float im = fmaf(c[5][j], Qa, fmaf(c[4][j], odr - xm, c[3][j] * (xa - xm)));
+    h.ta[j] = xa + ia;
+    h.tm[j] = xm + im;
+    const float m = j < valid ? 1.f : 0.f;
+    P = fmaf(on_n ? m : 0.f, h.cap[j] * p.hf.inv_cop, P);
+    const float d = fmaxf(fabsf(h.ta[j]) - half_db, 0.f);
+    const float pen = d * d * m;
+    ps = fmaf(pen, p.hf.inv_n, ps);
+    pm = fmaxf(pm, pen);
+    ds = fmaf(m, h.ta[j], ds);
+    d2 = fmaf(h.ta[j] * m, h.ta[j], d2);
+  }
+  h.flags = nf;
+  store4(pl.t_air + off, h.ta);
+  store4(pl.t_mass + off, h.tm);
+  store4i(pl.sso + off, h.sso);
+  store4b(pl.flags + off, h.flags);
+  red[0] = P; red[1] = ps; red[2] = pm; red[3] = ds; red[4] = d2;
+}
+
+template <bool ALWAYS_ADVANCE>
+DRSIM_D void house4_dispatch(const Planes<float> &pl, const SimParams &p, const KC<float> &, const StepIn &in,
+                             size_t off, int valid, float od_prev, float solar, House4<float> &h, float red[kRed]) {
+  static_assert(ALWAYS_ADVANCE, "lean path is only used by the fused kernel");
+  house4_step_f32(pl, p, in, off, valid, od_prev, solar, h, red);
+}
+template <bool ALWAYS_ADVANCE>
+DRSIM_D void house4_dispatch(const Planes<double> &pl, const SimParams &p, const KC<double> &kc, const StepIn &in,
+                             size_t off, int valid, double od_prev, double solar, House4<double> &h, double red[kRed]) {
+  house4_step<double, ALWAYS_ADVANCE>(pl, p, kc, in, off, valid, od_prev, solar, h, red);
+}
+
+// rewards_calculator.py:174-179 for one house, fp32 individual_L2 fast form
+DRSIM_D float reward_f32_individual(const SimParams &p, float xa, float rew_sig) {
+  const float d = fmaxf(fabsf(xa) - p.hf.half_db, 0.f);
+  return -fmaf(p.hf.rew_scale, d * d, rew_sig);
+}
+
 template <typename T, typename U>
 DRSIM_D void red_combine(T a[kRed], const U b[kRed]) {
   a[0] += (T)b[0]; a[1] += (T)b[1]; a[2] = a[2] > (T)b[2] ? a[2] : (T)b[2]; a[3] += (T)b[3]; a[4] += (T)b[4];
@@ -244,6 +324,7 @@ struct EnvRegs {
   // this step's pre-generated values (k_schedule), valid when StepIn::sched_od != NULL
   double s_od, s_solar, s_aux;
   int s_tsec;
+  double m[DRSIM_N_METRICS];  // running metrics, prefetched for the fast path
 };
 
 template <typename real>
@@ -259,6 +340,9 @@ DRSIM_D EnvRegs env_load(const Planes<real> &pl, const StepIn &in, int r) {
   e.t_since_interp = pl.t_since_interp[r];
   if (in.sched_od) {
     e.s_od = in.sched_od[r]; e.s_solar = in.sched_solar[r]; e.s_aux = in.sched_aux[r]; e.s_tsec = in.sched_tsec[r];
+    const double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
+#pragma unroll
+    for (int k = 0; k < DRSIM_N_METRICS; ++k) e.m[k] = m[k];
   }
   return e;
 }
@@ -366,6 +450,56 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
   return b;
 }
 
+// Fast epilogue of the fused kernel (schedule available, real step, no interpolator firing):
+// env_fast_compute is the short critical section between the two CTA barriers (only what the house
+// threads wait for); env_fast_store writes the env planes and metrics after the barrier is released.
+struct EnvFast {
+  double P, rew_sig, signal, solar_cur;
+};
+
+template <typename real>
+DRSIM_D EnvBroadcast<real> env_fast_compute(const SimParams &p, EnvRegs &e, const double red[kRed], EnvFast &f) {
+  f.P = red[0];
+  const double dev = (f.P - e.signal) * p.inv_n_global;            // rewards_calculator.py:198 (old signal, Q6)
+  f.rew_sig = p.alpha_sig * (dev * dev) * p.inv_norm_sig;
+  f.solar_cur = e.solar_next;
+  if (p.base_mode == DRSIM_BASE_CONSTANT) e.base_power = p.avg_power * (double)p.n_global;
+  f.signal = grid_signal_sched(p, e.base_power, e.s_tsec, e.s_aux, e.artificial_ratio, e.max_power);
+  EnvBroadcast<real> b;
+  b.power_n = (real)(f.P * p.inv_nrs);
+  b.signal_n = (real)(f.signal * p.inv_nrs * p.inv_n_global);
+  b.solar_n = (real)(f.solar_cur * 1e-3);
+  b.od_n = (real)((e.s_od - 20.0) * 0.2);
+  b.rew_sig = (real)f.rew_sig;
+  b.pen_common = (real)red[1];
+  b.pen_max = (real)red[2];
+  return b;
+}
+
+template <typename real>
+DRSIM_D void env_fast_store(const Planes<real> &pl, const SimParams &p, int r, const EnvRegs &e, const EnvFast &f,
+                            const double red[kRed]) {
+  pl.epoch[r] = e.epoch + p.dt;
+  pl.od_temp[r] = e.s_od;
+  pl.solar_next[r] = e.s_solar;
+  pl.solar_cur[r] = f.solar_cur;
+  pl.signal[r] = f.signal;
+  pl.base_power[r] = e.base_power;
+  pl.power[r] = f.P;
+  pl.pen_sum[r] = red[1];
+  pl.pen_max[r] = red[2];
+  pl.rew_sig[r] = f.rew_sig;
+  if (p.base_mode != DRSIM_BASE_CONSTANT) pl.t_since_interp[r] = e.t_since_interp + p.dt;
+  double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
+  const double d = f.P - e.signal;
+  m[0] = e.m[0] + 1.0;
+  m[1] = e.m[1] + mean_reward(p, red[1], red[2], f.rew_sig);
+  m[2] = e.m[2] + fabs(red[3]) * p.inv_n_global;
+  m[3] = e.m[3] + red[4] * p.inv_n_global;
+  m[4] = e.m[4] + fabs(d);
+  m[5] = e.m[5] + d * d;
+}
+
 // Pre-generation of the env-level time series: thread (k, r) evaluates, for step `step0 + k` of
 // replica r, the outdoor temperature (environment.py:132-159 with the Philox gauss draw), the
 // solar gain of the following step (utils.py:42-117), seconds since midnight and the
@@ -425,26 +559,26 @@ DRSIM_D int neighbour_of(const SimParams &p, const int32_t *table, int r, int n,
   return __ldg(table + base + (size_t)n * p.nb_comm + k);
 }
 
-// own-state part of the observation row (utils/norm.py:71-146)
+// own-state part of the observation row (utils/norm.py:71-146).  `what` selects the columns
+// written: bit0 = those that depend on the house only, bit1 = those that need the env epilogue
+// (cluster power, signal, solar gain, outdoor temperature).
 template <typename real>
 DRSIM_D int obs_own(real *row, const SimParams &p, uint32_t f, real sso_n, real ta20, real tm20, real tg20,
-                    const EnvBroadcast<real> &e, const real ratio[4]) {
+                    const EnvBroadcast<real> &e, const real ratio[4], int what = 3) {
   int i = 0;
-  row[i++] = (real)(f & 1u);
-  row[i++] = (real)((f >> 1) & 1u);
-  row[i++] = sso_n;
-  row[i++] = (real)1;
-  if (p.st_hvac) { row[i++] = (real)1; row[i++] = (real)1; }
-  row[i++] = e.power_n;
-  row[i++] = e.signal_n;
-  row[i++] = (real)p.deadband;
-  row[i++] = div5(ta20);
-  row[i++] = div5(tm20);
-  row[i++] = div5(tg20);
-  if (p.st_solar) row[i++] = e.solar_n;
+  const bool hs = what & 1, ev = what & 2;
+  if (hs) { row[i] = (real)(f & 1u); row[i + 1] = (real)((f >> 1) & 1u); row[i + 2] = sso_n; row[i + 3] = (real)1; }
+  i += 4;
+  if (p.st_hvac) { if (hs) { row[i] = (real)1; row[i + 1] = (real)1; } i += 2; }
+  if (ev) { row[i] = e.power_n; row[i + 1] = e.signal_n; }
+  i += 2;
+  if (hs) { row[i] = (real)p.deadband; row[i + 1] = div5(ta20); row[i + 2] = div5(tm20); row[i + 3] = div5(tg20); }
+  i += 4;
+  if (p.st_solar) { if (ev) row[i] = e.solar_n; i += 1; }
   if (p.st_thermal) {
-    row[i++] = (real)ratio[0]; row[i++] = (real)ratio[1]; row[i++] = (real)ratio[2]; row[i++] = (real)ratio[3];
-    row[i++] = e.od_n;
+    if (hs) { row[i] = ratio[0]; row[i + 1] = ratio[1]; row[i + 2] = ratio[2]; row[i + 3] = ratio[3]; }
+    if (ev) row[i + 4] = e.od_n;
+    i += 5;
   }
   return i;
 }
@@ -916,6 +1050,210 @@ k_fused(Planes<real> pl, SimParams p, StepIn in, FusedGeom g) {
     __syncthreads();
   }
   if (threadIdx.x == 0 && store_pending) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused path, "direct" variant -- the production kernel.
+//
+// The whole tile's observation rows fit the staging buffer, so every thread writes the rows of its
+// own 4 houses straight from registers.  Per tile there are exactly two CTA barriers, bracketing a
+// ~100-instruction critical section on E threads (combine the warp partials, signal penalty,
+// regulation signal); everything else the epilogue does (env plane stores, metrics) happens after
+// the barrier is released.  Row columns that depend on the house only are written before the first
+// barrier; the two env-dependent columns, the neighbour messages and the rewards after the second.
+// Each warp ships its own 128 rows with one TMA bulk store (no CTA barrier in front of it).
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(kThreads, FusedOcc<real>::min_ctas)
+k_fused_direct(Planes<real> pl, SimParams p, StepIn in, FusedGeom g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Msg4<real> *s_msg_base = reinterpret_cast<Msg4<real> *>(smem_raw + g.off_msg);  // [2][slots] if need_msg
+  EnvBroadcast<real> *s_env = reinterpret_cast<EnvBroadcast<real> *>(smem_raw + g.off_env);
+  double *s_wp = reinterpret_cast<double *>(smem_raw + g.off_wp);  // [warps][max_segs][kRed]
+  real *s_tile = reinterpret_cast<real *>(smem_raw + g.off_tile);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ns = p.Ns, D = p.obs_dim;
+  const int tile_slots = g.envs_per_tile * Ns;
+  const KC<real> kc(p);
+  const bool fast = in.sched_od != nullptr;
+  // lean row layout: fp32, no optional state/message columns, 4-float messages
+  const bool plain = sizeof(real) == 4 && p.own_dim == 10 && p.msg_dim == 4 && (D % 2) == 0;
+  bool store_pending = false;  // meaningful on lane 0 of each warp
+  int parity = 0;
+
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
+    const int r0 = tile * g.envs_per_tile;
+    const int E = min(g.envs_per_tile, p.R - r0);
+    const int slots = E * Ns;
+    const size_t base = (size_t)r0 * Ns;
+    Msg4<real> *s_msg = s_msg_base + (size_t)parity * tile_slots;
+
+    EnvRegs er;
+    if (threadIdx.x < E) er = env_load(pl, in, r0 + threadIdx.x);
+
+    // ---- phase 1: house update in registers, house-only row columns ----------------------
+    const int s0 = threadIdx.x * kHousesPerThread;
+    const bool active = s0 < slots;
+    const int e_loc = active ? (int)fast_div((uint32_t)s0, p.fd_ns) : -1 - warp;
+    const int n0 = s0 - e_loc * Ns;
+    House4<real> h;
+    real red[kRed] = {0, 0, 0, 0, 0};
+    // the warp's previous TMA store must have finished reading its rows before they are rewritten
+    if (lane == 0 && store_pending) bulk_store_wait_read();
+    __syncwarp();
+    if (active) {
+      const int r = r0 + e_loc;
+      house4_dispatch<true>(pl, p, kc, in, base + s0, min(4, p.N - n0), (real)pl.od_temp[r], (real)pl.solar_next[r], h, red);
+      EnvBroadcast<real> none{};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
+        const real sso_n = (real)fast_div((uint32_t)h.sso[j], p.fd_dur);            // norm.py:40-43, :79-82
+        if (g.need_msg) {
+          const real pmax_n = qdiv(qdiv(h.cap[j], kc.cop, kc.inv_cop), kc.nrs, kc.inv_nrs);
+          Msg4<real> m;
+          m.dT = div5(Rep<real>::dev(h.ta[j], h.target[j]));                        // norm.py:39
+          m.sso_n = sso_n;
+          m.p_n = (f & 1u) ? pmax_n : (real)0;
+          m.pmax_n = pmax_n;
+          if (j >= h.valid) { m.dT = m.sso_n = m.p_n = m.pmax_n = 0; }
+          s_msg[s0 + j] = m;
+        }
+        if (D > 0) {
+          real *row = s_tile + (size_t)(s0 + j) * D;
+          if (plain) {
+            // own_dim == 10, even D: rows are 8-byte aligned -> 64-bit shared stores
+            if constexpr (sizeof(real) == 4) {
+              float2 *r2 = reinterpret_cast<float2 *>(row);
+              const float tg = h.target[j] - 20.f;
+              const bool ok = j < h.valid;
+              r2[0] = make_float2(ok ? (float)(f & 1u) : 0.f, ok ? (float)((f >> 1) & 1u) : 0.f);
+              r2[1] = make_float2(ok ? sso_n : 0.f, ok ? 1.f : 0.f);
+              r2[3] = make_float2(ok ? p.hf.deadband : 0.f, ok ? (h.ta[j] + tg) * 0.2f : 0.f);
+              r2[4] = make_float2(ok ? (h.tm[j] + tg) * 0.2f : 0.f, ok ? tg * 0.2f : 0.f);
+              if (!ok) {
+                r2[2] = make_float2(0.f, 0.f);
+                for (int q = 5; q < D / 2; ++q) r2[q] = make_float2(0.f, 0.f);
+              }
+            }
+          } else if (j < h.valid) {
+            real ratio[4] = {0, 0, 0, 0};
+            if (p.st_thermal)
+              for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s0 + j];
+            obs_own<real>(row, p, f, sso_n, Rep<real>::minus20(h.ta[j], h.target[j]),
+                          Rep<real>::minus20(h.tm[j], h.target[j]), h.target[j] - (real)20, none, ratio, 1);
+          } else {
+            for (int q = 0; q < D; ++q) row[q] = (real)0;
+          }
+        }
+      }
+    }
+    // segmented warp reduction over clusters (lanes of one cluster are contiguous)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      real t[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+      const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
+      if (lane + o < 32 && eo == e_loc) red_combine(red, t);
+    }
+    const int e_prev = __shfl_up_sync(0xffffffffu, e_loc, 1);
+    const bool head = (lane == 0) || (e_prev != e_loc);
+    const int e_first = __shfl_sync(0xffffffffu, e_loc, 0);
+    if (head && e_loc >= 0) {
+      double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
+    }
+    __syncthreads();
+
+    // ---- phase 2: the short critical section on E threads ---------------------------------
+    double a[kRed] = {0, 0, 0, 0, 0};
+    EnvFast ef;
+    if (threadIdx.x < E) {
+      const int e = threadIdx.x;
+      const int w_lo = (e * Ns) / 128, w_hi = ((e + 1) * Ns - 1) / 128;
+      for (int w = w_lo; w <= w_hi; ++w) {
+        const int efst = (w * 128) / Ns;  // first cluster seen by warp w
+        red_combine(a, s_wp + ((size_t)w * g.max_segs + (e - efst)) * kRed);
+      }
+      if (fast) s_env[e] = env_fast_compute<real>(p, er, a, ef);
+      else s_env[e] = env_epilogue<real>(pl, p, in, r0 + e, er, a, 0.0);  // injected noise: full inline path
+    }
+    __syncthreads();
+
+    // ---- phase 3: env-dependent columns, neighbour messages, rewards ----------------------
+    if (active) {
+      const EnvBroadcast<real> e = s_env[e_loc];
+      real rw[4];
+      bool lean_reward = false;
+      if constexpr (sizeof(real) == 4) lean_reward = p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if constexpr (sizeof(real) == 4) {
+          rw[j] = lean_reward ? reward_f32_individual(p, h.ta[j], e.rew_sig) : house_reward<real>(p, kc, h.ta[j], h.target[j], e);
+          if (j >= h.valid) rw[j] = 0.f;
+        } else {
+          rw[j] = j < h.valid ? house_reward<real>(p, kc, h.ta[j], h.target[j], e) : (real)0;
+        }
+      }
+      store4(pl.reward + base + s0, rw);
+      if (D > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < h.valid) {
+            real *row = s_tile + (size_t)(s0 + j) * D;
+            if (plain) {
+              if constexpr (sizeof(real) == 4) {
+                float2 *r2 = reinterpret_cast<float2 *>(row);
+                r2[2] = make_float2(e.power_n, e.signal_n);
+                if (g.need_msg) {
+                  for (int k = 0; k < p.nb_comm; ++k) {
+                    const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
+                    const float4 mk = *reinterpret_cast<const float4 *>(&s_msg[e_loc * Ns + nb]);
+                    r2[5 + 2 * k] = make_float2(mk.x, mk.y);
+                    r2[6 + 2 * k] = make_float2(mk.z, mk.w);
+                  }
+                }
+              }
+              continue;
+            }
+            int q = obs_own<real>(row, p, 0u, (real)0, (real)0, (real)0, (real)0, e, nullptr, 2);
+            if (g.need_msg) {
+              for (int k = 0; k < p.nb_comm; ++k) {
+                const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
+                const Msg4<real> mk = s_msg[e_loc * Ns + nb];
+                row[q++] = mk.dT; row[q++] = mk.sso_n; row[q++] = mk.p_n; row[q++] = mk.pmax_n;
+                if (p.msg_thermal)
+                  for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][base + e_loc * Ns + nb];
+                if (p.msg_hvac) { row[q++] = (real)p.cop; row[q++] = (real)p.latent; row[q++] = (real)p.dcap; }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (D > 0) {
+      // every lane's generic-proxy writes to the warp's rows become visible to the async proxy,
+      // then lane 0 ships the warp's rows [128 w, 128 w + 128) with one bulk store
+      fence_proxy_async_smem();
+      __syncwarp();
+      const int w0 = warp * 128;
+      if (lane == 0 && w0 < slots) {
+        const int nrows = min(128, slots - w0);
+        bulk_store_s2g(pl.obs + (base + w0) * D, s_tile + (size_t)w0 * D, (uint32_t)((size_t)nrows * D * sizeof(real)));
+        store_pending = true;
+      }
+    }
+    // off the critical path: env planes + running metrics
+    if (threadIdx.x < E && fast) env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
+  }
+  if (lane == 0 && store_pending) {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #endif
