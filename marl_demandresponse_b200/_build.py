@@ -7,7 +7,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libdrsim.so")
+LIB = os.environ.get("DRSIM_LIB") or os.path.join(PKG, "libdrsim.so")
 SOURCES = ["drsim_api.cu"]
 HEADERS = ["drsim_kernels.cuh", "drsim_device.cuh", os.path.join("..", "..", "include", "drsim.h")]
 NVCC_FLAGS = [
@@ -37,7 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA extension for sm_100a; returns the path of the shared library."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("DRSIM_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(" ".join(cmd))
@@ -45,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libdrsim.so")
-    with open(os.path.join(PKG, "libdrsim.build.log"), "w") as f:
+    with open(LIB + ".build.log" if os.environ.get("DRSIM_LIB") else os.path.join(PKG, "libdrsim.build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     return LIB
 

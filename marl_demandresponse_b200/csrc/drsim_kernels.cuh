@@ -860,8 +860,13 @@ struct alignas(16) Own4 {
   real ta, tm, target, flags;
 };
 
+// resident CTAs per SM the fp32 fused kernel is compiled for.  Measured on B200 (C4 workload):
+// 2 (128 registers, no spills) 51.9 us/step; 3 (80 registers) 60.0 us; 4 (64 registers) 66.6 us.
+#ifndef DRSIM_FUSED_MINCTAS
+#define DRSIM_FUSED_MINCTAS 2
+#endif
 template <typename real> struct FusedOcc { static constexpr int min_ctas = 1; };
-template <> struct FusedOcc<float> { static constexpr int min_ctas = 3; };
+template <> struct FusedOcc<float> { static constexpr int min_ctas = DRSIM_FUSED_MINCTAS; };
 
 // ------------------------------------------------------------------------------------------
 // Fused path: one persistent kernel per step (always a real step: refreshes use the general path).
