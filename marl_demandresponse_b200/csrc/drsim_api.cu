@@ -199,23 +199,30 @@ static void plan_fused(drsim_handle *h) {
     auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
     g.off_msg = take((g.need_msg || !direct) ? (size_t)slots * 4 * rb * (direct ? 2 : 1) : 0);
     g.off_own = take(!direct ? (size_t)slots * 4 * rb : 0);
-    g.off_env = take((size_t)g.envs_per_tile * 8 * rb);
-    g.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double));
+    g.off_env = take((size_t)g.envs_per_tile * 8 * rb * 2);
+    g.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double) * 2);
+    g.off_sold = take((size_t)g.envs_per_tile * sizeof(double) * 2);
     g.off_tile = (int)off;
     g.chunk_rows = chunk;
-    g.smem_bytes = (int)(off + (size_t)chunk * row);
+    off += ((size_t)chunk * row + 127) / 128 * 128;
+    g.use_tma = (direct && rb == 4 && h->cfg.path != DRSIM_PATH_FUSED + 100) ? 1 : 0;
+    if (g.use_tma) {
+      g.off_in = take((size_t)kInPlanes * kTileSlots * 4);
+      g.off_bar = take((size_t)(kThreads / 32) * 8);
+    }
+    g.smem_bytes = (int)off;
     return off;
   };
-  // direct: the whole tile's rows staged at once (one TMA store per tile, rows from registers)
+  // direct: the whole tile's rows staged at once (one TMA store per warp, rows from registers)
   layout(true, row ? slots : 0);
-  if (g.smem_bytes > 100 * 1024) {
+  if (g.smem_bytes > 112 * 1024) {
     // chunked staging; aim for >= 2 resident CTAs per SM, fall back to one big CTA
-    const size_t fixed = layout(false, 0);
+    const size_t fixed = layout(false, 0) - 0;
     int chunk = 0;
     const size_t budgets[2] = {110 * 1024, 220 * 1024};
     for (size_t b : budgets) {
       if (fixed + 32 * row > b) continue;
-      chunk = (int)std::min<size_t>((b - fixed) / row, (size_t)slots) / 4 * 4;
+      chunk = (int)std::min<size_t>((b - fixed - 256) / row, (size_t)slots) / 4 * 4;
       if (chunk >= 32) break;
     }
     if (chunk < 4) return;  // does not fit: general path
@@ -231,7 +238,10 @@ static int configure_kernels(drsim_handle *h) {
     const bool direct = h->geom.chunk_rows == h->geom.envs_per_tile * h->p.Ns || h->p.obs_dim == 0;
     h->fused_direct = direct;
     int per_sm = 0;
-    if (direct) {
+    if (direct && h->geom.use_tma) {
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tma, kThreads, h->geom.smem_bytes));
+    } else if (direct) {
       CU_TRY(cudaFuncSetAttribute(k_fused_direct<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_direct<real>, kThreads, h->geom.smem_bytes));
     } else {
@@ -645,6 +655,11 @@ static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc
   return 0;
 }
 
+static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
+  const Planes<float> pl = make_planes<float>(h);
+  k_fused_tma<<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, h->p, in, h->geom);
+}
+
 template <typename real>
 static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
@@ -655,7 +670,8 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
     k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
     h->launches++;
   }
-  if (h->fused_direct) k_fused_direct<real><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
+  if (h->fused_direct && h->geom.use_tma) launch_tma(h, in, s);
+  else if (h->fused_direct) k_fused_direct<real><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   else k_fused<real, false><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   h->launches++;
   CU_TRY(cudaGetLastError());

@@ -309,6 +309,65 @@ DRSIM_D float reward_f32_individual(const SimParams &p, float xa, float rew_sig)
   return -fmaf(p.hf.rew_scale, d * d, rew_sig);
 }
 
+// Inputs of 4 houses as the fused fp32 kernel receives them (from shared memory / registers)
+struct Raw4f {
+  float ta[4], tm[4], target[4], cap[4], c[6][4];
+  int sso[4];
+  uint32_t flags, act;
+  float od, solar;
+};
+
+// COMPUTE half of the lean fp32 house step (see house4_step_f32): consumes a Raw4f.
+DRSIM_D void house4_compute_f32(const Planes<float> &pl, const SimParams &p, const Raw4f &w, size_t off, int valid,
+                                House4<float> &h, float red[kRed]) {
+  const int policy = p.policy;
+  h.valid = valid;
+  const int dt = p.dt, dur = p.lockout_duration;
+  const float half_db = p.hf.half_db;
+  float P = 0, ps = 0, pm = 0, ds = 0, d2 = 0;
+  uint32_t nf = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t f0 = (w.flags >> (8 * j)) & 0xffu;
+    const bool on = f0 & 1u;
+    bool a = (w.act >> (8 * j)) & 0xffu;
+    if (policy == DRSIM_POLICY_DEADBAND_BANGBANG) a = w.ta[j] < -half_db ? false : (w.ta[j] > half_db ? true : on);
+    else if (policy == DRSIM_POLICY_BANGBANG) a = w.ta[j] > 0.f;
+    else if (policy == DRSIM_POLICY_ALWAYS_ON) a = true;
+    int sso = w.sso[j] + (on ? 0 : dt);
+    bool lock = !on && sso < dur;
+    const bool on_n = !lock && a;
+    sso = on_n ? 0 : sso;
+    lock = lock || (!on_n && sso + dt < dur);
+    h.sso[j] = sso;
+    nf |= ((on_n ? 1u : 0u) | (lock ? 2u : 0u)) << (8 * j);
+    const float cap = w.cap[j], tg = w.target[j];
+    h.cap[j] = cap;
+    h.target[j] = tg;
+    const float Qa = (on_n ? cap * p.hf.neg_inv_opl : 0.f) + w.solar;
+    const float odr = w.od - tg;
+    const float xa = w.ta[j], xm = w.tm[j];
+    const float ia = fmaf(w.c[2][j], Qa, fmaf(w.c[1][j], odr - xa, w.c[0][j] * (xm - xa)));
+    const float im = fmaf(w.c[5][j], Qa, fmaf(w.c[4][j], odr - xm, w.c[3][j] * (xa - xm)));
+    h.ta[j] = xa + ia;
+    h.tm[j] = xm + im;
+    const float m = j < valid ? 1.f : 0.f;
+    P = fmaf(on_n ? m : 0.f, cap * p.hf.inv_cop, P);
+    const float d = fmaxf(fabsf(h.ta[j]) - half_db, 0.f);
+    const float pen = d * d * m;
+    ps = fmaf(pen, p.hf.inv_n, ps);
+    pm = fmaxf(pm, pen);
+    ds = fmaf(m, h.ta[j], ds);
+    d2 = fmaf(h.ta[j] * m, h.ta[j], d2);
+  }
+  h.flags = nf;
+  store4(pl.t_air + off, h.ta);
+  store4(pl.t_mass + off, h.tm);
+  store4i(pl.sso + off, h.sso);
+  store4b(pl.flags + off, h.flags);
+  red[0] = P; red[1] = ps; red[2] = pm; red[3] = ds; red[4] = d2;
+}
+
 template <typename T, typename U>
 DRSIM_D void red_combine(T a[kRed], const U b[kRed]) {
   a[0] += (T)b[0]; a[1] += (T)b[1]; a[2] = a[2] > (T)b[2] ? a[2] : (T)b[2]; a[3] += (T)b[3]; a[4] += (T)b[4];
@@ -456,6 +515,30 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
 struct EnvFast {
   double P, rew_sig, signal, solar_cur;
 };
+
+// The part of the fast epilogue that does not depend on this step's cluster power: available
+// BEFORE the tile barrier.  The power-dependent scalars (power_n, rew_sig) are folded in afterwards
+// by every house thread on its own (env_fold_power), so the tile has no serial section at all.
+template <typename real>
+DRSIM_D EnvBroadcast<real> env_pre_compute(const SimParams &p, EnvRegs &e, EnvFast &f) {
+  f.solar_cur = e.solar_next;
+  if (p.base_mode == DRSIM_BASE_CONSTANT) e.base_power = p.avg_power * (double)p.n_global;
+  f.signal = grid_signal_sched(p, e.base_power, e.s_tsec, e.s_aux, e.artificial_ratio, e.max_power);
+  EnvBroadcast<real> b;
+  b.power_n = (real)0;
+  b.signal_n = (real)(f.signal * p.inv_nrs * p.inv_n_global);
+  b.solar_n = (real)(f.solar_cur * 1e-3);
+  b.od_n = (real)((e.s_od - 20.0) * 0.2);
+  b.rew_sig = (real)0;
+  b.pen_common = (real)0;
+  b.pen_max = (real)0;
+  return b;
+}
+
+DRSIM_D double signal_penalty(const SimParams &p, double P, double s_old) {
+  const double dev = (P - s_old) * p.inv_n_global;               // rewards_calculator.py:198 (old signal, Q6)
+  return p.alpha_sig * (dev * dev) * p.inv_norm_sig;
+}
 
 template <typename real>
 DRSIM_D EnvBroadcast<real> env_fast_compute(const SimParams &p, EnvRegs &e, const double red[kRed], EnvFast &f) {
@@ -848,7 +931,8 @@ struct FusedGeom {
   int max_segs;        // max clusters overlapping one warp (+1)
   int need_msg;        // neighbour messages are gathered (hand-engineered layout with nb_comm > 0)
   // dynamic shared memory offsets (bytes)
-  int off_msg, off_own, off_env, off_wp, off_tile, smem_bytes;
+  int off_msg, off_own, off_env, off_wp, off_sold, off_tile, off_in, off_bar, smem_bytes;
+  int use_tma;         // fp32 direct tiles: inputs staged by TMA bulk loads (k_fused_tma)
 };
 
 template <typename real>
@@ -1257,6 +1341,336 @@ k_fused_direct(Planes<real> pl, SimParams p, StepIn in, FusedGeom g) {
     }
     // off the critical path: env planes + running metrics
     if (threadIdx.x < E && fast) env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
+  }
+  if (lane == 0 && store_pending) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk LOAD helpers (global -> shared::cta, completion on an mbarrier)
+// ------------------------------------------------------------------------------------------
+DRSIM_D void mbar_init(uint64_t *bar, uint32_t count) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+#endif
+}
+DRSIM_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+#endif
+}
+DRSIM_D void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+#endif
+}
+DRSIM_D void bulk_load_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+#endif
+}
+
+constexpr int kInPlanes = 12;  // fp32 planes staged by TMA: Ta, Tm, sso, target, cap, 6 coefficients (+1 spare)
+
+// ------------------------------------------------------------------------------------------
+// Fused path, fp32 production kernel with TMA-staged inputs.
+//
+// Same tile structure as k_fused_direct, but the eleven 32-bit input planes of a tile never go
+// through registers on their way in: each warp owns the 128 house slots it processes, prefetches
+// them for the NEXT tile with eleven TMA bulk loads (cp.async.bulk.shared.global, completion on the
+// warp's own mbarrier) as soon as it has consumed the current ones, and reads them back with
+// conflict-free 128-bit shared loads.  HBM therefore stays busy while the CTA sits in its two
+// barriers and assembles observation rows; the load path needs only warp-level synchronisation.
+// The two byte planes (flags, actions) are 8-byte aligned at odd replica indices, which the bulk
+// copy engine cannot address, so they are prefetched through two registers instead.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, DRSIM_FUSED_MINCTAS)
+k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
+  typedef float real;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Msg4<real> *s_msg_base = reinterpret_cast<Msg4<real> *>(smem_raw + g.off_msg);
+  // s_env / s_wp / s_sold are double-buffered by tile parity: a warp may run ahead into the next
+  // tile's phase 1 while slower warps still read this tile's values (one CTA barrier per tile)
+  EnvBroadcast<real> *s_env_base = reinterpret_cast<EnvBroadcast<real> *>(smem_raw + g.off_env);
+  double *s_wp_base = reinterpret_cast<double *>(smem_raw + g.off_wp);
+  double *s_sold_base = reinterpret_cast<double *>(smem_raw + g.off_sold);  // [2][E] previous signal
+  real *s_tile = reinterpret_cast<real *>(smem_raw + g.off_tile);
+  float *s_in = reinterpret_cast<float *>(smem_raw + g.off_in);        // [kInPlanes][kTileSlots]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + g.off_bar);  // [warps]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ns = p.Ns, D = p.obs_dim;
+  const int tile_slots = g.envs_per_tile * Ns;
+  const KC<real> kc(p);
+  const bool fast = in.sched_od != nullptr;
+  const bool plain = p.own_dim == 10 && p.msg_dim == 4 && (D % 2) == 0;
+  const bool ext = p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC;
+  const uint8_t *actions = in.actions ? in.actions : pl.actions;
+  bool store_pending = false;
+  int parity = 0;
+  uint32_t ld_phase = 0;  // phase of the warp's load mbarrier (flips only on tiles the warp takes part in)
+  const int s0 = threadIdx.x * kHousesPerThread;
+  const int w0 = warp * 128;
+
+  const float *planes[11] = {pl.t_air, pl.t_mass, reinterpret_cast<const float *>(pl.sso), pl.target, pl.cap,
+                             pl.coef[0], pl.coef[1], pl.coef[2], pl.coef[3], pl.coef[4], pl.coef[5]};
+
+  if (lane == 0) mbar_init(&s_bar[warp], 1);
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // warp-local prefetch of tile `t`: 11 bulk loads of the warp's slots + 2 byte-plane registers
+  uint32_t nx_flags = 0, nx_act = 0;
+  float nx_od = 0.f, nx_solar = 0.f;
+  auto prefetch = [&](int t) {
+    const int tr0 = t * g.envs_per_tile;
+    const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
+    const size_t tbase = (size_t)tr0 * Ns;
+    const int nw = min(128, tslots - w0);
+    if (lane == 0 && nw > 0) {
+      mbar_expect_tx(&s_bar[warp], (uint32_t)(11 * nw * 4));
+#pragma unroll
+      for (int k = 0; k < 11; ++k)
+        bulk_load_g2s(s_in + (size_t)k * kTileSlots + w0, planes[k] + tbase + w0, (uint32_t)(nw * 4), &s_bar[warp]);
+    }
+    if (s0 < tslots) {
+      nx_flags = load4b(pl.flags + tbase + s0);
+      if (ext) nx_act = load4b(actions + tbase + s0);
+      const int r = tr0 + (int)fast_div((uint32_t)s0, p.fd_ns);
+      nx_od = (float)pl.od_temp[r];
+      nx_solar = (float)pl.solar_next[r];
+    }
+  };
+  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
+    const int r0 = tile * g.envs_per_tile;
+    const int E = min(g.envs_per_tile, p.R - r0);
+    const int slots = E * Ns;
+    const size_t base = (size_t)r0 * Ns;
+    Msg4<real> *s_msg = s_msg_base + (size_t)parity * tile_slots;
+    EnvBroadcast<real> *s_env = s_env_base + (size_t)parity * g.envs_per_tile;
+    double *s_wp = s_wp_base + (size_t)parity * (kThreads / 32) * g.max_segs * kRed;
+    double *s_sold = s_sold_base + (size_t)parity * g.envs_per_tile;
+
+    EnvRegs er;
+    EnvFast ef;
+    if (threadIdx.x < E) {
+      er = env_load(pl, in, r0 + threadIdx.x);
+      if (fast) {  // power-independent part of the epilogue, ready before the barrier
+        s_env[threadIdx.x] = env_pre_compute<real>(p, er, ef);
+        s_sold[threadIdx.x] = er.signal;
+      }
+    }
+
+    // ---- phase 1 -----------------------------------------------------------------------
+    const bool active = s0 < slots;
+    const int e_loc = active ? (int)fast_div((uint32_t)s0, p.fd_ns) : -1 - warp;
+    const int n0 = s0 - e_loc * Ns;
+    House4<real> h;
+    real red[kRed] = {0, 0, 0, 0, 0};
+    if (lane == 0 && store_pending) bulk_store_wait_read();
+    __syncwarp();
+    if (w0 < slots) { mbar_wait(&s_bar[warp], ld_phase); ld_phase ^= 1u; }   // this tile's planes have landed
+    if (active) {
+      Raw4f w;
+      const float4 *in4 = reinterpret_cast<const float4 *>(s_in) + threadIdx.x;
+      auto ld = [&](int k, float v[4]) {
+        const float4 t = in4[(size_t)k * (kTileSlots / 4)];
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      };
+      ld(0, w.ta); ld(1, w.tm);
+      {
+        const int4 t = reinterpret_cast<const int4 *>(s_in)[(size_t)2 * (kTileSlots / 4) + threadIdx.x];
+        w.sso[0] = t.x; w.sso[1] = t.y; w.sso[2] = t.z; w.sso[3] = t.w;
+      }
+      ld(3, w.target); ld(4, w.cap);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ld(5 + k, w.c[k]);
+      w.flags = nx_flags; w.act = nx_act; w.od = nx_od; w.solar = nx_solar;
+      house4_compute_f32(pl, p, w, base + s0, min(4, p.N - n0), h, red);
+    }
+    // every lane of the warp has consumed its staged inputs: prefetch the next tile into them
+    fence_proxy_async_smem();
+    __syncwarp();
+    {
+      const int nt = tile + gridDim.x;
+      if (nt < g.n_tiles) prefetch(nt);
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
+        const real sso_n = (real)fast_div((uint32_t)h.sso[j], p.fd_dur);            // norm.py:40-43, :79-82
+        const bool ok = j < h.valid;
+        if (g.need_msg) {
+          const real pmax_n = h.cap[j] * p.hf.inv_cop * p.hf.inv_nrs;
+          Msg4<real> m;
+          m.dT = ok ? h.ta[j] * 0.2f : 0.f;                                         // norm.py:39
+          m.sso_n = ok ? sso_n : 0.f;
+          m.p_n = (ok && (f & 1u)) ? pmax_n : 0.f;
+          m.pmax_n = ok ? pmax_n : 0.f;
+          s_msg[s0 + j] = m;
+        }
+        if (D > 0) {
+          real *row = s_tile + (size_t)(s0 + j) * D;
+          if (plain) {
+            float2 *r2 = reinterpret_cast<float2 *>(row);
+            const float tg = h.target[j] - 20.f;
+            r2[0] = make_float2(ok ? (float)(f & 1u) : 0.f, ok ? (float)((f >> 1) & 1u) : 0.f);
+            r2[1] = make_float2(ok ? sso_n : 0.f, ok ? 1.f : 0.f);
+            r2[3] = make_float2(ok ? p.hf.deadband : 0.f, ok ? (h.ta[j] + tg) * 0.2f : 0.f);
+            r2[4] = make_float2(ok ? (h.tm[j] + tg) * 0.2f : 0.f, ok ? tg * 0.2f : 0.f);
+            if (!ok) {
+              r2[2] = make_float2(0.f, 0.f);
+              for (int q = 5; q < D / 2; ++q) r2[q] = make_float2(0.f, 0.f);
+            }
+          } else if (ok) {
+            EnvBroadcast<real> none{};
+            real ratio[4] = {0, 0, 0, 0};
+            if (p.st_thermal)
+              for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][base + s0 + j];
+            obs_own<real>(row, p, f, sso_n, h.ta[j] + (h.target[j] - 20.f), h.tm[j] + (h.target[j] - 20.f),
+                          h.target[j] - 20.f, none, ratio, 1);
+          } else {
+            for (int q = 0; q < D; ++q) row[q] = 0.f;
+          }
+        }
+      }
+    }
+    // segmented warp reduction over clusters (lanes of one cluster are contiguous)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      real t[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+      const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
+      if (lane + o < 32 && eo == e_loc) red_combine(red, t);
+    }
+    const int e_prev = __shfl_up_sync(0xffffffffu, e_loc, 1);
+    const bool head = (lane == 0) || (e_prev != e_loc);
+    const int e_first = __shfl_sync(0xffffffffu, e_loc, 0);
+    if (head && e_loc >= 0) {
+      double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
+    }
+    __syncthreads();
+
+    // ---- phase 2 -------------------------------------------------------------------------
+    // combine the warp partials of cluster e in warp order (deterministic, identical everywhere)
+    auto combine = [&](int e, double a[kRed], bool all) {
+      const int w_lo = (e * Ns) >> 7, w_hi = ((e + 1) * Ns - 1) >> 7;
+      for (int w = w_lo; w <= w_hi; ++w) {
+        const int efst = (int)fast_div((uint32_t)(w << 7), p.fd_ns);  // first cluster seen by warp w
+        const double *src = s_wp + ((size_t)w * g.max_segs + (e - efst)) * kRed;
+        if (all) red_combine(a, src);
+        else a[0] += src[0];
+      }
+    };
+    EnvBroadcast<real> eb{};
+    if (fast) {
+      // no serial section: every house thread folds the cluster power into the pre-computed
+      // broadcast values by itself
+      if (active) {
+        double a[kRed] = {0, 0, 0, 0, 0};
+        combine(e_loc, a, p.penalty_mode != DRSIM_PEN_INDIVIDUAL_L2);
+        eb = s_env[e_loc];
+        eb.power_n = (real)(a[0] * p.inv_nrs);
+        eb.rew_sig = (real)signal_penalty(p, a[0], s_sold[e_loc]);
+        eb.pen_common = (real)a[1];
+        eb.pen_max = (real)a[2];
+      }
+    } else {
+      if (threadIdx.x < E) {
+        double a[kRed] = {0, 0, 0, 0, 0};
+        combine(threadIdx.x, a, true);
+        s_env[threadIdx.x] = env_epilogue<real>(pl, p, in, r0 + threadIdx.x, er, a, 0.0);  // injected noise: inline
+      }
+      __syncthreads();
+      if (active) eb = s_env[e_loc];
+    }
+
+    // ---- phase 3 -----------------------------------------------------------------------
+    if (active) {
+      const EnvBroadcast<real> e = eb;
+      real rw[4];
+      const bool lean_reward = p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rw[j] = lean_reward ? reward_f32_individual(p, h.ta[j], e.rew_sig) : house_reward<real>(p, kc, h.ta[j], h.target[j], e);
+        if (j >= h.valid) rw[j] = 0.f;
+      }
+      store4(pl.reward + base + s0, rw);
+      if (D > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < h.valid) {
+            real *row = s_tile + (size_t)(s0 + j) * D;
+            if (plain) {
+              float2 *r2 = reinterpret_cast<float2 *>(row);
+              r2[2] = make_float2(e.power_n, e.signal_n);
+              if (g.need_msg) {
+                for (int k = 0; k < p.nb_comm; ++k) {
+                  const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
+                  const float4 mk = *reinterpret_cast<const float4 *>(&s_msg[e_loc * Ns + nb]);
+                  r2[5 + 2 * k] = make_float2(mk.x, mk.y);
+                  r2[6 + 2 * k] = make_float2(mk.z, mk.w);
+                }
+              }
+              continue;
+            }
+            int q = obs_own<real>(row, p, 0u, 0.f, 0.f, 0.f, 0.f, e, nullptr, 2);
+            if (g.need_msg) {
+              for (int k = 0; k < p.nb_comm; ++k) {
+                const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
+                const Msg4<real> mk = s_msg[e_loc * Ns + nb];
+                row[q++] = mk.dT; row[q++] = mk.sso_n; row[q++] = mk.p_n; row[q++] = mk.pmax_n;
+                if (p.msg_thermal)
+                  for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][base + e_loc * Ns + nb];
+                if (p.msg_hvac) { row[q++] = (real)p.cop; row[q++] = (real)p.latent; row[q++] = (real)p.dcap; }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (D > 0) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && w0 < slots) {
+        const int nrows = min(128, slots - w0);
+        bulk_store_s2g(pl.obs + (base + w0) * D, s_tile + (size_t)w0 * D, (uint32_t)((size_t)nrows * D * sizeof(real)));
+        store_pending = true;
+      }
+    }
+    // off the critical path: env planes + running metrics of cluster threadIdx.x
+    if (threadIdx.x < E && fast) {
+      double a[kRed] = {0, 0, 0, 0, 0};
+      combine(threadIdx.x, a, true);
+      ef.P = a[0];
+      ef.rew_sig = signal_penalty(p, a[0], er.signal);
+      env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
+    }
   }
   if (lane == 0 && store_pending) {
 #if defined(__CUDA_ARCH__)
