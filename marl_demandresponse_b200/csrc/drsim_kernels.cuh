@@ -1557,22 +1557,38 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         }
       }
     }
-    // segmented warp reduction over clusters (lanes of one cluster are contiguous)
+    if (g.envs_per_tile == 1) {
+      // one cluster per tile: plain butterfly, every warp stores one partial
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      real t[kRed];
+      for (int o = 16; o > 0; o >>= 1) {
+        real t[kRed];
 #pragma unroll
-      for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
-      const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
-      if (lane + o < 32 && eo == e_loc) red_combine(red, t);
-    }
-    const int e_prev = __shfl_up_sync(0xffffffffu, e_loc, 1);
-    const bool head = (lane == 0) || (e_prev != e_loc);
-    const int e_first = __shfl_sync(0xffffffffu, e_loc, 0);
-    if (head && e_loc >= 0) {
-      double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
+        for (int k = 0; k < kRed; ++k) t[k] = __shfl_xor_sync(0xffffffffu, red[k], o);
+        red_combine(red, t);
+      }
+      if (lane == 0) {
+        double *dst = s_wp + (size_t)warp * g.max_segs * kRed;
 #pragma unroll
-      for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
+        for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
+      }
+    } else {
+      // segmented warp reduction over clusters (lanes of one cluster are contiguous)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        real t[kRed];
+#pragma unroll
+        for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+        const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
+        if (lane + o < 32 && eo == e_loc) red_combine(red, t);
+      }
+      const int e_prev = __shfl_up_sync(0xffffffffu, e_loc, 1);
+      const bool head = (lane == 0) || (e_prev != e_loc);
+      const int e_first = __shfl_sync(0xffffffffu, e_loc, 0);
+      if (head && e_loc >= 0) {
+        double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
+#pragma unroll
+        for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
+      }
     }
     __syncthreads();
 
@@ -1591,7 +1607,29 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (fast) {
       // no serial section: every house thread folds the cluster power into the pre-computed
       // broadcast values by itself
-      if (active) {
+      if (g.envs_per_tile == 1) {
+        // one cluster per tile: lanes 0..7 fetch one warp partial each, a 3-level butterfly in
+        // fixed order gives every lane of every warp the same totals
+        double a[3] = {0, 0, 0};
+        if (lane < kThreads / 32 && lane * 128 < slots) {
+          const double *src = s_wp + (size_t)lane * g.max_segs * kRed;
+          a[0] = src[0]; a[1] = src[1]; a[2] = src[2];
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
+          a[1] += __shfl_xor_sync(0xffffffffu, a[1], o);
+          a[2] = fmax(a[2], __shfl_xor_sync(0xffffffffu, a[2], o));
+        }
+        a[0] = __shfl_sync(0xffffffffu, a[0], 0);
+        a[1] = __shfl_sync(0xffffffffu, a[1], 0);
+        a[2] = __shfl_sync(0xffffffffu, a[2], 0);
+        eb = s_env[0];
+        eb.power_n = (real)(a[0] * p.inv_nrs);
+        eb.rew_sig = (real)signal_penalty(p, a[0], s_sold[0]);
+        eb.pen_common = (real)a[1];
+        eb.pen_max = (real)a[2];
+      } else if (active) {
         double a[kRed] = {0, 0, 0, 0, 0};
         combine(e_loc, a, p.penalty_mode != DRSIM_PEN_INDIVIDUAL_L2);
         eb = s_env[e_loc];
