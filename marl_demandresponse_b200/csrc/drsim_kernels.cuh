@@ -74,12 +74,13 @@ struct StepIn {
 template <typename real>
 struct KC {
   real cop, nrs, db, one_plus_latent, norm_temp, n_glob;
-  real inv_cop, inv_nrs, inv_norm_temp, inv_n;
+  real inv_cop, inv_nrs, inv_norm_temp, inv_n, neg_inv_opl;
   DRSIM_D explicit KC(const SimParams &p) {
     cop = (real)p.cop; nrs = (real)p.nrs; db = (real)p.deadband; one_plus_latent = (real)(1.0 + p.latent);
     norm_temp = (real)p.norm_temp; n_glob = (real)p.n_global;
     inv_cop = (real)p.inv_cop; inv_nrs = (real)p.inv_nrs; inv_norm_temp = (real)p.inv_norm_temp;
     inv_n = (real)p.inv_n_global;
+    neg_inv_opl = (real)p.hf.neg_inv_opl;
   }
 };
 DRSIM_D float qdiv(float x, float, float inv) { return x * inv; }
@@ -135,8 +136,9 @@ DRSIM_D void thermal_step(float &ta, float &tm, const float *c, float od, float 
 DRSIM_D void thermal_step(double &ta, double &tm, const double *c, double od, double Qa) {
   thermal_step_f64(ta, tm, c, od, Qa);
 }
-DRSIM_D float hvac_heat(float cap, float one_plus_latent) { return -cap / one_plus_latent; }
-DRSIM_D double hvac_heat(double cap, double one_plus_latent) { return DR_DIV(DR_MUL(-1.0, cap), one_plus_latent); }
+// fp32: every kernel multiplies by the same host-rounded -1/(1+latent), so all paths are bit-identical
+DRSIM_D float hvac_heat(float cap, float, float neg_inv_opl) { return cap * neg_inv_opl; }
+DRSIM_D double hvac_heat(double cap, double one_plus_latent, double) { return DR_DIV(DR_MUL(-1.0, cap), one_plus_latent); }
 
 // Temperature representation of the t_air / t_mass planes (see drsim_ptrs.temp_is_deviation):
 // fp32 stores the deviation from the set-point, fp64 the absolute temperature (literal replay).
@@ -203,7 +205,7 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const KC<re
       const bool a = Rep<real>::act(p.policy, h.ta[j], h.target[j], db, f & 1u, ext);
       if (advance) {
         hvac_fsm(f, h.sso[j], a, p.dt, p.lockout_duration);
-        const real q = (f & 1u) ? hvac_heat(h.cap[j], kc.one_plus_latent) : (real)0;
+        const real q = (f & 1u) ? hvac_heat(h.cap[j], kc.one_plus_latent, kc.neg_inv_opl) : (real)0;
         real c[NC];
 #pragma unroll
         for (int k = 0; k < NC; ++k) c[k] = coef[k][j];
@@ -303,11 +305,6 @@ DRSIM_D void house4_dispatch(const Planes<double> &pl, const SimParams &p, const
   house4_step<double, ALWAYS_ADVANCE>(pl, p, kc, in, off, valid, od_prev, solar, h, red);
 }
 
-// rewards_calculator.py:174-179 for one house, fp32 individual_L2 fast form
-DRSIM_D float reward_f32_individual(const SimParams &p, float xa, float rew_sig) {
-  const float d = fmaxf(fabsf(xa) - p.hf.half_db, 0.f);
-  return -fmaf(p.hf.rew_scale, d * d, rew_sig);
-}
 
 // Inputs of 4 houses as the fused fp32 kernel receives them (from shared memory / registers)
 struct Raw4f {
@@ -422,6 +419,13 @@ DRSIM_D double mean_reward(const SimParams &p, double pen_mean, double pen_max, 
   return -(p.alpha_temp * pen / p.norm_temp + rew_sig);
 }
 
+// alpha_sig * ((P - S_old) / N)^2 / norm (rewards_calculator.py:198, :177), reciprocal form shared by
+// every kernel path so that they agree bit for bit
+DRSIM_D double signal_penalty(const SimParams &p, double P, double s_old) {
+  const double dev = (P - s_old) * p.inv_n_global;
+  return p.alpha_sig * (dev * dev) * p.inv_norm_sig;
+}
+
 template <typename real>
 DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams &p, const StepIn &in,
                                         int r, EnvRegs e, const double red[kRed], double interp_sum) {
@@ -432,14 +436,13 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
     e.epoch += p.dt;                                               // environment.py:87
     solar_cur = e.solar_next;                                      // gain used by this step's update
     P = red[0];
-    const double dev = (P - e.signal) / (double)p.n_global;        // rewards_calculator.py:198 (old signal, Q6)
-    rew_sig = p.alpha_sig * (dev * dev) / p.norm_sig;
+    rew_sig = signal_penalty(p, P, e.signal);                      // old signal (quirk Q6)
     // running rollout metrics (metrics_service.py:108-157 restated as per-cluster sums)
     double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
     m[0] += 1.0;
     m[1] += mean_reward(p, red[1], red[2], rew_sig);
-    m[2] += fabs(red[3]) / (double)p.n_global;
-    m[3] += red[4] / (double)p.n_global;
+    m[2] += fabs(red[3]) * p.inv_n_global;
+    m[3] += red[4] * p.inv_n_global;
     m[4] += fabs(P - e.signal);
     m[5] += (P - e.signal) * (P - e.signal);
   } else {
@@ -499,10 +502,10 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
   pl.rew_sig[r] = rew_sig;
   pl.t_since_interp[r] = e.t_since_interp;
   EnvBroadcast<real> b;
-  b.power_n = (real)(P / p.nrs);                                   // norm.py:144-146
-  b.signal_n = (real)(e.signal / (p.nrs * (double)p.n_global));    // norm.py:132-135
-  b.solar_n = (real)(solar_cur / 1000.0);                          // norm.py:113-114
-  b.od_n = (real)((e.od_temp - 20.0) / 5.0);                       // norm.py:164-165
+  b.power_n = (real)(P * p.inv_nrs);                               // norm.py:144-146
+  b.signal_n = (real)(e.signal * p.inv_nrs * p.inv_n_global);      // norm.py:132-135
+  b.solar_n = (real)(solar_cur * 1e-3);                            // norm.py:113-114
+  b.od_n = (real)((e.od_temp - 20.0) * 0.2);                       // norm.py:164-165
   b.rew_sig = (real)rew_sig;
   b.pen_common = (real)red[1];
   b.pen_max = (real)red[2];
@@ -535,16 +538,10 @@ DRSIM_D EnvBroadcast<real> env_pre_compute(const SimParams &p, EnvRegs &e, EnvFa
   return b;
 }
 
-DRSIM_D double signal_penalty(const SimParams &p, double P, double s_old) {
-  const double dev = (P - s_old) * p.inv_n_global;               // rewards_calculator.py:198 (old signal, Q6)
-  return p.alpha_sig * (dev * dev) * p.inv_norm_sig;
-}
-
 template <typename real>
 DRSIM_D EnvBroadcast<real> env_fast_compute(const SimParams &p, EnvRegs &e, const double red[kRed], EnvFast &f) {
   f.P = red[0];
-  const double dev = (f.P - e.signal) * p.inv_n_global;            // rewards_calculator.py:198 (old signal, Q6)
-  f.rew_sig = p.alpha_sig * (dev * dev) * p.inv_norm_sig;
+  f.rew_sig = signal_penalty(p, f.P, e.signal);
   f.solar_cur = e.solar_next;
   if (p.base_mode == DRSIM_BASE_CONSTANT) e.base_power = p.avg_power * (double)p.n_global;
   f.signal = grid_signal_sched(p, e.base_power, e.s_tsec, e.s_aux, e.artificial_ratio, e.max_power);
@@ -613,9 +610,18 @@ __global__ void k_schedule(Planes<real> pl, SimParams p, int64_t step0, int K, d
   aux[i] = a;
 }
 
+// rewards_calculator.py:174-179 for one house, fp32 individual_L2 fast form
+DRSIM_D float reward_f32_individual(const SimParams &p, float xa, float rew_sig) {
+  const float d = fmaxf(fabsf(xa) - p.hf.half_db, 0.f);
+  return -fmaf(p.hf.rew_scale, d * d, rew_sig);
+}
+
 // rewards_calculator.py:135-181 for one house
 template <typename real>
 DRSIM_D real house_reward(const SimParams &p, const KC<real> &kc, real ta, real target, const EnvBroadcast<real> &e) {
+  if constexpr (sizeof(real) == 4) {
+    if (p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2) return reward_f32_individual(p, ta, e.rew_sig);
+  }
   const real ind = Rep<real>::pen(target, kc.db, ta);
   real pen;
   switch (p.penalty_mode) {
@@ -850,10 +856,10 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
   const int D = p.obs_dim;
   const KC<real> kc(p);
   EnvBroadcast<real> e;
-  e.power_n = (real)(pl.power[r] / p.nrs);
-  e.signal_n = (real)(pl.signal[r] / (p.nrs * (double)p.n_global));
-  e.solar_n = (real)(pl.solar_cur[r] / 1000.0);
-  e.od_n = (real)((pl.od_temp[r] - 20.0) / 5.0);
+  e.power_n = (real)(pl.power[r] * p.inv_nrs);
+  e.signal_n = (real)(pl.signal[r] * p.inv_nrs * p.inv_n_global);
+  e.solar_n = (real)(pl.solar_cur[r] * 1e-3);
+  e.od_n = (real)((pl.od_temp[r] - 20.0) * 0.2);
   e.rew_sig = (real)pl.rew_sig[r];
   e.pen_common = (real)pl.pen_sum[r];
   e.pen_max = (real)pl.pen_max[r];

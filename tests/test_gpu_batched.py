@@ -1,0 +1,192 @@
+"""BatchedEnv / Philox / drop-in Environment on the GPU, against the NumPy oracle."""
+import copy
+import datetime as dt
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _prop(n, **over):
+    p = {"start_datetime": "2021-06-15T11:58:20", "start_datetime_mode": "fixed", "time_step": 4.0,
+         "cluster_prop": {"nb_agents": n, "house_prop": {"target_temp": 19.0}}}
+    for path, v in over.items():
+        d = p
+        keys = path.split("/")
+        for k in keys[:-1]:
+            d = d.setdefault(k, {})
+        d[keys[-1]] = v
+    return p
+
+
+def _oracle_run(prop, st, actions, od_noise, perlin):
+    from oracle.np_oracle import NpOracle
+
+    R = st["t_air"].shape[0]
+    orc = NpOracle(prop, R)
+    orc.set_state(st)
+    from oracle.np_oracle import from_epoch
+
+    orc.power_grid_step([from_epoch(e) for e in orc.state["epoch"]], perlin[0])   # PowerGrid.step at reset
+    rew = []
+    for t in range(actions.shape[0]):
+        rew.append(orc.step(actions[t], od_noise[t], perlin[t + 1]))
+    return orc, np.array(rew)
+
+
+@pytest.mark.parametrize("n,R,layout,path", [(100, 24, "hand_engineered", "auto"), (1000, 6, "tarmac", "auto"),
+                                             (1000, 3, "hand_engineered", "auto"), (2500, 2, "hand_engineered", "auto"),
+                                             (100, 24, "hand_engineered", "split"), (37, 9, "hand_engineered", "auto")])
+def test_batched_env_philox_matches_oracle(n, R, layout, path):
+    """Device Philox streams (od noise, perlin-like signal noise) == their NumPy restatement, and the
+    whole batched step == the oracle driven by those values."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle import philox
+
+    T, seed, off = 12, 77, 1000
+    prop = _prop(n)
+    env = BatchedEnv(prop, R, precision="f32", obs_layout=layout, noise="philox", seed=seed, path=path, rep_offset=off)
+    st = synthetic_state(prop, R, seed=5, rep_offset=off)
+    env.reset(copy.deepcopy(st))
+    rng = np.random.default_rng(3)
+    acts = (rng.random((T, R, n)) < 0.5).astype(np.uint8)
+    # the values the device streams must produce
+    epoch0 = int(st["epoch"][0])
+    sp = {"nb_octaves": 5, "octaves_step": 5, "period": 300}
+    od_noise = np.array([[philox.od_noise(seed, off + r, t, 1.0) for r in range(R)] for t in range(T)])
+    perlin = np.zeros((T + 1, R))
+    for t in range(T + 1):
+        tsec = (epoch0 + 4 * t) % 86400
+        for r in range(R):
+            perlin[t, r] = philox.perlin(seed, off + r, tsec / sp["period"], sp["nb_octaves"], sp["octaves_step"])
+    rewards = []
+    for t in range(T):
+        obs, rew = env.step(torch.as_tensor(acts[t], device="cuda"))
+        rewards.append(rew.double().cpu().numpy())
+    got = env.get_state()
+    orc, rew_ref = _oracle_run(prop, copy.deepcopy(st), acts, od_noise, perlin)
+    s = orc.state
+    for k in ("on", "lockout", "sso"):
+        assert np.array_equal(got[k].astype(np.int64), s[k].astype(np.int64)), k
+    assert np.array_equal(got["epoch"], s["epoch"])
+    np.testing.assert_allclose(got["od_temp"], s["od_temp"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got["signal"], s["signal"], rtol=1e-9)
+    np.testing.assert_allclose(got["power"], s["power"], rtol=1e-6)
+    np.testing.assert_allclose(got["t_air"], s["t_air"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(got["t_mass"], s["t_mass"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(np.array(rewards), rew_ref, rtol=1e-5, atol=1e-5)
+    want = orc.obs_vectors()
+    if layout == "tarmac":
+        want = want[:, :, :10]
+    np.testing.assert_allclose(env.obs.double().cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    # rollout metrics: steps and mean reward
+    m = env.metrics.cpu().numpy()
+    assert np.all(m[:, 0] == T)
+    np.testing.assert_allclose(m[:, 1], rew_ref.mean(axis=2).sum(axis=0), rtol=1e-4, atol=1e-4)
+
+
+def test_fused_and_general_paths_agree_and_are_deterministic():
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+
+    prop = _prop(200)
+    R, T = 40, 15
+    st = synthetic_state(prop, R, seed=9)
+    acts = (np.random.default_rng(1).random((T, R, 200)) < 0.5).astype(np.uint8)
+    out = []
+    for path in ("fused", "split", "fused"):
+        env = BatchedEnv(prop, R, precision="f32", noise="philox", seed=4, path=path)
+        env.reset(copy.deepcopy(st))
+        for t in range(T):
+            env.step(torch.as_tensor(acts[t], device="cuda"))
+        torch.cuda.synchronize()
+        v = env.state
+        out.append({k: v[k].clone().cpu().numpy() for k in ("dt_air", "dt_mass", "sso", "flags", "reward", "obs")})
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[2][k]), f"run-to-run difference in {k}"
+        if k in ("sso", "flags"):
+            assert np.array_equal(out[0][k], out[1][k]), k
+        else:
+            np.testing.assert_allclose(out[0][k], out[1][k], rtol=2e-6, atol=2e-6)
+
+
+def test_replica_placement_invariance():
+    """Shard [4, 8) of a 12-replica job == replicas 4..7 of the whole job (Philox keyed by the
+    global replica index, synthetic state keyed by it too): the basis of the multi-GPU sharding."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+
+    prop = _prop(64)
+    whole = BatchedEnv(prop, 12, noise="philox", seed=11)
+    part = BatchedEnv(prop, 4, noise="philox", seed=11, rep_offset=4)
+    whole.reset()
+    part.reset()
+    a = (torch.rand((12, 64), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) < 0.5).to(torch.uint8)
+    for t in range(10):
+        whole.step(a)
+        part.step(a[4:8].contiguous())
+    torch.cuda.synchronize()
+    for k in ("dt_air", "dt_mass", "sso", "flags", "reward", "obs", "signal", "od_temp"):
+        assert torch.equal(whole.state[k][4:8], part.state[k]), k
+
+
+def test_on_device_policies_match_oracle_controllers():
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle.np_oracle import NpOracle, deadband_bangbang, from_epoch, greedy_myopic
+
+    for policy, n in (("deadband_bangbang", 90), ("greedy_myopic", 300)):
+        prop = _prop(n, **{"cluster_prop/house_prop/deadband": 0.5, "power_grid_prop/signal_properties/mode": "sinusoidals"})
+        R, T = 3, 25
+        st = synthetic_state(prop, R, seed=21)
+        env = BatchedEnv(prop, R, precision="f64", policy=policy, noise="zero", path="auto")
+        env.reset(copy.deepcopy(st))
+        orc = NpOracle(prop, R)
+        orc.set_state(copy.deepcopy(st))
+        orc.power_grid_step([from_epoch(e) for e in orc.state["epoch"]], None)
+        for t in range(T):
+            s = orc.state
+            if policy == "deadband_bangbang":
+                a = deadband_bangbang(s["t_air"], s["target"], 0.5, s["on"])
+            else:
+                a = np.stack([greedy_myopic(s["t_air"][r], s["target"][r], s["cap"][r], 2.5, s["lockout"][r], s["signal"][r])
+                              for r in range(R)])
+            orc.step(a, np.zeros(R), None)
+            env.step(None)
+        got = env.get_state()
+        for k in ("on", "lockout", "sso"):
+            assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), (policy, k)
+        np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=1e-9)
+
+
+def test_clone_is_a_deep_copy():
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+
+    env = BatchedEnv(_prop(50), 8, noise="philox", seed=2)
+    env.reset()
+    a = torch.ones((8, 50), dtype=torch.uint8, device="cuda")
+    for _ in range(5):
+        env.step(a)
+    twin = copy.deepcopy(env)
+    for _ in range(7):
+        env.step(a)
+        twin.step(a)
+    torch.cuda.synchronize()
+    for k in ("dt_air", "sso", "flags", "obs", "reward", "signal"):
+        assert torch.equal(env.state[k], twin.state[k]), k
+    snap = twin.state["dt_air"].clone()
+    env.step(a)
+    torch.cuda.synchronize()
+    assert torch.equal(twin.state["dt_air"], snap), "stepping the original must not touch the clone"
