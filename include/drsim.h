@@ -217,11 +217,14 @@ int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal,
 
 /* Environment.step for ONE cluster whose houses are split across several handles / GPUs
  * (SURVEY 8e): drsim_step_begin updates the local houses and leaves this rank's partial sums in
- * drsim_ptrs.acc ([R][DRSIM_N_ACC]); the caller combines them across ranks (sum, except column 2 =
- * max) with its collective of choice and hands the combined device array to drsim_step_finish,
- * which runs the env epilogue, rewards and observations. */
+ * drsim_ptrs.acc ([R][DRSIM_N_ACC]: cluster power cluster.py:88, penalty sums, interpolated base
+ * power).  The caller all-gathers them across ranks (NCCL over NVLink: 48 bytes per rank) and hands
+ * the gathered device array [n_parts][R][DRSIM_N_ACC] (rank order) to drsim_step_finish, which
+ * combines it in rank order (deterministic, identical on every rank) and runs the env epilogue,
+ * rewards and observations.  acc_gathered = NULL uses the handle's own partials. */
 int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream);
-int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_combined, void *stream);
+int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_gathered, int n_parts,
+                      void *stream);
 
 /* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out
  * ([R][4] doubles: power, signal, od_temp, mean reward); copies are inside the call and ordered on

@@ -123,7 +123,7 @@ def lib():
         "drsim_step": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
         "drsim_refresh": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_void_p]),
         "drsim_step_begin": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
-        "drsim_step_finish": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p, C.c_void_p]),
+        "drsim_step_finish": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p, C.c_int, C.c_void_p]),
         "drsim_step_host": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "drsim_launch_count": (C.c_int64, [hp]),
         "drsim_host_solar_gain": (C.c_double, [_i64, _d, _d]),

@@ -319,9 +319,10 @@ class DrSim:
         a = self._args(actions, od_noise, perlin, interp_ids)
         _lib.check(self._L.drsim_step_begin(self._h, C.byref(a), self._stream(stream)))
 
-    def step_finish(self, acc, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
-        a = self._args(None, od_noise, perlin, interp_ids)
-        _lib.check(self._L.drsim_step_finish(self._h, C.byref(a), self._ptr(acc), self._stream(stream)))
+    def step_finish(self, acc=None, n_parts: int = 1, stream=None) -> None:
+        """``acc``: gathered per-rank partials ``[n_parts, R, N_ACC]`` (device fp64) or None."""
+        a = self._args()
+        _lib.check(self._L.drsim_step_finish(self._h, C.byref(a), self._ptr(acc), int(n_parts), self._stream(stream)))
 
     def step_host(self, actions: Optional[np.ndarray], od_noise=None, perlin=None, interp_ids=None,
                   env_out: Optional[np.ndarray] = None, stream=None) -> Optional[np.ndarray]:

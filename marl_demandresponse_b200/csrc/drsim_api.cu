@@ -645,10 +645,10 @@ static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s)
 }
 
 template <typename real>
-static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, cudaStream_t s) {
+static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, int n_parts, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
   const SimParams &p = h->p;
-  k_env<real><<<(p.R + 127) / 128, 128, 0, s>>>(pl, p, in, acc ? acc : pl.acc);
+  k_env<real><<<(p.R + 127) / 128, 128, 0, s>>>(pl, p, in, acc ? acc : pl.acc, acc ? n_parts : 1);
   k_obs<real><<<p.R * h->obs_chunks, kObsChunk, (size_t)kObsChunk * p.obs_dim * sizeof(real), s>>>(pl, p, in, h->obs_chunks);
   h->launches += 2;
   CU_TRY(cudaGetLastError());
@@ -730,7 +730,7 @@ static int run_step(drsim_handle *h, const drsim_step_args *a, int advance, int 
     if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "house-sharded cluster: use drsim_step_begin / drsim_step_finish");
     rc = dbl ? launch_house_phase<double>(h, in, s) : launch_house_phase<float>(h, in, s);
     if (rc) return rc;
-    rc = dbl ? launch_env_phase<double>(h, in, nullptr, s) : launch_env_phase<float>(h, in, nullptr, s);
+    rc = dbl ? launch_env_phase<double>(h, in, nullptr, 1, s) : launch_env_phase<float>(h, in, nullptr, 1, s);
   }
   return rc;
 }
@@ -764,13 +764,14 @@ extern "C" int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *s
                             : launch_house_phase<float>(h, in, (cudaStream_t)stream);
 }
 
-extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc, void *stream) {
+extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc, int n_parts, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   CU_TRY(cudaSetDevice(h->device));
   (void)args;
   const StepIn in = h->pending_in;
-  int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, (cudaStream_t)stream)
-                              : launch_env_phase<float>(h, in, acc, (cudaStream_t)stream);
+  if (acc && n_parts < 1) return fail(DRSIM_E_ARG, "n_parts must be >= 1");
+  int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, n_parts, (cudaStream_t)stream)
+                              : launch_env_phase<float>(h, in, acc, n_parts, (cudaStream_t)stream);
   if (!rc) h->step++;
   return rc;
 }

@@ -832,16 +832,21 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
   }
 }
 
-// General path, kernel 3: env epilogue, one thread per cluster.  `acc` holds the (possibly
-// cross-rank combined) reduced values.
+// General path, kernel 3: env epilogue, one thread per cluster.  `acc` holds `n_parts` per-rank
+// partial results [n_parts][R][kRed + 1] (n_parts = 1: this handle's own); they are combined here in
+// rank order (sums; column 2 is a max), so every rank derives bit-identical cluster totals.
 template <typename real>
-__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc) {
+__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc, int n_parts) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= p.R) return;
-  const double *a = acc + (size_t)r * (kRed + 1);
-  double red[kRed];
-  for (int k = 0; k < kRed; ++k) red[k] = a[k];
-  env_epilogue<real>(pl, p, in, r, env_load(pl, in, r), red, a[kRed]);
+  double red[kRed] = {0, 0, 0, 0, 0};
+  double isum = 0.0;
+  for (int q = 0; q < n_parts; ++q) {
+    const double *a = acc + ((size_t)q * p.R + r) * (kRed + 1);
+    red_combine(red, a);
+    isum += a[kRed];
+  }
+  env_epilogue<real>(pl, p, in, r, env_load(pl, in, r), red, isum);
 }
 
 // General path, kernel 4: rewards + observation rows for a chunk of kObsChunk houses.

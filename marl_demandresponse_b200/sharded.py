@@ -1,0 +1,84 @@
+"""One very large cluster split by houses across the GPUs of a box (BASELINE config 5).
+
+Each rank owns houses ``[rank * N / W, (rank + 1) * N / W)`` of every replica.  Per step:
+``drsim_step_begin`` (local house update + partial sums) -> one tiny all-gather of the per-rank
+partials over NCCL / NVLink (48 bytes per rank and replica) -> ``drsim_step_finish`` (identical
+combination on every rank, env epilogue, rewards, observations).  This is the only data-path
+collective in the package; replica-sharded runs (``BatchedEnv``) have none.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .batched import synthetic_state
+from .core import DrSim, flatten_config
+from .properties import as_props
+
+
+def house_shard(n_houses: int, rank: int, world: int):
+    """Contiguous, 4-aligned house ranges (the planes are accessed with 128-bit vectors)."""
+    per = (n_houses + world - 1) // world
+    per = (per + 3) // 4 * 4
+    lo = min(n_houses, rank * per)
+    hi = min(n_houses, lo + per)
+    return lo, hi
+
+
+class ShardedClusterEnv:
+    def __init__(self, env_props: Any, n_replicas: int = 1, rank: int = 0, world: int = 1, device: int = 0,
+                 precision: str = "f32", obs_layout: str = "tarmac", policy: str = "external", noise: str = "philox",
+                 seed: int = 0, group=None):
+        self.props = as_props(env_props)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.n_global = int(self.props.cluster_prop.nb_agents)
+        self.lo, self.hi = house_shard(self.n_global, rank, world)
+        if self.hi <= self.lo:
+            raise ValueError("more ranks than 4-house blocks")
+        cfg = flatten_config(self.props, n_replicas, precision, obs_layout, policy, noise, seed, "split",
+                             house_offset=self.lo, n_house_local=self.hi - self.lo)
+        self.sim = DrSim(cfg, device)
+        self.device = device
+        self._v = self.sim.views()
+        self._gathered = None
+
+    def reset(self, state: Optional[Dict[str, np.ndarray]] = None, seed: int = 1234):
+        """``state``: full-cluster state dict (every rank passes the same one) or None = synthetic."""
+        if state is None:
+            state = synthetic_state(self.props, self.sim.R, seed)
+        local = {}
+        for k, v in state.items():
+            v = np.asarray(v)
+            local[k] = v[:, self.lo:self.hi] if v.ndim == 2 else v
+        self.sim.set_state(local)
+        return self
+
+    def step(self, actions=None):
+        import torch
+
+        sim = self.sim
+        a = None
+        if actions is not None:
+            if sim.N == sim.Ns and actions.is_contiguous():
+                a = actions
+            else:
+                self._v["actions"].copy_(actions)
+        sim.step_begin(a)
+        acc = self._v["acc"]
+        if self.world > 1:
+            import torch.distributed as dist
+
+            if self._gathered is None:
+                # concatenation along dim 0 == [world][R][N_ACC] in rank order
+                self._gathered = torch.empty((self.world * acc.shape[0], acc.shape[1]), dtype=acc.dtype, device=acc.device)
+            dist.all_gather_into_tensor(self._gathered, acc, group=self.group)
+            sim.step_finish(self._gathered, self.world)
+        else:
+            sim.step_finish(None, 1)
+        return self._v["obs"], self._v["reward"]
+
+    @property
+    def state(self):
+        return self._v

@@ -190,3 +190,54 @@ def test_clone_is_a_deep_copy():
     env.step(a)
     torch.cuda.synchronize()
     assert torch.equal(twin.state["dt_air"], snap), "stepping the original must not touch the clone"
+
+
+def test_house_sharded_cluster_equals_unsharded():
+    """One cluster split over 3 handles (the per-rank partials gathered by hand, as the NCCL
+    all-gather would) == the same cluster on one handle: discrete state bit-exact, power / signal /
+    rewards identical, for the constant and the interpolated base power."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from marl_demandresponse_b200.sharded import ShardedClusterEnv
+    from oracle.config import synthetic_table
+
+    table = synthetic_table(7)
+    for base_mode in ("constant", "interpolation"):
+        n, R, W, T = 3000, 2, 3, 80 if base_mode == "interpolation" else 10
+        prop = _prop(n, **{"power_grid_prop/base_power_props/mode": base_mode,
+                           "power_grid_prop/signal_properties/mode": "sinusoidals"})
+        st = synthetic_state(prop, R, seed=3)
+        whole = BatchedEnv(prop, R, obs_layout="tarmac", noise="philox", seed=9, path="split",
+                           interp_table=table if base_mode == "interpolation" else None)
+        whole.reset(copy.deepcopy(st))
+        parts = [ShardedClusterEnv(prop, R, rank=r, world=W, obs_layout="tarmac", noise="philox", seed=9) for r in range(W)]
+        for p_ in parts:
+            if base_mode == "interpolation":
+                p_.sim.set_interp_table(table)
+            p_.reset(copy.deepcopy(st))
+            # the signal computed at reset by the unsharded env is an input of the sharded ones
+            p_.sim.set_state({"signal": whole.get_state(["signal"])["signal"],
+                              "base_power": whole.get_state(["base_power"])["base_power"],
+                              "t_since_interp": whole.get_state(["t_since_interp"])["t_since_interp"]})
+        acts = (np.random.default_rng(2).random((T, R, n)) < 0.5).astype(np.uint8)
+        for t in range(T):
+            a = torch.as_tensor(acts[t], device="cuda")
+            whole.step(a)
+            for p_ in parts:
+                p_.sim.views()["actions"].copy_(a[:, p_.lo:p_.hi])
+                p_.sim.step_begin(None)
+            gathered = torch.stack([p_.state["acc"] for p_ in parts]).contiguous()
+            for p_ in parts:
+                p_.sim.step_finish(gathered, W)
+        torch.cuda.synchronize()
+        ws = whole.state
+        for p_ in parts:
+            ps = p_.state
+            for k in ("sso", "flags", "dt_air", "dt_mass"):
+                assert torch.equal(ws[k][:, p_.lo:p_.hi], ps[k]), (base_mode, k)
+            for k in ("power", "signal", "od_temp", "base_power"):
+                torch.testing.assert_close(ws[k], ps[k], rtol=1e-12, atol=0)
+            torch.testing.assert_close(ws["reward"][:, p_.lo:p_.hi], ps["reward"], rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(ws["obs"][:, p_.lo:p_.hi], ps["obs"], rtol=1e-6, atol=1e-7)
