@@ -37,6 +37,9 @@ WORKLOADS = {
                rep_per_gpu=2048, n_houses=1000, obs="tarmac"),
     "c3": dict(name="C3: 4096 replicas/GPU x 100 houses, hand-engineered neighbour obs (D=50), external actions",
                rep_per_gpu=4096, n_houses=100, obs="hand_engineered"),
+    "c5": dict(name="C5: ONE 1,000,000-house cluster split by houses across the GPUs, TarMAC obs layout, "
+                    "per-step all-gather of the per-rank aggregate-power partials over NCCL",
+               rep_per_gpu=1, n_houses=1_000_000, obs="tarmac", sharded=True),
 }
 
 
@@ -208,14 +211,24 @@ def run_gpu_arm(args, wl) -> None:
         dist.init_process_group("nccl", device_id=dev)
 
     R, N = wl["rep_per_gpu"], wl["n_houses"]
-    env = BatchedEnv(env_prop_for(N), R, device=local, precision="f32", obs_layout=wl["obs"], policy="external",
-                     noise="philox", seed=1234, rep_offset=rank * R)
-    env.reset()
+    sharded = bool(wl.get("sharded"))
+    if sharded:
+        from marl_demandresponse_b200.sharded import ShardedClusterEnv
+
+        env = ShardedClusterEnv(env_prop_for(N), R, rank=rank, world=world, device=local, precision="f32",
+                                obs_layout=wl["obs"], noise="philox", seed=1234)
+        env.reset()
+        n_local = env.hi - env.lo
+    else:
+        env = BatchedEnv(env_prop_for(N), R, device=local, precision="f32", obs_layout=wl["obs"], policy="external",
+                         noise="philox", seed=1234, rep_offset=rank * R)
+        env.reset()
+        n_local = N
     D = env.sim.D
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     n_act = 4
-    acts = [(torch.rand((R, N), device=dev, generator=g) < 0.5).to(torch.uint8).contiguous() for _ in range(n_act)]
+    acts = [(torch.rand((R, n_local), device=dev, generator=g) < 0.5).to(torch.uint8).contiguous() for _ in range(n_act)]
     acts_host = [a.cpu().pin_memory() for a in acts]
     env_out = torch.zeros((R, 4), dtype=torch.float64).pin_memory()
 
@@ -239,7 +252,14 @@ def run_gpu_arm(args, wl) -> None:
         return float(ms.item())
 
     step_dev = lambda i: env.step(acts[i % n_act])
-    step_host = lambda i: env.step_host(acts_host[i % n_act], env_out)
+    if sharded:
+        def step_host(i):  # host actions in (pinned), per-replica results out, around the sharded step
+            env.state["actions"].copy_(acts_host[i % n_act], non_blocking=True)
+            env.step(None)
+            env_out[:, 0].copy_(env.state["power"], non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        step_host = lambda i: env.step_host(acts_host[i % n_act], env_out)
 
     for i in range(max(3, args.warmup)):
         step_dev(i)
@@ -255,9 +275,13 @@ def run_gpu_arm(args, wl) -> None:
     e2e_steps = max(3, min(args.steps, 50))
     ms_e2e = timed(step_host, e2e_steps)
 
-    total_houses = world * R * N
+    total_houses = R * N if sharded else world * R * N
     value = total_houses * args.steps / (ms * 1e-3)
     e2e_value = total_houses * e2e_steps / (ms_e2e * 1e-3)
+    # end-of-rollout metric reduction (one all-reduce of a handful of fp64 sums)
+    from marl_demandresponse_b200.distributed import reduce_rollout_metrics
+
+    rollout = reduce_rollout_metrics(env.state["metrics"])
 
     if rank == 0:
         peaks = {}
@@ -268,21 +292,28 @@ def run_gpu_arm(args, wl) -> None:
         peak = float(peaks.get("hbm_gbs", 6650.0))
         bytes_hs = algorithmic_bytes_per_house_step(4, D)
         launch_ms = ms / max(1, launches)
-        achieved = R * N * bytes_hs / (launch_ms * 1e-3) / 1e9
+        achieved = R * n_local * bytes_hs / (launch_ms * 1e-3) / 1e9
+        if sharded:  # the general path runs k_house + k_reduce + k_env + k_obs per step
+            achieved = R * n_local * bytes_hs / ((ms / args.steps) * 1e-3) / 1e9
         cpu = cpu_port_rate(N, wl["obs"], max(1, int(2e5 / N)), 1) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "replicas_per_gpu": R, "houses_per_cluster": N, "obs_dim": D,
-                       "parallelism": f"replica-sharded x{world}, no per-step collective",
-                       "l2": f"working set {R * N * bytes_hs / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                       "parallelism": (f"house-sharded x{world}, per-step all-gather of 48 B/rank" if sharded
+                                       else f"replica-sharded x{world}, no per-step collective"),
+                       "l2": f"working set {R * n_local * bytes_hs / 1e6:.0f} MB per step per GPU vs 126 MB L2"
+                             + ("" if R * n_local * bytes_hs > 126e6 else "; L2 flushed between steps by a 256 MB write"
+                                if args.flush_l2 else "; fits L2 (latency-bound workload, see DESIGN.md)"),
                        "actions": "4 rotating fixed-seed Bernoulli(0.5) u8 tensors (policy cost excluded)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * R * N,
+            "rollout_metrics": rollout,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_houses,
                     "d2h_bytes_per_step": world * R * 6 * 8, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "BatchedEnv.step_host -> drsim_step_host (pinned host actions in, per-replica results out)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_fused<float>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_house+k_obs (general path)" if sharded else "k_fused_tma",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "bytes_per_house_step": bytes_hs,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650"},
@@ -303,6 +334,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--flush-l2", action="store_true", help="write a 256 MB buffer between timed steps")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
