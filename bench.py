@@ -291,8 +291,15 @@ def run_gpu_arm(args, wl) -> None:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         bytes_hs = algorithmic_bytes_per_house_step(4, D)
-        launch_ms = ms / max(1, launches)
+        launch_ms = ms / args.steps   # one fused launch per step (+ one k_schedule every 64 steps, included)
         achieved = R * n_local * bytes_hs / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes of one launch from the committed ncu capture of this workload
+            t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+            if t:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:  # noqa: BLE001
+            pass
         if sharded:  # the general path runs k_house + k_reduce + k_env + k_obs per step
             achieved = R * n_local * bytes_hs / ((ms / args.steps) * 1e-3) / 1e9
         cpu = cpu_port_rate(N, wl["obs"], max(1, int(2e5 / N)), 1) if world == 1 and not args.no_cpu else None
@@ -314,7 +321,8 @@ def run_gpu_arm(args, wl) -> None:
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_house+k_obs (general path)" if sharded else "k_fused_tma",
                          "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": R * n_local * bytes_hs,
                          "bytes_per_house_step": bytes_hs,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650"},
             "clocks": clocks,
