@@ -239,8 +239,10 @@ static int configure_kernels(drsim_handle *h) {
     h->fused_direct = direct;
     int per_sm = 0;
     if (direct && h->geom.use_tma) {
-      CU_TRY(cudaFuncSetAttribute(k_fused_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
-      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tma, kThreads, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tma<0>, kThreads, h->geom.smem_bytes));
     } else if (direct) {
       CU_TRY(cudaFuncSetAttribute(k_fused_direct<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_direct<real>, kThreads, h->geom.smem_bytes));
@@ -655,9 +657,20 @@ static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc
   return 0;
 }
 
+// picks the compile-time specialisation of the production kernel (see k_fused_tma)
 static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
-  k_fused_tma<<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, h->p, in, h->geom);
+  const SimParams &p = h->p;
+  const FusedGeom &g = h->geom;
+  const bool plain = p.own_dim == 10 && p.msg_dim == 4 && (p.obs_dim % 2) == 0 && p.obs_dim > 0;
+  const bool common = plain && in.sched_od != nullptr && p.policy == DRSIM_POLICY_EXTERNAL &&
+                      p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+  if (common && !g.need_msg && g.envs_per_tile == 1)
+    k_fused_tma<1><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
+  else if (common && g.need_msg && g.envs_per_tile > 1)
+    k_fused_tma<2><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
+  else
+    k_fused_tma<0><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
 }
 
 template <typename real>

@@ -315,9 +315,10 @@ struct Raw4f {
 };
 
 // COMPUTE half of the lean fp32 house step (see house4_step_f32): consumes a Raw4f.
+template <bool EXT_ONLY>
 DRSIM_D void house4_compute_f32(const Planes<float> &pl, const SimParams &p, const Raw4f &w, size_t off, int valid,
                                 House4<float> &h, float red[kRed]) {
-  const int policy = p.policy;
+  const int policy = EXT_ONLY ? (int)DRSIM_POLICY_EXTERNAL : p.policy;
   h.valid = valid;
   const int dt = p.dt, dur = p.lockout_duration;
   const float half_db = p.hf.half_db;
@@ -1414,6 +1415,12 @@ constexpr int kInPlanes = 12;  // fp32 planes staged by TMA: Ta, Tm, sso, target
 // The two byte planes (flags, actions) are 8-byte aligned at odd replica indices, which the bulk
 // copy engine cannot address, so they are prefetched through two registers instead.
 // ------------------------------------------------------------------------------------------
+// MODE selects a compile-time specialisation so the hot instantiations carry no runtime layout /
+// policy branches: 0 = generic (everything decided at run time), 1 = one cluster per tile, plain
+// 10-column rows without neighbour messages, external actions, individual_L2, scheduled noise
+// (BASELINE config 4), 2 = several clusters per tile, plain rows WITH 4-float neighbour messages,
+// external actions, individual_L2, scheduled noise (config 3).
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, DRSIM_FUSED_MINCTAS)
 k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   typedef float real;
@@ -1432,9 +1439,12 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   const int Ns = p.Ns, D = p.obs_dim;
   const int tile_slots = g.envs_per_tile * Ns;
   const KC<real> kc(p);
-  const bool fast = in.sched_od != nullptr;
-  const bool plain = p.own_dim == 10 && p.msg_dim == 4 && (D % 2) == 0;
-  const bool ext = p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC;
+  const bool fast = MODE ? true : in.sched_od != nullptr;
+  const bool plain = MODE ? true : (p.own_dim == 10 && p.msg_dim == 4 && (D % 2) == 0);
+  const bool ext = MODE ? true : (p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC);
+  const bool need_msg = MODE == 1 ? false : (MODE == 2 ? true : g.need_msg != 0);
+  const bool one_env = MODE == 1 ? true : (MODE == 2 ? false : g.envs_per_tile == 1);
+  const bool individual = MODE ? true : p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   const uint8_t *actions = in.actions ? in.actions : pl.actions;
   bool store_pending = false;
   int parity = 0;
@@ -1466,7 +1476,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (s0 < tslots) {
       nx_flags = load4b(pl.flags + tbase + s0);
       if (ext) nx_act = load4b(actions + tbase + s0);
-      const int r = tr0 + (int)fast_div((uint32_t)s0, p.fd_ns);
+      const int r = tr0 + (one_env ? 0 : (int)fast_div((uint32_t)s0, p.fd_ns));
       nx_od = (float)pl.od_temp[r];
       nx_solar = (float)pl.solar_next[r];
     }
@@ -1495,7 +1505,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 
     // ---- phase 1 -----------------------------------------------------------------------
     const bool active = s0 < slots;
-    const int e_loc = active ? (int)fast_div((uint32_t)s0, p.fd_ns) : -1 - warp;
+    const int e_loc = active ? (one_env ? 0 : (int)fast_div((uint32_t)s0, p.fd_ns)) : -1 - warp;
     const int n0 = s0 - e_loc * Ns;
     House4<real> h;
     real red[kRed] = {0, 0, 0, 0, 0};
@@ -1518,7 +1528,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) ld(5 + k, w.c[k]);
       w.flags = nx_flags; w.act = nx_act; w.od = nx_od; w.solar = nx_solar;
-      house4_compute_f32(pl, p, w, base + s0, min(4, p.N - n0), h, red);
+      house4_compute_f32<MODE != 0>(pl, p, w, base + s0, min(4, p.N - n0), h, red);
     }
     // every lane of the warp has consumed its staged inputs: prefetch the next tile into them
     fence_proxy_async_smem();
@@ -1533,7 +1543,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
         const real sso_n = (real)fast_div((uint32_t)h.sso[j], p.fd_dur);            // norm.py:40-43, :79-82
         const bool ok = j < h.valid;
-        if (g.need_msg) {
+        if (need_msg) {
           const real pmax_n = h.cap[j] * p.hf.inv_cop * p.hf.inv_nrs;
           Msg4<real> m;
           m.dT = ok ? h.ta[j] * 0.2f : 0.f;                                         // norm.py:39
@@ -1568,7 +1578,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         }
       }
     }
-    if (g.envs_per_tile == 1) {
+    if (one_env) {
       // one cluster per tile: plain butterfly, every warp stores one partial
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -1618,7 +1628,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (fast) {
       // no serial section: every house thread folds the cluster power into the pre-computed
       // broadcast values by itself
-      if (g.envs_per_tile == 1) {
+      if (one_env) {
         // one cluster per tile: lanes 0..7 fetch one warp partial each, a 3-level butterfly in
         // fixed order gives every lane of every warp the same totals
         double a[3] = {0, 0, 0};
@@ -1642,14 +1652,14 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         eb.pen_max = (real)a[2];
       } else if (active) {
         double a[kRed] = {0, 0, 0, 0, 0};
-        combine(e_loc, a, p.penalty_mode != DRSIM_PEN_INDIVIDUAL_L2);
+        combine(e_loc, a, !individual);
         eb = s_env[e_loc];
         eb.power_n = (real)(a[0] * p.inv_nrs);
         eb.rew_sig = (real)signal_penalty(p, a[0], s_sold[e_loc]);
         eb.pen_common = (real)a[1];
         eb.pen_max = (real)a[2];
       }
-    } else {
+    } else if constexpr (MODE == 0) {
       if (threadIdx.x < E) {
         double a[kRed] = {0, 0, 0, 0, 0};
         combine(threadIdx.x, a, true);
@@ -1663,7 +1673,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (active) {
       const EnvBroadcast<real> e = eb;
       real rw[4];
-      const bool lean_reward = p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+      const bool lean_reward = individual;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         rw[j] = lean_reward ? reward_f32_individual(p, h.ta[j], e.rew_sig) : house_reward<real>(p, kc, h.ta[j], h.target[j], e);
@@ -1678,7 +1688,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
             if (plain) {
               float2 *r2 = reinterpret_cast<float2 *>(row);
               r2[2] = make_float2(e.power_n, e.signal_n);
-              if (g.need_msg) {
+              if (need_msg) {
                 for (int k = 0; k < p.nb_comm; ++k) {
                   const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
                   const float4 mk = *reinterpret_cast<const float4 *>(&s_msg[e_loc * Ns + nb]);
@@ -1689,7 +1699,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
               continue;
             }
             int q = obs_own<real>(row, p, 0u, 0.f, 0.f, 0.f, 0.f, e, nullptr, 2);
-            if (g.need_msg) {
+            if (need_msg) {
               for (int k = 0; k < p.nb_comm; ++k) {
                 const int nb = neighbour_of(p, pl.comm_table, r0 + e_loc, n0 + j, k);
                 const Msg4<real> mk = s_msg[e_loc * Ns + nb];
