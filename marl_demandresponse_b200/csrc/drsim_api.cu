@@ -208,7 +208,7 @@ static void plan_fused(drsim_handle *h) {
     g.use_tma = (direct && rb == 4 && h->cfg.path != DRSIM_PATH_FUSED + 100) ? 1 : 0;
     if (g.use_tma) {
       g.off_in = take((size_t)kInPlanes * kTileSlots * 4);
-      g.off_bar = take((size_t)(kThreads / 32) * 8);
+      g.off_bar = take((size_t)(kThreads / 32) * 8 + 16 * 8);  // mbarriers + plane base pointers
     }
     g.smem_bytes = (int)off;
     return off;

@@ -1452,9 +1452,13 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   const int s0 = threadIdx.x * kHousesPerThread;
   const int w0 = warp * 128;
 
-  const float *planes[11] = {pl.t_air, pl.t_mass, reinterpret_cast<const float *>(pl.sso), pl.target, pl.cap,
-                             pl.coef[0], pl.coef[1], pl.coef[2], pl.coef[3], pl.coef[4], pl.coef[5]};
-
+  // plane base pointers in shared memory so that lane k can fetch "its" plane without a local array
+  const float **s_planes = reinterpret_cast<const float **>(s_bar + kThreads / 32);
+  if (threadIdx.x == 0) {
+    s_planes[0] = pl.t_air; s_planes[1] = pl.t_mass; s_planes[2] = reinterpret_cast<const float *>(pl.sso);
+    s_planes[3] = pl.target; s_planes[4] = pl.cap;
+    for (int k = 0; k < 6; ++k) s_planes[5 + k] = pl.coef[k];
+  }
   if (lane == 0) mbar_init(&s_bar[warp], 1);
   fence_proxy_async_smem();
   __syncthreads();
@@ -1467,11 +1471,12 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
     const size_t tbase = (size_t)tr0 * Ns;
     const int nw = min(128, tslots - w0);
-    if (lane == 0 && nw > 0) {
-      mbar_expect_tx(&s_bar[warp], (uint32_t)(11 * nw * 4));
-#pragma unroll
-      for (int k = 0; k < 11; ++k)
-        bulk_load_g2s(s_in + (size_t)k * kTileSlots + w0, planes[k] + tbase + w0, (uint32_t)(nw * 4), &s_bar[warp]);
+    if (nw > 0) {
+      // lane 0 arms the barrier with the byte count, lanes 0..10 issue one plane each (the
+      // transaction count may go transiently negative; the phase cannot complete before lane 0's arrive)
+      if (lane == 0) mbar_expect_tx(&s_bar[warp], (uint32_t)(11 * nw * 4));
+      if (lane < 11)
+        bulk_load_g2s(s_in + (size_t)lane * kTileSlots + w0, s_planes[lane] + tbase + w0, (uint32_t)(nw * 4), &s_bar[warp]);
     }
     if (s0 < tslots) {
       nx_flags = load4b(pl.flags + tbase + s0);
