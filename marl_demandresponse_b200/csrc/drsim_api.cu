@@ -797,7 +797,10 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
   const SimParams &p = h->p;
   drsim_step_args a{};
   if (actions) {
-    CU_TRY(cudaMemcpy2DAsync(h->slab + h->o_actions, p.Ns, actions, p.N, p.N, p.R, cudaMemcpyHostToDevice, s));
+    if (p.Ns == p.N)  // contiguous rows: one linear DMA instead of R row descriptors
+      CU_TRY(cudaMemcpyAsync(h->slab + h->o_actions, actions, (size_t)p.R * p.N, cudaMemcpyHostToDevice, s));
+    else
+      CU_TRY(cudaMemcpy2DAsync(h->slab + h->o_actions, p.Ns, actions, p.N, p.N, p.R, cudaMemcpyHostToDevice, s));
     a.actions = h->at<uint8_t>(h->o_actions);
   }
   if (od_noise) {
