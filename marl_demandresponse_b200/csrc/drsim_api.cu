@@ -228,6 +228,23 @@ static void plan_fused(drsim_handle *h) {
     if (chunk < 4) return;  // does not fit: general path
     layout(false, chunk);
   }
+  // fp32 wide rows (hand-engineered layout that does not fit the direct staging): per-warp staging
+  if (g.chunk_rows != (row ? slots : 0) && rb == 4 && g.need_msg && p.own_dim == 10 && p.msg_dim == 4 &&
+      (p.obs_dim % 2) == 0 && slots % 4 == 0) {
+    FusedGeom w = g;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
+    w.off_msg = take((size_t)slots * 16 * 2);
+    w.off_own = take((size_t)slots * 16);
+    w.off_env = take((size_t)g.envs_per_tile * 32 * 2);
+    w.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double) * 2);
+    w.off_sold = take((size_t)g.envs_per_tile * sizeof(double) * 2);
+    w.off_tile = take((size_t)(kThreads / 32) * kRowGroup * row);
+    w.smem_bytes = (int)off;
+    w.use_rows = 1;
+    w.use_tma = 0;
+    if (off <= 113 * 1024) g = w;
+  }
   h->geom = g;
   h->fused_ok = true;
 }
@@ -238,7 +255,13 @@ static int configure_kernels(drsim_handle *h) {
     const bool direct = h->geom.chunk_rows == h->geom.envs_per_tile * h->p.Ns || h->p.obs_dim == 0;
     h->fused_direct = direct;
     int per_sm = 0;
-    if (direct && h->geom.use_tma) {
+    if (h->geom.use_rows) {
+      if (sizeof(real) == 4) {
+        CU_TRY(cudaFuncSetAttribute(k_fused_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_rows, kThreads, h->geom.smem_bytes));
+      }
+      CU_TRY(cudaFuncSetAttribute(k_fused<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    } else if (direct && h->geom.use_tma) {
       CU_TRY(cudaFuncSetAttribute(k_fused_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaFuncSetAttribute(k_fused_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaFuncSetAttribute(k_fused_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
@@ -673,6 +696,24 @@ static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
     k_fused_tma<0><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
 }
 
+static void launch_rows(drsim_handle *h, const StepIn &in, cudaStream_t s) {
+  const Planes<float> pl = make_planes<float>(h);
+  k_fused_rows<<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, h->p, in, h->geom);
+}
+
+// steps the wide-row kernel cannot take (injected noise, on-device policies, common penalty modes)
+// run on the general path
+template <typename real>
+static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s);
+template <typename real>
+static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, int n_parts, cudaStream_t s);
+template <typename real>
+static int launch_chunked_fallback(drsim_handle *h, const StepIn &in, cudaStream_t s) {
+  int rc = launch_house_phase<real>(h, in, s);
+  if (rc) return rc;
+  return launch_env_phase<real>(h, in, nullptr, 1, s);
+}
+
 template <typename real>
 static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
@@ -683,7 +724,11 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
     k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
     h->launches++;
   }
-  if (h->fused_direct && h->geom.use_tma) launch_tma(h, in, s);
+  const bool rows_ok = h->geom.use_rows && in.sched_od != nullptr && p.policy == DRSIM_POLICY_EXTERNAL &&
+                       p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+  if (h->geom.use_rows && !rows_ok) return launch_chunked_fallback<real>(h, in, s);
+  if (rows_ok) launch_rows(h, in, s);
+  else if (h->fused_direct && h->geom.use_tma) launch_tma(h, in, s);
   else if (h->fused_direct) k_fused_direct<real><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   else k_fused<real, false><<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, p, in, h->geom);
   h->launches++;

@@ -945,6 +945,7 @@ struct FusedGeom {
   // dynamic shared memory offsets (bytes)
   int off_msg, off_own, off_env, off_wp, off_sold, off_tile, off_in, off_bar, smem_bytes;
   int use_tma;         // fp32 direct tiles: inputs staged by TMA bulk loads (k_fused_tma)
+  int use_rows;        // fp32 wide rows: per-warp 32-row staging (k_fused_rows)
 };
 
 template <typename real>
@@ -1735,6 +1736,182 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       ef.rew_sig = signal_penalty(p, a[0], er.signal);
       env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
     }
+  }
+  if (lane == 0 && store_pending) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused path, fp32, wide rows (hand-engineered layout with neighbour messages, D = 10 + 4 c):
+// the tile's rows (1000 x 200 B for BASELINE config 3) do not fit a staging buffer, so each warp
+// assembles the rows of its own 128 slots 32 at a time -- lane l builds row 128 w + 32 g + l from
+// the own-state / message records in shared memory -- and ships every 32-row group (6.4 KB
+// contiguous) with one TMA bulk store.  Inputs come through 128-bit global loads.  Two CTA barriers
+// per tile (message records are read across warps; the power fold-in runs on E threads).
+// Conditions (checked by the host): plain columns, external actions, individual_L2, schedule.
+// ------------------------------------------------------------------------------------------
+DRSIM_D void raw_load_f32(const Planes<float> &pl, const StepIn &in, size_t off, int r, Raw4f &w) {
+  load4(pl.t_air + off, w.ta);
+  load4(pl.t_mass + off, w.tm);
+  load4i(pl.sso + off, w.sso);
+  w.flags = load4b(pl.flags + off);
+  load4_ro(pl.target + off, w.target);
+  load4_ro(pl.cap + off, w.cap);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) load4_ro(pl.coef[k] + off, w.c[k]);
+  w.act = load4b((in.actions ? in.actions : pl.actions) + off);
+  w.od = (float)pl.od_temp[r];
+  w.solar = (float)pl.solar_next[r];
+}
+
+constexpr int kRowGroup = 32;  // rows per warp-level TMA store in k_fused_rows
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
+  typedef float real;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *s_msg_base = reinterpret_cast<float4 *>(smem_raw + g.off_msg);   // [2][slots] (dT, sso_n, p_n, pmax_n)
+  float4 *s_own = reinterpret_cast<float4 *>(smem_raw + g.off_own);        // [slots] (ta_n, tm_n, tg_n, flags)
+  EnvBroadcast<real> *s_env_base = reinterpret_cast<EnvBroadcast<real> *>(smem_raw + g.off_env);
+  double *s_wp_base = reinterpret_cast<double *>(smem_raw + g.off_wp);
+  double *s_sold_base = reinterpret_cast<double *>(smem_raw + g.off_sold);
+  real *s_stage = reinterpret_cast<real *>(smem_raw + g.off_tile);         // [warps][kRowGroup][D]
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ns = p.Ns, D = p.obs_dim, nbc = p.nb_comm;
+  const int tile_slots = g.envs_per_tile * Ns;
+  const int s0 = threadIdx.x * kHousesPerThread;
+  const int w0 = warp * 128;
+  real *stage = s_stage + (size_t)warp * kRowGroup * D;
+  bool store_pending = false;
+  int parity = 0;
+
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
+    const int r0 = tile * g.envs_per_tile;
+    const int E = min(g.envs_per_tile, p.R - r0);
+    const int slots = E * Ns;
+    const size_t base = (size_t)r0 * Ns;
+    float4 *s_msg = s_msg_base + (size_t)parity * tile_slots;
+    EnvBroadcast<real> *s_env = s_env_base + (size_t)parity * g.envs_per_tile;
+    double *s_wp = s_wp_base + (size_t)parity * (kThreads / 32) * g.max_segs * kRed;
+    double *s_sold = s_sold_base + (size_t)parity * g.envs_per_tile;
+
+    EnvRegs er;
+    EnvFast ef;
+    if (threadIdx.x < E) {
+      er = env_load(pl, in, r0 + threadIdx.x);
+      s_env[threadIdx.x] = env_pre_compute<real>(p, er, ef);
+      s_sold[threadIdx.x] = er.signal;
+    }
+
+    // ---- phase 1: house update, own / message records ------------------------------------
+    const bool active = s0 < slots;
+    const int e_loc = active ? (int)fast_div((uint32_t)s0, p.fd_ns) : -1 - warp;
+    const int n0 = s0 - e_loc * Ns;
+    House4<real> h;
+    real red[kRed] = {0, 0, 0, 0, 0};
+    real pen_r[4] = {0, 0, 0, 0};
+    if (active) {
+      Raw4f w;
+      raw_load_f32(pl, in, base + s0, r0 + e_loc, w);
+      house4_compute_f32<true>(pl, p, w, base + s0, min(4, p.N - n0), h, red);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t f = (h.flags >> (8 * j)) & 0xffu;
+        const bool ok = j < h.valid;
+        const real sso_n = (real)fast_div((uint32_t)h.sso[j], p.fd_dur);
+        const real pmax_n = h.cap[j] * p.hf.inv_cop * p.hf.inv_nrs;
+        const float tg = h.target[j] - 20.f;
+        s_msg[s0 + j] = ok ? make_float4(h.ta[j] * 0.2f, sso_n, (f & 1u) ? pmax_n : 0.f, pmax_n) : make_float4(0, 0, 0, 0);
+        s_own[s0 + j] = make_float4((h.ta[j] + tg) * 0.2f, (h.tm[j] + tg) * 0.2f, tg * 0.2f, (float)f);
+        const float d = fmaxf(fabsf(h.ta[j]) - p.hf.half_db, 0.f);
+        pen_r[j] = ok ? p.hf.rew_scale * d * d : 0.f;
+      }
+    }
+    // segmented warp reduction over clusters
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      real t[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+      const int eo = __shfl_down_sync(0xffffffffu, e_loc, o);
+      if (lane + o < 32 && eo == e_loc) red_combine(red, t);
+    }
+    const int e_prev = __shfl_up_sync(0xffffffffu, e_loc, 1);
+    const bool head = (lane == 0) || (e_prev != e_loc);
+    const int e_first = __shfl_sync(0xffffffffu, e_loc, 0);
+    if (head && e_loc >= 0) {
+      double *dst = s_wp + ((size_t)warp * g.max_segs + (e_loc - e_first)) * kRed;
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
+    }
+    __syncthreads();
+
+    // ---- phase 2: fold the cluster power in (E threads, a few dozen instructions) ----------
+    double a[kRed] = {0, 0, 0, 0, 0};
+    if (threadIdx.x < E) {
+      const int e = threadIdx.x;
+      const int w_lo = (e * Ns) >> 7, w_hi = ((e + 1) * Ns - 1) >> 7;
+      for (int w = w_lo; w <= w_hi; ++w) {
+        const int efst = (int)fast_div((uint32_t)(w << 7), p.fd_ns);
+        red_combine(a, s_wp + ((size_t)w * g.max_segs + (e - efst)) * kRed);
+      }
+      ef.P = a[0];
+      ef.rew_sig = signal_penalty(p, a[0], er.signal);
+      s_env[e].power_n = (real)(a[0] * p.inv_nrs);
+      s_env[e].rew_sig = (real)ef.rew_sig;
+    }
+    __syncthreads();
+
+    // ---- phase 3: rewards, then the warp's rows 32 at a time -------------------------------
+    if (active) {
+      const real rs = s_env[e_loc].rew_sig;
+      real rw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rw[j] = j < h.valid ? -(pen_r[j] + rs) : 0.f;
+      store4(pl.reward + base + s0, rw);
+    }
+    for (int gidx = 0; gidx < 128 / kRowGroup; ++gidx) {
+      const int gs = w0 + gidx * kRowGroup;  // first slot of the group
+      if (gs >= slots) break;
+      if (lane == 0 && store_pending) bulk_store_wait_read();
+      __syncwarp();
+      const int s = gs + lane;
+      if (s < slots) {
+        const int e = (int)fast_div((uint32_t)s, p.fd_ns), n = s - e * Ns;
+        float2 *r2 = reinterpret_cast<float2 *>(stage + (size_t)lane * D);
+        if (n < p.N) {
+          const float4 o = s_own[s];
+          const float4 m = s_msg[s];
+          const EnvBroadcast<real> ev = s_env[e];
+          const uint32_t f = (uint32_t)o.w;
+          r2[0] = make_float2((float)(f & 1u), (float)((f >> 1) & 1u));
+          r2[1] = make_float2(m.y, 1.f);
+          r2[2] = make_float2(ev.power_n, ev.signal_n);
+          r2[3] = make_float2(p.hf.deadband, o.x);
+          r2[4] = make_float2(o.y, o.z);
+          const float4 *mb = s_msg + e * Ns;
+          for (int k = 0; k < nbc; ++k) {
+            const float4 mk = mb[neighbour_of(p, pl.comm_table, r0 + e, n, k)];
+            r2[5 + 2 * k] = make_float2(mk.x, mk.y);
+            r2[6 + 2 * k] = make_float2(mk.z, mk.w);
+          }
+        } else {
+          for (int q = 0; q < D / 2; ++q) r2[q] = make_float2(0.f, 0.f);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int nrows = min(kRowGroup, slots - gs);
+        bulk_store_s2g(pl.obs + (base + gs) * D, stage, (uint32_t)((size_t)nrows * D * sizeof(real)));
+        store_pending = true;
+      }
+    }
+    if (threadIdx.x < E) env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
   }
   if (lane == 0 && store_pending) {
 #if defined(__CUDA_ARCH__)

@@ -241,3 +241,43 @@ def test_house_sharded_cluster_equals_unsharded():
                 torch.testing.assert_close(ws[k], ps[k], rtol=1e-12, atol=0)
             torch.testing.assert_close(ws["reward"][:, p_.lo:p_.hi], ps["reward"], rtol=1e-6, atol=1e-7)
             torch.testing.assert_close(ws["obs"][:, p_.lo:p_.hi], ps["obs"], rtol=1e-6, atol=1e-7)
+
+
+def test_full_size_c4_spot_check_against_oracle():
+    """BASELINE config 4 at its full single-GPU size (2048 replicas x 1000 houses, TarMAC layout):
+    three replicas are re-simulated by the oracle from the same state / Philox noise; cluster power
+    must also equal the sum of the per-house powers implied by the discrete state everywhere."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle import philox
+
+    n, R, T, seed = 1000, 2048, 8, 1234
+    prop = _prop(n)
+    env = BatchedEnv(prop, R, precision="f32", obs_layout="tarmac", noise="philox", seed=seed)
+    st = synthetic_state(prop, R, seed=seed)
+    env.reset(st)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    acts = [(torch.rand((R, n), device="cuda", generator=g) < 0.5).to(torch.uint8) for _ in range(T)]
+    for t in range(T):
+        env.step(acts[t])
+    torch.cuda.synchronize()
+    got = env.get_state()
+    # size-independent property: aggregate power == sum over houses of on * cap / cop
+    p_sum = (got["on"].astype(np.float64) * got["cap"] / 2.5).sum(axis=1)
+    np.testing.assert_allclose(got["power"], p_sum, rtol=1e-6)
+    assert np.all(got["sso"][got["on"] == 1] == 0)
+    assert np.all(got["epoch"] == st["epoch"] + 4 * T)
+    pick = [0, 777, 2047]
+    sub = {k: (v[pick] if np.asarray(v).shape[:1] == (R,) else v) for k, v in st.items()}
+    epoch0 = int(st["epoch"][0])
+    od_noise = np.array([[philox.od_noise(seed, r, t, 1.0) for r in pick] for t in range(T)])
+    perlin = np.array([[philox.perlin(seed, r, ((epoch0 + 4 * t) % 86400) / 300, 5, 5) for r in pick] for t in range(T + 1)])
+    a_np = np.stack([a[pick].cpu().numpy() for a in acts])
+    orc, _ = _oracle_run(prop, sub, a_np, od_noise, perlin)
+    for k in ("on", "lockout", "sso"):
+        assert np.array_equal(got[k][pick].astype(np.int64), orc.state[k].astype(np.int64)), k
+    np.testing.assert_allclose(got["t_air"][pick], orc.state["t_air"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(got["signal"][pick], orc.state["signal"], rtol=1e-9)
+    np.testing.assert_allclose(env.obs[pick].double().cpu().numpy(), orc.obs_vectors()[:, :, :10], rtol=1e-5, atol=1e-5)
