@@ -281,3 +281,69 @@ def test_full_size_c4_spot_check_against_oracle():
     np.testing.assert_allclose(got["t_air"][pick], orc.state["t_air"], rtol=0, atol=2e-4)
     np.testing.assert_allclose(got["signal"][pick], orc.state["signal"], rtol=1e-9)
     np.testing.assert_allclose(env.obs[pick].double().cpu().numpy(), orc.obs_vectors()[:, :, :10], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,R", [(1, 5), (2, 3), (5, 300), (1023, 2), (1024, 2), (1025, 2)])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_edge_sizes_match_oracle(n, R, precision):
+    """Ragged / degenerate cluster sizes: a single house (no neighbours, D = 10), sizes that are not
+    multiples of the 4-house vector width, the tile capacity and one past it (general path)."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle import philox
+
+    T, seed = 6, 3
+    prop = _prop(n, **{"reward_prop/penalty_props/mode": "mixture", "cluster_prop/house_prop/deadband": 0.4})
+    env = BatchedEnv(prop, R, precision=precision, noise="philox", seed=seed)
+    st = synthetic_state(prop, R, seed=8)
+    env.reset(copy.deepcopy(st))
+    acts = (np.random.default_rng(4).random((T, R, n)) < 0.5).astype(np.uint8)
+    epoch0 = int(st["epoch"][0])
+    od_noise = np.array([[philox.od_noise(seed, r, t, 1.0) for r in range(R)] for t in range(T)])
+    perlin = np.array([[philox.perlin(seed, r, ((epoch0 + 4 * t) % 86400) / 300, 5, 5) for r in range(R)] for t in range(T + 1)])
+    rew = []
+    for t in range(T):
+        _, r_ = env.step(torch.as_tensor(acts[t], device="cuda"))
+        rew.append(r_.double().cpu().numpy())
+    orc, rew_ref = _oracle_run(prop, copy.deepcopy(st), acts, od_noise, perlin)
+    got = env.get_state()
+    for k in ("on", "lockout", "sso"):
+        assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), k
+    tol = 2e-4 if precision == "f32" else 1e-9
+    np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=tol)
+    np.testing.assert_allclose(np.array(rew), rew_ref, rtol=1e-5 if precision == "f32" else 1e-9, atol=tol)
+    assert env.obs.shape == (R, n, 10 + 4 * min(10, n - 1))
+    np.testing.assert_allclose(env.obs.double().cpu().numpy(), orc.obs_vectors(), rtol=1e-5, atol=1e-5 if precision == "f32" else 1e-9)
+
+
+def test_maximum_size_single_cluster_of_one_million_houses():
+    """BASELINE config 5 on one GPU: one 1,000,000-house cluster (general path, 977 CTAs per
+    cluster) against the oracle: discrete state bit-exact, aggregate power to fp32 accuracy."""
+    import torch
+
+    from marl_demandresponse_b200.batched import synthetic_state
+    from marl_demandresponse_b200.sharded import ShardedClusterEnv
+    from oracle import philox
+
+    n, T, seed = 1_000_000, 3, 5
+    prop = _prop(n)
+    st = synthetic_state(prop, 1, seed=2)
+    env = ShardedClusterEnv(prop, 1, rank=0, world=1, noise="philox", seed=seed)
+    env.reset(copy.deepcopy(st))
+    env.sim.refresh(True)
+    acts = (np.random.default_rng(6).random((T, 1, n)) < 0.5).astype(np.uint8)
+    epoch0 = int(st["epoch"][0])
+    od_noise = np.array([[philox.od_noise(seed, 0, t, 1.0)] for t in range(T)])
+    perlin = np.array([[philox.perlin(seed, 0, ((epoch0 + 4 * t) % 86400) / 300, 5, 5)] for t in range(T + 1)])
+    for t in range(T):
+        env.step(torch.as_tensor(acts[t], device="cuda"))
+    orc, rew_ref = _oracle_run(prop, copy.deepcopy(st), acts, od_noise, perlin)
+    got = env.sim.get_state()
+    for k in ("on", "lockout", "sso"):
+        assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), k
+    np.testing.assert_allclose(got["power"], orc.state["power"], rtol=1e-6)
+    np.testing.assert_allclose(got["signal"], orc.state["signal"], rtol=1e-9)
+    np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(env.state["reward"].double().cpu().numpy(), rew_ref[-1], rtol=1e-5, atol=1e-5)
