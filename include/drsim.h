@@ -200,6 +200,29 @@ int drsim_buffers(drsim_t *h, drsim_ptrs *out);
 int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *stream);
 int drsim_get_state(drsim_t *h, drsim_host_state *st, void *stream);
 
+/* Environment.reset / apply_noise on the device (environment.py:49-70,161-194; building.py:224-267;
+ * hvac.py:36-41,66-70): draws every house property from counter-based Philox streams
+ * keyed by (seed, global replica, global house, draw) instead of Python's Mersenne Twister -- the
+ * DISTRIBUTIONS are the reference's, the stream is ours.  mode 0 = reference reset (target +=
+ * |N(0, std_target)|, Ua = tri(lo, hi, 1) if quirk_ua else Ua * tri, Cm/Ca/Hm *= tri, capacity uniform
+ * in caps[], initial temperatures un-noised, HVAC on, quirks Q1-Q3); mode 1 = the synthetic benchmark
+ * state of SURVEY 8d (Ta, Tm = target + U(-2, 4), on ~ Bernoulli(1/2), sso = 0 | dt * U{0..15}).
+ * Also initialises the env scalars (start datetime + U{0..363} d + U{0..86399} s when randomize_date,
+ * outdoor temperature, max_power).  Follow with drsim_refresh(h, NULL, 1, stream). */
+typedef struct drsim_reset_args {
+  uint64_t seed;
+  int32_t mode;
+  int32_t randomize_date;
+  int64_t start_epoch;
+  double init_air_temp, init_mass_temp;
+  double std_target_temp;
+  double factor_low, factor_high;
+  int32_t quirk_ua;
+  int32_t n_caps;
+  double caps[8];
+} drsim_reset_args;
+int drsim_reset(drsim_t *h, const drsim_reset_args *args, void *stream);
+
 /* Cluster.agent_communicators (cluster.py:66-70): explicit neighbour table, host int32
  * [n_house][nb_comm] (per_replica = 0) or [n_rep][n_house][nb_comm] (per_replica = 1). */
 int drsim_set_comm_table(drsim_t *h, const int32_t *table, int per_replica, void *stream);
@@ -248,7 +271,7 @@ void drsim_host_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uin
 
 const char *drsim_last_error(void);
 int drsim_abi_version(void);
-/* sizeof(drsim_config / drsim_host_state / drsim_ptrs / drsim_step_args), for binding sanity checks */
+/* sizeof(drsim_config / drsim_host_state / drsim_ptrs / drsim_step_args / drsim_reset_args) */
 int drsim_sizeof(int which);
 
 #ifdef __cplusplus

@@ -89,6 +89,12 @@ class StepArgs(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("od_noise", C.c_void_p), ("perlin", C.c_void_p), ("interp_ids", C.c_void_p)]
 
 
+class ResetArgs(C.Structure):
+    _fields_ = [("seed", _u64), ("mode", _i32), ("randomize_date", _i32), ("start_epoch", _i64),
+                ("init_air_temp", _d), ("init_mass_temp", _d), ("std_target_temp", _d),
+                ("factor_low", _d), ("factor_high", _d), ("quirk_ua", _i32), ("n_caps", _i32), ("caps", _d * 8)]
+
+
 class DrsimError(RuntimeError):
     pass
 
@@ -118,6 +124,7 @@ def lib():
         "drsim_buffers": (C.c_int, [hp, C.POINTER(Ptrs)]),
         "drsim_set_state": (C.c_int, [hp, C.POINTER(HostState), C.c_void_p]),
         "drsim_get_state": (C.c_int, [hp, C.POINTER(HostState), C.c_void_p]),
+        "drsim_reset": (C.c_int, [hp, C.POINTER(ResetArgs), C.c_void_p]),
         "drsim_set_comm_table": (C.c_int, [hp, C.c_void_p, C.c_int, C.c_void_p]),
         "drsim_set_interp_table": (C.c_int, [hp, C.c_void_p, C.c_void_p]),
         "drsim_step": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
@@ -141,7 +148,7 @@ def lib():
         fn.argtypes = args
     if L.drsim_abi_version() != ABI_VERSION:
         raise DrsimError("libdrsim.so ABI version mismatch")
-    for which, st in enumerate((Config, HostState, Ptrs, StepArgs)):
+    for which, st in enumerate((Config, HostState, Ptrs, StepArgs, ResetArgs)):
         if L.drsim_sizeof(which) != C.sizeof(st):
             raise DrsimError(f"struct layout mismatch for {st.__name__}: C {L.drsim_sizeof(which)} vs ctypes {C.sizeof(st)}")
     _lib = L
@@ -149,7 +156,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state",
+    "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
     "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_refresh", "drsim_step_begin",
     "drsim_step_finish", "drsim_step_host", "drsim_launch_count", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",

@@ -120,9 +120,16 @@ class BatchedEnv:
         return torch.as_tensor(t, device=f"cuda:{self.device}")
 
     # ---- reset / state --------------------------------------------------------------------
-    def reset(self, state: Optional[Dict[str, np.ndarray]] = None, seed: Optional[int] = None):
+    def reset(self, state: Optional[Dict[str, np.ndarray]] = None, seed: Optional[int] = None,
+              device_mode: Optional[str] = None, quirk_ua: bool = True):
         """Inject ``state`` (default: the seeded synthetic state), compute the first regulation
-        signal (``PowerGrid.step`` at reset, environment.py:66-68) and return the observations."""
+        signal (``PowerGrid.step`` at reset, environment.py:66-68) and return the observations.
+        ``device_mode`` = "reference" | "synthetic" draws the state on the GPU instead
+        (``drsim_reset``: the reference's reset distributions from Philox streams)."""
+        if device_mode is not None:
+            self.sim.reset_device(self.props, self.seed if seed is None else seed, device_mode, quirk_ua)
+            self.sim.refresh(True)
+            return self.obs
         if state is None:
             state = synthetic_state(self.props, self.n_replicas, self.seed if seed is None else seed, self.rep_offset)
         self.sim.set_state(state)

@@ -277,6 +277,27 @@ class DrSim:
         _lib.check(self._L.drsim_get_state(self._h, C.byref(hs), self._stream(stream)))
         return out
 
+    def reset_device(self, props, seed: int, mode: str = "reference", quirk_ua: bool = True, stream=None) -> None:
+        """``drsim_reset``: draw every house property / initial state on the device from Philox
+        streams (the reference's distributions).  ``mode``: "reference" (Environment.reset
+        semantics incl. quirks Q1-Q3) or "synthetic" (benchmark state of SURVEY 8d)."""
+        p = as_props(props)
+        hp = p.cluster_prop.house_prop
+        a = _lib.ResetArgs()
+        a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.mode = {"reference": 0, "synthetic": 1}[mode]
+        a.randomize_date = int(p.start_datetime_mode == "random")
+        a.start_epoch = to_epoch(p.start_datetime)
+        a.init_air_temp, a.init_mass_temp = hp.init_air_temp, hp.init_mass_temp
+        a.std_target_temp = hp.noise_prop.std_target_temp
+        a.factor_low, a.factor_high = hp.noise_prop.factor_thermo_low, hp.noise_prop.factor_thermo_high
+        a.quirk_ua = int(quirk_ua)
+        caps = list(hp.hvac_prop.noise_prop.cooling_capacity_list)[:8]
+        a.n_caps = len(caps)
+        for i, c in enumerate(caps):
+            a.caps[i] = float(c)
+        _lib.check(self._L.drsim_reset(self._h, C.byref(a), self._stream(stream)))
+
     def set_comm_table(self, table: np.ndarray, stream=None) -> None:
         t = np.ascontiguousarray(np.asarray(table, dtype=np.int32))
         per_rep = 1 if t.ndim == 3 else 0

@@ -53,7 +53,8 @@ struct drsim_handle {
   size_t o_t_air, o_t_mass, o_sso, o_flags, o_target, o_cap, o_coef[9], o_ratio[4], o_sub, o_reward, o_obs,
       o_actions, o_epoch, o_od, o_solar_next, o_solar_cur, o_signal, o_base, o_power, o_art, o_maxp, o_pen_sum,
       o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids,
-      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec;
+      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec, o_ptrpack;
+  double cfg_artificial_ratio = 1.0;
   static constexpr int kSched = 64;  // steps pre-generated per k_schedule launch
   bool sched_valid = false;
   int64_t sched_base = 0;
@@ -342,6 +343,7 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   if (h->has_comm) h->o_comm = cv.take((size_t)p.R * p.N * p.nb_comm * 4);  // room for per-replica tables
   h->o_in_od = cv.take(E8); h->o_in_perlin = cv.take(E8);
   h->o_in_ids = cv.take((size_t)p.R * std::max(1, p.interp_k) * 4);
+  h->o_ptrpack = cv.take(256);
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
   h->o_sched_aux = cv.take(E8 * drsim_handle::kSched); h->o_sched_tsec = cv.take((size_t)p.R * 4 * drsim_handle::kSched);
   h->slab_bytes = cv.off;
@@ -883,6 +885,50 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
   return 0;
 }
 
+template <typename real>
+struct PtrPack {
+  real *coef[9];
+  real *ratio[4];
+};
+
+template <typename real>
+static int reset_t(drsim_handle *h, const ResetArgs &a, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  PtrPack<real> host{};
+  for (int k = 0; k < NCoef<real>::n; ++k) host.coef[k] = h->at<real>(h->o_coef[k]);
+  for (int k = 0; k < 4; ++k) host.ratio[k] = h->has_ratio ? h->at<real>(h->o_ratio[k]) : nullptr;
+  // the pointer tables live in the (otherwise unused at reset) injected-noise staging area
+  PtrPack<real> *dev = reinterpret_cast<PtrPack<real> *>(h->slab + h->o_ptrpack);
+  CU_TRY(cudaMemcpyAsync(dev, &host, sizeof(host), cudaMemcpyHostToDevice, s));
+  const int64_t n = (int64_t)h->p.R * h->p.Ns;
+  k_reset<real><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pl, h->p, a, dev->coef, dev->ratio);
+  h->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int drsim_reset(drsim_t *h, const drsim_reset_args *ra, void *stream) {
+  if (!h || !ra) return fail(DRSIM_E_ARG, "null argument");
+  if (ra->n_caps < 1 || ra->n_caps > 8) return fail(DRSIM_E_ARG, "n_caps must be in [1, 8]");
+  if (!(ra->factor_low < 1.0 && 1.0 < ra->factor_high)) return fail(DRSIM_E_ARG, "need factor_low < 1 < factor_high");
+  CU_TRY(cudaSetDevice(h->device));
+  ResetArgs a{};
+  a.seed = ra->seed; a.mode = ra->mode; a.randomize_date = ra->randomize_date; a.quirk_ua = ra->quirk_ua;
+  a.n_caps = ra->n_caps; a.start_epoch = ra->start_epoch; a.init_air = ra->init_air_temp; a.init_mass = ra->init_mass_temp;
+  a.std_target = ra->std_target_temp; a.f_lo = ra->factor_low; a.f_hi = ra->factor_high;
+  for (int k = 0; k < 8; ++k) a.caps[k] = ra->caps[k];
+  h->sched_valid = false;
+  h->step = 0;
+  h->t_since_interp = h->p.interp_period + 1;
+  // artificial ratio: power_grid.py:46-49 draws ratio * range^(2u - 1); range == 1 in every shipped config
+  {
+    std::vector<double> ar(h->p.R, h->cfg_artificial_ratio);
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_art, ar.data(), ar.size() * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  return h->real_bytes == 8 ? reset_t<double>(h, a, (cudaStream_t)stream) : reset_t<float>(h, a, (cudaStream_t)stream);
+}
+
 extern "C" int64_t drsim_launch_count(const drsim_t *h) { return h ? h->launches : 0; }
 
 // ---- host-side debug entry points ----------------------------------------------------------
@@ -913,6 +959,7 @@ extern "C" int drsim_sizeof(int which) {
     case 1: return (int)sizeof(drsim_host_state);
     case 2: return (int)sizeof(drsim_ptrs);
     case 3: return (int)sizeof(drsim_step_args);
+    case 4: return (int)sizeof(drsim_reset_args);
     default: return -1;
   }
 }

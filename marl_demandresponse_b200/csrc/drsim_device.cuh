@@ -132,7 +132,7 @@ DRSIM_HD U4 philox4x32_10(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c2, u
   return U4{c0, c1, c2, c3};
 }
 
-enum : uint32_t { PURPOSE_OD = 1, PURPOSE_PERLIN = 2, PURPOSE_INTERP = 3, PURPOSE_RESET = 4 };
+enum : uint32_t { PURPOSE_OD = 1, PURPOSE_PERLIN = 2, PURPOSE_INTERP = 3, PURPOSE_RESET = 4, PURPOSE_RESET_ENV = 5 };
 
 DRSIM_HD double u01_open_closed(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }  // (0,1]
 
@@ -142,6 +142,14 @@ DRSIM_HD double philox_normal(uint64_t key, uint32_t c0, uint32_t c1, uint32_t c
   const double u1 = u01_open_closed(r.x), u2 = u01_open_closed(r.y);
   return sqrt(-2.0 * log(u1)) * cos(2 * 3.141592653589793 * u2);
 }
+
+// random.triangular(low, high, mode) by inversion of the CDF
+DRSIM_HD double triangular_from_u(double u, double lo, double hi, double mode) {
+  const double fc = (mode - lo) / (hi - lo);
+  if (u < fc) return lo + sqrt(u * (hi - lo) * (mode - lo));
+  return hi - sqrt((1.0 - u) * (hi - lo) * (hi - mode));
+}
+DRSIM_HD double u01_half_open(uint32_t x) { return (double)x * 2.3283064365386963e-10; }  // [0,1)
 
 // 1-D gradient ("Perlin") noise with +-1 lattice gradients drawn from Philox, octave weights of
 // perlin.py:41-56 (note the last weight 1/(2^n - 1), quirk Q7).  Values are OUR definition: the
@@ -345,40 +353,36 @@ DRSIM_HD void thermal_step_f64(double &ta, double &tm, const double k[9], double
   tm = DR_SUB(nm, 273.0);
 }
 
-// host-side derivation of both coefficient sets (fp64)
-inline void thermal_coefs(double Ua, double Ca, double Cm, double Hm, int dt, double out12[12]) {
+// derivation of both coefficient sets (fp64); host (set_state) and device (k_reset)
+DRSIM_HD void thermal_coefs(double Ua, double Ca, double Cm, double Hm, int dt, double out12[12]) {
   const double a = Cm * Ca / Hm;
   const double b = Cm * (Ua + Hm) / Hm + Ca;
   const double c = Ua;
-  const double root = std::sqrt(b * b - 4 * a * c);
+  const double root = sqrt(b * b - 4 * a * c);
   const double r1 = (-b + root) / (2 * a);
   const double r2 = (-b - root) / (2 * a);
   const double A3 = r1 * Ca / Hm + (Ua + Hm) / Hm;
   const double A4 = r2 * Ca / Hm + (Ua + Hm) / Hm;
-  const double e1 = std::exp(r1 * dt), e2 = std::exp(r2 * dt);
-  // linear map (Ta, Tm, Tod, Qa) -> (Ta', Tm') evaluated on the basis vectors (temperatures in
+  const double e1 = exp(r1 * dt), e2 = exp(r2 * dt);
+  // linear map (Ta, Tm, Tod, Qa) -> (Ta', Tm') evaluated on the four basis vectors (temperatures in
   // kelvin enter linearly, so no offsets are needed)
-  auto F = [&](double ta, double tm, double od, double Qa, double &na, double &nm) {
+  const double basis[4][4] = {{0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}, {1, 0, 0, 0}};
+  double na[4], nm[4];
+  for (int i = 0; i < 4; ++i) {
+    const double ta = basis[i][0], tm = basis[i][1], od = basis[i][2], Qa = basis[i][3];
     const double d = Qa + Ua * od;
     const double dT = Hm * tm / Ca - (Ua + Hm) * ta / Ca + Ua * od / Ca + Qa / Ca;
     const double A1 = (r2 * ta - dT - r2 * d / c) / (r2 - r1);
     const double A2 = ta - d / c - A1;
-    na = A1 * e1 + A2 * e2 + d / c;
-    nm = A1 * A3 * e1 + A2 * A4 * e2 + d / c;
-  };
-  double na, nm;
-  F(0, 1, 0, 0, na, nm);  // d/dTm
-  out12[0] = na;
-  const double m22 = nm;
-  F(0, 0, 1, 0, na, nm);  // d/dTod
-  out12[1] = na;
-  out12[4] = nm;
-  F(0, 0, 0, 1, na, nm);  // d/dQa
-  out12[2] = na;
-  out12[5] = nm;
-  F(1, 0, 0, 0, na, nm);  // d/dTa
-  out12[3] = nm;
-  (void)m22;
+    na[i] = A1 * e1 + A2 * e2 + d / c;
+    nm[i] = A1 * A3 * e1 + A2 * A4 * e2 + d / c;
+  }
+  out12[0] = na[0];  // d Ta'/d Tm
+  out12[1] = na[1];  // d Ta'/d Tod
+  out12[2] = na[2];  // d Ta'/d Qa
+  out12[3] = nm[3];  // d Tm'/d Ta
+  out12[4] = nm[1];  // d Tm'/d Tod
+  out12[5] = nm[2];  // d Tm'/d Qa
   out12[6] = r1; out12[7] = r2; out12[8] = A3; out12[9] = A4; out12[10] = e1; out12[11] = e2;
 }
 

@@ -1921,6 +1921,108 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Reset on the device: property noise + initial state from Philox streams keyed by
+// (global replica, global house, draw) and (global replica, draw); the update coefficients are
+// derived in fp64 right here.  One thread per house; thread n == 0 of a replica also writes the env
+// scalars.  Distributions follow building.py:224-267 / hvac.py:36-41,66-70 / environment.py:176-194.
+// ------------------------------------------------------------------------------------------
+struct ResetArgs {
+  uint64_t seed;
+  int mode, randomize_date, quirk_ua, n_caps;
+  int64_t start_epoch;
+  double init_air, init_mass, std_target, f_lo, f_hi;
+  double caps[8];
+};
+
+template <typename real>
+__global__ void k_reset(Planes<real> pl, SimParams p, ResetArgs a, real *coef_w[9], real *ratio_w[4]) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)p.R * p.Ns) return;
+  const int r = (int)(i / p.Ns), n = (int)(i - (int64_t)r * p.Ns);
+  const uint32_t env = (uint32_t)(p.rep_offset + r), house = (uint32_t)(p.house_offset + n);
+  real *t_air = const_cast<real *>(pl.t_air), *t_mass = const_cast<real *>(pl.t_mass);
+  real *target_w = const_cast<real *>(pl.target), *cap_w = const_cast<real *>(pl.cap);
+  if (n >= p.N) {  // padding slot: neutral zeros
+    t_air[i] = 0; t_mass[i] = 0; pl.sso[i] = 0; pl.flags[i] = 0; target_w[i] = 0; cap_w[i] = 0;
+    for (int k = 0; k < NCoef<real>::n; ++k) coef_w[k][i] = 0;
+    return;
+  }
+  const U4 u0 = philox4x32_10(a.seed, env, house, 0u, PURPOSE_RESET);
+  const U4 u1 = philox4x32_10(a.seed, env, house, 1u, PURPOSE_RESET);
+  const U4 u2 = philox4x32_10(a.seed, env, house, 2u, PURPOSE_RESET);
+  // target_temp += |gauss(0, std_target)|  (building.py:236-238)
+  const double g = sqrt(-2.0 * log(u01_open_closed(u0.x))) * cos(2 * 3.141592653589793 * u01_open_closed(u0.y));
+  const double target = p.default_target + fabs(a.std_target * g);
+  const double fu = triangular_from_u(u01_half_open(u0.z), a.f_lo, a.f_hi, 1.0);
+  const double fcm = triangular_from_u(u01_half_open(u0.w), a.f_lo, a.f_hi, 1.0);
+  const double fca = triangular_from_u(u01_half_open(u1.x), a.f_lo, a.f_hi, 1.0);
+  const double fhm = triangular_from_u(u01_half_open(u1.y), a.f_lo, a.f_hi, 1.0);
+  const double Ua = a.quirk_ua ? fu : p.dUa * fu;          // '=' instead of '*=' (quirk Q1, building.py:245)
+  const double Cm = p.dCm * fcm, Ca = p.dCa * fca, Hm = p.dHm * fhm;
+  const int ci = min(a.n_caps - 1, (int)(((uint64_t)u1.z * (uint64_t)a.n_caps) >> 32));
+  const double cap = a.caps[ci];                           // random.choices(cooling_capacity_list), hvac.py:68
+  double ta, tm;
+  uint32_t flags;
+  int sso;
+  if (a.mode == 0) {  // Building.reset ran before the noise: un-noised temps, HVAC on (quirks Q2, Q3)
+    ta = a.init_air; tm = a.init_mass; flags = 1u; sso = 0;
+  } else {
+    ta = target + (-2.0 + 6.0 * u01_half_open(u1.w));
+    tm = target + (-2.0 + 6.0 * u01_half_open(u2.x));
+    const bool on = u2.y & 1u;
+    sso = on ? 0 : p.dt * (int)(u2.z & 15u);
+    flags = (on ? 1u : 0u) | ((!on && sso < p.lockout_duration) ? 2u : 0u);
+  }
+  double co[12];
+  thermal_coefs(Ua, Ca, Cm, Hm, p.dt, co);
+  if (sizeof(real) == 4) {
+    t_air[i] = (real)(ta - target); t_mass[i] = (real)(tm - target);
+    for (int k = 0; k < 6; ++k) coef_w[k][i] = (real)co[k];
+  } else {
+    t_air[i] = (real)ta; t_mass[i] = (real)tm;
+    coef_w[0][i] = (real)Ua; coef_w[1][i] = (real)Ca; coef_w[2][i] = (real)Hm;
+    for (int k = 0; k < 6; ++k) coef_w[3 + k][i] = (real)co[6 + k];
+  }
+  pl.sso[i] = sso;
+  pl.flags[i] = (uint8_t)flags;
+  target_w[i] = (real)target;
+  cap_w[i] = (real)cap;
+  if (ratio_w[0]) {
+    ratio_w[0][i] = (real)(Ua / p.dUa); ratio_w[1][i] = (real)(Ca / p.dCa);
+    ratio_w[2][i] = (real)(Cm / p.dCm); ratio_w[3][i] = (real)(Hm / p.dHm);
+  }
+  if (pl.interp_sub) {
+    auto near3 = [](double v) {
+      v = fmin(1.1, fmax(0.9, v));
+      const double d0 = fabs(0.9 - v), d1 = fabs(1.0 - v), d2 = fabs(1.1 - v);
+      return d1 < d0 ? (d2 < d1 ? 2 : 1) : (d2 < d0 ? 2 : 0);
+    };
+    const double cc = fmin(15000.0, fmax(10000.0, cap));
+    const int ihv = fabs(10000.0 - cc) <= fabs(15000.0 - cc) ? 0 : 1;
+    const_cast<uint8_t *>(pl.interp_sub)[i] =
+        (uint8_t)((((near3(Ua / p.dUa) * 3 + near3(Cm / p.dCm)) * 3 + near3(Ca / p.dCa)) * 3 + near3(Hm / p.dHm)) * 2 + ihv);
+  }
+  if (n == 0) {
+    const U4 e0 = philox4x32_10(a.seed, env, 0u, 0u, PURPOSE_RESET_ENV);
+    int64_t epoch = a.start_epoch;
+    if (a.randomize_date)  // environment.py:189-194: randrange(364) days + randrange(86400) seconds
+      epoch += (int64_t)(((uint64_t)e0.x * 364ull) >> 32) * 86400 + (int64_t)(((uint64_t)e0.y * 86400ull) >> 32);
+    const double noise = p.temp_std * sqrt(-2.0 * log(u01_open_closed(e0.z))) * cos(2 * 3.141592653589793 * u01_open_closed(e0.w));
+    pl.epoch[r] = epoch;
+    pl.od_temp[r] = od_temp_model(civil_from_epoch(epoch), p.day_temp, p.night_temp, p.phase, noise);
+    pl.solar_next[r] = p.solar_on ? solar_gain(civil_from_epoch(epoch + p.dt), p.window_area, p.shading) : 0.0;
+    pl.solar_cur[r] = 0.0;
+    pl.signal[r] = 0.0;
+    pl.base_power[r] = 0.0;
+    const double pmax0 = p.dcap / p.cop;
+    pl.max_power[r] = (double)p.n_global * pmax0;           // cached from the un-noised props (quirk Q2)
+    pl.power[r] = a.mode == 0 ? (double)p.n_global * pmax0 : 0.0;
+    pl.t_since_interp[r] = p.interp_period + 1;
+    for (int k = 0; k < DRSIM_N_METRICS; ++k) pl.metrics[(size_t)r * DRSIM_N_METRICS + k] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Greedy-myopic controller on device (greedy_myopic_controller.py:67-104): one CTA per cluster,
 // bitonic sort of (key, id) in shared memory, then the inherently sequential knapsack scan.
 // ------------------------------------------------------------------------------------------

@@ -68,3 +68,68 @@ def interp_choices(key: int, env: int, step: int, k: int, n: int):
     """``random.choices(ids, k)`` replacement keyed by (env, draw, step)."""
     x = philox4x32_10(key, env, np.arange(k), step, PURPOSE_INTERP)[0]
     return ((x.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
+
+
+PURPOSE_RESET_ENV = 5
+
+
+def _tri(u, lo, hi, mode=1.0):
+    """``random.triangular(lo, hi, mode)`` by CDF inversion (what the device kernel evaluates)."""
+    fc = (mode - lo) / (hi - lo)
+    return np.where(u < fc, lo + np.sqrt(u * (hi - lo) * (mode - lo)), hi - np.sqrt((1.0 - u) * (hi - lo) * (hi - mode)))
+
+
+def reset_state(seed: int, n_rep: int, env_prop: dict, mode: str = "reference", quirk_ua: bool = True, rep_offset: int = 0):
+    """NumPy restatement of ``k_reset`` (device-side Environment.reset): the
+    distributions of building.py:224-267 / hvac.py:66-70 / environment.py:176-194 evaluated on the
+    Philox streams keyed by (replica, house, draw).  Returns an oracle state dict."""
+    from .config import normalize_env_prop
+    from .np_oracle import from_epoch, od_temp_scalar, to_epoch
+
+    p = normalize_env_prop(env_prop)
+    hp, hv = p["cluster_prop"]["house_prop"], p["cluster_prop"]["house_prop"]["hvac_prop"]
+    N, R, dt = p["cluster_prop"]["nb_agents"], n_rep, p["time_step"]
+    env = (rep_offset + np.arange(R))[:, None]
+    house = np.arange(N)[None, :]
+    u0 = philox4x32_10(seed, env, house, 0, PURPOSE_RESET)
+    u1 = philox4x32_10(seed, env, house, 1, PURPOSE_RESET)
+    u2 = philox4x32_10(seed, env, house, 2, PURPOSE_RESET)
+    h01 = lambda x: x.astype(np.float64) * 2.3283064365386963e-10
+    g = np.sqrt(-2.0 * np.log(u01(u0[0]))) * np.cos(2 * np.pi * u01(u0[1]))
+    npz = hp["noise_prop"]
+    lo, hi = npz["factor_thermo_low"], npz["factor_thermo_high"]
+    st = {"target": hp["target_temp"] + np.abs(npz["std_target_temp"] * g)}
+    fu, fcm, fca, fhm = (_tri(h01(x), lo, hi) for x in (u0[2], u0[3], u1[0], u1[1]))
+    st["Ua"] = fu if quirk_ua else hp["Ua"] * fu
+    st["Cm"], st["Ca"], st["Hm"] = hp["Cm"] * fcm, hp["Ca"] * fca, hp["Hm"] * fhm
+    caps = np.asarray(hv["noise_prop"]["cooling_capacity_list"], dtype=np.float64)
+    ci = np.minimum(len(caps) - 1, ((u1[2].astype(np.uint64) * np.uint64(len(caps))) >> np.uint64(32)).astype(np.int64))
+    st["cap"] = caps[ci]
+    if mode == "reference":
+        st["t_air"] = np.full((R, N), float(hp["init_air_temp"]))
+        st["t_mass"] = np.full((R, N), float(hp["init_mass_temp"]))
+        st["on"] = np.ones((R, N), dtype=bool)
+        st["lockout"] = np.zeros((R, N), dtype=bool)
+        st["sso"] = np.zeros((R, N), dtype=np.int64)
+    else:
+        st["t_air"] = st["target"] + (-2.0 + 6.0 * h01(u1[3]))
+        st["t_mass"] = st["target"] + (-2.0 + 6.0 * h01(u2[0]))
+        on = (u2[1] & np.uint32(1)).astype(bool)
+        sso = np.where(on, 0, dt * (u2[2] & np.uint32(15)).astype(np.int64))
+        st["on"], st["sso"] = on, sso
+        st["lockout"] = (~on) & (sso < hv["lockout_duration"])
+    e0 = philox4x32_10(seed, env[:, 0], 0, 0, PURPOSE_RESET_ENV)
+    epoch = np.full(R, to_epoch(p["start_datetime"]), dtype=np.int64)
+    if p["start_datetime_mode"] == "random":
+        epoch = epoch + ((e0[0].astype(np.uint64) * np.uint64(364)) >> np.uint64(32)).astype(np.int64) * 86400 \
+            + ((e0[1].astype(np.uint64) * np.uint64(86400)) >> np.uint64(32)).astype(np.int64)
+    noise = p["temp_prop"]["temp_std"] * np.sqrt(-2.0 * np.log(u01(e0[2]))) * np.cos(2 * np.pi * u01(e0[3]))
+    st["epoch"] = epoch
+    st["od_temp"] = np.array([od_temp_scalar(from_epoch(e), p["temp_prop"], n) for e, n in zip(epoch, noise)])
+    pmax0 = hv["cooling_capacity"] / hv["cop"]
+    st["max_power"] = np.full(R, N * pmax0)
+    st["power"] = np.full(R, N * pmax0) if mode == "reference" else np.where(st["on"], st["cap"] / hv["cop"], 0.0).sum(axis=1)
+    st["signal"] = np.zeros(R)
+    st["base_power"] = np.zeros(R)
+    st["solar"] = np.zeros(R)
+    return st

@@ -347,3 +347,45 @@ def test_maximum_size_single_cluster_of_one_million_houses():
     np.testing.assert_allclose(got["signal"], orc.state["signal"], rtol=1e-9)
     np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=2e-4)
     np.testing.assert_allclose(env.state["reward"].double().cpu().numpy(), rew_ref[-1], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["reference", "synthetic"])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_device_reset_matches_numpy_restatement(mode, precision):
+    """drsim_reset (Environment.reset distributions on Philox streams) == its NumPy
+    restatement, then a few steps from that state == the oracle from the restated state."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from oracle import philox
+
+    n, R, seed, off, T = 150, 7, 99, 40, 5
+    prop = _prop(n, **{"start_datetime_mode": "random"})
+    env = BatchedEnv(prop, R, precision=precision, noise="philox", seed=seed, rep_offset=off)
+    env.reset(device_mode=mode)
+    got = env.get_state()
+    want = philox.reset_state(seed, R, prop, mode, True, off)
+    for k in ("on", "lockout", "sso", "epoch"):
+        assert np.array_equal(np.asarray(got[k]).astype(np.int64), np.asarray(want[k]).astype(np.int64)), k
+    tol = 1e-5 if precision == "f32" else 1e-12
+    for k in ("target", "cap", "t_air", "t_mass", "od_temp", "max_power"):
+        np.testing.assert_allclose(got[k], want[k], rtol=tol, atol=tol, err_msg=k)
+    # property-noise statistics are the reference's: target >= default, factors in [0.9, 1.1], caps in the list
+    assert np.all(got["target"] >= 19.0) and set(np.unique(got["cap"])) <= {12500.0, 15000.0, 17500.0}
+    if mode == "reference":
+        assert np.all(got["on"] == 1) and np.allclose(got["t_air"], 20.0, rtol=0, atol=1e-5)
+    # continue from the device-drawn state and compare with the oracle started from the restated one
+    acts = (np.random.default_rng(0).random((T, R, n)) < 0.5).astype(np.uint8)
+    od_noise = np.array([[philox.od_noise(seed, off + r, t, 1.0) for r in range(R)] for t in range(T)])
+    perlin = np.array([[philox.perlin(seed, off + r, ((int(want["epoch"][r]) + 4 * t) % 86400) / 300, 5, 5) for r in range(R)]
+                       for t in range(T + 1)])
+    for t in range(T):
+        env.step(torch.as_tensor(acts[t], device="cuda"))
+    if mode == "reference":
+        want["power"] = np.full(R, n * 6000.0)
+    orc, _ = _oracle_run(prop, want, acts, od_noise, perlin)
+    got = env.get_state()
+    for k in ("on", "lockout", "sso"):
+        assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), k
+    np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=2e-4 if precision == "f32" else 1e-8)
+    np.testing.assert_allclose(got["signal"], orc.state["signal"], rtol=1e-9)

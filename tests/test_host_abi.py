@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match():
     L = _lib.lib()
-    for which, st in enumerate((_lib.Config, _lib.HostState, _lib.Ptrs, _lib.StepArgs)):
+    for which, st in enumerate((_lib.Config, _lib.HostState, _lib.Ptrs, _lib.StepArgs, _lib.ResetArgs)):
         assert L.drsim_sizeof(which) == C.sizeof(st)
 
 
