@@ -126,6 +126,52 @@ DRSIM_D void store4i(int32_t *p, const int v[4]) {
 DRSIM_D uint32_t load4b(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 DRSIM_D void store4b(uint8_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
 
+// L2 eviction-priority policies (PTX createpolicy): the per-step working set is state + static planes
+// (~45 B/house, re-read every step) plus the streamed outputs (observation rows, rewards).  Marking the
+// former evict_last and the latter evict_first lets the 126 MB L2 keep the planes that the next step
+// reads again instead of the rows nobody on the device reads back.
+DRSIM_D uint64_t l2_policy_evict_first() {
+  uint64_t pol = 0;
+#if defined(__CUDA_ARCH__)
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+DRSIM_D uint64_t l2_policy_evict_last() {
+  uint64_t pol = 0;
+#if defined(__CUDA_ARCH__)
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+DRSIM_D void bulk_store_s2g_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(s),
+               "r"(bytes), "l"(pol)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+}
+DRSIM_D void st4_hint(float *p, const float v[4], uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "l"(pol)
+               : "memory");
+#endif
+}
+DRSIM_D void st4i_hint(int32_t *p, const int v[4], uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "l"(pol)
+               : "memory");
+#endif
+}
+DRSIM_D void st1u_hint(uint8_t *p, uint32_t v, uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+#endif
+}
 template <typename real> struct NCoef;
 template <> struct NCoef<float> { static constexpr int n = 6; };
 template <> struct NCoef<double> { static constexpr int n = 9; };
@@ -317,7 +363,7 @@ struct Raw4f {
 // COMPUTE half of the lean fp32 house step (see house4_step_f32): consumes a Raw4f.
 template <bool EXT_ONLY>
 DRSIM_D void house4_compute_f32(const Planes<float> &pl, const SimParams &p, const Raw4f &w, size_t off, int valid,
-                                House4<float> &h, float red[kRed]) {
+                                House4<float> &h, float red[kRed], uint64_t keep_policy = 0) {
   const int policy = EXT_ONLY ? (int)DRSIM_POLICY_EXTERNAL : p.policy;
   h.valid = valid;
   const int dt = p.dt, dur = p.lockout_duration;
@@ -359,10 +405,17 @@ DRSIM_D void house4_compute_f32(const Planes<float> &pl, const SimParams &p, con
     d2 = fmaf(h.ta[j] * m, h.ta[j], d2);
   }
   h.flags = nf;
-  store4(pl.t_air + off, h.ta);
-  store4(pl.t_mass + off, h.tm);
-  store4i(pl.sso + off, h.sso);
-  store4b(pl.flags + off, h.flags);
+  if (keep_policy) {  // state planes are re-read by the next step: keep them in L2
+    st4_hint(pl.t_air + off, h.ta, keep_policy);
+    st4_hint(pl.t_mass + off, h.tm, keep_policy);
+    st4i_hint(pl.sso + off, h.sso, keep_policy);
+    st1u_hint(pl.flags + off, h.flags, keep_policy);
+  } else {
+    store4(pl.t_air + off, h.ta);
+    store4(pl.t_mass + off, h.tm);
+    store4i(pl.sso + off, h.sso);
+    store4b(pl.flags + off, h.flags);
+  }
   red[0] = P; red[1] = ps; red[2] = pm; red[3] = ds; red[4] = d2;
 }
 
@@ -1402,6 +1455,16 @@ DRSIM_D void bulk_load_g2s(void *sdst, const void *gsrc, uint32_t bytes, uint64_
 #endif
 }
 
+DRSIM_D void bulk_load_g2s_hint(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          (uint32_t)__cvta_generic_to_shared(sdst)),
+      "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)), "l"(pol)
+      : "memory");
+#endif
+}
+
 constexpr int kInPlanes = 12;  // fp32 planes staged by TMA: Ta, Tm, sso, target, cap, 6 coefficients (+1 spare)
 
 // ------------------------------------------------------------------------------------------
@@ -1447,6 +1510,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   const bool one_env = MODE == 1 ? true : (MODE == 2 ? false : g.envs_per_tile == 1);
   const bool individual = MODE ? true : p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   const uint8_t *actions = in.actions ? in.actions : pl.actions;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   bool store_pending = false;
   int parity = 0;
   uint32_t ld_phase = 0;  // phase of the warp's load mbarrier (flips only on tiles the warp takes part in)
@@ -1477,7 +1541,8 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       // transaction count may go transiently negative; the phase cannot complete before lane 0's arrive)
       if (lane == 0) mbar_expect_tx(&s_bar[warp], (uint32_t)(11 * nw * 4));
       if (lane < 11)
-        bulk_load_g2s(s_in + (size_t)lane * kTileSlots + w0, s_planes[lane] + tbase + w0, (uint32_t)(nw * 4), &s_bar[warp]);
+        bulk_load_g2s_hint(s_in + (size_t)lane * kTileSlots + w0, s_planes[lane] + tbase + w0, (uint32_t)(nw * 4),
+                           &s_bar[warp], pol_keep);
     }
     if (s0 < tslots) {
       nx_flags = load4b(pl.flags + tbase + s0);
@@ -1534,7 +1599,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) ld(5 + k, w.c[k]);
       w.flags = nx_flags; w.act = nx_act; w.od = nx_od; w.solar = nx_solar;
-      house4_compute_f32<MODE != 0>(pl, p, w, base + s0, min(4, p.N - n0), h, red);
+      house4_compute_f32<MODE != 0>(pl, p, w, base + s0, min(4, p.N - n0), h, red, pol_keep);
     }
     // every lane of the warp has consumed its staged inputs: prefetch the next tile into them
     fence_proxy_async_smem();
@@ -1685,7 +1750,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         rw[j] = lean_reward ? reward_f32_individual(p, h.ta[j], e.rew_sig) : house_reward<real>(p, kc, h.ta[j], h.target[j], e);
         if (j >= h.valid) rw[j] = 0.f;
       }
-      store4(pl.reward + base + s0, rw);
+      st4_hint(pl.reward + base + s0, rw, pol_stream);
       if (D > 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1724,7 +1789,8 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       __syncwarp();
       if (lane == 0 && w0 < slots) {
         const int nrows = min(128, slots - w0);
-        bulk_store_s2g(pl.obs + (base + w0) * D, s_tile + (size_t)w0 * D, (uint32_t)((size_t)nrows * D * sizeof(real)));
+        bulk_store_s2g_hint(pl.obs + (base + w0) * D, s_tile + (size_t)w0 * D, (uint32_t)((size_t)nrows * D * sizeof(real)),
+                            pol_stream);
         store_pending = true;
       }
     }
