@@ -584,32 +584,70 @@ extern "C" int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *str
   return h->real_bytes == 8 ? set_state_t<double>(h, st, s) : set_state_t<float>(h, st, s);
 }
 
+// One D2H copy for the house planes and one for the env scalars (they are carved contiguously),
+// then the requested members are unpacked on the host: a full snapshot costs two memcpys + one sync.
 template <typename real>
 static int get_state_t(drsim_handle *h, drsim_host_state *st, cudaStream_t s) {
-  int rc;
-  if (st->t_air && (rc = download_house<real>(h, h->o_t_air, s, st->t_air))) return rc;
-  if (st->t_mass && (rc = download_house<real>(h, h->o_t_mass, s, st->t_mass))) return rc;
-  if (sizeof(real) == 4 && (st->t_air || st->t_mass)) {
-    const size_t n = (size_t)h->p.R * h->p.N;
-    std::vector<double> tgt(n);
-    if ((rc = download_house<real>(h, h->o_target, s, tgt.data()))) return rc;
-    if (st->t_air) for (size_t i = 0; i < n; ++i) st->t_air[i] += tgt[i];
-    if (st->t_mass) for (size_t i = 0; i < n; ++i) st->t_mass[i] += tgt[i];
+  const SimParams &p = h->p;
+  const size_t HP = (size_t)p.R * p.Ns;
+  const bool want_house = st->t_air || st->t_mass || st->target || st->cap || st->sso || st->on || st->lockout;
+  const bool want_env = st->epoch || st->od_temp || st->signal || st->base_power || st->power || st->solar ||
+                        st->artificial_ratio || st->max_power || st->t_since_interp;
+  const size_t h_lo = h->o_t_air, h_hi = h->o_cap + HP * sizeof(real);
+  const size_t e_lo = h->o_epoch, e_hi = h->o_tsi + (size_t)p.R * 4;
+  std::vector<unsigned char> hb, eb;
+  if (want_house) {
+    hb.resize(h_hi - h_lo);
+    CU_TRY(cudaMemcpyAsync(hb.data(), h->slab + h_lo, hb.size(), cudaMemcpyDeviceToHost, s));
   }
-  if (st->target && (rc = download_house<real>(h, h->o_target, s, st->target))) return rc;
-  if (st->cap && (rc = download_house<real>(h, h->o_cap, s, st->cap))) return rc;
-  if (st->sso && (rc = download_house<int32_t>(h, h->o_sso, s, st->sso))) return rc;
-  if (st->on && (rc = download_house<uint8_t>(h, h->o_flags, s, st->on, 0, 1))) return rc;
-  if (st->lockout && (rc = download_house<uint8_t>(h, h->o_flags, s, st->lockout, 1, 1))) return rc;
-  if (st->epoch && (rc = download_env<int64_t>(h, h->o_epoch, s, st->epoch))) return rc;
-  if (st->od_temp && (rc = download_env<double>(h, h->o_od, s, st->od_temp))) return rc;
-  if (st->signal && (rc = download_env<double>(h, h->o_signal, s, st->signal))) return rc;
-  if (st->base_power && (rc = download_env<double>(h, h->o_base, s, st->base_power))) return rc;
-  if (st->power && (rc = download_env<double>(h, h->o_power, s, st->power))) return rc;
-  if (st->solar && (rc = download_env<double>(h, h->o_solar_cur, s, st->solar))) return rc;
-  if (st->artificial_ratio && (rc = download_env<double>(h, h->o_art, s, st->artificial_ratio))) return rc;
-  if (st->max_power && (rc = download_env<double>(h, h->o_maxp, s, st->max_power))) return rc;
-  if (st->t_since_interp && (rc = download_env<int32_t>(h, h->o_tsi, s, st->t_since_interp))) return rc;
+  if (want_env) {
+    eb.resize(e_hi - e_lo);
+    CU_TRY(cudaMemcpyAsync(eb.data(), h->slab + e_lo, eb.size(), cudaMemcpyDeviceToHost, s));
+  }
+  CU_TRY(cudaStreamSynchronize(s));
+  auto house = [&](size_t off) { return hb.data() + (off - h_lo); };
+  auto env = [&](size_t off) { return eb.data() + (off - e_lo); };
+  const bool devi = sizeof(real) == 4;
+  const real *tgt = want_house ? reinterpret_cast<const real *>(house(h->o_target)) : nullptr;
+  auto unpack_real = [&](size_t off, double *dst, bool add_target) {
+    const real *src = reinterpret_cast<const real *>(house(off));
+    for (int r = 0; r < p.R; ++r)
+      for (int n = 0; n < p.N; ++n) {
+        const size_t i = (size_t)r * p.Ns + n;
+        dst[(size_t)r * p.N + n] = (double)src[i] + (add_target ? (double)tgt[i] : 0.0);
+      }
+  };
+  if (st->t_air) unpack_real(h->o_t_air, st->t_air, devi);
+  if (st->t_mass) unpack_real(h->o_t_mass, st->t_mass, devi);
+  if (st->target) unpack_real(h->o_target, st->target, false);
+  if (st->cap) unpack_real(h->o_cap, st->cap, false);
+  if (st->sso || st->on || st->lockout) {
+    const int32_t *sso = reinterpret_cast<const int32_t *>(house(h->o_sso));
+    const uint8_t *fl = house(h->o_flags);
+    for (int r = 0; r < p.R; ++r)
+      for (int n = 0; n < p.N; ++n) {
+        const size_t i = (size_t)r * p.Ns + n, o = (size_t)r * p.N + n;
+        if (st->sso) st->sso[o] = sso[i];
+        if (st->on) st->on[o] = fl[i] & 1u;
+        if (st->lockout) st->lockout[o] = (fl[i] >> 1) & 1u;
+      }
+  }
+  auto env_d = [&](size_t off, double *dst) {
+    if (!dst) return;
+    const double *src = reinterpret_cast<const double *>(env(off));
+    for (int r = 0; r < p.R; ++r) dst[r] = src[r];
+  };
+  if (st->epoch) {
+    const int64_t *src = reinterpret_cast<const int64_t *>(env(h->o_epoch));
+    for (int r = 0; r < p.R; ++r) st->epoch[r] = src[r];
+  }
+  env_d(h->o_od, st->od_temp); env_d(h->o_signal, st->signal); env_d(h->o_base, st->base_power);
+  env_d(h->o_power, st->power); env_d(h->o_solar_cur, st->solar); env_d(h->o_art, st->artificial_ratio);
+  env_d(h->o_maxp, st->max_power);
+  if (st->t_since_interp) {
+    const int32_t *src = reinterpret_cast<const int32_t *>(env(h->o_tsi));
+    for (int r = 0; r < p.R; ++r) st->t_since_interp[r] = src[r];
+  }
   return 0;
 }
 

@@ -348,18 +348,24 @@ class Environment:
 
     # ---- observations (environment.py:110-130, cluster.py:91-121, building.py:79-139) ------
     def get_obs(self) -> ObsDict:
-        s, hv = self._snap, self.init_props.cluster_prop.house_prop.hvac_prop
+        s = self._snap
         mp = self.init_props.cluster_prop.message_prop
         n = self.n
+        # plain Python lists: per-element numpy indexing would dominate the dict building
+        sso, on = s["sso"][0].tolist(), [bool(x) for x in s["on"][0].tolist()]
+        lock = [bool(x) for x in s["lockout"][0].tolist()]
+        ta, tm = s["t_air"][0].tolist(), s["t_mass"][0].tolist()
+        solar, power, signal = float(s["solar"][0]), float(s["power"][0]), float(s["signal"][0])
         msgs = []
         for i in range(n):
             hp_i, b = self._hvac_props[i], self._house_props[i]
+            pmax = hp_i.max_consumption
             m = {
-                "seconds_since_off": int(s["sso"][0, i]),
-                "curr_consumption": hp_i.max_consumption if s["on"][0, i] else 0.0,
-                "max_consumption": hp_i.max_consumption,
+                "seconds_since_off": sso[i],
+                "curr_consumption": pmax if on[i] else 0.0,
+                "max_consumption": pmax,
                 "lockout_duration": hp_i.lockout_duration,
-                "current_temp_diff_to_target": float(s["t_air"][0, i]) - b.target_temp,
+                "current_temp_diff_to_target": ta[i] - b.target_temp,
             }
             if mp.hvac:
                 m.update(cop=hp_i.cop, latent_cooling_fraction=hp_i.latent_cooling_fraction,
@@ -367,13 +373,14 @@ class Environment:
             if mp.thermal:
                 m.update(Ca=b.Ca, Ua=b.Ua, Cm=b.Cm, Hm=b.Hm)
             msgs.append(m)
+        table = self._table.tolist() if self._table.shape[1] else [[] for _ in range(n)]
         out = ObsDict()
         for i in range(n):
             hp_i, b = self._hvac_props[i], self._house_props[i]
             out[i] = {
-                "turned_on": bool(s["on"][0, i]),
-                "seconds_since_off": int(s["sso"][0, i]),
-                "lockout": bool(s["lockout"][0, i]),
+                "turned_on": on[i],
+                "seconds_since_off": sso[i],
+                "lockout": lock[i],
                 "cop": hp_i.cop,
                 "cooling_capacity": hp_i.cooling_capacity,
                 "latent_cooling_fraction": hp_i.latent_cooling_fraction,
@@ -381,14 +388,14 @@ class Environment:
                 "target_temp": b.target_temp,
                 "deadband": b.deadband,
                 "Ua": b.Ua, "Ca": b.Ca, "Cm": b.Cm, "Hm": b.Hm,
-                "indoor_temp": float(s["t_air"][0, i]),
-                "mass_temp": float(s["t_mass"][0, i]),
-                "solar_gain": float(s["solar"][0]),
-                "cluster_hvac_power": float(s["power"][0]),
-                "message": [dict(msgs[j]) for j in (self._table[i] if self._table.shape[1] else [])],
+                "indoor_temp": ta[i],
+                "mass_temp": tm[i],
+                "solar_gain": solar,
+                "cluster_hvac_power": power,
+                "message": [dict(msgs[j]) for j in table[i]],
                 "OD_temp": self.current_od_temp,
                 "datetime": self.date_time,
-                "reg_signal": float(s["signal"][0]),
+                "reg_signal": signal,
             }
         out.vectors = self._vectors
         return out
