@@ -38,7 +38,7 @@ WORKLOADS = {
     "c3": dict(name="C3: 4096 replicas/GPU x 100 houses, hand-engineered neighbour obs (D=50), external actions",
                rep_per_gpu=4096, n_houses=100, obs="hand_engineered"),
     "c5": dict(name="C5: ONE 1,000,000-house cluster split by houses across the GPUs, TarMAC obs layout, "
-                    "per-step all-gather of the per-rank aggregate-power partials over NCCL",
+                    "per-step exchange of the per-rank aggregate-power partials over NVLink",
                rep_per_gpu=1, n_houses=1_000_000, obs="tarmac", sharded=True),
 }
 
@@ -216,7 +216,7 @@ def run_gpu_arm(args, wl) -> None:
         from marl_demandresponse_b200.sharded import ShardedClusterEnv
 
         env = ShardedClusterEnv(env_prop_for(N), R, rank=rank, world=world, device=local, precision="f32",
-                                obs_layout=wl["obs"], noise="philox", seed=1234)
+                                obs_layout=wl["obs"], noise="philox", seed=1234, exchange=args.exchange)
         env.reset()
         n_local = env.hi - env.lo
     else:
@@ -308,7 +308,7 @@ def run_gpu_arm(args, wl) -> None:
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "replicas_per_gpu": R, "houses_per_cluster": N, "obs_dim": D,
-                       "parallelism": (f"house-sharded x{world}, per-step all-gather of 48 B/rank" if sharded
+                       "parallelism": (f"house-sharded x{world}, per-step exchange of 48 B/rank via {args.exchange if world > 1 else 'none'}" if sharded
                                        else f"replica-sharded x{world}, no per-step collective"),
                        "l2": f"working set {R * n_local * bytes_hs / 1e6:.0f} MB per step per GPU vs 126 MB L2"
                              + ("" if R * n_local * bytes_hs > 126e6 else "; L2 flushed between steps by a 256 MB write"
@@ -343,6 +343,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--flush-l2", action="store_true", help="write a 256 MB buffer between timed steps")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="c5 only: per-step exchange of the aggregate-power partials (peer-memory stores vs NCCL all-gather)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

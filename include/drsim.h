@@ -249,6 +249,15 @@ int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream);
 int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_gathered, int n_parts,
                       void *stream);
 
+/* Peer-memory variant of the same exchange (no NCCL on the step path): every rank exports an IPC
+ * handle of its slab + the offsets of its "inbox" (80 bytes), the handles of all ranks are attached,
+ * and from then on drsim_step_begin pushes this rank's partial sums straight into every rank's inbox
+ * over NVLink from the tail of the reduction kernel, and drsim_step_finish(h, args, NULL, -1, stream)
+ * waits (bounded, ~2 s) for all rows inside the epilogue kernel.  drsim_peer_status reports a timeout. */
+int drsim_ipc_export(drsim_t *h, void *out80);
+int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles80, void *stream);
+int drsim_peer_status(drsim_t *h, void *stream);
+
 /* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out
  * ([R][4] doubles: power, signal, od_temp, mean reward); copies are inside the call and ordered on
  * `stream`; the call returns after the results have landed (stream synchronised). */

@@ -345,6 +345,19 @@ class DrSim:
         a = self._args()
         _lib.check(self._L.drsim_step_finish(self._h, C.byref(a), self._ptr(acc), int(n_parts), self._stream(stream)))
 
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(80)
+        _lib.check(self._L.drsim_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_attach(self, rank: int, world: int, handles: list, stream=None) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == 80 * world
+        _lib.check(self._L.drsim_ipc_attach(self._h, int(rank), int(world), blob, self._stream(stream)))
+
+    def peer_status(self, stream=None) -> None:
+        _lib.check(self._L.drsim_peer_status(self._h, self._stream(stream)))
+
     def step_host(self, actions: Optional[np.ndarray], od_noise=None, perlin=None, interp_ids=None,
                   env_out: Optional[np.ndarray] = None, stream=None) -> Optional[np.ndarray]:
         """Host-buffer step (``drsim_step_host``): numpy (or pinned torch CPU) buffers in and out."""

@@ -67,6 +67,10 @@ struct drsim_handle {
   int64_t step = 0;
   int t_since_interp = 0;  // host mirror of PowerGrid.time_since_last_interp (common to all replicas)
   int64_t launches = 0;
+  // peer-memory exchange (house-sharded cluster over several GPUs)
+  int peer_world = 1, peer_rank = 0;
+  size_t o_inbox = 0, o_pflags = 0, o_peer_tab = 0, o_peer_err = 0;
+  std::vector<void *> peer_mapped;  // cudaIpcOpenMemHandle results to close
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
   StepIn pending_in{};
   // pinned staging for drsim_step_host
@@ -344,6 +348,13 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   h->o_in_od = cv.take(E8); h->o_in_perlin = cv.take(E8);
   h->o_in_ids = cv.take((size_t)p.R * std::max(1, p.interp_k) * 4);
   h->o_ptrpack = cv.take(256);
+  {
+    const int wmax = 16;  // ranks of one box
+    h->o_inbox = cv.take((size_t)2 * wmax * p.R * DRSIM_N_ACC * 8);
+    h->o_pflags = cv.take((size_t)2 * wmax * p.R * 8);
+    h->o_peer_tab = cv.take((size_t)2 * wmax * 8);
+    h->o_peer_err = cv.take(8);
+  }
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
   h->o_sched_aux = cv.take(E8 * drsim_handle::kSched); h->o_sched_tsec = cv.take((size_t)p.R * 4 * drsim_handle::kSched);
   h->slab_bytes = cv.off;
@@ -368,6 +379,7 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
 extern "C" int drsim_destroy(drsim_t *h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  for (void *ptr : h->peer_mapped) cudaIpcCloseMemHandle(ptr);
   if (h->slab) cudaFree(h->slab);
   if (h->h_env) cudaFreeHost(h->h_env);
   delete h;
@@ -692,6 +704,16 @@ extern "C" int drsim_set_interp_table(drsim_t *h, const double *sub, void *strea
 }
 
 // ---- stepping ------------------------------------------------------------------------------
+static PeerCtx make_peer(const drsim_handle *h) {
+  PeerCtx pc{};
+  pc.world = h->peer_world;
+  pc.rank = h->peer_rank;
+  pc.inbox = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab);
+  pc.flags = reinterpret_cast<unsigned long long *const *>(h->slab + h->o_peer_tab + 16 * 8);
+  pc.err = reinterpret_cast<int *>(h->slab + h->o_peer_err);
+  return pc;
+}
+
 template <typename real>
 static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
@@ -703,7 +725,7 @@ static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s)
     h->launches++;
   }
   k_house<real><<<p.R * h->chunks, kThreads, 0, s>>>(pl, p, in, h->chunks);
-  k_reduce<real><<<p.R, 128, 0, s>>>(pl, p, in, h->chunks);
+  k_reduce<real><<<p.R, 128, 0, s>>>(pl, p, in, h->chunks, make_peer(h));
   h->launches += 2;
   CU_TRY(cudaGetLastError());
   return 0;
@@ -713,7 +735,9 @@ template <typename real>
 static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, int n_parts, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
   const SimParams &p = h->p;
-  k_env<real><<<(p.R + 127) / 128, 128, 0, s>>>(pl, p, in, acc ? acc : pl.acc, acc ? n_parts : 1);
+  PeerCtx pc = make_peer(h);
+  if (acc || n_parts >= 0) pc.world = 1;  // explicit partials (or the handle's own): no peer wait
+  k_env<real><<<(p.R + 127) / 128, 128, 0, s>>>(pl, p, in, acc ? acc : pl.acc, acc ? n_parts : 1, pc);
   k_obs<real><<<p.R * h->obs_chunks, kObsChunk, (size_t)kObsChunk * p.obs_dim * sizeof(real), s>>>(pl, p, in, h->obs_chunks);
   h->launches += 2;
   CU_TRY(cudaGetLastError());
@@ -868,6 +892,7 @@ extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const 
   (void)args;
   const StepIn in = h->pending_in;
   if (acc && n_parts < 1) return fail(DRSIM_E_ARG, "n_parts must be >= 1");
+  if (!acc && n_parts < 0 && h->peer_world < 2) return fail(DRSIM_E_STATE, "peer exchange requested but drsim_ipc_attach was not called");
   int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, n_parts, (cudaStream_t)stream)
                               : launch_env_phase<float>(h, in, acc, n_parts, (cudaStream_t)stream);
   if (!rc) h->step++;
@@ -965,6 +990,59 @@ extern "C" int drsim_reset(drsim_t *h, const drsim_reset_args *ra, void *stream)
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   }
   return h->real_bytes == 8 ? reset_t<double>(h, a, (cudaStream_t)stream) : reset_t<float>(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int drsim_ipc_export(drsim_t *h, void *out80) {
+  if (!h || !out80) return fail(DRSIM_E_ARG, "null argument");
+  CU_TRY(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  CU_TRY(cudaIpcGetMemHandle(&mh, h->slab));
+  unsigned char *o = static_cast<unsigned char *>(out80);
+  memcpy(o, &mh, 64);
+  const uint64_t off[2] = {(uint64_t)h->o_inbox, (uint64_t)h->o_pflags};
+  memcpy(o + 64, off, 16);
+  return 0;
+}
+
+extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles80, void *stream) {
+  if (!h || !handles80) return fail(DRSIM_E_ARG, "null argument");
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(DRSIM_E_ARG, "rank / world");
+  CU_TRY(cudaSetDevice(h->device));
+  const unsigned char *in = static_cast<const unsigned char *>(handles80);
+  std::vector<uint64_t> tab(32, 0);
+  for (int q = 0; q < world; ++q) {
+    cudaIpcMemHandle_t mh;
+    uint64_t off[2];
+    memcpy(&mh, in + (size_t)q * 80, 64);
+    memcpy(off, in + (size_t)q * 80 + 64, 16);
+    unsigned char *base = nullptr;
+    if (q == rank) base = h->slab;
+    else {
+      void *ptr = nullptr;
+      CU_TRY(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_mapped.push_back(ptr);
+      base = static_cast<unsigned char *>(ptr);
+    }
+    tab[q] = (uint64_t)(uintptr_t)(base + off[0]);
+    tab[16 + q] = (uint64_t)(uintptr_t)(base + off[1]);
+  }
+  auto s = (cudaStream_t)stream;
+  CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 32 * 8, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemsetAsync(h->slab + h->o_pflags, 0, (size_t)2 * 16 * h->p.R * 8, s));
+  CU_TRY(cudaMemsetAsync(h->slab + h->o_peer_err, 0, 8, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  h->peer_world = world;
+  h->peer_rank = rank;
+  return 0;
+}
+
+extern "C" int drsim_peer_status(drsim_t *h, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  int err = 0;
+  CU_TRY(cudaMemcpyAsync(&err, h->slab + h->o_peer_err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (err) return fail(DRSIM_E_STATE, "a peer-exchange wait timed out (a rank did not deliver its partial sums)");
+  return 0;
 }
 
 extern "C" int64_t drsim_launch_count(const drsim_t *h) { return h ? h->launches : 0; }

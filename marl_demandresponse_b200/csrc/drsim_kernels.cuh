@@ -69,6 +69,19 @@ struct StepIn {
   int advance;  // 1 = real step, 0 = refresh (recompute signal / obs without advancing time)
 };
 
+// Peer-memory exchange of the per-rank partial sums of ONE house-sharded cluster: every
+// rank owns an "inbox" [2 parities][world][R][kRed + 1] in its own slab plus step-stamped flags; the
+// tail of k_reduce stores this rank's row straight into every peer's inbox over NVLink (st + release
+// fence + flag store, system scope) and k_env spins on its own flags (acquire, bounded) before
+// combining the rows in rank order -- compute, reduction and collective in the same two kernels, no
+// NCCL call on the step path.
+struct PeerCtx {
+  int world, rank;
+  double *const *inbox;               // [world] base of each rank's inbox (peer-mapped)
+  unsigned long long *const *flags;   // [world] base of each rank's flags [2][world][R]
+  int *err;                           // local: set when a wait timed out
+};
+
 // Launch-invariant constants in registers.  The fp32 build multiplies by reciprocals (<= 1 ulp
 // from the true quotient, far inside the 1e-5 budget); the fp64 build divides like the reference.
 template <typename real>
@@ -813,7 +826,7 @@ DRSIM_D real interp5(const real *sub, const real x[5]) {
 // power of the sampled houses this handle owns).  One CTA per cluster.
 // ------------------------------------------------------------------------------------------
 template <typename real>
-__global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, StepIn in, int chunks) {
+__global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, StepIn in, int chunks, PeerCtx peer) {
   const int r = blockIdx.x;
   double red[kRed] = {0, 0, 0, 0, 0};
   // fixed assignment + fixed combine order => deterministic
@@ -883,6 +896,23 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
     double *dst = pl.acc + (size_t)r * (kRed + 1);
     for (int k = 0; k < kRed; ++k) dst[k] = a[k];
     dst[kRed] = s;
+    if (peer.world > 1) {
+      // the collective: this rank's row goes into slot [parity][rank][r] of EVERY rank's inbox
+      const int parity = (int)(in.step & 1);
+      const size_t row = (((size_t)parity * peer.world + peer.rank) * p.R + r);
+      for (int q = 0; q < peer.world; ++q) {
+        double *ib = peer.inbox[q] + row * (kRed + 1);
+        for (int k = 0; k < kRed; ++k) ib[k] = a[k];
+        ib[kRed] = s;
+      }
+      __threadfence_system();
+      for (int q = 0; q < peer.world; ++q) {
+        unsigned long long *f = peer.flags[q] + row;
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)(in.step + 1)) : "memory");
+#endif
+      }
+    }
   }
 }
 
@@ -890,11 +920,29 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
 // partial results [n_parts][R][kRed + 1] (n_parts = 1: this handle's own); they are combined here in
 // rank order (sums; column 2 is a max), so every rank derives bit-identical cluster totals.
 template <typename real>
-__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc, int n_parts) {
+__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc, int n_parts, PeerCtx peer) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= p.R) return;
   double red[kRed] = {0, 0, 0, 0, 0};
   double isum = 0.0;
+  if (peer.world > 1) {
+    // wait (bounded) until every rank's row for this step has landed in the local inbox
+    const int parity = (int)(in.step & 1);
+    const unsigned long long want = (unsigned long long)(in.step + 1);
+    const long long t0 = clock64();
+    for (int q = 0; q < peer.world; ++q) {
+      const unsigned long long *f = peer.flags[peer.rank] + (((size_t)parity * peer.world + q) * p.R + r);
+      unsigned long long v = 0;
+      do {
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+#endif
+        if (v != want && clock64() - t0 > 4000000000ll) { *peer.err = 1; break; }  // ~2 s: give up, flag the error
+      } while (v != want);
+    }
+    acc = peer.inbox[peer.rank] + (size_t)parity * peer.world * p.R * (kRed + 1);
+    n_parts = peer.world;
+  }
   for (int q = 0; q < n_parts; ++q) {
     const double *a = acc + ((size_t)q * p.R + r) * (kRed + 1);
     red_combine(red, a);

@@ -30,7 +30,7 @@ def house_shard(n_houses: int, rank: int, world: int):
 class ShardedClusterEnv:
     def __init__(self, env_props: Any, n_replicas: int = 1, rank: int = 0, world: int = 1, device: int = 0,
                  precision: str = "f32", obs_layout: str = "tarmac", policy: str = "external", noise: str = "philox",
-                 seed: int = 0, group=None):
+                 seed: int = 0, group=None, exchange: str = "nccl"):
         self.props = as_props(env_props)
         self.rank, self.world, self.group = int(rank), int(world), group
         self.n_global = int(self.props.cluster_prop.nb_agents)
@@ -43,6 +43,15 @@ class ShardedClusterEnv:
         self.device = device
         self._v = self.sim.views()
         self._gathered = None
+        self.exchange = exchange if world > 1 else "none"
+        if self.exchange == "peer":
+            # one-off: swap CUDA IPC handles of the slabs so the kernels can store into peer inboxes
+            import torch.distributed as dist
+
+            handles = [None] * world
+            dist.all_gather_object(handles, self.sim.ipc_export(), group=group)
+            self.sim.ipc_attach(rank, world, handles)
+            dist.barrier(group=group)
 
     def reset(self, state: Optional[Dict[str, np.ndarray]] = None, seed: int = 1234):
         """``state``: full-cluster state dict (every rank passes the same one) or None = synthetic."""
@@ -67,7 +76,9 @@ class ShardedClusterEnv:
                 self._v["actions"].copy_(actions)
         sim.step_begin(a)
         acc = self._v["acc"]
-        if self.world > 1:
+        if self.exchange == "peer":
+            sim.step_finish(None, -1)          # the exchange happened inside the kernels (NVLink peer stores)
+        elif self.world > 1:
             import torch.distributed as dist
 
             if self._gathered is None:
