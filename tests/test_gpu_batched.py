@@ -389,3 +389,26 @@ def test_device_reset_matches_numpy_restatement(mode, precision):
         assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), k
     np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=2e-4 if precision == "f32" else 1e-8)
     np.testing.assert_allclose(got["signal"], orc.state["signal"], rtol=1e-9)
+
+
+def test_monte_carlo_table_generator_matches_oracle():
+    """the GPU generator of the interpolation table (4,199,040 single-house bang-bang
+    simulations x 75 steps) against the oracle restatement of monteCarlo.py on a random sample of
+    grid points (fp64 build: exact closed loop), plus shape / range checks on a larger fp32 run."""
+    from marl_demandresponse_b200 import montecarlo as mc
+    from oracle.montecarlo import table_entries
+
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(4_199_040, size=3000, replace=False))
+    got = mc.generate_table(idx, precision="f64")
+    prop = mc.env_prop_for_table()
+    pts = mc.grid_points(idx)
+    want = table_entries(prop, mc.initial_state(pts, prop), pts["OD_temp"])
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-6)
+    # physical sanity: between 0 and the HVAC electrical power, hotter start -> not less consumption on average
+    assert np.all(got >= 0) and np.all(got <= pts["HVAC_power"] / 2.5 + 1e-6)
+    got32 = mc.generate_table(idx, precision="f32")
+    # fp32 closed loop may flip a bang-bang decision on a tie; the table average is robust to it
+    close = np.isclose(got32, want, rtol=1e-4, atol=0.5)
+    assert close.mean() > 0.995, close.mean()
+    assert abs(got32.mean() - want.mean()) < 1e-3 * want.mean()
