@@ -47,7 +47,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libdrsim.so")
     with open(LIB + ".build.log" if os.environ.get("DRSIM_LIB") else os.path.join(PKG, "libdrsim.build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+        # compile times differ from build to build: keep them out of the tracked log
+        log = "\n".join(l for l in (res.stdout + res.stderr).splitlines() if "Compile time" not in l)
+        f.write(" ".join(cmd) + "\n" + log + "\n")
     return LIB
 
 
