@@ -53,7 +53,7 @@ struct drsim_handle {
   size_t o_t_air, o_t_mass, o_sso, o_flags, o_target, o_cap, o_coef[9], o_ratio[4], o_sub, o_reward, o_obs,
       o_actions, o_epoch, o_od, o_solar_next, o_solar_cur, o_signal, o_base, o_power, o_art, o_maxp, o_pen_sum,
       o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids,
-      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec, o_ptrpack;
+      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec, o_sched_rec, o_ptrpack;
   double cfg_artificial_ratio = 1.0;
   static constexpr int kSched = 64;  // steps pre-generated per k_schedule launch
   bool sched_valid = false;
@@ -199,7 +199,7 @@ static void plan_fused(drsim_handle *h) {
   const int rb = h->real_bytes;
   const int slots = g.envs_per_tile * p.Ns;
   const size_t row = (size_t)p.obs_dim * rb;
-  auto layout = [&](bool direct, int chunk) {
+  auto layout = [&](bool direct, int chunk, bool allow_tma = true) {
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
     g.off_msg = take((g.need_msg || !direct) ? (size_t)slots * 4 * rb * (direct ? 2 : 1) : 0);
@@ -210,18 +210,22 @@ static void plan_fused(drsim_handle *h) {
     g.off_tile = (int)off;
     g.chunk_rows = chunk;
     off += ((size_t)chunk * row + 127) / 128 * 128;
-    g.use_tma = (direct && rb == 4 && h->cfg.path != DRSIM_PATH_FUSED + 100) ? 1 : 0;
+    g.use_tma = (direct && rb == 4 && allow_tma) ? 1 : 0;
     if (g.use_tma) {
       g.off_in = take((size_t)kInPlanes * kTileSlots * 4);
       g.off_bar = take((size_t)(kThreads / 32) * 8 + 16 * 8);  // mbarriers + plane base pointers
+      g.off_stage = take((size_t)g.envs_per_tile * sizeof(EnvStage) * 2);
     }
     g.smem_bytes = (int)off;
     return off;
   };
   // direct: the whole tile's rows staged at once (one TMA store per warp, rows from registers)
   layout(true, row ? slots : 0);
+  // many tiny clusters per tile: the per-cluster schedule records of the TMA variant may not fit
+  if (g.smem_bytes > 112 * 1024) layout(true, row ? slots : 0, false);
   if (g.smem_bytes > 112 * 1024) {
     // chunked staging; aim for >= 2 resident CTAs per SM, fall back to one big CTA
+    if (row == 0) return;  // nothing to chunk: general path
     const size_t fixed = layout(false, 0) - 0;
     int chunk = 0;
     const size_t budgets[2] = {110 * 1024, 220 * 1024};
@@ -245,6 +249,7 @@ static void plan_fused(drsim_handle *h) {
     w.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double) * 2);
     w.off_sold = take((size_t)g.envs_per_tile * sizeof(double) * 2);
     w.off_tile = take((size_t)(kThreads / 32) * kRowGroup * row);
+    w.off_stage = take((size_t)g.envs_per_tile * sizeof(EnvStage) * 2);
     w.smem_bytes = (int)off;
     w.use_rows = 1;
     w.use_tma = 0;
@@ -357,6 +362,7 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   }
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
   h->o_sched_aux = cv.take(E8 * drsim_handle::kSched); h->o_sched_tsec = cv.take((size_t)p.R * 4 * drsim_handle::kSched);
+  h->o_sched_rec = cv.take((size_t)p.R * sizeof(SchedRec) * drsim_handle::kSched);
   h->slab_bytes = cv.off;
   cudaError_t e = cudaMalloc(&h->slab, h->slab_bytes);
   if (e != cudaSuccess) {
@@ -807,7 +813,10 @@ static void launch_schedule(drsim_handle *h, cudaStream_t s) {
   k_schedule<real><<<(n + 127) / 128, 128, 0, s>>>(pl, h->p, h->step, drsim_handle::kSched, h->at<double>(h->o_sched_od),
                                                     h->at<double>(h->o_sched_solar), h->at<double>(h->o_sched_aux),
                                                     h->at<int32_t>(h->o_sched_tsec));
-  h->launches++;
+  k_schedule_pack<real><<<(n + 127) / 128, 128, 0, s>>>(pl, h->p, drsim_handle::kSched, h->at<double>(h->o_sched_od),
+                                                         h->at<double>(h->o_sched_solar), h->at<double>(h->o_sched_aux),
+                                                         h->at<int32_t>(h->o_sched_tsec), h->at<SchedRec>(h->o_sched_rec));
+  h->launches += 2;
 }
 
 // When no noise is injected for this step the env-level time series comes from the pre-generated
@@ -829,6 +838,7 @@ static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, in
     in.sched_solar = h->at<double>(h->o_sched_solar) + slot;
     in.sched_aux = h->at<double>(h->o_sched_aux) + slot;
     in.sched_tsec = h->at<int32_t>(h->o_sched_tsec) + slot;
+    in.sched_rec = h->at<SchedRec>(h->o_sched_rec) + slot;
   }
   return in;
 }
@@ -854,6 +864,9 @@ static int run_step(drsim_handle *h, const drsim_step_args *a, int advance, int 
     if (rc) return rc;
     rc = dbl ? launch_env_phase<double>(h, in, nullptr, 1, s) : launch_env_phase<float>(h, in, nullptr, 1, s);
   }
+  // the packed schedule records chain each step to the one before it (previous signal / outdoor
+  // temperature, base power): any step that did not follow the schedule ends their validity
+  if (!(advance && in.sched_rec && do_interp <= 0)) h->sched_valid = false;
   return rc;
 }
 

@@ -56,7 +56,24 @@ struct Planes {
   const real *interp_table;  // [162][9][5][8][12][6]
 };
 
+// One packed record per (scheduled step, replica): every env-level value of that step that does NOT
+// depend on the step's cluster power, pre-computed by k_schedule_pack with the very expressions of
+// env_pre_compute / env_fast_store.  The fused fp32 kernels fetch it with a few 16-byte cp.async
+// copies one tile ahead, so the per-tile env thread has no global round trip and no fp64 chain on
+// the path every other warp waits for at the tile barrier.
+struct alignas(16) SchedRec {
+  double signal, signal_prev;    // this step's signal; the one before it (reward pairs new power with old signal, Q6)
+  double od, solar_next;         // -> pl.od_temp, pl.solar_next after the step
+  double solar_cur, base_power;  // gain used by this step's house update; base power
+  long long epoch;               // epoch after the step
+  float od_prev_f, solar_f;      // house-update inputs: previous outdoor temperature, this step's gain (fp32)
+  float signal_n, solar_n, od_n; // normalised observation columns (norm.py:113-114,132-135,164-165)
+  int tsi;                       // t_since_interp after the step
+};
+static_assert(sizeof(SchedRec) == 80, "SchedRec is copied in five 16-byte pieces");
+
 struct StepIn {
+  const SchedRec *sched_rec;  // this step's records [R], or NULL (inline evaluation)
   const uint8_t *actions;
   const double *od_noise;
   const double *perlin;
@@ -677,6 +694,34 @@ __global__ void k_schedule(Planes<real> pl, SimParams p, int64_t step0, int K, d
   aux[i] = a;
 }
 
+// Second pass of the schedule: packs step k of replica r into its SchedRec from the time series of
+// k_schedule and the env planes as they are at schedule time (k = 0 takes its "previous" values from
+// the planes, k > 0 from step k - 1 of the series).
+template <typename real>
+__global__ void k_schedule_pack(Planes<real> pl, SimParams p, int K, const double *od, const double *solar,
+                                const double *aux, const int32_t *tsec, SchedRec *rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * p.R) return;
+  const int k = i / p.R, r = i - k * p.R;
+  const double base = p.base_mode == DRSIM_BASE_CONSTANT ? p.avg_power * (double)p.n_global : pl.base_power[r];
+  const double ratio = pl.artificial_ratio[r], maxp = pl.max_power[r];
+  SchedRec c;
+  c.signal = grid_signal_sched(p, base, tsec[i], aux[i], ratio, maxp);
+  c.signal_prev = k == 0 ? pl.signal[r] : grid_signal_sched(p, base, tsec[i - p.R], aux[i - p.R], ratio, maxp);
+  c.od = od[i];
+  c.solar_next = solar[i];
+  c.solar_cur = k == 0 ? pl.solar_next[r] : solar[i - p.R];
+  c.base_power = base;
+  c.epoch = pl.epoch[r] + (long long)(k + 1) * p.dt;
+  c.od_prev_f = (float)(k == 0 ? pl.od_temp[r] : od[i - p.R]);
+  c.solar_f = (float)c.solar_cur;
+  c.signal_n = (float)(c.signal * p.inv_nrs * p.inv_n_global);
+  c.solar_n = (float)(c.solar_cur * 1e-3);
+  c.od_n = (float)((c.od - 20.0) * 0.2);
+  c.tsi = pl.t_since_interp[r] + (k + 1) * p.dt;
+  rec[i] = c;
+}
+
 // rewards_calculator.py:174-179 for one house, fp32 individual_L2 fast form
 DRSIM_D float reward_f32_individual(const SimParams &p, float xa, float rew_sig) {
   const float d = fmaxf(fabsf(xa) - p.hf.half_db, 0.f);
@@ -1044,7 +1089,7 @@ struct FusedGeom {
   int max_segs;        // max clusters overlapping one warp (+1)
   int need_msg;        // neighbour messages are gathered (hand-engineered layout with nb_comm > 0)
   // dynamic shared memory offsets (bytes)
-  int off_msg, off_own, off_env, off_wp, off_sold, off_tile, off_in, off_bar, smem_bytes;
+  int off_msg, off_own, off_env, off_wp, off_sold, off_tile, off_in, off_bar, off_stage, smem_bytes;
   int use_tma;         // fp32 direct tiles: inputs staged by TMA bulk loads (k_fused_tma)
   int use_rows;        // fp32 wide rows: per-warp 32-row staging (k_fused_rows)
 };
@@ -1513,6 +1558,65 @@ DRSIM_D void bulk_load_g2s_hint(void *sdst, const void *gsrc, uint32_t bytes, ui
 #endif
 }
 
+// 16-byte asynchronous copies global -> shared (LDGSTS), used for the per-cluster schedule record
+DRSIM_D void cp_async16(void *sdst, const void *gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc)
+               : "memory");
+#endif
+}
+DRSIM_D void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// per-cluster record staged in shared memory by the fused fp32 kernels: the step's SchedRec followed
+// by the running metrics of the cluster (read-modify-write at the end of the tile)
+struct alignas(16) EnvStage {
+  SchedRec rec;
+  double m[DRSIM_N_METRICS];
+};
+static_assert(sizeof(EnvStage) == 128 && DRSIM_N_METRICS == 6, "EnvStage: 5 + 3 cp.async pieces");
+
+// issued by thread e < E for cluster r: 8 copies, no registers held while they fly
+DRSIM_D void env_stage_fetch(EnvStage *dst, const SchedRec *rec, const double *metrics, int r) {
+  const char *src = reinterpret_cast<const char *>(rec + r);
+  char *d = reinterpret_cast<char *>(dst);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) cp_async16(d + 16 * k, src + 16 * k);
+  const char *ms = reinterpret_cast<const char *>(metrics + (size_t)r * DRSIM_N_METRICS);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cp_async16(d + 80 + 16 * k, ms + 16 * k);
+}
+
+// env_fast_store from a staged record: env planes + running metrics of cluster r after the step
+template <typename real>
+DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, const EnvStage &st, const double red[kRed]) {
+  const SchedRec &c = st.rec;
+  const double P = red[0];
+  const double rew_sig = signal_penalty(p, P, c.signal_prev);
+  pl.epoch[r] = c.epoch;
+  pl.od_temp[r] = c.od;
+  pl.solar_next[r] = c.solar_next;
+  pl.solar_cur[r] = c.solar_cur;
+  pl.signal[r] = c.signal;
+  pl.base_power[r] = c.base_power;
+  pl.power[r] = P;
+  pl.pen_sum[r] = red[1];
+  pl.pen_max[r] = red[2];
+  pl.rew_sig[r] = rew_sig;
+  if (p.base_mode != DRSIM_BASE_CONSTANT) pl.t_since_interp[r] = c.tsi;
+  double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
+  const double d = P - c.signal_prev;
+  m[0] = st.m[0] + 1.0;
+  m[1] = st.m[1] + mean_reward(p, red[1], red[2], rew_sig);
+  m[2] = st.m[2] + fabs(red[3]) * p.inv_n_global;
+  m[3] = st.m[3] + red[4] * p.inv_n_global;
+  m[4] = st.m[4] + fabs(d);
+  m[5] = st.m[5] + d * d;
+}
+
 constexpr int kInPlanes = 12;  // fp32 planes staged by TMA: Ta, Tm, sso, target, cap, 6 coefficients (+1 spare)
 
 // ------------------------------------------------------------------------------------------
@@ -1543,6 +1647,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   EnvBroadcast<real> *s_env_base = reinterpret_cast<EnvBroadcast<real> *>(smem_raw + g.off_env);
   double *s_wp_base = reinterpret_cast<double *>(smem_raw + g.off_wp);
   double *s_sold_base = reinterpret_cast<double *>(smem_raw + g.off_sold);  // [2][E] previous signal
+  EnvStage *s_stage_base = reinterpret_cast<EnvStage *>(smem_raw + g.off_stage);  // [2][E] schedule record + metrics
   real *s_tile = reinterpret_cast<real *>(smem_raw + g.off_tile);
   float *s_in = reinterpret_cast<float *>(smem_raw + g.off_in);        // [kInPlanes][kTileSlots]
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + g.off_bar);  // [warps]
@@ -1596,11 +1701,25 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       nx_flags = load4b(pl.flags + tbase + s0);
       if (ext) nx_act = load4b(actions + tbase + s0);
       const int r = tr0 + (one_env ? 0 : (int)fast_div((uint32_t)s0, p.fd_ns));
-      nx_od = (float)pl.od_temp[r];
-      nx_solar = (float)pl.solar_next[r];
+      if (fast) {  // fp32 house-update inputs straight from the step's record (no fp64 conversion)
+        const float2 v = *reinterpret_cast<const float2 *>(&in.sched_rec[r].od_prev_f);
+        nx_od = v.x; nx_solar = v.y;
+      } else {
+        nx_od = (float)pl.od_temp[r];
+        nx_solar = (float)pl.solar_next[r];
+      }
     }
   };
-  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x);
+  // schedule record + running metrics of tile t's clusters -> shared memory (threads e < E, cp.async)
+  auto fetch_env = [&](int t, int par) {
+    const int tr0 = t * g.envs_per_tile;
+    if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
+      env_stage_fetch(s_stage_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
+  };
+  if ((int)blockIdx.x < g.n_tiles) {
+    prefetch(blockIdx.x);
+    if (fast) fetch_env(blockIdx.x, 0);
+  }
 
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
     const int r0 = tile * g.envs_per_tile;
@@ -1612,14 +1731,10 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     double *s_wp = s_wp_base + (size_t)parity * (kThreads / 32) * g.max_segs * kRed;
     double *s_sold = s_sold_base + (size_t)parity * g.envs_per_tile;
 
+    const EnvStage *s_stage = s_stage_base + (size_t)parity * g.envs_per_tile;
     EnvRegs er;
-    EnvFast ef;
-    if (threadIdx.x < E) {
-      er = env_load(pl, in, r0 + threadIdx.x);
-      if (fast) {  // power-independent part of the epilogue, ready before the barrier
-        s_env[threadIdx.x] = env_pre_compute<real>(p, er, ef);
-        s_sold[threadIdx.x] = er.signal;
-      }
+    if constexpr (MODE == 0) {
+      if (!fast && threadIdx.x < E) er = env_load(pl, in, r0 + threadIdx.x);
     }
 
     // ---- phase 1 -----------------------------------------------------------------------
@@ -1628,8 +1743,6 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     const int n0 = s0 - e_loc * Ns;
     House4<real> h;
     real red[kRed] = {0, 0, 0, 0, 0};
-    if (lane == 0 && store_pending) bulk_store_wait_read();
-    __syncwarp();
     if (w0 < slots) { mbar_wait(&s_bar[warp], ld_phase); ld_phase ^= 1u; }   // this tile's planes have landed
     if (active) {
       Raw4f w;
@@ -1656,6 +1769,10 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       const int nt = tile + gridDim.x;
       if (nt < g.n_tiles) prefetch(nt);
     }
+    // the previous tile's row store must have drained the warp's staging rows before they are rewritten
+    // (waited for here, after the house update, not at the top of the tile)
+    if (lane == 0 && store_pending) bulk_store_wait_read();
+    __syncwarp();
     if (active) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1730,7 +1847,13 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
       }
     }
+    if (fast && threadIdx.x < E) cp_async_wait_all();  // this tile's records (issued a whole tile ago) are in s_stage
     __syncthreads();
+    // every warp is past the previous tile's phase 3: the other parity of s_stage is free again
+    if (fast) {
+      const int nt = tile + gridDim.x;
+      if (nt < g.n_tiles) fetch_env(nt, parity ^ 1);
+    }
 
     // ---- phase 2 -------------------------------------------------------------------------
     // combine the warp partials of cluster e in warp order (deterministic, identical everywhere)
@@ -1764,17 +1887,19 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         a[0] = __shfl_sync(0xffffffffu, a[0], 0);
         a[1] = __shfl_sync(0xffffffffu, a[1], 0);
         a[2] = __shfl_sync(0xffffffffu, a[2], 0);
-        eb = s_env[0];
+        const SchedRec &c = s_stage[0].rec;
+        eb.signal_n = c.signal_n; eb.solar_n = c.solar_n; eb.od_n = c.od_n;
         eb.power_n = (real)(a[0] * p.inv_nrs);
-        eb.rew_sig = (real)signal_penalty(p, a[0], s_sold[0]);
+        eb.rew_sig = (real)signal_penalty(p, a[0], c.signal_prev);
         eb.pen_common = (real)a[1];
         eb.pen_max = (real)a[2];
       } else if (active) {
         double a[kRed] = {0, 0, 0, 0, 0};
         combine(e_loc, a, !individual);
-        eb = s_env[e_loc];
+        const SchedRec &c = s_stage[e_loc].rec;
+        eb.signal_n = c.signal_n; eb.solar_n = c.solar_n; eb.od_n = c.od_n;
         eb.power_n = (real)(a[0] * p.inv_nrs);
-        eb.rew_sig = (real)signal_penalty(p, a[0], s_sold[e_loc]);
+        eb.rew_sig = (real)signal_penalty(p, a[0], c.signal_prev);
         eb.pen_common = (real)a[1];
         eb.pen_max = (real)a[2];
       }
@@ -1846,9 +1971,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (threadIdx.x < E && fast) {
       double a[kRed] = {0, 0, 0, 0, 0};
       combine(threadIdx.x, a, true);
-      ef.P = a[0];
-      ef.rew_sig = signal_penalty(p, a[0], er.signal);
-      env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
+      env_stage_store<real>(pl, p, r0 + threadIdx.x, s_stage[threadIdx.x], a);
     }
   }
   if (lane == 0 && store_pending) {
@@ -1877,8 +2000,9 @@ DRSIM_D void raw_load_f32(const Planes<float> &pl, const StepIn &in, size_t off,
 #pragma unroll
   for (int k = 0; k < 6; ++k) load4_ro(pl.coef[k] + off, w.c[k]);
   w.act = load4b((in.actions ? in.actions : pl.actions) + off);
-  w.od = (float)pl.od_temp[r];
-  w.solar = (float)pl.solar_next[r];
+  // fp32 house-update inputs straight from the step's record (no fp64 conversion)
+  const float2 v = *reinterpret_cast<const float2 *>(&in.sched_rec[r].od_prev_f);
+  w.od = v.x; w.solar = v.y;
 }
 
 constexpr int kRowGroup = 32;  // rows per warp-level TMA store in k_fused_rows
@@ -1893,6 +2017,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   double *s_wp_base = reinterpret_cast<double *>(smem_raw + g.off_wp);
   double *s_sold_base = reinterpret_cast<double *>(smem_raw + g.off_sold);
   real *s_stage = reinterpret_cast<real *>(smem_raw + g.off_tile);         // [warps][kRowGroup][D]
+  EnvStage *s_rec_base = reinterpret_cast<EnvStage *>(smem_raw + g.off_stage);  // [2][E] schedule record + metrics
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Ns = p.Ns, D = p.obs_dim, nbc = p.nb_comm;
@@ -1902,6 +2027,14 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   real *stage = s_stage + (size_t)warp * kRowGroup * D;
   bool store_pending = false;
   int parity = 0;
+
+  // schedule record + running metrics of tile t's clusters -> shared memory (threads e < E, cp.async)
+  auto fetch_env = [&](int t, int par) {
+    const int tr0 = t * g.envs_per_tile;
+    if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
+      env_stage_fetch(s_rec_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
+  };
+  if ((int)blockIdx.x < g.n_tiles) fetch_env(blockIdx.x, 0);
 
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
     const int r0 = tile * g.envs_per_tile;
@@ -1913,13 +2046,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     double *s_wp = s_wp_base + (size_t)parity * (kThreads / 32) * g.max_segs * kRed;
     double *s_sold = s_sold_base + (size_t)parity * g.envs_per_tile;
 
-    EnvRegs er;
-    EnvFast ef;
-    if (threadIdx.x < E) {
-      er = env_load(pl, in, r0 + threadIdx.x);
-      s_env[threadIdx.x] = env_pre_compute<real>(p, er, ef);
-      s_sold[threadIdx.x] = er.signal;
-    }
+    const EnvStage *s_rec = s_rec_base + (size_t)parity * g.envs_per_tile;
 
     // ---- phase 1: house update, own / message records ------------------------------------
     const bool active = s0 < slots;
@@ -1962,7 +2089,12 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 #pragma unroll
       for (int k = 0; k < kRed; ++k) dst[k] = (double)red[k];
     }
+    if (threadIdx.x < E) cp_async_wait_all();  // this tile's records (issued a whole tile ago) are in s_rec
     __syncthreads();
+    {  // every warp is past the previous tile: the other parity of s_rec is free again
+      const int nt = tile + gridDim.x;
+      if (nt < g.n_tiles) fetch_env(nt, parity ^ 1);
+    }
 
     // ---- phase 2: fold the cluster power in (E threads, a few dozen instructions) ----------
     double a[kRed] = {0, 0, 0, 0, 0};
@@ -1973,10 +2105,10 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         const int efst = (int)fast_div((uint32_t)(w << 7), p.fd_ns);
         red_combine(a, s_wp + ((size_t)w * g.max_segs + (e - efst)) * kRed);
       }
-      ef.P = a[0];
-      ef.rew_sig = signal_penalty(p, a[0], er.signal);
+      const SchedRec &c = s_rec[e].rec;
+      s_env[e].signal_n = c.signal_n;
       s_env[e].power_n = (real)(a[0] * p.inv_nrs);
-      s_env[e].rew_sig = (real)ef.rew_sig;
+      s_env[e].rew_sig = (real)signal_penalty(p, a[0], c.signal_prev);
     }
     __syncthreads();
 
@@ -2025,7 +2157,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         store_pending = true;
       }
     }
-    if (threadIdx.x < E) env_fast_store<real>(pl, p, r0 + threadIdx.x, er, ef, a);
+    if (threadIdx.x < E) env_stage_store<real>(pl, p, r0 + threadIdx.x, s_rec[threadIdx.x], a);
   }
   if (lane == 0 && store_pending) {
 #if defined(__CUDA_ARCH__)
