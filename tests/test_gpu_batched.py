@@ -117,6 +117,49 @@ def test_fused_and_general_paths_agree_and_are_deterministic():
             np.testing.assert_allclose(out[0][k], out[1][k], rtol=2e-6, atol=2e-6)
 
 
+def test_schedule_records_follow_mixed_step_kinds():
+    """The packed schedule records chain every step to the one before it.  A rollout that mixes
+    scheduled steps, steps with injected outdoor noise, interpolator firings (every 5th step) and a
+    refresh must give the same trajectory on the fused kernels (records) as on the general path
+    (inline env epilogue): env scalars identical to the last bit, discrete state bit-exact."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle.config import synthetic_table
+
+    table = synthetic_table(7)
+    for n, layout, sig in ((96, "hand_engineered", "sinusoidals"), (1000, "tarmac", "perlin")):
+        R, T = 7, 70
+        prop = _prop(n, **{"power_grid_prop/base_power_props/mode": "interpolation",
+                           "power_grid_prop/base_power_props/interp_update_period": 20,
+                           "power_grid_prop/signal_properties/mode": sig})
+        st = synthetic_state(prop, R, seed=3)
+        acts = (np.random.default_rng(2).random((T, R, n)) < 0.5).astype(np.uint8)
+        inj = torch.as_tensor(np.random.default_rng(4).normal(size=(T, R)), device="cuda")
+        out = {}
+        for path in ("fused", "split"):
+            env = BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=9, path=path, interp_table=table)
+            env.reset(copy.deepcopy(st))
+            snaps = []
+            for t in range(T):
+                od = inj[t].contiguous() if t % 11 == 3 else None     # a step that leaves the schedule
+                env.step(torch.as_tensor(acts[t], device="cuda"), od_noise=od)
+                if t == 40:
+                    env.sim.refresh(True)
+                if t % 9 == 0 or t == T - 1:
+                    torch.cuda.synchronize()
+                    snaps.append({k: env.state[k].clone() for k in
+                                  ("signal", "od_temp", "base_power", "power", "epoch", "sso", "flags", "dt_air", "reward", "obs",
+                                   "metrics")})
+            out[path] = snaps
+        for a, b in zip(out["fused"], out["split"]):
+            for k in ("signal", "od_temp", "base_power", "epoch", "sso", "flags"):
+                assert torch.equal(a[k], b[k]), (n, k)
+            for k in ("power", "dt_air", "reward", "obs", "metrics"):
+                torch.testing.assert_close(a[k], b[k], rtol=2e-6, atol=2e-6)
+
+
 def test_replica_placement_invariance():
     """Shard [4, 8) of a 12-replica job == replicas 4..7 of the whole job (Philox keyed by the
     global replica index, synthetic state keyed by it too): the basis of the multi-GPU sharding."""
