@@ -750,6 +750,24 @@ static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc
   return 0;
 }
 
+// Launch with programmatic stream serialisation (PDL): the kernel may become resident while the
+// previous kernel of the stream drains; it calls griddepcontrol.wait before it touches anything an
+// earlier kernel wrote (see pdl_wait in drsim_kernels.cuh).
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // picks the compile-time specialisation of the production kernel (see k_fused_tma)
 static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
@@ -759,16 +777,16 @@ static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const bool common = plain && in.sched_od != nullptr && p.policy == DRSIM_POLICY_EXTERNAL &&
                       p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   if (common && !g.need_msg && g.envs_per_tile == 1)
-    k_fused_tma<1><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
+    launch_pdl(k_fused_tma<1>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
   else if (common && g.need_msg && g.envs_per_tile > 1)
-    k_fused_tma<2><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
+    launch_pdl(k_fused_tma<2>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
   else
-    k_fused_tma<0><<<h->fused_grid, kThreads, g.smem_bytes, s>>>(pl, p, in, g);
+    launch_pdl(k_fused_tma<0>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
 }
 
 static void launch_rows(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
-  k_fused_rows<<<h->fused_grid, kThreads, h->geom.smem_bytes, s>>>(pl, h->p, in, h->geom);
+  launch_pdl(k_fused_rows, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
 }
 
 // steps the wide-row kernel cannot take (injected noise, on-device policies, common penalty modes)

@@ -1661,6 +1661,23 @@ DRSIM_D void cp_async4(void *sdst, const void *gsrc) {
 #define DRSIM_STAGE_BULK 0  // 1: inputs staged by per-warp TMA bulk loads; 0: by thread-private cp.async copies
 #endif
 
+// Programmatic dependent launch (PDL): the fused step kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so step t+1's CTAs become resident while step
+// t's last CTAs drain.  pdl_trigger lets the next kernel in the stream start launching; pdl_wait
+// blocks until every kernel before this one in the stream has completed and flushed its writes --
+// nothing written by an earlier kernel (state planes, actions, schedule records) is touched before
+// it, only the launch-invariant static planes.  Both are no-ops in a normal launch.
+DRSIM_D void pdl_trigger() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+DRSIM_D void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, DRSIM_FUSED_MINCTAS)
 k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
@@ -1719,11 +1736,13 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   // none of the per-copy issue latency of 512-byte TMA bulk loads (measured: 20 % of the stall samples)
   uint32_t nx_flags = 0, nx_act = 0;
   float nx_od = 0.f, nx_solar = 0.f;
-  auto prefetch = [&](int t) {
+  // `part`: 1 = launch-invariant static planes only (may run before pdl_wait), 2 = the rest, 3 = both
+  auto prefetch = [&](int t, int part) {
     const int tr0 = t * g.envs_per_tile;
     const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
     const size_t tbase = (size_t)tr0 * Ns;
 #if DRSIM_STAGE_BULK
+    if (part == 1) return;
     const int nw = min(128, tslots - w0);
     if (nw > 0) {
       // lane 0 arms the barrier with the byte count, lanes 0..10 issue one plane each (the
@@ -1746,18 +1765,22 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 #else
       const size_t o = tbase + s0;
       float *d = s_in + s0;
-      cp_async16_hint(d, pl.t_air + o, pol_keep);
-      cp_async16_hint(d + kTileSlots, pl.t_mass + o, pol_keep);
-      cp_async16_hint(d + 2 * kTileSlots, pl.sso + o, pol_keep);
-      cp_async16_hint(d + 3 * kTileSlots, pl.target + o, pol_keep);
-      cp_async16_hint(d + 4 * kTileSlots, pl.cap + o, pol_keep);
+      if (part & 1) {
+        cp_async16_hint(d + 3 * kTileSlots, pl.target + o, pol_keep);
+        cp_async16_hint(d + 4 * kTileSlots, pl.cap + o, pol_keep);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) cp_async16_hint(d + (5 + c) * kTileSlots, pl.coef[c] + o, pol_keep);
-      cp_async4(s_flags + threadIdx.x, pl.flags + o);
-      if (ext) cp_async4(s_act + threadIdx.x, actions + o);
-      if (fast) cp_async8(s_os + threadIdx.x, &in.sched_rec[r].od_prev_f);
+        for (int c = 0; c < 6; ++c) cp_async16_hint(d + (5 + c) * kTileSlots, pl.coef[c] + o, pol_keep);
+      }
+      if (part & 2) {
+        cp_async16_hint(d, pl.t_air + o, pol_keep);
+        cp_async16_hint(d + kTileSlots, pl.t_mass + o, pol_keep);
+        cp_async16_hint(d + 2 * kTileSlots, pl.sso + o, pol_keep);
+        cp_async4(s_flags + threadIdx.x, pl.flags + o);
+        if (ext) cp_async4(s_act + threadIdx.x, actions + o);
+        if (fast) cp_async8(s_os + threadIdx.x, &in.sched_rec[r].od_prev_f);
+      }
 #endif
-      if (!fast) {
+      if (!fast && (part & 2)) {
         nx_od = (float)pl.od_temp[r];
         nx_solar = (float)pl.solar_next[r];
       }
@@ -1769,8 +1792,11 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
       env_stage_fetch(s_stage_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
   };
+  pdl_trigger();
+  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x, 1);
+  pdl_wait();
   if ((int)blockIdx.x < g.n_tiles) {
-    prefetch(blockIdx.x);
+    prefetch(blockIdx.x, 2);
     if (fast) fetch_env(blockIdx.x, 0);
   }
 
@@ -1825,7 +1851,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     __syncwarp();
     {
       const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) prefetch(nt);
+      if (nt < g.n_tiles) prefetch(nt, 3);
     }
 #else
       w.flags = s_flags[threadIdx.x];
@@ -1837,7 +1863,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     // issued now and have the whole tile to land
     {
       const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) prefetch(nt);
+      if (nt < g.n_tiles) prefetch(nt, 3);
     }
     if (active) house4_compute_f32<MODE != 0>(pl, p, w, base + s0, min(4, p.N - n0), h, red, pol_keep);
 #endif
@@ -2046,11 +2072,8 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       env_stage_store<real>(pl, p, r0 + threadIdx.x, s_stage[threadIdx.x], a);
     }
   }
-  if (lane == 0 && store_pending) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
-  }
+  // shared memory must outlive the reads of the last row store; its global writes complete with the grid
+  if (lane == 0 && store_pending) bulk_store_wait_read();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2106,6 +2129,8 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
       env_stage_fetch(s_rec_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
   };
+  pdl_trigger();
+  pdl_wait();
   if ((int)blockIdx.x < g.n_tiles) fetch_env(blockIdx.x, 0);
 
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
@@ -2231,11 +2256,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     }
     if (threadIdx.x < E) env_stage_store<real>(pl, p, r0 + threadIdx.x, s_rec[threadIdx.x], a);
   }
-  if (lane == 0 && store_pending) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
-  }
+  if (lane == 0 && store_pending) bulk_store_wait_read();
 }
 
 // ------------------------------------------------------------------------------------------
