@@ -55,6 +55,7 @@ struct drsim_handle {
       o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids,
       o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec, o_sched_rec, o_ptrpack;
   double cfg_artificial_ratio = 1.0;
+  int fused_per_sm = 1;  // resident CTAs per SM of the fused kernel in use
   static constexpr int kSched = 64;  // steps pre-generated per k_schedule launch
   bool sched_valid = false;
   int64_t sched_base = 0;
@@ -186,13 +187,13 @@ static int fill_params(const drsim_config &c, SimParams &p, std::string &why) {
   return 0;
 }
 
-static void plan_fused(drsim_handle *h) {
+static void plan_fused(drsim_handle *h, int e_cap = 1 << 30) {
   const SimParams &p = h->p;
   h->fused_ok = false;
   if (h->cfg.path == DRSIM_PATH_SPLIT) return;
   if (p.Ns > kTileSlots || p.N != p.n_global) return;
   FusedGeom g{};
-  g.envs_per_tile = std::min(p.R, kTileSlots / p.Ns);
+  g.envs_per_tile = std::max(1, std::min(std::min(p.R, kTileSlots / p.Ns), e_cap));
   g.n_tiles = (p.R + g.envs_per_tile - 1) / g.envs_per_tile;
   g.max_segs = p.Ns >= 128 ? 2 : (128 + p.Ns - 1) / p.Ns + 1;
   g.need_msg = (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0) ? 1 : 0;
@@ -284,7 +285,7 @@ static int configure_kernels(drsim_handle *h) {
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<real, false>, kThreads, h->geom.smem_bytes));
     }
     if (per_sm < 1) { h->fused_ok = false; }
-    else h->fused_grid = std::min(h->geom.n_tiles, per_sm * h->sm_count);
+    else { h->fused_grid = std::min(h->geom.n_tiles, per_sm * h->sm_count); h->fused_per_sm = per_sm; }
   }
   const size_t obs_smem = (size_t)kObsChunk * h->p.obs_dim * sizeof(real);
   if (obs_smem > 48 * 1024)
@@ -374,6 +375,35 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   plan_fused(h);
   int rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
   if (rc) { drsim_destroy(h); return rc; }
+  if (h->fused_ok && h->geom.envs_per_tile > 1) {
+    // Tile-size selection.  The grid is persistent (one wave of resident CTAs), so a step costs
+    // ceil(n_tiles / resident) rounds of one tile each: with the largest tile that fits, BASELINE
+    // config 3 (4096 x 100 houses) is 410 tiles on 296 CTAs = 2 rounds, the second 38 % full.  Pick the
+    // clusters-per-tile count that minimises rounds x (tile slots + a fixed per-tile cost).
+    const int resident = std::max(1, h->fused_per_sm * h->sm_count);
+    const int e_max = h->geom.envs_per_tile;
+    const long fixed_slots = 96;   // per-tile overhead (barriers, reductions, env records) in house-slot units
+    long best_cost = -1;
+    int best_e = e_max;
+    for (int e = e_max; e >= 1; --e) {
+      const long tiles = (p.R + e - 1) / e;
+      const long rounds = (tiles + resident - 1) / resident;
+      const long cost = rounds * ((long)e * p.Ns + fixed_slots);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_e = e; }
+    }
+    if (best_e != e_max) {
+      const FusedGeom keep = h->geom;
+      const int keep_grid = h->fused_grid;
+      plan_fused(h, best_e);
+      rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
+      if (rc) { drsim_destroy(h); return rc; }
+      if (!h->fused_ok) {  // the smaller tile did not configure: keep the first plan
+        h->geom = keep; h->fused_grid = keep_grid; h->fused_ok = true;
+        rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
+        if (rc) { drsim_destroy(h); return rc; }
+      }
+    }
+  }
   if (cfg->path == DRSIM_PATH_FUSED && !h->fused_ok) {
     drsim_destroy(h);
     return fail(DRSIM_E_ARG, "path=FUSED requested but the cluster does not fit a tile (N > 1024, sharded, or obs row too large)");
