@@ -752,9 +752,10 @@ DRSIM_D real house_reward(const SimParams &p, const KC<real> &kc, real ta, real 
 DRSIM_D int neighbour_of(const SimParams &p, const int32_t *table, int r, int n, int k) {
   if (p.comm_mode == DRSIM_COMM_RING) {
     const int N = (int)p.n_global, lo = p.nb_comm / 2;
+    // nb_comm <= N - 1, so v lies in (-N, 2N): one conditional wrap is the exact `mod N`
     int v = k < lo ? n - lo + k : n + 1 + (k - lo);
-    v %= N;
-    return v < 0 ? v + N : v;
+    v = v < 0 ? v + N : v;
+    return v >= N ? v - N : v;
   }
   const size_t base = p.comm_per_rep ? (size_t)r * p.N * p.nb_comm : 0;
   return __ldg(table + base + (size_t)n * p.nb_comm + k);
