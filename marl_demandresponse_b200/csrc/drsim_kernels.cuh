@@ -2218,9 +2218,13 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       for (int j = 0; j < 4; ++j) rw[j] = j < h.valid ? -(pen_r[j] + rs) : 0.f;
       store4(pl.reward + base + s0, rw);
     }
-    for (int gidx = 0; gidx < 128 / kRowGroup; ++gidx) {
-      const int gs = w0 + gidx * kRowGroup;  // first slot of the group
-      if (gs >= slots) break;
+    // the tile's 32-row groups are dealt round-robin to ALL warps (own / message records of every slot
+    // are in shared memory), so warps whose house slots lie beyond the tile's end assemble rows too
+    const int n_groups = (slots + kRowGroup - 1) / kRowGroup;
+    const bool ring = p.comm_mode == DRSIM_COMM_RING;
+    const int nb_lo = nbc / 2, nb_hi = nbc - nb_lo;
+    for (int gidx = warp; gidx < n_groups; gidx += kThreads / 32) {
+      const int gs = gidx * kRowGroup;  // first slot of the group
       if (lane == 0 && store_pending) bulk_store_wait_read();
       __syncwarp();
       const int s = gs + lane;
@@ -2238,10 +2242,29 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
           r2[3] = make_float2(p.hf.deadband, o.x);
           r2[4] = make_float2(o.y, o.z);
           const float4 *mb = s_msg + e * Ns;
-          for (int k = 0; k < nbc; ++k) {
-            const float4 mk = mb[neighbour_of(p, pl.comm_table, r0 + e, n, k)];
-            r2[5 + 2 * k] = make_float2(mk.x, mk.y);
-            r2[6 + 2 * k] = make_float2(mk.z, mk.w);
+          if (ring && n >= nb_lo && n + nb_hi < p.N) {
+            // ring neighbours that do not wrap are two contiguous runs of message records
+            // (agent_communication_builder.py:74-84): n - lo .. n - 1 and n + 1 .. n + hi
+            const float4 *src = mb + (n - nb_lo);
+            float2 *dst = r2 + 5;
+            for (int k = 0; k < nb_lo; ++k) {
+              const float4 mk = src[k];
+              dst[2 * k] = make_float2(mk.x, mk.y);
+              dst[2 * k + 1] = make_float2(mk.z, mk.w);
+            }
+            src = mb + (n + 1);
+            dst += 2 * nb_lo;
+            for (int k = 0; k < nb_hi; ++k) {
+              const float4 mk = src[k];
+              dst[2 * k] = make_float2(mk.x, mk.y);
+              dst[2 * k + 1] = make_float2(mk.z, mk.w);
+            }
+          } else {
+            for (int k = 0; k < nbc; ++k) {
+              const float4 mk = mb[neighbour_of(p, pl.comm_table, r0 + e, n, k)];
+              r2[5 + 2 * k] = make_float2(mk.x, mk.y);
+              r2[6 + 2 * k] = make_float2(mk.z, mk.w);
+            }
           }
         } else {
           for (int q = 0; q < D / 2; ++q) r2[q] = make_float2(0.f, 0.f);
