@@ -267,6 +267,14 @@ int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, 
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 int64_t drsim_launch_count(const drsim_t *h);
 
+/* Geometry of the fused step kernel chosen for this handle (diagnostics and tests):
+ * out[0] = variant (0 none: general path only, 1 chunked rows, 2 register-direct, 3 staged inputs +
+ * whole-tile rows, 4 staged inputs + per-warp row groups), out[1] = clusters per tile,
+ * out[2] = tiles, out[3] = grid (CTAs), out[4] = dynamic shared memory per CTA (bytes),
+ * out[5] = resident CTAs per SM.  The environment variable DRSIM_TILE_ENVS (read by drsim_create)
+ * caps the clusters per tile instead of the built-in round-count heuristic. */
+int drsim_fused_info(const drsim_t *h, int32_t out[6]);
+
 /* Host-side restatements of the env-level scalars, exported for CPU tests of the shared
  * __host__ __device__ code (utils/utils.py:42-117, environment.py:132-159). */
 double drsim_host_solar_gain(int64_t epoch, double window_area, double shading_coeff);

@@ -136,6 +136,7 @@ def lib():
         "drsim_peer_status": (C.c_int, [hp, C.c_void_p]),
         "drsim_step_host": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "drsim_launch_count": (C.c_int64, [hp]),
+        "drsim_fused_info": (C.c_int, [hp, C.POINTER(_i32 * 6)]),
         "drsim_host_solar_gain": (C.c_double, [_i64, _d, _d]),
         "drsim_host_od_temp": (C.c_double, [_i64, _d, _d, _d, _d]),
         "drsim_host_civil": (None, [_i64, C.POINTER(_i32 * 7)]),
@@ -161,7 +162,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
     "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_refresh", "drsim_step_begin",
-    "drsim_step_finish", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_launch_count", "drsim_host_solar_gain", "drsim_host_od_temp",
+    "drsim_step_finish", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_launch_count", "drsim_fused_info", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",
     "drsim_sizeof",
 ]

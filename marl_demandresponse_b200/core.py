@@ -382,6 +382,14 @@ class DrSim:
     def launch_count(self) -> int:
         return int(self._L.drsim_launch_count(self._h))
 
+    def fused_info(self) -> Dict[str, int]:
+        """Geometry of the fused step kernel chosen for this handle (``drsim_fused_info``)."""
+        out = (C.c_int32 * 6)()
+        _lib.check(self._L.drsim_fused_info(self._h, C.byref(out)))
+        names = ("none", "chunked", "direct", "staged", "staged_rows")
+        return {"variant": names[out[0]], "envs_per_tile": out[1], "tiles": out[2], "grid": out[3],
+                "smem_bytes": out[4], "ctas_per_sm": out[5]}
+
     # ---- zero-copy torch views ------------------------------------------------------------
     def views(self) -> Dict[str, Any]:
         """Torch CUDA tensors aliasing the library's buffers (no copies).  House planes are

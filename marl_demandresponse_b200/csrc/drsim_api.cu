@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -245,12 +246,14 @@ static void plan_fused(drsim_handle *h, int e_cap = 1 << 30) {
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
     w.off_msg = take((size_t)slots * 16 * 2);
-    w.off_own = take((size_t)slots * 16);
+    w.off_own = take((size_t)slots * 16 * 2);
     w.off_env = take((size_t)g.envs_per_tile * 32 * 2);
     w.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double) * 2);
     w.off_sold = take((size_t)g.envs_per_tile * sizeof(double) * 2);
     w.off_tile = take((size_t)(kThreads / 32) * kRowGroup * row);
     w.off_stage = take((size_t)g.envs_per_tile * sizeof(EnvStage) * 2);
+    w.in_stride = slots;
+    w.off_in = take((size_t)11 * slots * 4 + (size_t)kThreads * 16);
     w.smem_bytes = (int)off;
     w.use_rows = 1;
     w.use_tma = 0;
@@ -375,33 +378,40 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   plan_fused(h);
   int rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
   if (rc) { drsim_destroy(h); return rc; }
-  if (h->fused_ok && h->geom.envs_per_tile > 1) {
+  const int e_max0 = p.Ns <= kTileSlots ? std::min(p.R, kTileSlots / p.Ns) : 0;
+  if (e_max0 > 1 && cfg->path != DRSIM_PATH_SPLIT && p.N == p.n_global) {
     // Tile-size selection.  The grid is persistent (one wave of resident CTAs), so a step costs
     // ceil(n_tiles / resident) rounds of one tile each: with the largest tile that fits, BASELINE
     // config 3 (4096 x 100 houses) is 410 tiles on 296 CTAs = 2 rounds, the second 38 % full.  Pick the
-    // clusters-per-tile count that minimises rounds x (tile slots + a fixed per-tile cost).
-    const int resident = std::max(1, h->fused_per_sm * h->sm_count);
-    const int e_max = h->geom.envs_per_tile;
+    // clusters-per-tile count that minimises rounds x (tile slots + a fixed per-tile cost), planning
+    // every candidate so that its kernel variant and shared-memory footprint are the real ones.
+    const int e_max = e_max0;
     const long fixed_slots = 96;   // per-tile overhead (barriers, reductions, env records) in house-slot units
-    long best_cost = -1;
+    double best_cost = -1;
     int best_e = e_max;
     for (int e = e_max; e >= 1; --e) {
-      const long tiles = (p.R + e - 1) / e;
-      const long rounds = (tiles + resident - 1) / resident;
-      const long cost = rounds * ((long)e * p.Ns + fixed_slots);
+      plan_fused(h, e);
+      if (!h->fused_ok) continue;
+      const FusedGeom &g = h->geom;
+      const bool direct = g.chunk_rows == g.envs_per_tile * p.Ns || p.obs_dim == 0;
+      const bool lean = g.use_rows || direct;   // the chunked k_fused variant is markedly slower
+      const int per_sm = rb == 8 ? 1 : std::max(1, std::min(2, (int)(226 * 1024 / std::max(1, g.smem_bytes))));
+      const long resident = (long)per_sm * h->sm_count;
+      const long rounds = (g.n_tiles + resident - 1) / resident;
+      const double cost = (double)rounds * ((double)e * p.Ns + fixed_slots) * (lean ? 1.0 : 1.6);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_e = e; }
     }
-    if (best_e != e_max) {
-      const FusedGeom keep = h->geom;
-      const int keep_grid = h->fused_grid;
-      plan_fused(h, best_e);
+    if (const char *force = getenv("DRSIM_TILE_ENVS")) {
+      const int e = atoi(force);
+      if (e >= 1) best_e = std::min(e, e_max);
+    }
+    plan_fused(h, best_e);
+    rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
+    if (rc) { drsim_destroy(h); return rc; }
+    if (!h->fused_ok) {  // the chosen tile did not configure: back to the largest one
+      plan_fused(h);
       rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
       if (rc) { drsim_destroy(h); return rc; }
-      if (!h->fused_ok) {  // the smaller tile did not configure: keep the first plan
-        h->geom = keep; h->fused_grid = keep_grid; h->fused_ok = true;
-        rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
-        if (rc) { drsim_destroy(h); return rc; }
-      }
     }
   }
   if (cfg->path == DRSIM_PATH_FUSED && !h->fused_ok) {
@@ -1107,6 +1117,24 @@ extern "C" int drsim_peer_status(drsim_t *h, void *stream) {
 }
 
 extern "C" int64_t drsim_launch_count(const drsim_t *h) { return h ? h->launches : 0; }
+
+extern "C" int drsim_fused_info(const drsim_t *h, int32_t out[6]) {
+  if (!h || !out) return fail(DRSIM_E_ARG, "null argument");
+  int variant = 0;
+  if (h->fused_ok) {
+    if (h->geom.use_rows) variant = 4;
+    else if (h->fused_direct && h->geom.use_tma) variant = 3;
+    else if (h->fused_direct) variant = 2;
+    else variant = 1;
+  }
+  out[0] = variant;
+  out[1] = h->fused_ok ? h->geom.envs_per_tile : 0;
+  out[2] = h->fused_ok ? h->geom.n_tiles : 0;
+  out[3] = h->fused_ok ? h->fused_grid : 0;
+  out[4] = h->fused_ok ? h->geom.smem_bytes : 0;
+  out[5] = h->fused_ok ? h->fused_per_sm : 0;
+  return 0;
+}
 
 // ---- host-side debug entry points ----------------------------------------------------------
 extern "C" double drsim_host_solar_gain(int64_t epoch, double window_area, double shading_coeff) {

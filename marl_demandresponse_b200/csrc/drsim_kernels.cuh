@@ -1091,6 +1091,7 @@ struct FusedGeom {
   int need_msg;        // neighbour messages are gathered (hand-engineered layout with nb_comm > 0)
   // dynamic shared memory offsets (bytes)
   int off_msg, off_own, off_env, off_wp, off_sold, off_tile, off_in, off_bar, off_stage, smem_bytes;
+  int in_stride;       // k_fused_rows: floats per staged input plane (= tile slots)
   int use_tma;         // fp32 direct tiles: inputs staged by TMA bulk loads (k_fused_tma)
   int use_rows;        // fp32 wide rows: per-warp 32-row staging (k_fused_rows)
 };
@@ -2101,14 +2102,16 @@ DRSIM_D void raw_load_f32(const Planes<float> &pl, const StepIn &in, size_t off,
   w.od = v.x; w.solar = v.y;
 }
 
-constexpr int kRowGroup = 32;  // rows per warp-level TMA store in k_fused_rows
+constexpr int kRowGroup = 16;  // rows per warp-level TMA store in k_fused_rows (two lanes assemble one row)
 
 __global__ void __launch_bounds__(kThreads, 2)
 k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   typedef float real;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *s_msg_base = reinterpret_cast<float4 *>(smem_raw + g.off_msg);   // [2][slots] (dT, sso_n, p_n, pmax_n)
-  float4 *s_own = reinterpret_cast<float4 *>(smem_raw + g.off_own);        // [slots] (ta_n, tm_n, tg_n, flags)
+  // own records are double-buffered like the messages: any warp assembles any row group, so a warp
+  // already in the next tile's phase 1 must not overwrite records a slower warp still reads
+  float4 *s_own_base = reinterpret_cast<float4 *>(smem_raw + g.off_own);   // [2][slots] (ta_n, tm_n, tg_n, flags)
   EnvBroadcast<real> *s_env_base = reinterpret_cast<EnvBroadcast<real> *>(smem_raw + g.off_env);
   double *s_wp_base = reinterpret_cast<double *>(smem_raw + g.off_wp);
   double *s_sold_base = reinterpret_cast<double *>(smem_raw + g.off_sold);
@@ -2130,9 +2133,45 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
       env_stage_fetch(s_rec_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
   };
+  // thread-private input staging (see k_fused_tma): the 16 bytes a thread consumes of each of the
+  // eleven 32-bit planes, its flags / action words and its cluster's two fp32 scalars are copied into
+  // the thread's own slots with cp.async one tile ahead; `part` 1 = static planes (before pdl_wait)
+  float *s_in = reinterpret_cast<float *>(smem_raw + g.off_in);   // [11][in_stride] + small inputs
+  const int in_stride = g.in_stride;
+  uint32_t *s_flags = reinterpret_cast<uint32_t *>(s_in + (size_t)11 * in_stride);
+  uint32_t *s_act = s_flags + kThreads;
+  float2 *s_os = reinterpret_cast<float2 *>(s_act + kThreads);
+  const uint8_t *actions = in.actions ? in.actions : pl.actions;
+  // (plain cp.async here: with a run-time plane stride, ptxas 12.9 encodes the L2::cache_hint form of
+  // LDGSTS with a uniform-register shared offset that the B200 rejects as an illegal instruction)
+  auto prefetch = [&](int t, int part) {
+    const int tr0 = t * g.envs_per_tile;
+    const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
+    if (s0 >= tslots) return;
+    const size_t o = (size_t)tr0 * Ns + s0;
+    float *d = s_in + s0;
+    if (part & 1) {
+      cp_async16(d + 3 * in_stride, pl.target + o);
+      cp_async16(d + 4 * in_stride, pl.cap + o);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) cp_async16(d + (5 + c) * in_stride, pl.coef[c] + o);
+    }
+    if (part & 2) {
+      cp_async16(d, pl.t_air + o);
+      cp_async16(d + in_stride, pl.t_mass + o);
+      cp_async16(d + 2 * in_stride, pl.sso + o);
+      cp_async4(s_flags + threadIdx.x, pl.flags + o);
+      cp_async4(s_act + threadIdx.x, actions + o);
+      cp_async8(s_os + threadIdx.x, &in.sched_rec[tr0 + (int)fast_div((uint32_t)s0, p.fd_ns)].od_prev_f);
+    }
+  };
   pdl_trigger();
+  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x, 1);
   pdl_wait();
-  if ((int)blockIdx.x < g.n_tiles) fetch_env(blockIdx.x, 0);
+  if ((int)blockIdx.x < g.n_tiles) {
+    prefetch(blockIdx.x, 2);
+    fetch_env(blockIdx.x, 0);
+  }
 
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
     const int r0 = tile * g.envs_per_tile;
@@ -2140,6 +2179,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     const int slots = E * Ns;
     const size_t base = (size_t)r0 * Ns;
     float4 *s_msg = s_msg_base + (size_t)parity * tile_slots;
+    float4 *s_own = s_own_base + (size_t)parity * tile_slots;
     EnvBroadcast<real> *s_env = s_env_base + (size_t)parity * g.envs_per_tile;
     double *s_wp = s_wp_base + (size_t)parity * (kThreads / 32) * g.max_segs * kRed;
     double *s_sold = s_sold_base + (size_t)parity * g.envs_per_tile;
@@ -2153,9 +2193,32 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     House4<real> h;
     real red[kRed] = {0, 0, 0, 0, 0};
     real pen_r[4] = {0, 0, 0, 0};
+    cp_async_wait_all();   // the thread's own staging copies of this tile have landed
+    Raw4f w;
     if (active) {
-      Raw4f w;
-      raw_load_f32(pl, in, base + s0, r0 + e_loc, w);
+      const float4 *in4 = reinterpret_cast<const float4 *>(s_in + s0);
+      auto ld = [&](int q, float v[4]) {
+        const float4 t = in4[(size_t)q * (in_stride / 4)];
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      };
+      ld(0, w.ta); ld(1, w.tm);
+      {
+        const int4 t = reinterpret_cast<const int4 *>(s_in + s0)[(size_t)2 * (in_stride / 4)];
+        w.sso[0] = t.x; w.sso[1] = t.y; w.sso[2] = t.z; w.sso[3] = t.w;
+      }
+      ld(3, w.target); ld(4, w.cap);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) ld(5 + q, w.c[q]);
+      w.flags = s_flags[threadIdx.x];
+      w.act = s_act[threadIdx.x];
+      const float2 v = s_os[threadIdx.x];
+      w.od = v.x; w.solar = v.y;
+    }
+    {  // the thread holds its inputs in registers: the next tile's copies fly during this tile
+      const int nt = tile + gridDim.x;
+      if (nt < g.n_tiles) prefetch(nt, 3);
+    }
+    if (active) {
       house4_compute_f32<true>(pl, p, w, base + s0, min(4, p.N - n0), h, red);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -2227,47 +2290,43 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       const int gs = gidx * kRowGroup;  // first slot of the group
       if (lane == 0 && store_pending) bulk_store_wait_read();
       __syncwarp();
-      const int s = gs + lane;
+      const int row = lane >> 1, half = lane & 1;   // two lanes per row: own part + first run | second run
+      const int s = gs + row;
       if (s < slots) {
         const int e = (int)fast_div((uint32_t)s, p.fd_ns), n = s - e * Ns;
-        float2 *r2 = reinterpret_cast<float2 *>(stage + (size_t)lane * D);
+        float2 *r2 = reinterpret_cast<float2 *>(stage + (size_t)row * D);
         if (n < p.N) {
-          const float4 o = s_own[s];
-          const float4 m = s_msg[s];
-          const EnvBroadcast<real> ev = s_env[e];
-          const uint32_t f = (uint32_t)o.w;
-          r2[0] = make_float2((float)(f & 1u), (float)((f >> 1) & 1u));
-          r2[1] = make_float2(m.y, 1.f);
-          r2[2] = make_float2(ev.power_n, ev.signal_n);
-          r2[3] = make_float2(p.hf.deadband, o.x);
-          r2[4] = make_float2(o.y, o.z);
+          if (half == 0) {
+            const float4 o = s_own[s];
+            const float4 m = s_msg[s];
+            const EnvBroadcast<real> ev = s_env[e];
+            const uint32_t f = (uint32_t)o.w;
+            r2[0] = make_float2((float)(f & 1u), (float)((f >> 1) & 1u));
+            r2[1] = make_float2(m.y, 1.f);
+            r2[2] = make_float2(ev.power_n, ev.signal_n);
+            r2[3] = make_float2(p.hf.deadband, o.x);
+            r2[4] = make_float2(o.y, o.z);
+          }
           const float4 *mb = s_msg + e * Ns;
+          const int k0 = half ? nb_lo : 0, k1 = half ? nbc : nb_lo;
           if (ring && n >= nb_lo && n + nb_hi < p.N) {
             // ring neighbours that do not wrap are two contiguous runs of message records
             // (agent_communication_builder.py:74-84): n - lo .. n - 1 and n + 1 .. n + hi
-            const float4 *src = mb + (n - nb_lo);
-            float2 *dst = r2 + 5;
-            for (int k = 0; k < nb_lo; ++k) {
-              const float4 mk = src[k];
-              dst[2 * k] = make_float2(mk.x, mk.y);
-              dst[2 * k + 1] = make_float2(mk.z, mk.w);
-            }
-            src = mb + (n + 1);
-            dst += 2 * nb_lo;
-            for (int k = 0; k < nb_hi; ++k) {
-              const float4 mk = src[k];
-              dst[2 * k] = make_float2(mk.x, mk.y);
-              dst[2 * k + 1] = make_float2(mk.z, mk.w);
+            const float4 *src = mb + (half ? n + 1 - nb_lo : n - nb_lo);
+            for (int q = k0; q < k1; ++q) {
+              const float4 mk = src[q];
+              r2[5 + 2 * q] = make_float2(mk.x, mk.y);
+              r2[6 + 2 * q] = make_float2(mk.z, mk.w);
             }
           } else {
-            for (int k = 0; k < nbc; ++k) {
-              const float4 mk = mb[neighbour_of(p, pl.comm_table, r0 + e, n, k)];
-              r2[5 + 2 * k] = make_float2(mk.x, mk.y);
-              r2[6 + 2 * k] = make_float2(mk.z, mk.w);
+            for (int q = k0; q < k1; ++q) {
+              const float4 mk = mb[neighbour_of(p, pl.comm_table, r0 + e, n, q)];
+              r2[5 + 2 * q] = make_float2(mk.x, mk.y);
+              r2[6 + 2 * q] = make_float2(mk.z, mk.w);
             }
           }
         } else {
-          for (int q = 0; q < D / 2; ++q) r2[q] = make_float2(0.f, 0.f);
+          for (int q = half; q < D / 2; q += 2) r2[q] = make_float2(0.f, 0.f);
         }
       }
       fence_proxy_async_smem();

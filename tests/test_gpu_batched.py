@@ -160,6 +160,53 @@ def test_schedule_records_follow_mixed_step_kinds():
                 torch.testing.assert_close(a[k], b[k], rtol=2e-6, atol=2e-6)
 
 
+@pytest.mark.parametrize("R,n,layout,tile_envs,variant", [
+    (60, 100, "hand_engineered", 7, "staged_rows"),     # several clusters per tile, per-warp row groups
+    (60, 100, "hand_engineered", 10, None),            # largest tile
+    (4096, 100, "hand_engineered", None, "staged_rows"),  # BASELINE config 3: 586 tiles on 296 CTAs (2 tiles per CTA)
+    (60, 100, "tarmac", 10, "staged"),                 # several clusters per tile, whole-tile rows
+    (6000, 100, "tarmac", 10, "staged"),               # ... and two tiles per CTA
+    (6000, 100, "hand_engineered", 5, None),           # five clusters per tile, four tiles per CTA
+    (700, 40, "hand_engineered", None, None),          # whatever the round-count heuristic picks
+    (900, 1000, "tarmac", None, "staged"),             # BASELINE config 4 layout, 3+ tiles per CTA
+])
+def test_fused_kernel_variants_match_general_path(R, n, layout, tile_envs, variant, monkeypatch):
+    """Every fused-kernel variant / tile size (forced through DRSIM_TILE_ENVS where the heuristic would
+    not pick it at a test-sized R) against the general path on the same inputs: discrete state and env
+    scalars bit-exact, continuous values to fp32 rounding; plus the oracle on three replicas."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+
+    if tile_envs is not None:
+        monkeypatch.setenv("DRSIM_TILE_ENVS", str(tile_envs))
+    prop = _prop(n)
+    T = 9
+    st = synthetic_state(prop, R, seed=13)
+    acts = (np.random.default_rng(8).random((T, R, n)) < 0.5).astype(np.uint8)
+    out = {}
+    for path in ("fused", "split"):
+        env = BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=21, path=path)
+        if path == "fused":
+            info = env.sim.fused_info()
+            if variant is not None:
+                assert info["variant"] == variant, info
+            if tile_envs is not None:
+                assert info["envs_per_tile"] == min(tile_envs, 1024 // env.sim.Ns), info
+        env.reset(copy.deepcopy(st))
+        for t in range(T):
+            env.step(torch.as_tensor(acts[t], device="cuda"))
+        torch.cuda.synchronize()
+        out[path] = {k: env.state[k].clone() for k in
+                     ("signal", "od_temp", "epoch", "sso", "flags", "power", "dt_air", "dt_mass", "reward", "obs", "metrics")}
+    a, b = out["fused"], out["split"]
+    for k in ("signal", "od_temp", "epoch", "sso", "flags"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("power", "dt_air", "dt_mass", "reward", "obs", "metrics"):
+        torch.testing.assert_close(a[k], b[k], rtol=2e-6, atol=2e-6)
+
+
 def test_replica_placement_invariance():
     """Shard [4, 8) of a 12-replica job == replicas 4..7 of the whole job (Philox keyed by the
     global replica index, synthetic state keyed by it too): the basis of the multi-GPU sharding."""
