@@ -75,8 +75,10 @@ struct drsim_handle {
   std::vector<void *> peer_mapped;  // cudaIpcOpenMemHandle results to close
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
   StepIn pending_in{};
-  // pinned staging for drsim_step_host
+  // pinned staging for drsim_step_host; h_env_dev = the same memory as the device sees it (mapped)
   double *h_env = nullptr;
+  double *h_env_dev = nullptr;
+  bool mirror_next = false;   // the next fused step writes its per-cluster results straight into h_env
 
   template <typename T>
   T *at(size_t off) const {
@@ -374,7 +376,11 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     return fail(DRSIM_E_CUDA, std::string("cudaMalloc of ") + std::to_string(cv.off) + " bytes: " + cudaGetErrorString(e));
   }
   cudaMemset(h->slab, 0, h->slab_bytes);
-  cudaMallocHost(&h->h_env, E8 * 6);
+  cudaHostAlloc(&h->h_env, E8 * 6, cudaHostAllocMapped);
+  if (h->h_env && cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_env_dev), h->h_env, 0) != cudaSuccess) {
+    h->h_env_dev = nullptr;
+    cudaGetLastError();
+  }
   plan_fused(h);
   int rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
   if (rc) { drsim_destroy(h); return rc; }
@@ -882,6 +888,7 @@ static void launch_schedule(drsim_handle *h, cudaStream_t s) {
 static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp, cudaStream_t s) {
   StepIn in{};
   if (a) { in.actions = a->actions; in.od_noise = a->od_noise; in.perlin = a->perlin; in.interp_ids = a->interp_ids; }
+  in.host_env = h->mirror_next ? h->h_env_dev : nullptr;
   in.step = h->step;
   in.advance = advance;
   in.do_interp = do_interp;
@@ -970,6 +977,21 @@ extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const 
   return rc;
 }
 
+// true when this step will run on one of the staged fused kernels with the scheduled (fast) env path:
+// those prefetch their inputs one tile ahead (so actions can be read in place from mapped host memory)
+// and mirror the per-cluster results into the mapped result buffer
+static bool staged_fast_step(const drsim_handle *h, int do_interp, bool injected) {
+  if (!h->fused_ok || h->real_bytes != 4 || do_interp > 0 || injected) return false;
+  const SimParams &p = h->p;
+  if (h->geom.use_rows) return p.policy == DRSIM_POLICY_EXTERNAL && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+  return h->fused_direct && h->geom.use_tma;
+}
+
+// Host-buffer step.  On the staged fused path nothing is copied by the copy engines: the kernel reads
+// the action bytes in place from the caller's pinned (device-mapped) buffer -- the PCIe transfer then
+// overlaps the kernel's own HBM traffic instead of preceding it -- and writes the per-cluster results
+// straight into the handle's mapped result buffer.  Pageable buffers, padded rows (N % 4 != 0) and
+// every other step kind use explicit copies.
 extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                                const int32_t *interp_ids, double *env_out, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
@@ -977,12 +999,26 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
   auto s = (cudaStream_t)stream;
   const SimParams &p = h->p;
   drsim_step_args a{};
+  const int di = interp_decision(h);
+  const bool staged = staged_fast_step(h, di, od_noise || perlin);
   if (actions) {
-    if (p.Ns == p.N)  // contiguous rows: one linear DMA instead of R row descriptors
-      CU_TRY(cudaMemcpyAsync(h->slab + h->o_actions, actions, (size_t)p.R * p.N, cudaMemcpyHostToDevice, s));
-    else
-      CU_TRY(cudaMemcpy2DAsync(h->slab + h->o_actions, p.Ns, actions, p.N, p.N, p.R, cudaMemcpyHostToDevice, s));
-    a.actions = h->at<uint8_t>(h->o_actions);
+    const uint8_t *mapped = nullptr;
+    if (staged && p.Ns == p.N && (p.policy == DRSIM_POLICY_EXTERNAL)) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, actions) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+        mapped = static_cast<const uint8_t *>(at.devicePointer);
+      else
+        cudaGetLastError();
+    }
+    if (mapped) {
+      a.actions = mapped;
+    } else {
+      if (p.Ns == p.N)  // contiguous rows: one linear DMA instead of R row descriptors
+        CU_TRY(cudaMemcpyAsync(h->slab + h->o_actions, actions, (size_t)p.R * p.N, cudaMemcpyHostToDevice, s));
+      else
+        CU_TRY(cudaMemcpy2DAsync(h->slab + h->o_actions, p.Ns, actions, p.N, p.N, p.R, cudaMemcpyHostToDevice, s));
+      a.actions = h->at<uint8_t>(h->o_actions);
+    }
   }
   if (od_noise) {
     CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_od, od_noise, (size_t)p.R * 8, cudaMemcpyHostToDevice, s));
@@ -996,22 +1032,30 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
     CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_ids, interp_ids, (size_t)p.R * p.interp_k * 4, cudaMemcpyHostToDevice, s));
     a.interp_ids = h->at<int32_t>(h->o_in_ids);
   }
-  int rc = drsim_step(h, &a, stream);
+  const bool mirror = staged && env_out && h->h_env_dev;
+  h->mirror_next = mirror;
+  int rc = run_step(h, &a, 1, di, s);
+  h->mirror_next = false;
   if (rc) return rc;
+  h->step++;
   if (env_out) {
     const size_t E8 = (size_t)p.R * 8;
-    CU_TRY(cudaMemcpyAsync(h->h_env, h->slab + h->o_power, E8 * 6, cudaMemcpyDeviceToHost, s));
+    if (!mirror) CU_TRY(cudaMemcpyAsync(h->h_env, h->slab + h->o_power, E8 * 6, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
-    const double *pw = h->h_env, *sg = pw + p.R, *od = sg + p.R, *ps = od + p.R, *pm = ps + p.R, *rs = pm + p.R;
+    // mirror: [R][6] records (power, signal, od, pen_sum, pen_max, rew_sig); copy: six [R] planes
+    const size_t sr = mirror ? 6 : 1, sk = mirror ? 1 : (size_t)p.R;
+    const double *v = h->h_env;
     for (int r = 0; r < p.R; ++r) {
-      double pen = ps[r];  // mean individual penalty == common_L2 value
-      if (p.penalty_mode == DRSIM_PEN_COMMON_MAX) pen = pm[r];
+      const double *q = v + (size_t)r * sr;
+      const double ps = q[3 * sk], pm = q[4 * sk];
+      double pen = ps;  // mean individual penalty == common_L2 value
+      if (p.penalty_mode == DRSIM_PEN_COMMON_MAX) pen = pm;
       else if (p.penalty_mode == DRSIM_PEN_MIXTURE)
-        pen = (p.a_ind * ps[r] + p.a_cl2 * ps[r] + p.a_cmax * pm[r]) / (p.a_ind + p.a_cl2 + p.a_cmax);
-      env_out[r * 4 + 0] = pw[r];
-      env_out[r * 4 + 1] = sg[r];
-      env_out[r * 4 + 2] = od[r];
-      env_out[r * 4 + 3] = -(p.alpha_temp * pen / p.norm_temp + rs[r]);
+        pen = (p.a_ind * ps + p.a_cl2 * ps + p.a_cmax * pm) / (p.a_ind + p.a_cl2 + p.a_cmax);
+      env_out[r * 4 + 0] = q[0];
+      env_out[r * 4 + 1] = q[1 * sk];
+      env_out[r * 4 + 2] = q[2 * sk];
+      env_out[r * 4 + 3] = -(p.alpha_temp * pen / p.norm_temp + q[5 * sk]);
     }
   } else {
     CU_TRY(cudaStreamSynchronize(s));

@@ -74,6 +74,7 @@ static_assert(sizeof(SchedRec) == 80, "SchedRec is copied in five 16-byte pieces
 
 struct StepIn {
   const SchedRec *sched_rec;  // this step's records [R], or NULL (inline evaluation)
+  double *host_env;           // drsim_step_host: mapped pinned mirror [R][6] of the per-cluster results, or NULL
   const uint8_t *actions;
   const double *od_noise;
   const double *perlin;
@@ -1594,7 +1595,8 @@ DRSIM_D void env_stage_fetch(EnvStage *dst, const SchedRec *rec, const double *m
 
 // env_fast_store from a staged record: env planes + running metrics of cluster r after the step
 template <typename real>
-DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, const EnvStage &st, const double red[kRed]) {
+DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, const EnvStage &st, const double red[kRed],
+                             double *host_env = nullptr) {
   const SchedRec &c = st.rec;
   const double P = red[0];
   const double rew_sig = signal_penalty(p, P, c.signal_prev);
@@ -1617,6 +1619,10 @@ DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, 
   m[3] = st.m[3] + red[4] * p.inv_n_global;
   m[4] = st.m[4] + fabs(d);
   m[5] = st.m[5] + d * d;
+  if (host_env) {  // zero-copy result mirror of drsim_step_host (posted writes over PCIe, no D2H copy)
+    double *o = host_env + (size_t)r * 6;
+    o[0] = P; o[1] = c.signal; o[2] = c.od; o[3] = red[1]; o[4] = red[2]; o[5] = rew_sig;
+  }
 }
 
 constexpr int kInPlanes = 12;  // fp32 planes staged by TMA: Ta, Tm, sso, target, cap, 6 coefficients (+1 spare)
@@ -2071,7 +2077,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (threadIdx.x < E && fast) {
       double a[kRed] = {0, 0, 0, 0, 0};
       combine(threadIdx.x, a, true);
-      env_stage_store<real>(pl, p, r0 + threadIdx.x, s_stage[threadIdx.x], a);
+      env_stage_store<real>(pl, p, r0 + threadIdx.x, s_stage[threadIdx.x], a, in.host_env);
     }
   }
   // shared memory must outlive the reads of the last row store; its global writes complete with the grid
@@ -2337,7 +2343,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         store_pending = true;
       }
     }
-    if (threadIdx.x < E) env_stage_store<real>(pl, p, r0 + threadIdx.x, s_rec[threadIdx.x], a);
+    if (threadIdx.x < E) env_stage_store<real>(pl, p, r0 + threadIdx.x, s_rec[threadIdx.x], a, in.host_env);
   }
   if (lane == 0 && store_pending) bulk_store_wait_read();
 }

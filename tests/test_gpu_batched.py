@@ -207,6 +207,49 @@ def test_fused_kernel_variants_match_general_path(R, n, layout, tile_envs, varia
         torch.testing.assert_close(a[k], b[k], rtol=2e-6, atol=2e-6)
 
 
+@pytest.mark.parametrize("n,R,layout,base_mode", [(1000, 300, "tarmac", "constant"), (100, 2500, "hand_engineered", "constant"),
+                                                 (100, 64, "tarmac", "interpolation"), (37, 9, "hand_engineered", "constant")])
+def test_step_host_zero_copy_equals_device_step(n, R, layout, base_mode):
+    """drsim_step_host with PINNED host buffers (actions read in place over PCIe by the staged fused
+    kernel, results mirrored into mapped memory -- no copy-engine transfers), with pageable buffers
+    (explicit copies) and the device-resident step: identical state, identical per-replica results,
+    including the steps on which the interpolator fires (general path) and padded rows (N % 4 != 0)."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle.config import synthetic_table
+
+    over = {"power_grid_prop/base_power_props/mode": base_mode}
+    if base_mode == "interpolation":
+        over["power_grid_prop/base_power_props/interp_update_period"] = 20
+    prop = _prop(n, **over)
+    T = 14
+    st = synthetic_state(prop, R, seed=5)
+    acts = (np.random.default_rng(6).random((T, R, n)) < 0.5).astype(np.uint8)
+    table = synthetic_table(7) if base_mode == "interpolation" else None
+    envs = [BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=3, interp_table=table) for _ in range(3)]
+    for e in envs:
+        e.reset(copy.deepcopy(st))
+    out_pin = torch.zeros((R, 4), dtype=torch.float64).pin_memory()
+    for t in range(T):
+        envs[0].step(torch.as_tensor(acts[t], device="cuda"))
+        a_pin = torch.as_tensor(acts[t]).pin_memory()
+        envs[1].step_host(a_pin, out_pin)
+        out_page = envs[2].step_host(acts[t])
+        torch.cuda.synchronize()
+        ref = envs[0].state
+        mean_rew = ref["reward"].double().mean(dim=1).cpu().numpy()
+        for out in (out_pin.numpy(), out_page):
+            assert np.array_equal(out[:, 0], ref["power"].cpu().numpy()), t
+            assert np.array_equal(out[:, 1], ref["signal"].cpu().numpy()), t
+            assert np.array_equal(out[:, 2], ref["od_temp"].cpu().numpy()), t
+            np.testing.assert_allclose(out[:, 3], mean_rew, rtol=1e-5, atol=1e-6)
+    for e in envs[1:]:
+        for k in ("sso", "flags", "dt_air", "dt_mass", "reward", "obs", "signal", "power", "metrics"):
+            assert torch.equal(envs[0].state[k], e.state[k]), k
+
+
 def test_replica_placement_invariance():
     """Shard [4, 8) of a 12-replica job == replicas 4..7 of the whole job (Philox keyed by the
     global replica index, synthetic state keyed by it too): the basis of the multi-GPU sharding."""
