@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DRSIM_ABI_VERSION 1
+#define DRSIM_ABI_VERSION 2
 #define DRSIM_MAX_SIGNAL_TERMS 8
 #define DRSIM_INTERP_SUBTABLES 162      /* 3*3*3*3*2 nearest-neighbour cells            */
 #define DRSIM_INTERP_SUBTABLE_LEN 25920 /* 9*5*8*12*6 values of the 5-D multilinear part */
@@ -172,7 +172,14 @@ typedef struct drsim_ptrs {
   double *metrics;             /* f64   [R][DRSIM_N_METRICS] running rollout accumulators */
   double *acc;                 /* f64   [R][DRSIM_N_ACC] per-rank partial sums of drsim_step_begin */
   double *rew_sig;             /* f64   [R] alpha_sig * signal penalty / norm of the last step */
+  /* House-sharded ring cluster with neighbour messages: [R][nb_comm][DRSIM_HALO_FIELDS] message records
+   * of this shard's edge houses after drsim_step_begin -- entries [0, H) = its FIRST H houses, entries
+   * [H, H + L) = its LAST L houses, L = nb_comm / 2, H = nb_comm - L
+   * (agent_communication_builder.py:74-84); NULL when no halo is exchanged. */
+  double *halo_out;
 } drsim_ptrs;
+
+#define DRSIM_HALO_FIELDS 8 /* (Ta-target)/5, sso/dur, P/nrs, Pmax/nrs (norm.py:31-48), 4 thermal ratios (:50-57) */
 
 #define DRSIM_N_ACC 6 /* P, sum pen/N, max pen, sum dT, sum dT^2, interpolated base-power sum */
 
@@ -248,14 +255,20 @@ int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal,
 int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream);
 int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_gathered, int n_parts,
                       void *stream);
+/* Same, for a sharded cluster whose observation rows carry ring-neighbour messages (cluster.py:91-111):
+ * halo_gathered = the drsim_ptrs.halo_out blocks of all ranks, all-gathered in rank order
+ * ([n_parts][R][nb_comm][DRSIM_HALO_FIELDS]); `rank` = this handle's position in that order.  The
+ * neighbours that fall outside the shard are read from the adjacent ranks' blocks. */
+int drsim_step_finish_gathered(drsim_t *h, const double *acc_gathered, const double *halo_gathered, int n_parts,
+                               int rank, void *stream);
 
 /* Peer-memory variant of the same exchange (no NCCL on the step path): every rank exports an IPC
- * handle of its slab + the offsets of its "inbox" (80 bytes), the handles of all ranks are attached,
+ * handle of its slab + the offsets of its "inbox" (96 bytes), the handles of all ranks are attached,
  * and from then on drsim_step_begin pushes this rank's partial sums straight into every rank's inbox
  * over NVLink from the tail of the reduction kernel, and drsim_step_finish(h, args, NULL, -1, stream)
  * waits (bounded, ~2 s) for all rows inside the epilogue kernel.  drsim_peer_status reports a timeout. */
-int drsim_ipc_export(drsim_t *h, void *out80);
-int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles80, void *stream);
+int drsim_ipc_export(drsim_t *h, void *out96);
+int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles96, void *stream);
 int drsim_peer_status(drsim_t *h, void *stream);
 
 /* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out

@@ -9,12 +9,13 @@ import os
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SIGNAL_TERMS = 8
 INTERP_SUBTABLES = 162
 INTERP_SUBTABLE_LEN = 25920
 N_METRICS = 6
 N_ACC = 6
+HALO_FIELDS = 8
 
 F32, F64 = 0, 1
 PEN = {"individual_L2": 0, "common_L2": 1, "common_max_error": 2, "mixture": 3}
@@ -82,6 +83,7 @@ class Ptrs(C.Structure):
         ("od_temp", C.c_void_p), ("signal", C.c_void_p), ("base_power", C.c_void_p), ("power", C.c_void_p),
         ("solar", C.c_void_p), ("pen_sum", C.c_void_p), ("pen_max", C.c_void_p),
         ("comm_table", C.c_void_p), ("metrics", C.c_void_p), ("acc", C.c_void_p), ("rew_sig", C.c_void_p),
+        ("halo_out", C.c_void_p),
     ]
 
 
@@ -131,6 +133,7 @@ def lib():
         "drsim_refresh": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_void_p]),
         "drsim_step_begin": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
         "drsim_step_finish": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p, C.c_int, C.c_void_p]),
+        "drsim_step_finish_gathered": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
         "drsim_ipc_export": (C.c_int, [hp, C.c_void_p]),
         "drsim_ipc_attach": (C.c_int, [hp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
         "drsim_peer_status": (C.c_int, [hp, C.c_void_p]),
@@ -162,7 +165,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
     "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_refresh", "drsim_step_begin",
-    "drsim_step_finish", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_launch_count", "drsim_fused_info", "drsim_host_solar_gain", "drsim_host_od_temp",
+    "drsim_step_finish", "drsim_step_finish_gathered", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_launch_count", "drsim_fused_info", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",
     "drsim_sizeof",
 ]

@@ -345,14 +345,20 @@ class DrSim:
         a = self._args()
         _lib.check(self._L.drsim_step_finish(self._h, C.byref(a), self._ptr(acc), int(n_parts), self._stream(stream)))
 
+    def step_finish_gathered(self, acc, halo, n_parts: int, rank: int, stream=None) -> None:
+        """Gathered partials ``[n_parts, R, N_ACC]`` + gathered halo records
+        ``[n_parts, R, nb_comm, HALO_FIELDS]`` (or None when no halo is exchanged), rank order."""
+        _lib.check(self._L.drsim_step_finish_gathered(self._h, self._ptr(acc), self._ptr(halo), int(n_parts), int(rank),
+                                                      self._stream(stream)))
+
     def ipc_export(self) -> bytes:
-        buf = C.create_string_buffer(80)
+        buf = C.create_string_buffer(96)
         _lib.check(self._L.drsim_ipc_export(self._h, buf))
         return buf.raw
 
     def ipc_attach(self, rank: int, world: int, handles: list, stream=None) -> None:
         blob = b"".join(handles)
-        assert len(blob) == 80 * world
+        assert len(blob) == 96 * world
         _lib.check(self._L.drsim_ipc_attach(self._h, int(rank), int(world), blob, self._stream(stream)))
 
     def peer_status(self, stream=None) -> None:
@@ -429,6 +435,8 @@ class DrSim:
             v[k] = t(getattr(p, k), (R,), "<f8")
         v["metrics"] = t(p.metrics, (R, _lib.N_METRICS), "<f8")
         v["acc"] = t(p.acc, (R, _lib.N_ACC), "<f8")
+        if p.halo_out:
+            v["halo_out"] = t(p.halo_out, (R, int(p.nb_comm), _lib.HALO_FIELDS), "<f8")
         if p.comm_table:
             v["comm_table"] = t(p.comm_table, (N, p.nb_comm), "<i4")
         self._views = v

@@ -54,7 +54,7 @@ struct drsim_handle {
   size_t o_t_air, o_t_mass, o_sso, o_flags, o_target, o_cap, o_coef[9], o_ratio[4], o_sub, o_reward, o_obs,
       o_actions, o_epoch, o_od, o_solar_next, o_solar_cur, o_signal, o_base, o_power, o_art, o_maxp, o_pen_sum,
       o_pen_max, o_rew_sig, o_tsi, o_metrics, o_partials, o_acc, o_comm, o_interp, o_in_od, o_in_perlin, o_in_ids,
-      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec, o_sched_rec, o_ptrpack;
+      o_sched_od, o_sched_solar, o_sched_aux, o_sched_tsec, o_sched_rec, o_ptrpack, o_halo_out, o_halo_in;
   double cfg_artificial_ratio = 1.0;
   int fused_per_sm = 1;  // resident CTAs per SM of the fused kernel in use
   static constexpr int kSched = 64;  // steps pre-generated per k_schedule launch
@@ -120,6 +120,7 @@ static Planes<real> make_planes(const drsim_handle *h) {
   pl.acc = h->at<double>(h->o_acc);
   pl.comm_table = h->has_comm ? h->at<int32_t>(h->o_comm) : nullptr;
   pl.interp_table = h->has_interp ? h->at<real>(h->o_interp) : nullptr;
+  pl.halo_out = needs_halo(h->p) ? h->at<double>(h->o_halo_out) : nullptr;
   return pl;
 }
 
@@ -173,8 +174,10 @@ static int fill_params(const drsim_config &c, SimParams &p, std::string &why) {
   else if (p.obs_layout == DRSIM_OBS_TARMAC) p.obs_dim = p.own_dim;
   else if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) p.obs_dim = p.own_dim + p.nb_comm * p.msg_dim;
   else { why = "obs_layout"; return -1; }
-  if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0 && p.N != p.n_global) {
-    why = "hand-engineered neighbour messages are not supported on a house-sharded cluster yet";
+  if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0 && p.N != p.n_global &&
+      (p.comm_mode != DRSIM_COMM_RING || p.N < p.nb_comm)) {
+    why = "house-sharded cluster with neighbour messages: only the ring (`neighbours`) mode is exchanged as a halo, and every "
+          "shard must hold at least nb_comm houses";
     return -1;
   }
   if (p.base_mode == DRSIM_BASE_INTERPOLATION && (p.interp_k < 1 || p.interp_period < 1)) { why = "interp props"; return -1; }
@@ -363,7 +366,10 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     const int wmax = 16;  // ranks of one box
     h->o_inbox = cv.take((size_t)2 * wmax * p.R * DRSIM_N_ACC * 8);
     h->o_pflags = cv.take((size_t)2 * wmax * p.R * 8);
-    h->o_peer_tab = cv.take((size_t)2 * wmax * 8);
+    h->o_peer_tab = cv.take((size_t)3 * wmax * 8);
+    const size_t halo = needs_halo(p) ? (size_t)p.R * p.nb_comm * kHaloFields * 8 : 0;
+    h->o_halo_out = cv.take(halo);
+    h->o_halo_in = cv.take(2 * halo);
     h->o_peer_err = cv.take(8);
   }
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
@@ -463,6 +469,7 @@ extern "C" int drsim_buffers(drsim_t *h, drsim_ptrs *o) {
   o->sso = h->at<int32_t>(h->o_sso); o->flags = h->at<uint8_t>(h->o_flags);
   o->target = h->slab + h->o_target; o->cap = h->slab + h->o_cap;
   o->reward = h->slab + h->o_reward; o->obs = h->p.obs_dim ? h->slab + h->o_obs : nullptr;
+  o->halo_out = needs_halo(h->p) ? h->at<double>(h->o_halo_out) : nullptr;
   o->actions = h->at<uint8_t>(h->o_actions);
   o->epoch = h->at<int64_t>(h->o_epoch);
   o->od_temp = h->at<double>(h->o_od); o->signal = h->at<double>(h->o_signal);
@@ -762,6 +769,7 @@ static PeerCtx make_peer(const drsim_handle *h) {
   pc.rank = h->peer_rank;
   pc.inbox = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab);
   pc.flags = reinterpret_cast<unsigned long long *const *>(h->slab + h->o_peer_tab + 16 * 8);
+  pc.halo = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab + 32 * 8);
   pc.err = reinterpret_cast<int *>(h->slab + h->o_peer_err);
   return pc;
 }
@@ -964,17 +972,48 @@ extern "C" int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *s
                             : launch_house_phase<float>(h, in, (cudaStream_t)stream);
 }
 
-extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc, int n_parts, void *stream) {
-  if (!h) return fail(DRSIM_E_ARG, "null handle");
+static int step_finish_impl(drsim_handle *h, const double *acc, const double *halo, int n_parts, int rank,
+                            cudaStream_t stream) {
   CU_TRY(cudaSetDevice(h->device));
-  (void)args;
-  const StepIn in = h->pending_in;
+  StepIn in = h->pending_in;
   if (acc && n_parts < 1) return fail(DRSIM_E_ARG, "n_parts must be >= 1");
   if (!acc && n_parts < 0 && h->peer_world < 2) return fail(DRSIM_E_STATE, "peer exchange requested but drsim_ipc_attach was not called");
-  int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, n_parts, (cudaStream_t)stream)
-                              : launch_env_phase<float>(h, in, acc, n_parts, (cudaStream_t)stream);
+  if (needs_halo(h->p)) {
+    const SimParams &p = h->p;
+    const int c = p.nb_comm, L = c / 2, H = c - L;
+    const size_t per_rank = (size_t)p.R * c * kHaloFields;
+    if (halo) {
+      // gathered halo_out blocks of all ranks, rank order: the previous rank's LAST L houses are this
+      // shard's left halo, the next rank's FIRST H houses its right halo
+      if (n_parts < 2 || rank < 0 || rank >= n_parts) return fail(DRSIM_E_ARG, "halo_gathered needs n_parts >= 2 and a valid rank");
+      in.halo_left = halo + (size_t)((rank + n_parts - 1) % n_parts) * per_rank + (size_t)H * kHaloFields;
+      in.halo_right = halo + (size_t)((rank + 1) % n_parts) * per_rank;
+    } else if (!acc && n_parts < 0) {
+      const double *inbox = h->at<double>(h->o_halo_in) + (size_t)(in.step & 1) * per_rank;   // pushed by the peers
+      in.halo_left = inbox;
+      in.halo_right = inbox + (size_t)L * kHaloFields;
+    } else {
+      return fail(DRSIM_E_ARG, "this house-sharded cluster exchanges neighbour messages: pass the gathered halo records "
+                               "(drsim_step_finish_gathered) or use the peer exchange");
+    }
+  }
+  int rc = h->real_bytes == 8 ? launch_env_phase<double>(h, in, acc, n_parts, stream)
+                              : launch_env_phase<float>(h, in, acc, n_parts, stream);
   if (!rc) h->step++;
   return rc;
+}
+
+extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc, int n_parts, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  (void)args;
+  return step_finish_impl(h, acc, nullptr, n_parts, -1, (cudaStream_t)stream);
+}
+
+extern "C" int drsim_step_finish_gathered(drsim_t *h, const double *acc_gathered, const double *halo_gathered, int n_parts,
+                                          int rank, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  if (!acc_gathered) return fail(DRSIM_E_ARG, "acc_gathered is required");
+  return step_finish_impl(h, acc_gathered, halo_gathered, n_parts, rank, (cudaStream_t)stream);
 }
 
 // true when this step will run on one of the staged fused kernels with the scheduled (fast) env path:
@@ -1107,29 +1146,29 @@ extern "C" int drsim_reset(drsim_t *h, const drsim_reset_args *ra, void *stream)
   return h->real_bytes == 8 ? reset_t<double>(h, a, (cudaStream_t)stream) : reset_t<float>(h, a, (cudaStream_t)stream);
 }
 
-extern "C" int drsim_ipc_export(drsim_t *h, void *out80) {
-  if (!h || !out80) return fail(DRSIM_E_ARG, "null argument");
+extern "C" int drsim_ipc_export(drsim_t *h, void *out96) {
+  if (!h || !out96) return fail(DRSIM_E_ARG, "null argument");
   CU_TRY(cudaSetDevice(h->device));
   cudaIpcMemHandle_t mh;
   CU_TRY(cudaIpcGetMemHandle(&mh, h->slab));
-  unsigned char *o = static_cast<unsigned char *>(out80);
+  unsigned char *o = static_cast<unsigned char *>(out96);
   memcpy(o, &mh, 64);
-  const uint64_t off[2] = {(uint64_t)h->o_inbox, (uint64_t)h->o_pflags};
-  memcpy(o + 64, off, 16);
+  const uint64_t off[4] = {(uint64_t)h->o_inbox, (uint64_t)h->o_pflags, (uint64_t)h->o_halo_in, 0};
+  memcpy(o + 64, off, 32);
   return 0;
 }
 
-extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles80, void *stream) {
-  if (!h || !handles80) return fail(DRSIM_E_ARG, "null argument");
+extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles96, void *stream) {
+  if (!h || !handles96) return fail(DRSIM_E_ARG, "null argument");
   if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(DRSIM_E_ARG, "rank / world");
   CU_TRY(cudaSetDevice(h->device));
-  const unsigned char *in = static_cast<const unsigned char *>(handles80);
-  std::vector<uint64_t> tab(32, 0);
+  const unsigned char *in = static_cast<const unsigned char *>(handles96);
+  std::vector<uint64_t> tab(48, 0);
   for (int q = 0; q < world; ++q) {
     cudaIpcMemHandle_t mh;
-    uint64_t off[2];
-    memcpy(&mh, in + (size_t)q * 80, 64);
-    memcpy(off, in + (size_t)q * 80 + 64, 16);
+    uint64_t off[4];
+    memcpy(&mh, in + (size_t)q * 96, 64);
+    memcpy(off, in + (size_t)q * 96 + 64, 32);
     unsigned char *base = nullptr;
     if (q == rank) base = h->slab;
     else {
@@ -1140,9 +1179,10 @@ extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *han
     }
     tab[q] = (uint64_t)(uintptr_t)(base + off[0]);
     tab[16 + q] = (uint64_t)(uintptr_t)(base + off[1]);
+    tab[32 + q] = (uint64_t)(uintptr_t)(base + off[2]);
   }
   auto s = (cudaStream_t)stream;
-  CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 32 * 8, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 48 * 8, cudaMemcpyHostToDevice, s));
   CU_TRY(cudaMemsetAsync(h->slab + h->o_pflags, 0, (size_t)2 * 16 * h->p.R * 8, s));
   CU_TRY(cudaMemsetAsync(h->slab + h->o_peer_err, 0, 8, s));
   CU_TRY(cudaStreamSynchronize(s));

@@ -28,6 +28,7 @@ constexpr int kHousesPerThread = 4; // one 128-bit access per fp32 plane
 constexpr int kTileSlots = kThreads * kHousesPerThread;
 constexpr int kRed = 5;             // reduced per cluster: P, sum pen/N, max pen, sum dT, sum dT^2
 constexpr int kObsChunk = 128;      // houses per k_obs CTA (general path)
+constexpr int kHaloFields = 8;      // halo record of one edge house: dT/5, sso/dur, P/nrs, Pmax/nrs, 4 thermal ratios
 
 template <typename real>
 struct Planes {
@@ -54,6 +55,7 @@ struct Planes {
   double *acc;       // [R][kRed + 1]      (general path: reduced values + interpolated sum)
   const int32_t *comm_table;
   const real *interp_table;  // [162][9][5][8][12][6]
+  double *halo_out;          // [R][nb_comm][kHaloFields]: message records of this shard's edge houses, or NULL
 };
 
 // One packed record per (scheduled step, replica): every env-level value of that step that does NOT
@@ -75,6 +77,9 @@ static_assert(sizeof(SchedRec) == 80, "SchedRec is copied in five 16-byte pieces
 struct StepIn {
   const SchedRec *sched_rec;  // this step's records [R], or NULL (inline evaluation)
   double *host_env;           // drsim_step_host: mapped pinned mirror [R][6] of the per-cluster results, or NULL
+  // house-sharded ring cluster: message records of the L houses before / the H houses after this
+  // shard, element (r, j) at base + (r * nb_comm + j) * kHaloFields (see k_reduce / k_obs)
+  const double *halo_left, *halo_right;
   const uint8_t *actions;
   const double *od_noise;
   const double *perlin;
@@ -97,8 +102,15 @@ struct PeerCtx {
   int world, rank;
   double *const *inbox;               // [world] base of each rank's inbox (peer-mapped)
   unsigned long long *const *flags;   // [world] base of each rank's flags [2][world][R]
+  double *const *halo;                // [world] base of each rank's halo inbox [2][R][nb_comm][kHaloFields]
   int *err;                           // local: set when a wait timed out
 };
+
+// a house-sharded cluster whose observation rows carry ring-neighbour messages exchanges the message
+// records of the shard's edge houses every step ("halo")
+DRSIM_HD bool needs_halo(const SimParams &p) {
+  return p.N != (int)p.n_global && p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0;
+}
 
 // Launch-invariant constants in registers.  The fp32 build multiplies by reciprocals (<= 1 ulp
 // from the true quotient, far inside the 1e-5 budget); the fp64 build divides like the reference.
@@ -935,6 +947,33 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
     for (int k = 0; k < kRed; ++k) wp[w][k] = red[k];
     wp[w][kRed] = isum;
   }
+  if (needs_halo(p) && in.advance && (int)threadIdx.x < p.nb_comm) {
+    // halo records of the shard's edge houses (post-update state): entries [0, H) = my FIRST H houses
+    // (the "after" neighbours of the previous shard's last houses), entries [H, H + L) = my LAST L
+    // houses (the "before" neighbours of the next shard's first houses); L = c / 2, H = c - L
+    const int c = p.nb_comm, L = c / 2, H = c - L, t = threadIdx.x;
+    const int n = t < H ? t : p.N - L + (t - H);
+    const size_t o = (size_t)r * p.Ns + n;
+    const KC<real> kc(p);
+    const real pmax = qdiv(pl.cap[o], kc.cop, kc.inv_cop);
+    double rec[kHaloFields];
+    rec[0] = (double)div5(Rep<real>::dev(pl.t_air[o], pl.target[o]));          // norm.py:39
+    rec[1] = (double)(real)fast_div((uint32_t)pl.sso[o], p.fd_dur);            // norm.py:40-43
+    rec[2] = (double)qdiv((pl.flags[o] & 1u) ? pmax : (real)0, kc.nrs, kc.inv_nrs);
+    rec[3] = (double)qdiv(pmax, kc.nrs, kc.inv_nrs);
+    for (int m = 0; m < 4; ++m) rec[4 + m] = p.msg_thermal ? (double)pl.ratio[m][o] : 0.0;
+    double *mine = pl.halo_out + ((size_t)r * c + t) * kHaloFields;
+    for (int m = 0; m < kHaloFields; ++m) mine[m] = rec[m];
+    if (peer.world > 1) {
+      // my first houses are the RIGHT halo of the previous rank, my last houses the LEFT halo of the next
+      const int parity = (int)(in.step & 1);
+      const int dst_rank = t < H ? (peer.rank + peer.world - 1) % peer.world : (peer.rank + 1) % peer.world;
+      const int slot = t < H ? L + t : t - H;
+      double *dst = peer.halo[dst_rank] + (((size_t)parity * p.R + r) * c + slot) * kHaloFields;
+      for (int m = 0; m < kHaloFields; ++m) dst[m] = rec[m];
+      __threadfence_system();   // each writer orders its own stores before the flag thread 0 releases below
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double a[kRed] = {0, 0, 0, 0, 0};
@@ -1032,8 +1071,26 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
         int i = obs_own<real>(row, p, f, (real)fast_div((uint32_t)pl.sso[o], p.fd_dur), Rep<real>::minus20(ta, tgt),
                               Rep<real>::minus20(tm, tgt), tgt - (real)20, e, ratio);
         if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
+          const bool halo = needs_halo(p);
           for (int k = 0; k < p.nb_comm; ++k) {
-            const int nb = neighbour_of(p, pl.comm_table, r, n, k);
+            int nb = neighbour_of(p, pl.comm_table, r, n + (halo ? (int)p.house_offset : 0), k);
+            if (halo) {
+              // ring neighbour by GLOBAL index; outside this shard it comes from the exchanged halo
+              nb -= (int)p.house_offset;
+              if (nb < 0 || nb >= p.N) {
+                const int L = p.nb_comm / 2;
+                int d = nb < 0 ? nb + (int)p.n_global : nb;   // offset from the shard start, wrapped into [0, n_global)
+                d = d >= (int)p.n_global ? d - (int)p.n_global : d;
+                const bool left = d >= (int)p.n_global - L;
+                const double *rec = left ? in.halo_left + ((size_t)r * p.nb_comm + (d - ((int)p.n_global - L))) * kHaloFields
+                                         : in.halo_right + ((size_t)r * p.nb_comm + (d - p.N)) * kHaloFields;
+                for (int m = 0; m < 4; ++m) row[i++] = (real)rec[m];
+                if (p.msg_thermal)
+                  for (int m = 0; m < 4; ++m) row[i++] = (real)rec[4 + m];
+                if (p.msg_hvac) { row[i++] = (real)p.cop; row[i++] = (real)p.latent; row[i++] = (real)p.dcap; }
+                continue;
+              }
+            }
             const size_t q = rb + nb;
             const real pmax = qdiv(pl.cap[q], kc.cop, kc.inv_cop);
             row[i++] = div5(Rep<real>::dev(pl.t_air[q], pl.target[q]));        // norm.py:39

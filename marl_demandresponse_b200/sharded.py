@@ -5,6 +5,12 @@ Each rank owns houses ``[rank * N / W, (rank + 1) * N / W)`` of every replica.  
 partials over NCCL / NVLink (48 bytes per rank and replica) -> ``drsim_step_finish`` (identical
 combination on every rank, env epilogue, rewards, observations).  This is the only data-path
 collective in the package; replica-sharded runs (``BatchedEnv``) have none.
+
+With the hand-engineered observation layout the rows carry the messages of ring neighbours
+(cluster.py:91-111), so the shards also exchange a *halo*: the message records of each shard's first
+``ceil(c/2)`` and last ``floor(c/2)`` houses (64 bytes per house).  ``exchange="peer"`` pushes them
+into the adjacent ranks' inboxes with the same NVLink stores as the partial sums; ``exchange="nccl"``
+all-gathers the ``halo_out`` blocks next to the partials.
 """
 from __future__ import annotations
 
@@ -43,6 +49,7 @@ class ShardedClusterEnv:
         self.device = device
         self._v = self.sim.views()
         self._gathered = None
+        self._halo_gathered = None
         self.exchange = exchange if world > 1 else "none"
         if self.exchange == "peer":
             # one-off: swap CUDA IPC handles of the slabs so the kernels can store into peer inboxes
@@ -85,7 +92,14 @@ class ShardedClusterEnv:
                 # concatenation along dim 0 == [world][R][N_ACC] in rank order
                 self._gathered = torch.empty((self.world * acc.shape[0], acc.shape[1]), dtype=acc.dtype, device=acc.device)
             dist.all_gather_into_tensor(self._gathered, acc, group=self.group)
-            sim.step_finish(self._gathered, self.world)
+            halo = self._v.get("halo_out")
+            if halo is None:
+                sim.step_finish(self._gathered, self.world)
+            else:
+                if self._halo_gathered is None:
+                    self._halo_gathered = torch.empty((self.world,) + tuple(halo.shape), dtype=halo.dtype, device=halo.device)
+                dist.all_gather_into_tensor(self._halo_gathered, halo, group=self.group)
+                sim.step_finish_gathered(self._gathered, self._halo_gathered, self.world, self.rank)
         else:
             sim.step_finish(None, 1)
         return self._v["obs"], self._v["reward"]

@@ -328,7 +328,9 @@ def test_clone_is_a_deep_copy():
 def test_house_sharded_cluster_equals_unsharded():
     """One cluster split over 3 handles (the per-rank partials gathered by hand, as the NCCL
     all-gather would) == the same cluster on one handle: discrete state bit-exact, power / signal /
-    rewards identical, for the constant and the interpolated base power."""
+    rewards identical, for the constant and the interpolated base power; with the hand-engineered
+    layout the observation rows (ring-neighbour messages across the shard edges, exchanged as a halo)
+    must be identical too."""
     import torch
 
     from marl_demandresponse_b200 import BatchedEnv
@@ -337,15 +339,15 @@ def test_house_sharded_cluster_equals_unsharded():
     from oracle.config import synthetic_table
 
     table = synthetic_table(7)
-    for base_mode in ("constant", "interpolation"):
+    for base_mode, layout in (("constant", "tarmac"), ("interpolation", "tarmac"), ("constant", "hand_engineered")):
         n, R, W, T = 3000, 2, 3, 80 if base_mode == "interpolation" else 10
         prop = _prop(n, **{"power_grid_prop/base_power_props/mode": base_mode,
                            "power_grid_prop/signal_properties/mode": "sinusoidals"})
         st = synthetic_state(prop, R, seed=3)
-        whole = BatchedEnv(prop, R, obs_layout="tarmac", noise="philox", seed=9, path="split",
+        whole = BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=9, path="split",
                            interp_table=table if base_mode == "interpolation" else None)
         whole.reset(copy.deepcopy(st))
-        parts = [ShardedClusterEnv(prop, R, rank=r, world=W, obs_layout="tarmac", noise="philox", seed=9) for r in range(W)]
+        parts = [ShardedClusterEnv(prop, R, rank=r, world=W, obs_layout=layout, noise="philox", seed=9) for r in range(W)]
         for p_ in parts:
             if base_mode == "interpolation":
                 p_.sim.set_interp_table(table)
@@ -362,6 +364,11 @@ def test_house_sharded_cluster_equals_unsharded():
                 p_.sim.views()["actions"].copy_(a[:, p_.lo:p_.hi])
                 p_.sim.step_begin(None)
             gathered = torch.stack([p_.state["acc"] for p_ in parts]).contiguous()
+            if layout == "hand_engineered":   # ring-neighbour messages cross the shard edges: halo records too
+                halo = torch.stack([p_.state["halo_out"] for p_ in parts]).contiguous()
+                for i, p_ in enumerate(parts):
+                    p_.sim.step_finish_gathered(gathered, halo, W, i)
+                continue
             for p_ in parts:
                 p_.sim.step_finish(gathered, W)
         torch.cuda.synchronize()
