@@ -33,6 +33,12 @@ METRIC = "house-steps/sec"
 UNIT = "house-steps/s"
 
 WORKLOADS = {
+    "c1": dict(name="C1: default cluster of 10 houses, 1 replica, DeadbandBangBang controller on the device, hand-engineered obs "
+                    "(latency-bound: one tiny launch per step)",
+               rep_per_gpu=1, n_houses=10, obs="hand_engineered", policy="deadband_bangbang"),
+    "c2": dict(name="C2: 1,000-house cluster, 1 replica, interpolated base power (synthetic table, 100 sampled houses every 75 "
+                    "steps), lock-out 40 s, greedy-myopic controller on the device (latency-bound)",
+               rep_per_gpu=1, n_houses=1000, obs="hand_engineered", policy="greedy_myopic", base_mode="interpolation"),
     "c4": dict(name="C4: 2048 replicas/GPU x 1000 houses, TarMAC obs layout (D=10), external actions",
                rep_per_gpu=2048, n_houses=1000, obs="tarmac"),
     "c3": dict(name="C3: 4096 replicas/GPU x 100 houses, hand-engineered neighbour obs (D=50), external actions",
@@ -43,11 +49,14 @@ WORKLOADS = {
 }
 
 
-def env_prop_for(n_houses: int) -> dict:
-    return {
+def env_prop_for(n_houses: int, base_mode: str = "constant") -> dict:
+    prop = {
         "start_datetime": "2021-06-15T12:00:00", "start_datetime_mode": "fixed", "time_step": 4.0,
         "cluster_prop": {"nb_agents": n_houses, "house_prop": {"target_temp": 19.0}},
     }
+    if base_mode != "constant":
+        prop["power_grid_prop"] = {"base_power_props": {"mode": base_mode}}
+    return prop
 
 
 def algorithmic_bytes_per_house_step(real_bytes: int, obs_dim: int) -> int:
@@ -220,8 +229,14 @@ def run_gpu_arm(args, wl) -> None:
         env.reset()
         n_local = env.hi - env.lo
     else:
-        env = BatchedEnv(env_prop_for(N), R, device=local, precision="f32", obs_layout=wl["obs"], policy="external",
-                         noise="philox", seed=1234, rep_offset=rank * R)
+        table = None
+        if wl.get("base_mode") == "interpolation":
+            # seeded stand-in for the reference's missing mergedGridSearchResultFinal.npy,
+            # shape of interp_parameters_dict.json: 4,199,040 entries
+            table = np.random.default_rng(2024).uniform(0.0, 6000.0, 3 * 3 * 3 * 3 * 9 * 5 * 8 * 2 * 12 * 6)
+        env = BatchedEnv(env_prop_for(N, wl.get("base_mode", "constant")), R, device=local, precision="f32",
+                         obs_layout=wl["obs"], policy=wl.get("policy", "external"), noise="philox", seed=1234,
+                         rep_offset=rank * R, interp_table=table)
         env.reset()
         n_local = N
     D = env.sim.D
@@ -251,13 +266,16 @@ def run_gpu_arm(args, wl) -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    step_dev = lambda i: env.step(acts[i % n_act])
+    on_device_policy = wl.get("policy", "external") != "external"
+    step_dev = (lambda i: env.step(None)) if on_device_policy else (lambda i: env.step(acts[i % n_act]))
     if sharded:
         def step_host(i):  # host actions in (pinned), per-replica results out, around the sharded step
             env.state["actions"].copy_(acts_host[i % n_act], non_blocking=True)
             env.step(None)
             env_out[:, 0].copy_(env.state["power"], non_blocking=True)
             torch.cuda.synchronize()
+    elif on_device_policy:
+        step_host = lambda i: env.step_host(None, env_out)   # no actions to send: per-replica results out, sync
     else:
         step_host = lambda i: env.step_host(acts_host[i % n_act], env_out)
 
@@ -313,16 +331,21 @@ def run_gpu_arm(args, wl) -> None:
                        "l2": f"working set {R * n_local * bytes_hs / 1e6:.0f} MB per step per GPU vs 126 MB L2"
                              + ("" if R * n_local * bytes_hs > 126e6 else "; L2 flushed between steps by a 256 MB write"
                                 if args.flush_l2 else "; fits L2 (latency-bound workload, see DESIGN.md)"),
-                       "actions": "4 rotating fixed-seed Bernoulli(0.5) u8 tensors (policy cost excluded)"},
+                       "actions": (f"on-device controller ({wl['policy']})" if on_device_policy else
+                                   "4 rotating fixed-seed Bernoulli(0.5) u8 tensors (policy cost excluded)")},
             "rollout_metrics": rollout,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_houses,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0 if on_device_policy else total_houses,
                     "d2h_bytes_per_step": world * R * 6 * 8, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "BatchedEnv.step_host -> drsim_step_host: pinned host actions in, per-replica results out, one stream "
                            "sync per step; on the staged fused path the kernel reads the action bytes in place over PCIe and "
                            "mirrors the results into mapped host memory (no copy-engine transfers)"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_house+k_obs (general path)" if sharded else "k_fused_tma",
+            "roofline": {"bound": "hbm", "kernel": "k_house+k_obs (general path)" if sharded else
+                         {"staged": "k_fused_tma", "staged_rows": "k_fused_rows", "direct": "k_fused_direct", "chunked": "k_fused",
+                          "none": "k_house+k_reduce+k_env+k_obs"}[env.sim.fused_info()["variant"]],
                          "achieved": achieved, "peak": peak,
+                         **({"note": "latency-bound workload (one small cluster): the fraction is reported for completeness"}
+                            if R * n_local < 100000 else {}),
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": R * n_local * bytes_hs,
                          "bytes_per_house_step": bytes_hs,

@@ -247,22 +247,24 @@ static void plan_fused(drsim_handle *h, int e_cap = 1 << 30) {
   // fp32 wide rows (hand-engineered layout that does not fit the direct staging): per-warp staging
   if (g.chunk_rows != (row ? slots : 0) && rb == 4 && g.need_msg && p.own_dim == 10 && p.msg_dim == 4 &&
       (p.obs_dim % 2) == 0 && slots % 4 == 0) {
-    FusedGeom w = g;
-    size_t off = 0;
-    auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
-    w.off_msg = take((size_t)slots * 16 * 2);
-    w.off_own = take((size_t)slots * 16 * 2);
-    w.off_env = take((size_t)g.envs_per_tile * 32 * 2);
-    w.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double) * 2);
-    w.off_sold = take((size_t)g.envs_per_tile * sizeof(double) * 2);
-    w.off_tile = take((size_t)(kThreads / 32) * kRowGroup * row);
-    w.off_stage = take((size_t)g.envs_per_tile * sizeof(EnvStage) * 2);
-    w.in_stride = slots;
-    w.off_in = take((size_t)11 * slots * 4 + (size_t)kThreads * 16);
-    w.smem_bytes = (int)off;
-    w.use_rows = 1;
-    w.use_tma = 0;
-    if (off <= 113 * 1024) g = w;
+    for (int staged = 1; staged >= 0; --staged) {
+      FusedGeom w = g;
+      size_t off = 0;
+      auto take = [&](size_t b) { size_t o = off; off += (b + 127) / 128 * 128; return (int)o; };
+      w.off_msg = take((size_t)slots * 16 * 2);
+      w.off_own = take((size_t)slots * 16 * 2);
+      w.off_env = take((size_t)g.envs_per_tile * 32 * 2);
+      w.off_wp = take((size_t)(kThreads / 32) * g.max_segs * kRed * sizeof(double) * 2);
+      w.off_sold = take((size_t)g.envs_per_tile * sizeof(double) * 2);
+      w.off_tile = take((size_t)(kThreads / 32) * kRowGroup * row);
+      w.off_stage = take((size_t)g.envs_per_tile * sizeof(EnvStage) * 2);
+      w.in_stride = staged ? slots : 0;   // 0: inputs through registers (k_fused_rows<false>)
+      w.off_in = staged ? take((size_t)11 * slots * 4 + (size_t)kThreads * 16) : 0;
+      w.smem_bytes = (int)off;
+      w.use_rows = 1;
+      w.use_tma = 0;
+      if (off <= 113 * 1024) { g = w; break; }
+    }
   }
   h->geom = g;
   h->fused_ok = true;
@@ -276,8 +278,9 @@ static int configure_kernels(drsim_handle *h) {
     int per_sm = 0;
     if (h->geom.use_rows) {
       if (sizeof(real) == 4) {
-        CU_TRY(cudaFuncSetAttribute(k_fused_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_rows, kThreads, h->geom.smem_bytes));
+        auto kern = h->geom.in_stride ? k_fused_rows<true> : k_fused_rows<false>;
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, h->geom.smem_bytes));
       }
       CU_TRY(cudaFuncSetAttribute(k_fused<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     } else if (direct && h->geom.use_tma) {
@@ -301,7 +304,7 @@ static int configure_kernels(drsim_handle *h) {
   if (h->p.policy == DRSIM_POLICY_GREEDY_MYOPIC) {
     int n2 = 1;
     while (n2 < h->p.N) n2 <<= 1;
-    const size_t sm = (size_t)n2 * 12;
+    const size_t sm = (size_t)n2 * 13;
     if (sm > 200 * 1024) return fail(DRSIM_E_ARG, "greedy-myopic: cluster too large for the shared-memory sort");
     if (sm > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_greedy<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   }
@@ -781,7 +784,7 @@ static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s)
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 13, s>>>(pl, p, n2);
     h->launches++;
   }
   k_house<real><<<p.R * h->chunks, kThreads, 0, s>>>(pl, p, in, h->chunks);
@@ -840,7 +843,8 @@ static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
 
 static void launch_rows(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
-  launch_pdl(k_fused_rows, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+  if (h->geom.in_stride) launch_pdl(k_fused_rows<true>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+  else launch_pdl(k_fused_rows<false>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
 }
 
 // steps the wide-row kernel cannot take (injected noise, on-device policies, common penalty modes)
@@ -863,10 +867,12 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 12, s>>>(pl, p, n2);
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 13, s>>>(pl, p, n2);
     h->launches++;
   }
-  const bool rows_ok = h->geom.use_rows && in.sched_od != nullptr && p.policy == DRSIM_POLICY_EXTERNAL &&
+  // (greedy-myopic actions were just written into the action plane by k_greedy: external to the step kernel)
+  const bool rows_ok = h->geom.use_rows && in.sched_od != nullptr &&
+                       (p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC) &&
                        p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   if (h->geom.use_rows && !rows_ok) return launch_chunked_fallback<real>(h, in, s);
   if (rows_ok) launch_rows(h, in, s);
@@ -1022,7 +1028,8 @@ extern "C" int drsim_step_finish_gathered(drsim_t *h, const double *acc_gathered
 static bool staged_fast_step(const drsim_handle *h, int do_interp, bool injected) {
   if (!h->fused_ok || h->real_bytes != 4 || do_interp > 0 || injected) return false;
   const SimParams &p = h->p;
-  if (h->geom.use_rows) return p.policy == DRSIM_POLICY_EXTERNAL && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+  if (h->geom.use_rows)
+    return (p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC) && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   return h->fused_direct && h->geom.use_tma;
 }
 

@@ -2167,6 +2167,9 @@ DRSIM_D void raw_load_f32(const Planes<float> &pl, const StepIn &in, size_t off,
 
 constexpr int kRowGroup = 16;  // rows per warp-level TMA store in k_fused_rows (two lanes assemble one row)
 
+// STAGED = inputs prefetched one tile ahead into thread-private shared-memory slots (needs 44 B of
+// shared memory per house slot); false = 128-bit register loads at the top of the tile (large clusters)
+template <bool STAGED>
 __global__ void __launch_bounds__(kThreads, 2)
 k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   typedef float real;
@@ -2208,6 +2211,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   // (plain cp.async here: with a run-time plane stride, ptxas 12.9 encodes the L2::cache_hint form of
   // LDGSTS with a uniform-register shared offset that the B200 rejects as an illegal instruction)
   auto prefetch = [&](int t, int part) {
+    if constexpr (!STAGED) return;
     const int tr0 = t * g.envs_per_tile;
     const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
     if (s0 >= tslots) return;
@@ -2258,7 +2262,9 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     real pen_r[4] = {0, 0, 0, 0};
     cp_async_wait_all();   // the thread's own staging copies of this tile have landed
     Raw4f w;
-    if (active) {
+    if constexpr (!STAGED) {
+      if (active) raw_load_f32(pl, in, base + s0, r0 + e_loc, w);
+    } else if (active) {
       const float4 *in4 = reinterpret_cast<const float4 *>(s_in + s0);
       auto ld = [&](int q, float v[4]) {
         const float4 t = in4[(size_t)q * (in_stride / 4)];
@@ -2543,21 +2549,54 @@ __global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, i
       __syncthreads();
     }
   }
-  for (int i = threadIdx.x; i < p.Ns; i += blockDim.x) pl.actions[rb + i] = 0;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  // gather the scan's inputs in sorted order, in parallel: the keys are dead, their slots take the
+  // per-house power cap / cop (greedy_myopic_controller.py:93); lock-out bit and verdict share a byte
+  uint8_t *mark = reinterpret_cast<uint8_t *>(idx + n_pow2);
+  bool nonneg = true;
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    const int hh = idx[i];
+    const double pw = (double)pl.cap[rb + hh] / p.cop;
+    key[i] = pw;
+    mark[i] = (pl.flags[rb + hh] >> 1) & 1u;
+    nonneg = nonneg && pw >= 0.0;
+  }
+  for (int i = p.N + threadIdx.x; i < p.Ns; i += blockDim.x) pl.actions[rb + i] = 0;   // padding slots
+  const bool all_nonneg = __syncthreads_and(nonneg);
+  if (threadIdx.x < 32) {
+    // The knapsack scan (:95-102) is inherently sequential in `total`; one warp runs it 32 houses at a
+    // time: every lane fetches one house, the values reach all lanes through shuffles that do not depend
+    // on `total`, and all lanes replay the same fp64 chain (DADD -> compare -> select), so `total` stays
+    // warp-uniform and the only serial cost is that chain.  pw + total == total + pw bit for bit.
+    const int lane = threadIdx.x;
     const double target = pl.signal[r];
     double total = 0.0;
-    for (int i = 0; i < p.N; ++i) {
-      const int hh = idx[i];
-      const double pw = (double)pl.cap[rb + hh] / p.cop;
-      const bool lock = (pl.flags[rb + hh] >> 1) & 1u;
-      if (pw + total < target || (fabs(pw + total - target) < fabs(total - target) && !lock)) {
-        total += pw;
-        pl.actions[rb + hh] = 1;
+    for (int base = 0; base < p.N; base += 32) {
+      const int i = base + lane;
+      // powers >= 0: once the total has reached the target neither clause can accept any more
+      if (all_nonneg && total >= target) {
+        if (i < p.N) mark[i] = 0;
+        continue;
       }
+      const double my_pw = i < p.N ? key[i] : 0.0;
+      const int my_lock = i < p.N ? (int)(mark[i] & 1u) : 1;
+      const int cnt = min(32, p.N - base);
+      bool my_take = false;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double pw = __shfl_sync(0xffffffffu, my_pw, j);
+        const int lock = __shfl_sync(0xffffffffu, my_lock, j);
+        if (j < cnt) {
+          const double t1 = pw + total;
+          const bool take = t1 < target || (fabs(t1 - target) < fabs(total - target) && !lock);
+          total = take ? t1 : total;
+          if (j == lane) my_take = take;
+        }
+      }
+      if (i < p.N) mark[i] = my_take ? 1 : 0;
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) pl.actions[rb + idx[i]] = mark[i];
 }
 
 }  // namespace drsim

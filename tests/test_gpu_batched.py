@@ -169,6 +169,7 @@ def test_schedule_records_follow_mixed_step_kinds():
     (6000, 100, "hand_engineered", 5, None),           # five clusters per tile, four tiles per CTA
     (700, 40, "hand_engineered", None, None),          # whatever the round-count heuristic picks
     (900, 1000, "tarmac", None, "staged"),             # BASELINE config 4 layout, 3+ tiles per CTA
+    (600, 1000, "hand_engineered", None, "staged_rows"),  # 1000-house clusters with D = 50: row groups, inputs through registers
 ])
 def test_fused_kernel_variants_match_general_path(R, n, layout, tile_envs, variant, monkeypatch):
     """Every fused-kernel variant / tile size (forced through DRSIM_TILE_ENVS where the heuristic would
