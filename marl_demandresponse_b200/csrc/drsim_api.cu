@@ -304,7 +304,7 @@ static int configure_kernels(drsim_handle *h) {
   if (h->p.policy == DRSIM_POLICY_GREEDY_MYOPIC) {
     int n2 = 1;
     while (n2 < h->p.N) n2 <<= 1;
-    const size_t sm = (size_t)n2 * 13;
+    const size_t sm = (size_t)n2 * 24;
     if (sm > 200 * 1024) return fail(DRSIM_E_ARG, "greedy-myopic: cluster too large for the shared-memory sort");
     if (sm > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_greedy<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   }
@@ -784,7 +784,7 @@ static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s)
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 13, s>>>(pl, p, n2);
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
     h->launches++;
   }
   k_house<real><<<p.R * h->chunks, kThreads, 0, s>>>(pl, p, in, h->chunks);
@@ -867,7 +867,7 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2 / 2)), (size_t)n2 * 13, s>>>(pl, p, n2);
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
     h->launches++;
   }
   // (greedy-myopic actions were just written into the action plane by k_greedy: external to the step kernel)

@@ -2524,6 +2524,39 @@ __global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, i
   int *idx = reinterpret_cast<int *>(key + n_pow2);
   const int r = blockIdx.x;
   const size_t rb = (size_t)r * p.Ns;
+  if (n_pow2 <= (int)blockDim.x) {
+    // one element per thread: compare-exchange distances below 32 go through warp shuffles (no shared
+    // memory, no barrier), only the 15 of 55 stages with a distance >= 32 (n = 1024) cross warps
+    const int i = threadIdx.x;
+    double ki = INFINITY;
+    int ii = 0x7fffffff;
+    if (i < p.N) {
+      ki = -(double)Rep<real>::dev(pl.t_air[rb + i], pl.target[rb + i]);
+      ii = i;
+    }
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        double kl;
+        int il;
+        if (j >= 32) {
+          if (i < n_pow2) { key[i] = ki; idx[i] = ii; }
+          __syncthreads();
+          kl = i < n_pow2 ? key[i ^ j] : ki;
+          il = i < n_pow2 ? idx[i ^ j] : ii;
+          __syncthreads();
+        } else {
+          kl = __shfl_xor_sync(0xffffffffu, ki, j);
+          il = __shfl_xor_sync(0xffffffffu, ii, j);
+        }
+        const bool lower = (i & j) == 0, up = (i & k) == 0;
+        const bool gt = (ki > kl) || (ki == kl && ii > il);   // (key, id) order == stable sort
+        // the lower index of an ascending pair keeps the smaller element, and so on
+        if (gt == (lower == up)) { ki = kl; ii = il; }
+      }
+    }
+    if (i < n_pow2) { key[i] = ki; idx[i] = ii; }
+    __syncthreads();
+  } else {
   for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
     if (i < p.N) {
       key[i] = -(double)Rep<real>::dev(pl.t_air[rb + i], pl.target[rb + i]);
@@ -2549,28 +2582,67 @@ __global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, i
       __syncthreads();
     }
   }
+  }
   // gather the scan's inputs in sorted order, in parallel: the keys are dead, their slots take the
   // per-house power cap / cop (greedy_myopic_controller.py:93); lock-out bit and verdict share a byte
   uint8_t *mark = reinterpret_cast<uint8_t *>(idx + n_pow2);
-  bool nonneg = true;
+  double *pre = reinterpret_cast<double *>(smem_raw + (size_t)n_pow2 * 16);   // inclusive prefix sums (exact path)
+  __shared__ double s_warp[32];
+  __shared__ int s_first;
+  bool nonneg = true, quant = true;
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
     const int hh = idx[i];
     const double pw = (double)pl.cap[rb + hh] / p.cop;
     key[i] = pw;
     mark[i] = (pl.flags[rb + hh] >> 1) & 1u;
     nonneg = nonneg && pw >= 0.0;
+    const double q = pw * 4096.0;                           // multiples of 2^-12 W below 2^20 W: every partial sum of
+    quant = quant && q == floor(q) && fabs(q) < 4294967296.0;  // <= 2^16 of them is exact in fp64, in ANY order
   }
   for (int i = p.N + threadIdx.x; i < p.Ns; i += blockDim.x) pl.actions[rb + i] = 0;   // padding slots
+  if (threadIdx.x == 0) s_first = p.N;
   const bool all_nonneg = __syncthreads_and(nonneg);
+  const bool exact = __syncthreads_and(quant) && all_nonneg && p.N <= 65536;
+  const double target = pl.signal[r];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int pos = 0;          // first house the sequential scan still has to look at
+  double total = 0.0;   // accepted power before `pos`
+  if (exact) {
+    // The scan (:95-102) accepts every house while `pw + total < target`; up to the first refusal `total`
+    // is the running sum of the sorted powers.  With exactly representable sums that prefix is the same
+    // in any association, so it is computed by a block-wide parallel scan and the sequential part starts
+    // at the first refusal instead of at house 0.
+    const int per = (n_pow2 + blockDim.x - 1) / blockDim.x, i0 = threadIdx.x * per;
+    double run = 0.0;
+    for (int i = i0; i < i0 + per && i < p.N; ++i) { run += key[i]; pre[i] = run; }
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    double off = inc - run;                                  // exclusive offset inside the warp
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    int first = p.N;
+    for (int i = i0; i < i0 + per && i < p.N; ++i) {
+      const double v = pre[i] + off;
+      pre[i] = v;
+      if (v >= target && first == p.N) first = i;            // first-clause refusal (given all before accepted)
+    }
+    if (first < p.N) atomicMin(&s_first, first);
+    __syncthreads();
+    pos = s_first;
+    total = pos > 0 ? pre[pos - 1] : 0.0;
+    for (int i = threadIdx.x; i < pos; i += blockDim.x) mark[i] = 1;
+    __syncthreads();
+  }
   if (threadIdx.x < 32) {
-    // The knapsack scan (:95-102) is inherently sequential in `total`; one warp runs it 32 houses at a
-    // time: every lane fetches one house, the values reach all lanes through shuffles that do not depend
-    // on `total`, and all lanes replay the same fp64 chain (DADD -> compare -> select), so `total` stays
-    // warp-uniform and the only serial cost is that chain.  pw + total == total + pw bit for bit.
-    const int lane = threadIdx.x;
-    const double target = pl.signal[r];
-    double total = 0.0;
-    for (int base = 0; base < p.N; base += 32) {
+    // The rest is sequential in `total`; one warp runs it 32 houses at a time: every lane fetches one
+    // house, the values reach all lanes through shuffles, and all lanes replay the same fp64 chain
+    // (DADD -> compare -> select), so `total` stays warp-uniform.  pw + total == total + pw bit for bit.
+    for (int base = pos; base < p.N; base += 32) {
       const int i = base + lane;
       // powers >= 0: once the total has reached the target neither clause can accept any more
       if (all_nonneg && total >= target) {

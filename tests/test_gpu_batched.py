@@ -279,8 +279,12 @@ def test_on_device_policies_match_oracle_controllers():
     from marl_demandresponse_b200.batched import synthetic_state
     from oracle.np_oracle import NpOracle, deadband_bangbang, from_epoch, greedy_myopic
 
-    for policy, n in (("deadband_bangbang", 90), ("greedy_myopic", 300)):
-        prop = _prop(n, **{"cluster_prop/house_prop/deadband": 0.5, "power_grid_prop/signal_properties/mode": "sinusoidals"})
+    # greedy-myopic: cop 2.5 gives exactly representable powers (parallel-prefix path of k_greedy), cop 2.3
+    # does not (fully sequential scan); 1000 houses = 32 chunks of the warp-cooperative scan
+    for policy, n, cop in (("deadband_bangbang", 90, 2.5), ("greedy_myopic", 300, 2.5), ("greedy_myopic", 1000, 2.5),
+                           ("greedy_myopic", 300, 2.3), ("greedy_myopic", 37, 2.3)):
+        prop = _prop(n, **{"cluster_prop/house_prop/deadband": 0.5, "power_grid_prop/signal_properties/mode": "sinusoidals",
+                           "cluster_prop/house_prop/hvac_prop/cop": cop})
         R, T = 3, 25
         st = synthetic_state(prop, R, seed=21)
         env = BatchedEnv(prop, R, precision="f64", policy=policy, noise="zero", path="auto")
@@ -293,13 +297,13 @@ def test_on_device_policies_match_oracle_controllers():
             if policy == "deadband_bangbang":
                 a = deadband_bangbang(s["t_air"], s["target"], 0.5, s["on"])
             else:
-                a = np.stack([greedy_myopic(s["t_air"][r], s["target"][r], s["cap"][r], 2.5, s["lockout"][r], s["signal"][r])
+                a = np.stack([greedy_myopic(s["t_air"][r], s["target"][r], s["cap"][r], cop, s["lockout"][r], s["signal"][r])
                               for r in range(R)])
             orc.step(a, np.zeros(R), None)
             env.step(None)
         got = env.get_state()
         for k in ("on", "lockout", "sso"):
-            assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), (policy, k)
+            assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), (policy, n, cop, k)
         np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=1e-9)
 
 
