@@ -217,6 +217,8 @@ def run_gpu_arm(args, wl) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     R, N = wl["rep_per_gpu"], wl["n_houses"]
