@@ -277,6 +277,25 @@ int drsim_peer_status(drsim_t *h, void *stream);
 int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                     const int32_t *interp_ids, double *env_out, void *stream);
 
+/* MA-PPO actor of the reference (agents/trainables/network.py:14-35: Linear(obs_dim, h1) - ReLU -
+ * Linear(h1, h2) - ReLU - Linear(h2, 2) - softmax), all DEVICE pointers in torch.nn.Linear layout
+ * (weight [out][in], row-major fp32). */
+typedef struct drsim_actor_net {
+  const float *w1, *b1; /* [h1][obs_dim], [h1] */
+  const float *w2, *b2; /* [h2][h1], [h2] */
+  const float *w3, *b3; /* [2][h2], [2] */
+  int32_t h1, h2;       /* 1 .. 128 each */
+} drsim_actor_net;
+
+/* MAPPO.select_actions (mappo.py:83-97) for every house of every replica, on the device:
+ * the actor runs on the handle's observation rows (fp32 build, obs_dim <= 64) as two tcgen05 TF32 GEMMs
+ * per 128-row tile, the categorical draw uses a Philox uniform keyed (seed, replica, house, step), the
+ * chosen actions go into the handle's action plane (so the next drsim_step with args->actions == NULL
+ * consumes them) and, when the pointers are not NULL, prob_drawn[R][stride] receives the probability of
+ * the drawn action (the PPO ratio's denominator) and prob_on[R][stride] the probability of action 1. */
+int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_t seed, float *prob_drawn, float *prob_on,
+                      void *stream);
+
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 int64_t drsim_launch_count(const drsim_t *h);
 

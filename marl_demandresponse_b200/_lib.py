@@ -73,6 +73,13 @@ class HostState(C.Structure):
     ]
 
 
+class ActorNet(C.Structure):
+    """Mirror of ``drsim_actor_net``."""
+
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w3", C.c_void_p), ("b3", C.c_void_p), ("h1", C.c_int32), ("h2", C.c_int32)]
+
+
 class Ptrs(C.Structure):
     _fields_ = [
         ("n_rep", _i32), ("n_house", _i32), ("house_stride", _i32), ("obs_dim", _i32), ("real_bytes", _i32),
@@ -138,6 +145,7 @@ def lib():
         "drsim_ipc_attach": (C.c_int, [hp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
         "drsim_peer_status": (C.c_int, [hp, C.c_void_p]),
         "drsim_step_host": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "drsim_policy_step": (C.c_int, [hp, C.POINTER(ActorNet), _u64, C.c_void_p, C.c_void_p, C.c_void_p]),
         "drsim_launch_count": (C.c_int64, [hp]),
         "drsim_fused_info": (C.c_int, [hp, C.POINTER(_i32 * 6)]),
         "drsim_host_solar_gain": (C.c_double, [_i64, _d, _d]),
@@ -165,7 +173,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
     "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_refresh", "drsim_step_begin",
-    "drsim_step_finish", "drsim_step_finish_gathered", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_launch_count", "drsim_fused_info", "drsim_host_solar_gain", "drsim_host_od_temp",
+    "drsim_step_finish", "drsim_step_finish_gathered", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",
     "drsim_sizeof",
 ]

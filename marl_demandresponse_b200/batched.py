@@ -189,6 +189,47 @@ class BatchedEnv:
         sim.step(a, od_noise, perlin, interp_ids)
         return self._v["obs"], self._v["reward"]
 
+    # ---- on-device MA-PPO actor ----------------------------------------------
+    @staticmethod
+    def actor_weights(actor) -> tuple:
+        """``(w1, b1, w2, b2, w3, b3)`` fp32 CUDA tensors of a reference-style ``Actor`` module
+        (``network.py:14-35``: ``actor.fc`` = three ``nn.Linear``) or of any sequence of three
+        ``(weight, bias)`` pairs."""
+        import torch
+
+        layers = list(actor.fc) if hasattr(actor, "fc") else list(actor)
+        if len(layers) != 3:
+            raise ValueError("the on-device actor is the reference's two-hidden-layer MLP (three Linear layers)")
+        out = []
+        for lin in layers:
+            w, b = (lin.weight, lin.bias) if hasattr(lin, "weight") else lin
+            out += [w.detach().to(device="cuda", dtype=torch.float32).contiguous(),
+                    b.detach().to(device="cuda", dtype=torch.float32).contiguous()]
+        return tuple(out)
+
+    def policy_step(self, weights, seed: Optional[int] = None, want_prob: bool = True):
+        """``MAPPO.select_actions`` (mappo.py:83-97) for all ``R * N`` agents in one kernel: actor
+        forward on the current observation rows (tcgen05 TF32 GEMMs), softmax, categorical draw from a
+        Philox uniform keyed (seed, replica, house, step).  The drawn actions land in the action plane
+        (``state["actions"]``); returns ``(actions u8 [R,N], prob_of_drawn_action f32 [R,N] | None)``."""
+        import torch
+
+        sim = self.sim
+        prob = None
+        if want_prob:
+            if getattr(self, "_prob", None) is None:
+                self._prob = torch.zeros((sim.R, sim.Ns), dtype=torch.float32, device=f"cuda:{self.device}")
+            prob = self._prob
+        sim.policy_step(weights, self.seed if seed is None else seed, prob_drawn=prob)
+        return self._v["actions"], (prob[:, :sim.N] if prob is not None else None)
+
+    def rollout_step(self, weights, seed: Optional[int] = None):
+        """One transition of a rollout entirely on the device: actor + draw, then the environment
+        step on the drawn actions.  Returns ``(obs', reward, actions, prob_of_drawn_action)``."""
+        actions, prob = self.policy_step(weights, seed)
+        self.sim.step(None)
+        return self._v["obs"], self._v["reward"], actions, prob
+
     def step_host(self, actions_host, env_out=None):
         """End-to-end step with HOST buffers: ``actions_host`` uint8 ``[R, N]`` (pinned torch CPU
         tensor or numpy) is copied in, the per-replica results ``[R, 4]`` = (power, signal,

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "drsim_kernels.cuh"
+#include "drsim_actor.cuh"
 
 using namespace drsim;
 
@@ -1204,6 +1205,39 @@ extern "C" int drsim_peer_status(drsim_t *h, void *stream) {
   CU_TRY(cudaMemcpyAsync(&err, h->slab + h->o_peer_err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   if (err) return fail(DRSIM_E_STATE, "a peer-exchange wait timed out (a rank did not deliver its partial sums)");
+  return 0;
+}
+
+extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_t seed, float *prob_drawn, float *prob_on,
+                                 void *stream) {
+  if (!h || !net) return fail(DRSIM_E_ARG, "null argument");
+  const SimParams &p = h->p;
+  if (h->real_bytes != 4) return fail(DRSIM_E_ARG, "drsim_policy_step needs the fp32 build (observation rows are its input)");
+  if (p.obs_dim < 1 || p.obs_dim > 64) return fail(DRSIM_E_ARG, "drsim_policy_step: obs_dim must be in [1, 64]");
+  if (net->h1 < 1 || net->h1 > 128 || net->h2 < 1 || net->h2 > 128) return fail(DRSIM_E_ARG, "drsim_policy_step: h1, h2 in [1, 128]");
+  if (!net->w1 || !net->b1 || !net->w2 || !net->b2 || !net->w3 || !net->b3) return fail(DRSIM_E_ARG, "drsim_policy_step: null weight pointer");
+  CU_TRY(cudaSetDevice(h->device));
+  ActorArgs a{};
+  a.obs = h->at<float>(h->o_obs);
+  a.w1 = net->w1; a.b1 = net->b1; a.w2 = net->w2; a.b2 = net->b2; a.w3 = net->w3; a.b3 = net->b3;
+  a.actions = h->at<uint8_t>(h->o_actions);
+  a.prob = prob_drawn; a.prob_on = prob_on;
+  a.rows = (long long)p.R * p.Ns;
+  a.Ns = p.Ns; a.N = p.N; a.D = p.obs_dim; a.h1 = net->h1; a.h2 = net->h2;
+  a.K1 = (a.D + 7) / 8 * 8; a.N1 = (a.h1 + 15) / 16 * 16;
+  a.K2 = (a.h1 + 7) / 8 * 8; a.N2 = (a.h2 + 15) / 16 * 16;
+  int off = 0;
+  auto take = [&](int b) { int o = off; off += (b + 127) / 128 * 128; return o; };
+  a.off_w1 = take(a.N1 * a.K1 * 4); a.off_w2 = take(a.N2 * a.K2 * 4);
+  a.off_a1 = take(kActRows * a.K1 * 4); a.off_a2 = take(kActRows * a.K2 * 4);
+  a.off_vec = take((a.N1 + 3 * a.N2) * 4); a.off_bar = take(16);
+  a.smem_bytes = off;
+  a.seed = seed; a.step = h->step; a.rep_offset = p.rep_offset;
+  CU_TRY(cudaFuncSetAttribute(k_actor, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
+  const int tiles = (int)((a.rows + kActRows - 1) / kActRows);
+  k_actor<<<std::min(tiles, h->sm_count), kActThreads, a.smem_bytes, (cudaStream_t)stream>>>(a);
+  h->launches++;
+  CU_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -251,6 +251,79 @@ def test_step_host_zero_copy_equals_device_step(n, R, layout, base_mode):
             assert torch.equal(envs[0].state[k], e.state[k]), k
 
 
+def _torch_actor(D, h1, h2, seed):
+    """The reference's Actor (network.py:14-35) restated in plain PyTorch fp32."""
+    import torch
+
+    torch.manual_seed(seed)
+    fc = torch.nn.ModuleList([torch.nn.Linear(D, h1), torch.nn.Linear(h1, h2), torch.nn.Linear(h2, 2)]).cuda()
+
+    def forward(x):
+        x = torch.relu(fc[0](x))
+        x = torch.relu(fc[1](x))
+        return torch.softmax(fc[2](x), dim=1)
+
+    return fc, forward
+
+
+@pytest.mark.parametrize("R,n,layout,h1,h2", [(300, 100, "hand_engineered", 100, 100), (7, 1000, "tarmac", 100, 100),
+                                              (33, 37, "hand_engineered", 64, 48), (5, 9, "tarmac", 128, 128)])
+def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
+    """the tcgen05 actor + categorical draw against a plain PyTorch fp32 forward of the same
+    weights.  Probabilities: TF32 operands (10-bit mantissa, rounded to nearest), fp32 accumulation -> |dp| <= 5e-3
+    on logits three times wider than the default initialisation gives.  The draw
+    must be the inverse-CDF rule on the Philox uniform of (seed, replica, house, step), recomputed here
+    with the NumPy restatement of the generator; the drawn actions must then drive the next env step."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle import philox
+
+    prop = _prop(n)
+    env = BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=17, rep_offset=40)
+    env.reset(synthetic_state(prop, R, seed=4, rep_offset=40))
+    D = env.sim.D
+    fc, forward = _torch_actor(D, h1, h2, seed=3)
+    with torch.no_grad():
+        for lin in fc:                       # wider logits than the default init: probabilities away from 1/2
+            lin.weight.mul_(3.0)
+    weights = BatchedEnv.actor_weights(fc)
+    a0 = (torch.rand((R, n), device="cuda") < 0.5).to(torch.uint8)
+    env.step(a0)                             # step 0 -> observations of step 1
+    obs = env.obs.clone()
+    with torch.no_grad():
+        p_ref = forward(obs.reshape(-1, D)).reshape(R, n, 2)
+    prob_on = torch.zeros((R, env.sim.Ns), dtype=torch.float32, device="cuda")
+    prob = torch.zeros_like(prob_on)
+    env.sim.policy_step(weights, seed=99, prob_drawn=prob, prob_on=prob_on)
+    torch.cuda.synchronize()
+    act = env.state["actions"][:, :n].clone()
+    p_on = prob_on[:, :n]
+    assert float((p_on - p_ref[..., 1]).abs().max()) <= 5e-3
+    # probability reported for the drawn action
+    want = torch.where(act.bool(), p_on, 1.0 - p_on)
+    torch.testing.assert_close(prob[:, :n], want, rtol=0, atol=1e-6)
+    # the draw: u < p0 -> action 0, with u from the 24 top bits of Philox word 0 of (replica, house, step, purpose 6)
+    step = 1
+    u = np.empty((R, n))
+    for r in range(R):
+        x = philox.philox4x32_10(99, 40 + r, np.arange(n), step, 6)[0]
+        u[r] = (np.asarray(x, dtype=np.uint64) >> np.uint64(8)).astype(np.float64) * 2.0 ** -24
+    p0 = (1.0 - p_on).double().cpu().numpy()
+    expect = (u >= p0).astype(np.uint8)
+    clear = np.abs(u - p0) > 1e-6            # away from the threshold the rule is unambiguous
+    assert np.array_equal(act.cpu().numpy()[clear], expect[clear])
+    assert clear.mean() > 0.999
+    # the drawn actions are what the next step consumes
+    ref = env.clone()
+    env.sim.step(None)
+    ref.step(act.contiguous())
+    torch.cuda.synchronize()
+    for k in ("sso", "flags", "dt_air", "reward", "obs"):
+        assert torch.equal(env.state[k], ref.state[k]), k
+
+
 def test_replica_placement_invariance():
     """Shard [4, 8) of a 12-replica job == replicas 4..7 of the whole job (Philox keyed by the
     global replica index, synthetic state keyed by it too): the basis of the multi-GPU sharding."""
