@@ -277,6 +277,229 @@ __global__ void __launch_bounds__(kActThreads, 1) k_actor(ActorArgs a) {
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kActTmemCols) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------
+// k_actor2: the same computation with two tiles in flight per CTA and no shared-memory round trip
+// between the layers.
+//   * 256 threads = two warpgroups; warpgroup g owns tile slot g: its own observation buffers, TMEM
+//     columns, mbarrier and named barrier, so the two slots interleave freely on the SM (one runs its
+//     epilogue on the CUDA cores while the other's GEMM occupies the tensor core); weights are shared.
+//   * the hidden activations never leave tensor memory: epilogue 1 reads D1 with tcgen05.ld, applies
+//     bias + ReLU and writes the row back IN PLACE with tcgen05.st; layer 2 takes its A operand from
+//     TMEM (tcgen05.mma with [a_tmem], B from shared memory) -- no A2 staging, no proxy fence.
+//   * the observation tile of the slot's NEXT tile is fetched with cp.async straight into the canonical
+//     operand layout of the other buffer while the current tile computes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAct2Threads = 256;
+constexpr int kAct2TmemCols = 512;
+
+DRSIM_D void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+DRSIM_D void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+DRSIM_D void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+DRSIM_D void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+DRSIM_D void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+DRSIM_D void slot_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+
+__global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *s_w1 = smem + a.off_w1, *s_w2 = smem + a.off_w2;
+  float *s_b1 = reinterpret_cast<float *>(smem + a.off_vec);   // [N1]
+  float *s_b2 = s_b1 + a.N1;                                     // [N2]
+  float *s_w3 = s_b2 + a.N2;                                     // [2][N2]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // [2 slots]
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, slot = tid >> 7, t = tid & 127;
+  const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
+  const int a1_bytes = kActRows * a.K1 * 4;
+  unsigned char *s_a1 = smem + a.off_a1 + slot * 2 * a1_bytes;         // this slot's two observation buffers
+
+  for (int i = tid; i < a.N1 * a.K1; i += kAct2Threads) {
+    const int n = i / a.K1, k = i - n * a.K1;
+    *reinterpret_cast<float *>(s_w1 + umma_kmajor_off(a.N1, n, k)) = (n < a.h1 && k < a.D) ? to_tf32(a.w1[(size_t)n * a.D + k]) : 0.f;
+  }
+  for (int i = tid; i < a.N2 * a.K2; i += kAct2Threads) {
+    const int n = i / a.K2, k = i - n * a.K2;
+    *reinterpret_cast<float *>(s_w2 + umma_kmajor_off(a.N2, n, k)) = (n < a.h2 && k < a.h1) ? to_tf32(a.w2[(size_t)n * a.h1 + k]) : 0.f;
+  }
+  for (int i = tid; i < a.N1; i += kAct2Threads) s_b1[i] = i < a.h1 ? a.b1[i] : 0.f;
+  for (int i = tid; i < a.N2; i += kAct2Threads) {
+    s_b2[i] = i < a.h2 ? a.b2[i] : 0.f;
+    s_w3[i] = i < a.h2 ? a.w3[i] : 0.f;
+    s_w3[a.N2 + i] = i < a.h2 ? a.w3[a.h2 + i] : 0.f;
+  }
+  // padding columns [D, K1) of all four observation buffers stay zero for the whole kernel
+  for (int i = tid; i < 4 * kActRows * (a.K1 - a.D); i += kAct2Threads) {
+    const int buf = i / (kActRows * (a.K1 - a.D)), j = i - buf * kActRows * (a.K1 - a.D);
+    const int row = j / (a.K1 - a.D), k = a.D + j % (a.K1 - a.D);
+    *reinterpret_cast<float *>(smem + a.off_a1 + buf * a1_bytes + umma_kmajor_off(kActRows, row, k)) = 0.f;
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                 "r"((uint32_t)kAct2TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem + (uint32_t)(slot * 256);              // this slot's 256 columns: D1/A2 at 0, D2 at N1
+  const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2);
+  const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(s_w1), w2_addr = (uint32_t)__cvta_generic_to_shared(s_w2);
+  const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quadrant
+  uint64_t *bar = s_bar + slot;
+  uint32_t phase = 0;
+  int buf = 0;
+
+  // observation rows [tile * 128, +128) -> buffer b, straight into the canonical layout (8-byte cp.async;
+  // rows past the end re-read the last valid row: their results are never written)
+  auto fetch = [&](int tile, int b) {
+    const long long row0 = (long long)tile * kActRows;
+    const int n_valid = (int)min((long long)kActRows, a.rows - row0);
+    const float *src = a.obs + (size_t)row0 * a.D;
+    unsigned char *dst = s_a1 + b * a1_bytes;
+    if ((a.D & 1) == 0) {
+      const int half = a.D >> 1;
+      for (int i = t; i < kActRows * half; i += 128) {
+        const int row = i / half, k = (i - row * half) * 2;
+        const int rs = min(row, n_valid - 1);
+        cp_async8(dst + umma_kmajor_off(kActRows, row, k), src + (size_t)rs * a.D + k);
+      }
+    } else {
+      for (int i = t; i < kActRows * a.D; i += 128) {
+        const int row = i / a.D, k = i - row * a.D;
+        const int rs = min(row, n_valid - 1);
+        cp_async4(dst + umma_kmajor_off(kActRows, row, k), src + (size_t)rs * a.D + k);
+      }
+    }
+  };
+  const int stride = 2 * gridDim.x;
+  int tile = 2 * blockIdx.x + slot;
+  if (tile < n_tiles) fetch(tile, 0);
+
+  for (; tile < n_tiles; tile += stride, buf ^= 1) {
+    const long long row0 = (long long)tile * kActRows;
+    cp_async_wait_all();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    slot_barrier(slot);   // the tile's rows are in shared memory; every lane is done with the previous tile's TMEM
+    if (tile + stride < n_tiles) fetch(tile + stride, buf ^ 1);   // flies during this tile's GEMMs and epilogues
+    const uint32_t a1_addr = (uint32_t)__cvta_generic_to_shared(s_a1 + buf * a1_bytes);
+    // ---- layer 1: D1[128 x N1] = A1 . W1^T ----------------------------------------------------------
+    if (t == 0) {
+      tc_fence_after();
+      for (int ks = 0; ks < a.K1 / 8; ++ks)
+        umma_tf32_ss(tmem, umma_smem_desc(a1_addr + ks * 2 * lbo_a, lbo_a, 128),
+                     umma_smem_desc(w1_addr + ks * 2 * lbo_w1, lbo_w1, 128), idesc1, ks > 0);
+      umma_commit(bar);
+    }
+    mbar_wait_bounded(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    // ---- epilogue 1, in place in tensor memory: D1 row -> + b1, ReLU, TF32 -> A2 row --------------------
+    for (int c0 = 0; c0 < a.K2; c0 += 32) {
+      uint32_t r[2][16];
+      tmem_ld16_issue(lane_addr + (uint32_t)c0, r[0]);
+      if (c0 + 16 < a.N1) tmem_ld16_issue(lane_addr + (uint32_t)(c0 + 16), r[1]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (c0 + 16 * q < a.N1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            r[q][j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(r[q][j]) + s_b1[c0 + 16 * q + j], 0.f)));
+          tmem_st16(lane_addr + (uint32_t)(c0 + 16 * q), r[q]);
+        }
+      }
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    slot_barrier(slot);
+    // ---- layer 2: D2[128 x N2] = A2 (tensor memory) . W2^T ---------------------------------------------
+    if (t == 0) {
+      tc_fence_after();
+      for (int ks = 0; ks < a.K2 / 8; ++ks)
+        umma_tf32_ts(tmem + (uint32_t)a.N1, tmem + (uint32_t)(ks * 8), umma_smem_desc(w2_addr + ks * 2 * lbo_w2, lbo_w2, 128),
+                     idesc2, ks > 0);
+      umma_commit(bar);
+    }
+    mbar_wait_bounded(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    // ---- epilogue 2: + b2, ReLU, output layer on the CUDA cores, softmax, categorical draw ---------------
+    float l0 = a.b3[0], l1 = a.b3[1];
+    for (int c0 = 0; c0 < a.N2; c0 += 32) {
+      uint32_t r[2][16];
+      tmem_ld16_issue(lane_addr + (uint32_t)(a.N1 + c0), r[0]);
+      if (c0 + 16 < a.N2) tmem_ld16_issue(lane_addr + (uint32_t)(a.N1 + c0 + 16), r[1]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (c0 + 16 * q < a.N2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c0 + 16 * q + j;
+            const float h = fmaxf(__uint_as_float(r[q][j]) + s_b2[c], 0.f);
+            l0 = fmaf(h, s_w3[c], l0);
+            l1 = fmaf(h, s_w3[a.N2 + c], l1);
+          }
+        }
+      }
+    }
+    const long long row = row0 + t;
+    if (row < a.rows) {
+      const long long rr = row / a.Ns;
+      const int n = (int)(row - rr * a.Ns);
+      uint8_t act = 0;
+      float p_draw = 0.f, p1 = 0.f;
+      if (n < a.N) {
+        const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
+        const float e0 = __expf(l0 - m), e1 = __expf(l1 - m);
+        const float p0 = e0 / (e0 + e1);
+        p1 = 1.f - p0;
+        const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + rr), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
+        const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
+        act = uf < p0 ? 0 : 1;
+        p_draw = act ? p1 : p0;
+      }
+      a.actions[row] = act;
+      if (a.prob) a.prob[row] = p_draw;
+      if (a.prob_on) a.prob_on[row] = p1;
+    }
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"((uint32_t)kAct2TmemCols) : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace drsim

@@ -1228,14 +1228,24 @@ extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_
   a.K2 = (a.h1 + 7) / 8 * 8; a.N2 = (a.h2 + 15) / 16 * 16;
   int off = 0;
   auto take = [&](int b) { int o = off; off += (b + 127) / 128 * 128; return o; };
-  a.off_w1 = take(a.N1 * a.K1 * 4); a.off_w2 = take(a.N2 * a.K2 * 4);
-  a.off_a1 = take(kActRows * a.K1 * 4); a.off_a2 = take(kActRows * a.K2 * 4);
-  a.off_vec = take((a.N1 + 3 * a.N2) * 4); a.off_bar = take(16);
-  a.smem_bytes = off;
   a.seed = seed; a.step = h->step; a.rep_offset = p.rep_offset;
-  CU_TRY(cudaFuncSetAttribute(k_actor, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
   const int tiles = (int)((a.rows + kActRows - 1) / kActRows);
-  k_actor<<<std::min(tiles, h->sm_count), kActThreads, a.smem_bytes, (cudaStream_t)stream>>>(a);
+  const char *v1 = getenv("DRSIM_ACTOR_V1");   // single-tile variant with the hidden layer staged in shared memory
+  a.off_w1 = take(a.N1 * a.K1 * 4); a.off_w2 = take(a.N2 * a.K2 * 4);
+  if (v1 && v1[0] == '1') {
+    a.off_a1 = take(kActRows * a.K1 * 4); a.off_a2 = take(kActRows * a.K2 * 4);
+    a.off_vec = take((a.N1 + 3 * a.N2) * 4); a.off_bar = take(16);
+    a.smem_bytes = off;
+    CU_TRY(cudaFuncSetAttribute(k_actor, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
+    k_actor<<<std::min(tiles, h->sm_count), kActThreads, a.smem_bytes, (cudaStream_t)stream>>>(a);
+  } else {
+    a.off_a1 = take(4 * kActRows * a.K1 * 4);   // two tile slots x two observation buffers
+    a.off_a2 = 0;
+    a.off_vec = take((a.N1 + 3 * a.N2) * 4); a.off_bar = take(32);
+    a.smem_bytes = off;
+    CU_TRY(cudaFuncSetAttribute(k_actor2, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
+    k_actor2<<<std::min((tiles + 1) / 2, h->sm_count), kAct2Threads, a.smem_bytes, (cudaStream_t)stream>>>(a);
+  }
   h->launches++;
   CU_TRY(cudaGetLastError());
   return 0;
