@@ -38,7 +38,7 @@ struct ActorArgs {
   float *prob_on;          // [rows] or NULL: probability of action 1
   long long rows;          // R * Ns (padding slots included; they get action 0)
   int Ns, N, D, h1, h2;
-  int K1, N1, K2, N2;      // padded: K multiple of 8 (UMMA_K of tf32), N multiple of 16
+  int K1, N1, K2, N2, K3;  // padded: K multiple of 8 (UMMA_K of tf32), N multiple of 16 (K3: k_actor2's output layer)
   int off_w1, off_w2, off_a1, off_a2, off_vec, off_bar, smem_bytes;
   unsigned long long seed;
   long long step, rep_offset;
@@ -279,19 +279,25 @@ __global__ void __launch_bounds__(kActThreads, 1) k_actor(ActorArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_actor2: the same computation with two tiles in flight per CTA and no shared-memory round trip
-// between the layers.
-//   * 256 threads = two warpgroups; warpgroup g owns tile slot g: its own observation buffers, TMEM
-//     columns, mbarrier and named barrier, so the two slots interleave freely on the SM (one runs its
-//     epilogue on the CUDA cores while the other's GEMM occupies the tensor core); weights are shared.
-//   * the hidden activations never leave tensor memory: epilogue 1 reads D1 with tcgen05.ld, applies
-//     bias + ReLU and writes the row back IN PLACE with tcgen05.st; layer 2 takes its A operand from
-//     TMEM (tcgen05.mma with [a_tmem], B from shared memory) -- no A2 staging, no proxy fence.
-//   * the observation tile of the slot's NEXT tile is fetched with cp.async straight into the canonical
-//     operand layout of the other buffer while the current tile computes.
+// k_actor2: the production variant.  Same network, but
+//   * two tiles in flight per CTA: 512 threads = two groups of 8 warps; group g owns tile slot g (its own
+//     observation buffers, TMEM columns, mbarrier and named barrier), so one slot runs its epilogue on the
+//     CUDA cores while the other's GEMM occupies the tensor core; the weights are shared;
+//   * all THREE layers are tcgen05 GEMMs and the activations never leave tensor memory: each epilogue
+//     reads its accumulator row with tcgen05.ld, applies ReLU + TF32 rounding and writes it back IN PLACE
+//     with tcgen05.st; the next layer takes its A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc);
+//   * the biases ride in the GEMMs: operand A carries a constant-one column (index D resp. h1, h2: a
+//     padding column), the weight matrix the bias in that column, plus one extra output row that
+//     regenerates the one for the next layer -- the epilogues are max(x, 0) only;
+//   * the 128 observation rows of the slot's NEXT tile (one contiguous run) arrive by a single TMA bulk
+//     copy in a raw staging buffer while the current tile computes, and are re-tiled into the canonical
+//     operand layout by the slot's threads;
+//   * two threads per row: warps w and w + 4 of a slot address the same TMEM lane quadrant and split the
+//     row's columns, halving every latency-bound epilogue pass.
 // ------------------------------------------------------------------------------------------------
-constexpr int kAct2Threads = 256;
+constexpr int kAct2Threads = 512;   // two tile slots x (128 rows x 2 column halves)
 constexpr int kAct2TmemCols = 512;
+constexpr int kActN3 = 16;   // the 2-wide output layer, padded to the smallest UMMA N for M = 128
 
 DRSIM_D void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -319,44 +325,73 @@ DRSIM_D void tmem_st16(uint32_t taddr, const uint32_t r[16]) {
       : "memory");
 }
 DRSIM_D void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-DRSIM_D void slot_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+DRSIM_D void slot_barrier(int slot) { asm volatile("bar.sync %0, 256;" ::"r"(slot + 1) : "memory"); }
+
+// ReLU + TF32 rounding of the accumulator columns [c_begin, cols) of this thread's TMEM lane, in place,
+// 32 columns per load / store round trip (64 per round trip spills at 128 registers and is slower)
+DRSIM_D void tmem_relu_inplace(uint32_t lane_addr, int c_begin, int cols) {
+  for (int c0 = c_begin; c0 < cols; c0 += 32) {
+    uint32_t r[2][16];
+    const bool two = c0 + 16 < cols;
+    tmem_ld16_issue(lane_addr + (uint32_t)c0, r[0]);
+    if (two) tmem_ld16_issue(lane_addr + (uint32_t)(c0 + 16), r[1]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[0][j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(r[0][j]), 0.f)));
+    tmem_st16(lane_addr + (uint32_t)c0, r[0]);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[1][j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(r[1][j]), 0.f)));
+      tmem_st16(lane_addr + (uint32_t)(c0 + 16), r[1]);
+    }
+  }
+  tmem_wait_st();
+}
+
+// weight matrix [n_out][n_in] (+ bias) -> canonical K-major operand with the bias in column n_in and the
+// "one regenerating" row n_out (0 ... 0 1 0 ...), everything else zero; `gen_one` = 0 for the last layer
+DRSIM_D void pack_weights(unsigned char *dst, const float *w, const float *b, int n_out, int n_in, int Np, int Kp,
+                          bool gen_one, int tid, int nthreads) {
+  for (int n = tid / 8; n < Np; n += nthreads / 8) {
+    for (int k = tid % 8; k < Kp; k += 8) {
+      float v = 0.f;
+      if (n < n_out) v = k < n_in ? w[(size_t)n * n_in + k] : (k == n_in ? b[n] : 0.f);
+      else if (n == n_out && gen_one && k == n_in) v = 1.f;
+      *reinterpret_cast<float *>(dst + umma_kmajor_off(Np, n, k)) = to_tf32(v);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *s_w1 = smem + a.off_w1, *s_w2 = smem + a.off_w2;
-  float *s_b1 = reinterpret_cast<float *>(smem + a.off_vec);   // [N1]
-  float *s_b2 = s_b1 + a.N1;                                     // [N2]
-  float *s_w3 = s_b2 + a.N2;                                     // [2][N2]
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // [2 slots]
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, slot = tid >> 7, t = tid & 127;
+  unsigned char *s_w1 = smem + a.off_w1, *s_w2 = smem + a.off_w2, *s_w3 = smem + a.off_vec;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // [2 slots] MMA completion, [2 slots] bulk-copy completion
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
+  // slot = tile slot; t = row of the tile (= TMEM lane); part = which half of the row's columns this thread
+  // handles (warps w and w + 4 of a slot address the same TMEM lane quadrant)
+  const int tid = threadIdx.x, warp = tid >> 5, slot = tid >> 8, t = tid & 127, part = (tid >> 7) & 1;
   const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
   const int a1_bytes = kActRows * a.K1 * 4;
-  unsigned char *s_a1 = smem + a.off_a1 + slot * 2 * a1_bytes;         // this slot's two observation buffers
+  const int k3 = a.K3;
+  unsigned char *s_a1 = smem + a.off_a1 + slot * a1_bytes;             // this slot's observation operand (canonical layout)
+  const int stage_bytes = (kActRows * a.D * 4 + 127) / 128 * 128;
+  float *s_stage = reinterpret_cast<float *>(smem + a.off_a2 + slot * stage_bytes);   // this slot's raw row-major tile
+  uint64_t *ldbar = s_bar + 2 + slot;                                  // completion of the slot's bulk copy
 
-  for (int i = tid; i < a.N1 * a.K1; i += kAct2Threads) {
-    const int n = i / a.K1, k = i - n * a.K1;
-    *reinterpret_cast<float *>(s_w1 + umma_kmajor_off(a.N1, n, k)) = (n < a.h1 && k < a.D) ? to_tf32(a.w1[(size_t)n * a.D + k]) : 0.f;
-  }
-  for (int i = tid; i < a.N2 * a.K2; i += kAct2Threads) {
-    const int n = i / a.K2, k = i - n * a.K2;
-    *reinterpret_cast<float *>(s_w2 + umma_kmajor_off(a.N2, n, k)) = (n < a.h2 && k < a.h1) ? to_tf32(a.w2[(size_t)n * a.h1 + k]) : 0.f;
-  }
-  for (int i = tid; i < a.N1; i += kAct2Threads) s_b1[i] = i < a.h1 ? a.b1[i] : 0.f;
-  for (int i = tid; i < a.N2; i += kAct2Threads) {
-    s_b2[i] = i < a.h2 ? a.b2[i] : 0.f;
-    s_w3[i] = i < a.h2 ? a.w3[i] : 0.f;
-    s_w3[a.N2 + i] = i < a.h2 ? a.w3[a.h2 + i] : 0.f;
-  }
-  // padding columns [D, K1) of all four observation buffers stay zero for the whole kernel
-  for (int i = tid; i < 4 * kActRows * (a.K1 - a.D); i += kAct2Threads) {
-    const int buf = i / (kActRows * (a.K1 - a.D)), j = i - buf * kActRows * (a.K1 - a.D);
-    const int row = j / (a.K1 - a.D), k = a.D + j % (a.K1 - a.D);
-    *reinterpret_cast<float *>(smem + a.off_a1 + buf * a1_bytes + umma_kmajor_off(kActRows, row, k)) = 0.f;
+  pack_weights(s_w1, a.w1, a.b1, a.h1, a.D, a.N1, a.K1, true, tid, kAct2Threads);
+  pack_weights(s_w2, a.w2, a.b2, a.h2, a.h1, a.N2, a.K2, true, tid, kAct2Threads);
+  pack_weights(s_w3, a.w3, a.b3, 2, a.h2, kActN3, k3, false, tid, kAct2Threads);
+  // observation buffers: the constant-one column at k = D, the other padding columns zero
+  for (int i = tid; i < 2 * kActRows; i += kAct2Threads) {
+    const int b = i / kActRows, row = i - b * kActRows;
+    for (int k = a.D; k < a.K1; ++k)
+      *reinterpret_cast<float *>(smem + a.off_a1 + b * a1_bytes + umma_kmajor_off(kActRows, row, k)) = k == a.D ? 1.f : 0.f;
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 1)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 2)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 3)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -366,54 +401,79 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *s_tmem + (uint32_t)(slot * 256);              // this slot's 256 columns: D1/A2 at 0, D2 at N1
-  const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2);
-  const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(s_w1), w2_addr = (uint32_t)__cvta_generic_to_shared(s_w2);
-  const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128;
+  // this slot's 256 TMEM columns: D1 -> A2 at [0, N1), D2 -> A3 at [N1, N1 + N2), D3 re-uses [0, 16)
+  const uint32_t tmem = *s_tmem + (uint32_t)(slot * 256);
+  const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2),
+                 idesc3 = umma_instr_desc_tf32(kActRows, kActN3);
+  const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(s_w1), w2_addr = (uint32_t)__cvta_generic_to_shared(s_w2),
+                 w3_addr = (uint32_t)__cvta_generic_to_shared(s_w3);
+  const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128, lbo_w3 = (kActN3 / 8) * 128;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quadrant
   uint64_t *bar = s_bar + slot;
   uint32_t phase = 0;
-  int buf = 0;
 
-  // observation rows [tile * 128, +128) -> buffer b, straight into the canonical layout (8-byte cp.async;
-  // rows past the end re-read the last valid row: their results are never written)
-  auto fetch = [&](int tile, int b) {
-    const long long row0 = (long long)tile * kActRows;
-    const int n_valid = (int)min((long long)kActRows, a.rows - row0);
-    const float *src = a.obs + (size_t)row0 * a.D;
-    unsigned char *dst = s_a1 + b * a1_bytes;
-    if ((a.D & 1) == 0) {
-      const int half = a.D >> 1;
-      for (int i = t; i < kActRows * half; i += 128) {
-        const int row = i / half, k = (i - row * half) * 2;
-        const int rs = min(row, n_valid - 1);
-        cp_async8(dst + umma_kmajor_off(kActRows, row, k), src + (size_t)rs * a.D + k);
-      }
-    } else {
-      for (int i = t; i < kActRows * a.D; i += 128) {
-        const int row = i / a.D, k = i - row * a.D;
-        const int rs = min(row, n_valid - 1);
-        cp_async4(dst + umma_kmajor_off(kActRows, row, k), src + (size_t)rs * a.D + k);
-      }
+  // The 128 observation rows of a tile are one contiguous run of global memory: a single TMA bulk copy
+  // (cp.async.bulk, completion on the slot's mbarrier) brings it into a raw row-major staging buffer one
+  // tile ahead; the threads then re-tile it (row t by thread t: 8-byte shared loads, TF32 rounding,
+  // conflict-free stores) into the canonical operand layout.  (cp.async pieces straight into the operand
+  // layout cost 2.8k cycles per tile: 32 sectors per warp instruction on the global side, or 16-way bank
+  // conflicts on the shared side; a tiled TMA cannot address rows of 200 bytes -- pitch not 16-byte aligned.)
+  auto fetch = [&](int tile) {
+    if (t == 0 && part == 0) {
+      const long long row0 = (long long)tile * kActRows;
+      const int n_valid = (int)min((long long)kActRows, a.rows - row0);
+      const uint32_t bytes = (uint32_t)(n_valid * a.D * 4);     // rows % 4 == 0: a multiple of 16
+      mbar_expect_tx(ldbar, bytes);
+      bulk_load_g2s(s_stage, a.obs + (size_t)row0 * a.D, bytes, ldbar);
     }
   };
+  uint32_t ld_phase = 0;
   const int stride = 2 * gridDim.x;
   int tile = 2 * blockIdx.x + slot;
-  if (tile < n_tiles) fetch(tile, 0);
+  if (tile < n_tiles) fetch(tile);
 
-  for (; tile < n_tiles; tile += stride, buf ^= 1) {
+#if defined(DRSIM_ACTOR_PROF)
+  long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = clock64();
+#define PROF(i) { const long long now = clock64(); tq[i] += now - tl; tl = now; }
+#else
+#define PROF(i)
+#endif
+  for (; tile < n_tiles; tile += stride) {
     const long long row0 = (long long)tile * kActRows;
-    cp_async_wait_all();
+    {
+      // raw tile -> canonical operand (the previous tile's layer-1 GEMM, the buffer's last reader, has completed)
+      const int n_valid = (int)min((long long)kActRows, a.rows - row0);
+      mbar_wait_bounded(ldbar, ld_phase);
+      ld_phase ^= 1u;
+      unsigned char *d = s_a1 + umma_kmajor_off(kActRows, t, 0);
+      const float *g = s_stage + (size_t)t * a.D;
+      const bool live = t < n_valid;
+      const int k_mid = ((a.D / 2) + 1) & ~1, k_lo = part ? k_mid : 0, k_hi = part ? a.D : k_mid;   // this thread's half of the row
+      if ((a.D & 1) == 0) {
+#pragma unroll 4
+        for (int k = k_lo; k < k_hi; k += 2) {
+          const float2 v = live ? *reinterpret_cast<const float2 *>(g + k) : make_float2(0.f, 0.f);
+          *reinterpret_cast<float2 *>(d + (k >> 2) * (int)((kActRows / 8) * 128) + (k & 3) * 4) = make_float2(to_tf32(v.x), to_tf32(v.y));
+        }
+      } else {
+#pragma unroll 4
+        for (int k = k_lo; k < k_hi; ++k)
+          *reinterpret_cast<float *>(d + (k >> 2) * (int)((kActRows / 8) * 128) + (k & 3) * 4) = live ? to_tf32(g[k]) : 0.f;
+      }
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
-    slot_barrier(slot);   // the tile's rows are in shared memory; every lane is done with the previous tile's TMEM
-    if (tile + stride < n_tiles) fetch(tile + stride, buf ^ 1);   // flies during this tile's GEMMs and epilogues
-    const uint32_t a1_addr = (uint32_t)__cvta_generic_to_shared(s_a1 + buf * a1_bytes);
-    // ---- layer 1: D1[128 x N1] = A1 . W1^T ----------------------------------------------------------
-    if (t == 0) {
+    slot_barrier(slot);   // operand complete, staging buffer drained; every lane is done with the previous tile's TMEM
+    PROF(0)
+    if (tile + stride < n_tiles) fetch(tile + stride);   // flies during this tile's GEMMs and epilogues
+    PROF(1)
+    const uint32_t a1_addr = (uint32_t)__cvta_generic_to_shared(s_a1);
+    // ---- layer 1: D1[128 x N1] = [obs | 1] . [W1 | b1]^T ------------------------------------------------
+    if (t == 0 && part == 0) {
       tc_fence_after();
       for (int ks = 0; ks < a.K1 / 8; ++ks)
         umma_tf32_ss(tmem, umma_smem_desc(a1_addr + ks * 2 * lbo_a, lbo_a, 128),
@@ -423,27 +483,16 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
     mbar_wait_bounded(bar, phase);
     phase ^= 1u;
     tc_fence_after();
-    // ---- epilogue 1, in place in tensor memory: D1 row -> + b1, ReLU, TF32 -> A2 row --------------------
-    for (int c0 = 0; c0 < a.K2; c0 += 32) {
-      uint32_t r[2][16];
-      tmem_ld16_issue(lane_addr + (uint32_t)c0, r[0]);
-      if (c0 + 16 < a.N1) tmem_ld16_issue(lane_addr + (uint32_t)(c0 + 16), r[1]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (c0 + 16 * q < a.N1) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            r[q][j] = __float_as_uint(to_tf32(fmaxf(__uint_as_float(r[q][j]) + s_b1[c0 + 16 * q + j], 0.f)));
-          tmem_st16(lane_addr + (uint32_t)(c0 + 16 * q), r[q]);
-        }
-      }
+    PROF(2)
+    {                                                         // A2 = relu(D1) (column h1 = 1), half the columns per thread
+      const int mid = (a.K2 / 2 + 15) & ~15;
+      tmem_relu_inplace(lane_addr, part ? mid : 0, part ? a.K2 : mid);
     }
-    tmem_wait_st();
     tc_fence_before();
     slot_barrier(slot);
-    // ---- layer 2: D2[128 x N2] = A2 (tensor memory) . W2^T ---------------------------------------------
-    if (t == 0) {
+    PROF(3)
+    // ---- layer 2: D2[128 x N2] = A2 (tensor memory) . [W2 | b2]^T ---------------------------------------
+    if (t == 0 && part == 0) {
       tc_fence_after();
       for (int ks = 0; ks < a.K2 / 8; ++ks)
         umma_tf32_ts(tmem + (uint32_t)a.N1, tmem + (uint32_t)(ks * 8), umma_smem_desc(w2_addr + ks * 2 * lbo_w2, lbo_w2, 128),
@@ -453,28 +502,32 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
     mbar_wait_bounded(bar, phase);
     phase ^= 1u;
     tc_fence_after();
-    // ---- epilogue 2: + b2, ReLU, output layer on the CUDA cores, softmax, categorical draw ---------------
-    float l0 = a.b3[0], l1 = a.b3[1];
-    for (int c0 = 0; c0 < a.N2; c0 += 32) {
-      uint32_t r[2][16];
-      tmem_ld16_issue(lane_addr + (uint32_t)(a.N1 + c0), r[0]);
-      if (c0 + 16 < a.N2) tmem_ld16_issue(lane_addr + (uint32_t)(a.N1 + c0 + 16), r[1]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (c0 + 16 * q < a.N2) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + 16 * q + j;
-            const float h = fmaxf(__uint_as_float(r[q][j]) + s_b2[c], 0.f);
-            l0 = fmaf(h, s_w3[c], l0);
-            l1 = fmaf(h, s_w3[a.N2 + c], l1);
-          }
-        }
-      }
+    PROF(4)
+    {                                                         // A3 = relu(D2) (column h2 = 1)
+      const int mid = (k3 / 2 + 15) & ~15;
+      tmem_relu_inplace(lane_addr + (uint32_t)a.N1, part ? mid : 0, part ? k3 : mid);
     }
+    tc_fence_before();
+    slot_barrier(slot);
+    PROF(5)
+    // ---- layer 3: D3[128 x 16] = A3 . [W3 | b3]^T (two real output columns) -----------------------------
+    if (t == 0 && part == 0) {
+      tc_fence_after();
+      for (int ks = 0; ks < k3 / 8; ++ks)
+        umma_tf32_ts(tmem, tmem + (uint32_t)(a.N1 + ks * 8), umma_smem_desc(w3_addr + ks * 2 * lbo_w3, lbo_w3, 128), idesc3, ks > 0);
+      umma_commit(bar);
+    }
+    mbar_wait_bounded(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    PROF(6)
+    // ---- softmax + categorical draw -------------------------------------------------------------------
+    uint32_t lg[16];
+    tmem_ld16_issue(lane_addr, lg);
+    tmem_wait_ld();
+    const float l0 = __uint_as_float(lg[0]), l1 = __uint_as_float(lg[1]);
     const long long row = row0 + t;
-    if (row < a.rows) {
+    if (row < a.rows && part == 0) {
       const long long rr = row / a.Ns;
       const int n = (int)(row - rr * a.Ns);
       uint8_t act = 0;
@@ -493,8 +546,12 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
       if (a.prob) a.prob[row] = p_draw;
       if (a.prob_on) a.prob_on[row] = p1;
     }
+    PROF(7)
   }
-  cp_async_wait_all();
+#if defined(DRSIM_ACTOR_PROF)
+  if (blockIdx.x == 3 && t == 5 && part == 0 && a.prob_on)
+    for (int i = 0; i < 8; ++i) a.prob_on[slot * 8 + i] = (float)tq[i];
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0)
