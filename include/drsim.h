@@ -284,7 +284,7 @@ typedef struct drsim_actor_net {
   const float *w1, *b1; /* [h1][obs_dim], [h1] */
   const float *w2, *b2; /* [h2][h1], [h2] */
   const float *w3, *b3; /* [2][h2], [2] */
-  int32_t h1, h2;       /* 1 .. 127 each */
+  int32_t h1, h2;       /* 1 .. 111 each */
 } drsim_actor_net;
 
 /* MAPPO.select_actions (mappo.py:83-97) for every house of every replica, on the device:

@@ -365,8 +365,8 @@ DRSIM_D void pack_weights(unsigned char *dst, const float *w, const float *b, in
 __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *s_w1 = smem + a.off_w1, *s_w2 = smem + a.off_w2, *s_w3 = smem + a.off_vec;
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // [2 slots] MMA completion, [2 slots] bulk-copy completion
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // per slot: GEMM1 [0,2), bulk copy [2,4), GEMM2 [4,6), GEMM3 [6,8)
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
   // slot = tile slot; t = row of the tile (= TMEM lane); part = which half of the row's columns this thread
   // handles (warps w and w + 4 of a slot address the same TMEM lane quadrant)
   const int tid = threadIdx.x, warp = tid >> 5, slot = tid >> 8, t = tid & 127, part = (tid >> 7) & 1;
@@ -390,8 +390,8 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 1)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 2)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 3)));
+    for (int i = 2; i < 8; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // this slot's 256 TMEM columns: D1 -> A2 at [0, N1), D2 -> A3 at [N1, N1 + N2), D3 re-uses [0, 16)
+  // this slot's 256 TMEM columns: D1 -> A2 at [0, N1), D2 -> A3 at [N1, N1 + N2), D3 at [N1 + N2, +16)
   const uint32_t tmem = *s_tmem + (uint32_t)(slot * 256);
   const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2),
                  idesc3 = umma_instr_desc_tf32(kActRows, kActN3);
@@ -414,7 +414,6 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128, lbo_w3 = (kActN3 / 8) * 128;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quadrant
   uint64_t *bar = s_bar + slot;
-  uint32_t phase = 0;
 
   // The 128 observation rows of a tile are one contiguous run of global memory: a single TMA bulk copy
   // (cp.async.bulk, completion on the slot's mbarrier) brings it into a raw row-major staging buffer one
@@ -433,19 +432,25 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   };
   uint32_t ld_phase = 0;
   const int stride = 2 * gridDim.x;
-  int tile = 2 * blockIdx.x + slot;
-  if (tile < n_tiles) fetch(tile);
+  const uint32_t a1_addr = (uint32_t)__cvta_generic_to_shared(s_a1);
+  const uint32_t r1 = tmem, r2 = tmem + (uint32_t)a.N1, r3 = tmem + (uint32_t)(a.N1 + a.N2);   // D1/A2, D2/A3, D3
+  uint64_t *bar1 = bar, *bar2 = s_bar + 4 + slot, *bar3 = s_bar + 6 + slot;
+  uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
+  const bool issuer = t == 0 && part == 0;
 
-#if defined(DRSIM_ACTOR_PROF)
-  long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = clock64();
-#define PROF(i) { const long long now = clock64(); tq[i] += now - tl; tl = now; }
-#else
-#define PROF(i)
-#endif
-  for (; tile < n_tiles; tile += stride) {
-    const long long row0 = (long long)tile * kActRows;
-    {
-      // raw tile -> canonical operand (the previous tile's layer-1 GEMM, the buffer's last reader, has completed)
+  // Software pipeline over the slot's tiles, two tiles in different stages at any time.  The tensor pipe
+  // executes the GEMMs of a slot in issue order, which is what makes the TMEM regions safe to recycle:
+  //   S1(b): re-tile b, issue GEMM1(b) -> R1          (R1's last reader, GEMM2(a), was issued earlier)
+  //   S2(a): wait GEMM2(a), ReLU R2 in place, issue GEMM3(a): R2 -> R3
+  //   S3(b): wait GEMM1(b), ReLU R1 in place, issue GEMM2(b): R1 -> R2   (after GEMM3(a), which reads R2)
+  //   S4(a): wait GEMM3(a), softmax + draw from R3
+  // so every GEMM round trip is covered by the other tile's epilogue work.
+  int tile_b = 2 * blockIdx.x + slot, tile_a = -1;
+  if (tile_b < n_tiles) fetch(tile_b);
+  while (tile_b < n_tiles || tile_a >= 0) {
+    const bool has_b = tile_b < n_tiles, has_a = tile_a >= 0;
+    if (has_b) {   // ---- S1(b)
+      const long long row0 = (long long)tile_b * kActRows;
       const int n_valid = (int)min((long long)kActRows, a.rows - row0);
       mbar_wait_bounded(ldbar, ld_phase);
       ld_phase ^= 1u;
@@ -464,94 +469,80 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
         for (int k = k_lo; k < k_hi; ++k)
           *reinterpret_cast<float *>(d + (k >> 2) * (int)((kActRows / 8) * 128) + (k & 3) * 4) = live ? to_tf32(g[k]) : 0.f;
       }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    slot_barrier(slot);   // operand complete, staging buffer drained; every lane is done with the previous tile's TMEM
-    PROF(0)
-    if (tile + stride < n_tiles) fetch(tile + stride);   // flies during this tile's GEMMs and epilogues
-    PROF(1)
-    const uint32_t a1_addr = (uint32_t)__cvta_generic_to_shared(s_a1);
-    // ---- layer 1: D1[128 x N1] = [obs | 1] . [W1 | b1]^T ------------------------------------------------
-    if (t == 0 && part == 0) {
-      tc_fence_after();
-      for (int ks = 0; ks < a.K1 / 8; ++ks)
-        umma_tf32_ss(tmem, umma_smem_desc(a1_addr + ks * 2 * lbo_a, lbo_a, 128),
-                     umma_smem_desc(w1_addr + ks * 2 * lbo_w1, lbo_w1, 128), idesc1, ks > 0);
-      umma_commit(bar);
-    }
-    mbar_wait_bounded(bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    PROF(2)
-    {                                                         // A2 = relu(D1) (column h1 = 1), half the columns per thread
-      const int mid = (a.K2 / 2 + 15) & ~15;
-      tmem_relu_inplace(lane_addr, part ? mid : 0, part ? a.K2 : mid);
-    }
-    tc_fence_before();
-    slot_barrier(slot);
-    PROF(3)
-    // ---- layer 2: D2[128 x N2] = A2 (tensor memory) . [W2 | b2]^T ---------------------------------------
-    if (t == 0 && part == 0) {
-      tc_fence_after();
-      for (int ks = 0; ks < a.K2 / 8; ++ks)
-        umma_tf32_ts(tmem + (uint32_t)a.N1, tmem + (uint32_t)(ks * 8), umma_smem_desc(w2_addr + ks * 2 * lbo_w2, lbo_w2, 128),
-                     idesc2, ks > 0);
-      umma_commit(bar);
-    }
-    mbar_wait_bounded(bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    PROF(4)
-    {                                                         // A3 = relu(D2) (column h2 = 1)
-      const int mid = (k3 / 2 + 15) & ~15;
-      tmem_relu_inplace(lane_addr + (uint32_t)a.N1, part ? mid : 0, part ? k3 : mid);
-    }
-    tc_fence_before();
-    slot_barrier(slot);
-    PROF(5)
-    // ---- layer 3: D3[128 x 16] = A3 . [W3 | b3]^T (two real output columns) -----------------------------
-    if (t == 0 && part == 0) {
-      tc_fence_after();
-      for (int ks = 0; ks < k3 / 8; ++ks)
-        umma_tf32_ts(tmem, tmem + (uint32_t)(a.N1 + ks * 8), umma_smem_desc(w3_addr + ks * 2 * lbo_w3, lbo_w3, 128), idesc3, ks > 0);
-      umma_commit(bar);
-    }
-    mbar_wait_bounded(bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    PROF(6)
-    // ---- softmax + categorical draw -------------------------------------------------------------------
-    uint32_t lg[16];
-    tmem_ld16_issue(lane_addr, lg);
-    tmem_wait_ld();
-    const float l0 = __uint_as_float(lg[0]), l1 = __uint_as_float(lg[1]);
-    const long long row = row0 + t;
-    if (row < a.rows && part == 0) {
-      const long long rr = row / a.Ns;
-      const int n = (int)(row - rr * a.Ns);
-      uint8_t act = 0;
-      float p_draw = 0.f, p1 = 0.f;
-      if (n < a.N) {
-        const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
-        const float e0 = __expf(l0 - m), e1 = __expf(l1 - m);
-        const float p0 = e0 / (e0 + e1);
-        p1 = 1.f - p0;
-        const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + rr), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
-        const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
-        act = uf < p0 ? 0 : 1;
-        p_draw = act ? p1 : p0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      slot_barrier(slot);   // operand complete, staging buffer drained
+      if (tile_b + stride < n_tiles) fetch(tile_b + stride);   // flies during the next stages
+      if (issuer) {         // layer 1: D1[128 x N1] = [obs | 1] . [W1 | b1]^T
+        tc_fence_after();
+        for (int ks = 0; ks < a.K1 / 8; ++ks)
+          umma_tf32_ss(r1, umma_smem_desc(a1_addr + ks * 2 * lbo_a, lbo_a, 128),
+                       umma_smem_desc(w1_addr + ks * 2 * lbo_w1, lbo_w1, 128), idesc1, ks > 0);
+        umma_commit(bar1);
       }
-      a.actions[row] = act;
-      if (a.prob) a.prob[row] = p_draw;
-      if (a.prob_on) a.prob_on[row] = p1;
     }
-    PROF(7)
+    if (has_a) {   // ---- S2(a)
+      mbar_wait_bounded(bar2, ph2);
+      ph2 ^= 1u;
+      tc_fence_after();
+      const int mid = (k3 / 2 + 15) & ~15;                    // A3 = relu(D2) (column h2 = 1)
+      tmem_relu_inplace(lane_addr + (uint32_t)a.N1, part ? mid : 0, part ? k3 : mid);
+      tc_fence_before();
+      slot_barrier(slot);
+      if (issuer) {         // layer 3: D3[128 x 16] = A3 . [W3 | b3]^T (two real output columns)
+        tc_fence_after();
+        for (int ks = 0; ks < k3 / 8; ++ks)
+          umma_tf32_ts(r3, r2 + (uint32_t)(ks * 8), umma_smem_desc(w3_addr + ks * 2 * lbo_w3, lbo_w3, 128), idesc3, ks > 0);
+        umma_commit(bar3);
+      }
+    }
+    if (has_b) {   // ---- S3(b)
+      mbar_wait_bounded(bar1, ph1);
+      ph1 ^= 1u;
+      tc_fence_after();
+      const int mid = (a.K2 / 2 + 15) & ~15;                  // A2 = relu(D1) (column h1 = 1), half the columns per thread
+      tmem_relu_inplace(lane_addr, part ? mid : 0, part ? a.K2 : mid);
+      tc_fence_before();
+      slot_barrier(slot);
+      if (issuer) {         // layer 2: D2[128 x N2] = A2 (tensor memory) . [W2 | b2]^T
+        tc_fence_after();
+        for (int ks = 0; ks < a.K2 / 8; ++ks)
+          umma_tf32_ts(r2, r1 + (uint32_t)(ks * 8), umma_smem_desc(w2_addr + ks * 2 * lbo_w2, lbo_w2, 128), idesc2, ks > 0);
+        umma_commit(bar2);
+      }
+    }
+    if (has_a) {   // ---- S4(a): softmax + categorical draw
+      mbar_wait_bounded(bar3, ph3);
+      ph3 ^= 1u;
+      tc_fence_after();
+      uint32_t lg[16];
+      tmem_ld16_issue(lane_addr + (uint32_t)(a.N1 + a.N2), lg);
+      tmem_wait_ld();
+      const float l0 = __uint_as_float(lg[0]), l1 = __uint_as_float(lg[1]);
+      const long long row = (long long)tile_a * kActRows + t;
+      if (row < a.rows && part == 0) {
+        const long long rr = row / a.Ns;
+        const int n = (int)(row - rr * a.Ns);
+        uint8_t act = 0;
+        float p_draw = 0.f, p1 = 0.f;
+        if (n < a.N) {
+          const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
+          const float e0 = __expf(l0 - m), e1 = __expf(l1 - m);
+          const float p0 = e0 / (e0 + e1);
+          p1 = 1.f - p0;
+          const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + rr), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
+          const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
+          act = uf < p0 ? 0 : 1;
+          p_draw = act ? p1 : p0;
+        }
+        a.actions[row] = act;
+        if (a.prob) a.prob[row] = p_draw;
+        if (a.prob_on) a.prob_on[row] = p1;
+      }
+    }
+    tile_a = has_b ? tile_b : -1;
+    tile_b += stride;
   }
-#if defined(DRSIM_ACTOR_PROF)
-  if (blockIdx.x == 3 && t == 5 && part == 0 && a.prob_on)
-    for (int i = 0; i < 8; ++i) a.prob_on[slot * 8 + i] = (float)tq[i];
-#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0)

@@ -1244,12 +1244,13 @@ extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_
     a.K1 = (a.D + 1 + 7) / 8 * 8; a.N1 = (a.h1 + 1 + 15) / 16 * 16;
     a.K2 = (a.h1 + 1 + 7) / 8 * 8; a.N2 = (a.h2 + 1 + 15) / 16 * 16;
     a.K3 = (a.h2 + 1 + 7) / 8 * 8;
-    if (a.N1 + a.N2 > 256) return fail(DRSIM_E_ARG, "drsim_policy_step: h1 + h2 too wide for two tile slots in tensor memory (<= 127 each)");
+    if (a.N1 + a.N2 + kActN3 > 256)
+      return fail(DRSIM_E_ARG, "drsim_policy_step: h1 + h2 too wide for two tile slots in tensor memory (<= 111 each, 224 together)");
     a.off_w1 = take(a.N1 * a.K1 * 4); a.off_w2 = take(a.N2 * a.K2 * 4);
     a.off_vec = take(kActN3 * a.K3 * 4);          // output-layer operand
     a.off_a1 = take(2 * kActRows * a.K1 * 4);     // two tile slots: observation operand (canonical layout)
     a.off_a2 = take(2 * ((kActRows * a.D * 4 + 127) / 128 * 128));   // two tile slots: raw row-major staging of the next tile
-    a.off_bar = take(64);
+    a.off_bar = take(128);
     a.smem_bytes = off;
     if (a.smem_bytes > 227 * 1024) return fail(DRSIM_E_ARG, "drsim_policy_step: network / observation too wide for shared memory");
     CU_TRY(cudaFuncSetAttribute(k_actor2, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));

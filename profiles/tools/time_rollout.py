@@ -23,6 +23,7 @@ acts = (torch.rand((R, N), device="cuda") < 0.5).to(torch.uint8)
 
 
 def timed(fn, k=200):
+    """CUDA-graph replay when the work is short enough to be bound by the Python launch rate."""
     for _ in range(20):
         fn()
     torch.cuda.synchronize()

@@ -267,7 +267,7 @@ def _torch_actor(D, h1, h2, seed):
 
 
 @pytest.mark.parametrize("R,n,layout,h1,h2", [(300, 100, "hand_engineered", 100, 100), (7, 1000, "tarmac", 100, 100),
-                                              (33, 37, "hand_engineered", 64, 48), (5, 9, "tarmac", 127, 120)])
+                                              (33, 37, "hand_engineered", 64, 48), (5, 9, "tarmac", 111, 96)])
 def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
     """the tcgen05 actor + categorical draw against a plain PyTorch fp32 forward of the same
     weights.  Probabilities: TF32 operands (10-bit mantissa, rounded to nearest), fp32 accumulation -> |dp| <= 5e-3
