@@ -778,36 +778,6 @@ static PeerCtx make_peer(const drsim_handle *h) {
   return pc;
 }
 
-template <typename real>
-static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s) {
-  const Planes<real> pl = make_planes<real>(h);
-  const SimParams &p = h->p;
-  if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
-    int n2 = 1;
-    while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
-    h->launches++;
-  }
-  k_house<real><<<p.R * h->chunks, kThreads, 0, s>>>(pl, p, in, h->chunks);
-  k_reduce<real><<<p.R, 128, 0, s>>>(pl, p, in, h->chunks, make_peer(h));
-  h->launches += 2;
-  CU_TRY(cudaGetLastError());
-  return 0;
-}
-
-template <typename real>
-static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, int n_parts, cudaStream_t s) {
-  const Planes<real> pl = make_planes<real>(h);
-  const SimParams &p = h->p;
-  PeerCtx pc = make_peer(h);
-  if (acc || n_parts >= 0) pc.world = 1;  // explicit partials (or the handle's own): no peer wait
-  k_env<real><<<(p.R + 127) / 128, 128, 0, s>>>(pl, p, in, acc ? acc : pl.acc, acc ? n_parts : 1, pc);
-  k_obs<real><<<p.R * h->obs_chunks, kObsChunk, (size_t)kObsChunk * p.obs_dim * sizeof(real), s>>>(pl, p, in, h->obs_chunks);
-  h->launches += 2;
-  CU_TRY(cudaGetLastError());
-  return 0;
-}
-
 // Launch with programmatic stream serialisation (PDL): the kernel may become resident while the
 // previous kernel of the stream drains; it calls griddepcontrol.wait before it touches anything an
 // earlier kernel wrote (see pdl_wait in drsim_kernels.cuh).
@@ -824,6 +794,36 @@ static void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
   cfg.attrs = at;
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+template <typename real>
+static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const SimParams &p = h->p;
+  if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
+    int n2 = 1;
+    while (n2 < p.N) n2 <<= 1;
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
+    h->launches++;
+  }
+  launch_pdl(k_house<real>, p.R * h->chunks, kThreads, 0, s, pl, p, in, h->chunks);
+  launch_pdl(k_reduce<real>, p.R, 128, 0, s, pl, p, in, h->chunks, make_peer(h));
+  h->launches += 2;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <typename real>
+static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc, int n_parts, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const SimParams &p = h->p;
+  PeerCtx pc = make_peer(h);
+  if (acc || n_parts >= 0) pc.world = 1;  // explicit partials (or the handle's own): no peer wait
+  launch_pdl(k_env<real>, (p.R + 127) / 128, 128, 0, s, pl, p, in, (const double *)(acc ? acc : pl.acc), acc ? n_parts : 1, pc);
+  launch_pdl(k_obs<real>, p.R * h->obs_chunks, kObsChunk, (size_t)kObsChunk * p.obs_dim * sizeof(real), s, pl, p, in, h->obs_chunks);
+  h->launches += 2;
+  CU_TRY(cudaGetLastError());
+  return 0;
 }
 
 // picks the compile-time specialisation of the production kernel (see k_fused_tma)

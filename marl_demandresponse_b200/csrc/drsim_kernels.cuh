@@ -169,6 +169,23 @@ DRSIM_D void store4i(int32_t *p, const int v[4]) {
 DRSIM_D uint32_t load4b(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
 DRSIM_D void store4b(uint8_t *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v; }
 
+// Programmatic dependent launch (PDL): the fused step kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so step t+1's CTAs become resident while step
+// t's last CTAs drain.  pdl_trigger lets the next kernel in the stream start launching; pdl_wait
+// blocks until every kernel before this one in the stream has completed and flushed its writes --
+// nothing written by an earlier kernel (state planes, actions, schedule records) is touched before
+// it, only the launch-invariant static planes.  Both are no-ops in a normal launch.
+DRSIM_D void pdl_trigger() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+DRSIM_D void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // L2 eviction-priority policies (PTX createpolicy): the per-step working set is state + static planes
 // (~45 B/house, re-read every step) plus the streamed outputs (observation rows, rewards).  Marking the
 // former evict_last and the latter evict_first lets the 126 MB L2 keep the planes that the next step
@@ -824,6 +841,8 @@ DRSIM_D void block_reduce(real red[kRed], double out[kRed], double (*wp)[kRed]) 
 // ------------------------------------------------------------------------------------------
 template <typename real>
 __global__ void __launch_bounds__(kThreads) k_house(Planes<real> pl, SimParams p, StepIn in, int chunks) {
+  pdl_wait();      // general path: plain stream order, but the launch latencies of the four kernels overlap
+  pdl_trigger();
   const int r = blockIdx.x / chunks, c = blockIdx.x % chunks;
   const int n0 = (c * kThreads + threadIdx.x) * kHousesPerThread;
   const KC<real> kc(p);
@@ -886,6 +905,8 @@ DRSIM_D real interp5(const real *sub, const real x[5]) {
 // ------------------------------------------------------------------------------------------
 template <typename real>
 __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, StepIn in, int chunks, PeerCtx peer) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x;
   double red[kRed] = {0, 0, 0, 0, 0};
   // fixed assignment + fixed combine order => deterministic
@@ -1007,6 +1028,8 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
 // rank order (sums; column 2 is a max), so every rank derives bit-identical cluster totals.
 template <typename real>
 __global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc, int n_parts, PeerCtx peer) {
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= p.R) return;
   double red[kRed] = {0, 0, 0, 0, 0};
@@ -1044,6 +1067,8 @@ template <typename real>
 __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p, StepIn in, int chunks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   real *tile = reinterpret_cast<real *>(smem_raw);
+  pdl_wait();
+  pdl_trigger();
   const int r = blockIdx.x / chunks, c = blockIdx.x % chunks;
   const int n = c * kObsChunk + threadIdx.x;
   const int D = p.obs_dim;
@@ -1726,22 +1751,6 @@ DRSIM_D void cp_async4(void *sdst, const void *gsrc) {
 #define DRSIM_STAGE_BULK 0  // 1: inputs staged by per-warp TMA bulk loads; 0: by thread-private cp.async copies
 #endif
 
-// Programmatic dependent launch (PDL): the fused step kernels are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so step t+1's CTAs become resident while step
-// t's last CTAs drain.  pdl_trigger lets the next kernel in the stream start launching; pdl_wait
-// blocks until every kernel before this one in the stream has completed and flushed its writes --
-// nothing written by an earlier kernel (state planes, actions, schedule records) is touched before
-// it, only the launch-invariant static planes.  Both are no-ops in a normal launch.
-DRSIM_D void pdl_trigger() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-DRSIM_D void pdl_wait() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, DRSIM_FUSED_MINCTAS)
