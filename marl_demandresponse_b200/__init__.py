@@ -6,6 +6,7 @@ Public surface
                     (``reset()`` / ``step(action_dict)`` returning per-agent dicts).
 ``BatchedEnv``      thousands of independent replicas with zero-copy torch tensor views.
 ``norm_state_dict`` the reference's observation normaliser, served from device tensors.
+``MADemandResponseEnv`` / ``norm_state_dict_v0``  the legacy gym-style env of ``server/v0`` (``v0.py``).
 ``DrSim``           thin owner of the C handle (``include/drsim.h``).
 
 The CUDA extension (``libdrsim.so``, sm_100a) is mandatory; there is no CPU fallback.
@@ -19,6 +20,10 @@ def __getattr__(name):
         from . import environment
 
         return getattr(environment, name)
+    if name in ("MADemandResponseEnv", "norm_state_dict_v0", "props_from_v0"):
+        from . import v0
+
+        return getattr(v0, name)
     if name in ("BatchedEnv", "synthetic_state"):
         from . import batched
 

@@ -110,3 +110,34 @@ def test_philox_matches_numpy_restatement():
         L.drsim_host_philox(key, *c, C.byref(out))
         want = philox.philox4x32_10(key, *c)
         assert [int(v) for v in out] == [int(w) for w in want]
+
+
+def test_v0_config_translation_and_norm_vector():
+    """Legacy config_dict -> app-style property tree (no GPU needed), and the legacy normStateDict
+    restatement on a hand-made observation dict (v0/utils.py:541-657: float lock-out ratio, power over
+    norm_reg_sig * nb_agents)."""
+    import datetime as dt
+    import json
+    import os
+
+    import numpy as np
+
+    from marl_demandresponse_b200.v0 import norm_state_dict_v0, props_from_v0
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "v0_n20_sinus_mixture_flags.npz"))
+    cfg = json.loads(str(z["config_json"]))
+    p = props_from_v0(cfg)
+    assert p.cluster_prop.nb_agents == 20 and p.cluster_prop.agents_comm_prop.mode == "closed_groups"
+    assert p.cluster_prop.agents_comm_prop.max_nb_agents_communication == 4
+    assert p.power_grid_prop.signal_properties.mode == "sinusoidals" and p.reward_prop.penalty_props.mode == "mixture"
+    assert p.cluster_prop.house_prop.hvac_prop.noise_prop.cooling_capacity_list == [12500, 15000, 17500]
+    assert p.time_step == dt.timedelta(seconds=4) and p.start_datetime_mode == "random"
+    obs = {"house_temp": 22.0, "house_mass_temp": 21.0, "house_target_temp": 20.0, "house_deadband": 0.0, "OD_temp": 30.0,
+           "house_solar_gain": 500.0, "hvac_cooling_capacity": 15000, "house_Ua": 218.0, "house_Cm": 3.45e6, "house_Ca": 9.08e5,
+           "house_Hm": 2840.0, "hvac_COP": 2.5, "hvac_latent_cooling_fraction": 0.35, "hvac_turned_on": True, "hvac_lockout": False,
+           "hvac_seconds_since_off": 12, "hvac_lockout_duration": 40, "reg_signal": 75000.0, "cluster_hvac_power": 30000.0,
+           "datetime": dt.datetime(2021, 1, 1), "message": []}
+    d = norm_state_dict_v0(obs, cfg, return_dict=True)
+    assert d["hvac_seconds_since_off"] == 0.3 and d["house_temp"] == 0.4 and d["OD_temp"] == 2.0
+    assert d["cluster_hvac_power"] == 30000.0 / (7500 * 20) and d["reg_signal"] == 0.5 and d["house_solar_gain"] == 0.5
+    assert norm_state_dict_v0(obs, cfg).shape == (len(d) - 1,)
