@@ -33,6 +33,34 @@ def house_shard(n_houses: int, rank: int, world: int):
     return lo, hi
 
 
+def halo_edge_houses(n_global: int, rank: int, world: int, nb_comm: int):
+    """Global ids of the houses whose message records ``drsim_ptrs.halo_out`` of ``rank`` carries after a
+    step: its FIRST ``H = ceil(c/2)`` houses (entries ``[0, H)``) and its LAST ``L = floor(c/2)`` houses
+    (entries ``[H, H + L)``) -- the ring neighbours of agent_communication_builder.py:74-84 that the two
+    adjacent shards cannot find at home."""
+    lo, hi = house_shard(n_global, rank, world)
+    L = nb_comm // 2
+    H = nb_comm - L
+    return list(range(lo, lo + H)) + list(range(hi - L, hi))
+
+
+def halo_lookup(gathered, n_global: int, rank: int, world: int, nb_comm: int, house: int, k: int):
+    """Host restatement of how ``k_obs`` resolves ring neighbour ``k`` of global ``house`` on ``rank``
+    from the all-gathered halo blocks ``gathered[world][nb_comm]`` (``drsim_step_finish_gathered``):
+    returns ``("local", global_id)`` or ``("halo", entry)`` with the entry taken from the previous
+    rank's LAST-houses part or the next rank's FIRST-houses part."""
+    lo, hi = house_shard(n_global, rank, world)
+    L = nb_comm // 2
+    H = nb_comm - L
+    nb = (house - L + k) % n_global if k < L else (house + 1 + (k - L)) % n_global
+    if lo <= nb < hi:
+        return "local", nb
+    d = (nb - lo) % n_global
+    if d >= n_global - L:                                  # one of the L houses before the shard
+        return "halo", gathered[(rank - 1) % world][H + (d - (n_global - L))]
+    return "halo", gathered[(rank + 1) % world][d - (hi - lo)]
+
+
 class ShardedClusterEnv:
     def __init__(self, env_props: Any, n_replicas: int = 1, rank: int = 0, world: int = 1, device: int = 0,
                  precision: str = "f32", obs_layout: str = "tarmac", policy: str = "external", noise: str = "philox",

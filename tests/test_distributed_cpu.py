@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from marl_demandresponse_b200.batched import synthetic_state
 from marl_demandresponse_b200.distributed import reduce_rollout_metrics, replica_shard
-from marl_demandresponse_b200.sharded import house_shard
+from marl_demandresponse_b200.sharded import halo_edge_houses, halo_lookup, house_shard
 
 
 def test_replica_shard_partitions_exactly():
@@ -89,3 +89,54 @@ def test_gloo_world2_metric_reduction_and_gather_layout():
     np.testing.assert_allclose(res["mean_reward"], full[:, 1].sum() / 50)
     np.testing.assert_allclose(res["rms_signal_error"], (full[:, 5].sum() / 50) ** 0.5)
     assert np.all(gathered[0] == 1.0) and np.all(gathered[1] == 2.0)
+
+
+def test_halo_lookup_finds_every_ring_neighbour():
+    """The halo layout of a house-sharded ring cluster (host restatement of k_reduce / k_obs): with every
+    rank publishing the ids of its edge houses, each rank must resolve every ring neighbour of every house
+    it owns either locally or to the right entry of an adjacent rank's block."""
+    for n_global, world, c in ((1000, 2, 10), (1000, 8, 10), (96, 3, 5), (64, 4, 1), (20000, 8, 12)):
+        blocks = [halo_edge_houses(n_global, r, world, c) for r in range(world)]
+        L = c // 2
+        for rank in range(world):
+            lo, hi = house_shard(n_global, rank, world)
+            assert hi - lo >= c
+            for house in list(range(lo, min(hi, lo + c + 2))) + list(range(max(lo, hi - c - 2), hi)):
+                for k in range(c):
+                    want = (house - L + k) % n_global if k < L else (house + 1 + (k - L)) % n_global
+                    where, got = halo_lookup(blocks, n_global, rank, world, c, house, k)
+                    assert got == want, (n_global, world, c, rank, house, k, where)
+
+
+def _halo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_global, c = 40, 6
+        mine = torch.tensor(halo_edge_houses(n_global, rank, world, c), dtype=torch.float64)   # stands for halo_out
+        gathered = torch.empty((world, c), dtype=torch.float64)
+        dist.all_gather_into_tensor(gathered.view(-1), mine)
+        lo, hi = house_shard(n_global, rank, world)
+        bad = 0
+        for house in range(lo, hi):
+            for k in range(c):
+                want = (house - c // 2 + k) % n_global if k < c // 2 else (house + 1 + (k - c // 2)) % n_global
+                _, got = halo_lookup(gathered.tolist(), n_global, rank, world, c, house, k)
+                bad += int(got != want)
+        out.put((rank, bad))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_halo_all_gather_layout():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(out.get() for _ in range(2)) == [(0, 0), (1, 0)]
