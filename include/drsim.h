@@ -272,8 +272,11 @@ int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles96, voi
 int drsim_peer_status(drsim_t *h, void *stream);
 
 /* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out
- * ([R][4] doubles: power, signal, od_temp, mean reward); copies are inside the call and ordered on
- * `stream`; the call returns after the results have landed (stream synchronised). */
+ * ([R][4] doubles: power, signal, od_temp, mean reward); transfers are inside the call and ordered on
+ * `stream`; the call returns after the results have landed (stream synchronised).  When the step runs on
+ * one of the staged fused kernels and `actions` is pinned (device-mapped) memory with N % 4 == 0, nothing
+ * goes through the copy engines: the kernel reads the action bytes in place over PCIe, one tile ahead of
+ * their use, and writes the results into a mapped buffer of the handle; otherwise explicit copies are used. */
 int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                     const int32_t *interp_ids, double *env_out, void *stream);
 
