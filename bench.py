@@ -295,6 +295,23 @@ def run_gpu_arm(args, wl) -> None:
     e2e_steps = max(3, min(args.steps, 500))
     ms_e2e = timed(step_host, e2e_steps)
 
+    rollout_line = None
+    if args.rollout and not sharded and not on_device_policy:
+        # the whole rollout transition on the device -- MA-PPO actor (reference default
+        # [D -> 100 -> 100 -> 2], random-init weights) + categorical draw + environment step
+        torch.manual_seed(4 + rank)
+        fc = torch.nn.ModuleList([torch.nn.Linear(D, 100), torch.nn.Linear(100, 100), torch.nn.Linear(100, 2)]).to(dev)
+        weights = BatchedEnv.actor_weights(fc)
+        for i in range(5):
+            env.rollout_step(weights)
+        r_steps = max(3, min(args.steps, 500))
+        ms_pol = timed(lambda i: env.policy_step(weights), r_steps)
+        ms_roll = timed(lambda i: env.rollout_step(weights), r_steps)
+        flops = 2.0 * R * N * (D * 100 + 100 * 100 + 100 * 2)
+        rollout_line = {"agent_steps_per_s": world * R * N * r_steps / (ms_roll * 1e-3), "us_per_transition": 1e3 * ms_roll / r_steps,
+                        "actor_us": 1e3 * ms_pol / r_steps, "actor_tflops": flops * r_steps / (ms_pol * 1e-3) / 1e12,
+                        "actor": f"tcgen05 TF32, [{D} -> 100 -> 100 -> 2], random-init weights", "steps": r_steps}
+
     total_houses = R * N if sharded else world * R * N
     value = total_houses * args.steps / (ms * 1e-3)
     e2e_value = total_houses * e2e_steps / (ms_e2e * 1e-3)
@@ -356,6 +373,8 @@ def run_gpu_arm(args, wl) -> None:
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if rollout_line:
+            line["rollout"] = rollout_line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -370,6 +389,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--flush-l2", action="store_true", help="write a 256 MB buffer between timed steps")
+    ap.add_argument("--rollout", action="store_true",
+                    help="also time the on-device rollout transition (MA-PPO actor + draw + env step) -> \"rollout\" key")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="c5 only: per-step exchange of the aggregate-power partials (peer-memory stores vs NCCL all-gather)")
     args = ap.parse_args()
