@@ -30,6 +30,7 @@ constexpr uint32_t PURPOSE_POLICY = 6;
 
 struct ActorArgs {
   const float *obs;        // [rows][D]
+  const unsigned char *image;   // k_actor2: packed weight operands (k_actor_pack)
   const float *w1, *b1;    // [h1][D], [h1]
   const float *w2, *b2;    // [h2][h1], [h2]
   const float *w3, *b3;    // [2][h2], [2]
@@ -349,24 +350,35 @@ DRSIM_D void tmem_relu_inplace(uint32_t lane_addr, int c_begin, int cols) {
 }
 
 // weight matrix [n_out][n_in] (+ bias) -> canonical K-major operand with the bias in column n_in and the
-// "one regenerating" row n_out (0 ... 0 1 0 ...), everything else zero; `gen_one` = 0 for the last layer
+// "one regenerating" row n_out (0 ... 0 1 0 ...), everything else zero; `gen_one` = 0 for the last layer.
+// Thread `tid` of `nthreads` (a whole grid in k_actor_pack).
 DRSIM_D void pack_weights(unsigned char *dst, const float *w, const float *b, int n_out, int n_in, int Np, int Kp,
                           bool gen_one, int tid, int nthreads) {
-  for (int n = tid / 8; n < Np; n += nthreads / 8) {
-    for (int k = tid % 8; k < Kp; k += 8) {
-      float v = 0.f;
-      if (n < n_out) v = k < n_in ? w[(size_t)n * n_in + k] : (k == n_in ? b[n] : 0.f);
-      else if (n == n_out && gen_one && k == n_in) v = 1.f;
-      *reinterpret_cast<float *>(dst + umma_kmajor_off(Np, n, k)) = to_tf32(v);
-    }
+  for (int e = tid; e < Np * Kp; e += nthreads) {
+    const int n = e / Kp, k = e - n * Kp;
+    float v = 0.f;
+    if (n < n_out) v = k < n_in ? __ldg(w + (size_t)n * n_in + k) : (k == n_in ? __ldg(b + n) : 0.f);
+    else if (n == n_out && gen_one && k == n_in) v = 1.f;
+    *reinterpret_cast<float *>(dst + umma_kmajor_off(Np, n, k)) = to_tf32(v);
   }
+}
+
+// The three weight operands in their shared-memory image (offsets off_w1 / off_w2 / off_vec of ActorArgs),
+// packed ONCE per launch by a small grid instead of once per CTA: k_actor2 then fetches the whole image
+// with a single TMA bulk copy (the per-CTA packing cost ~20k scattered loads = 10-15 us of every launch).
+__global__ void k_actor_pack(ActorArgs a, unsigned char *image) {
+  pdl_trigger();   // k_actor2 may set itself up (TMEM, barriers, constant columns) while this grid runs
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  pack_weights(image + a.off_w1, a.w1, a.b1, a.h1, a.D, a.N1, a.K1, true, tid, nt);
+  pack_weights(image + a.off_w2, a.w2, a.b2, a.h2, a.h1, a.N2, a.K2, true, tid, nt);
+  pack_weights(image + a.off_vec, a.w3, a.b3, 2, a.h2, kActN3, a.K3, false, tid, nt);
 }
 
 __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *s_w1 = smem + a.off_w1, *s_w2 = smem + a.off_w2, *s_w3 = smem + a.off_vec;
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // per slot: GEMM1 [0,2), bulk copy [2,4), GEMM2 [4,6), GEMM3 [6,8)
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 8);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 9);
   // slot = tile slot; t = row of the tile (= TMEM lane); part = which half of the row's columns this thread
   // handles (warps w and w + 4 of a slot address the same TMEM lane quadrant)
   const int tid = threadIdx.x, warp = tid >> 5, slot = tid >> 8, t = tid & 127, part = (tid >> 7) & 1;
@@ -378,9 +390,6 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   float *s_stage = reinterpret_cast<float *>(smem + a.off_a2 + slot * stage_bytes);   // this slot's raw row-major tile
   uint64_t *ldbar = s_bar + 2 + slot;                                  // completion of the slot's bulk copy
 
-  pack_weights(s_w1, a.w1, a.b1, a.h1, a.D, a.N1, a.K1, true, tid, kAct2Threads);
-  pack_weights(s_w2, a.w2, a.b2, a.h2, a.h1, a.N2, a.K2, true, tid, kAct2Threads);
-  pack_weights(s_w3, a.w3, a.b3, 2, a.h2, kActN3, k3, false, tid, kAct2Threads);
   // observation buffers: the constant-one column at k = D, the other padding columns zero
   for (int i = tid; i < 2 * kActRows; i += kAct2Threads) {
     const int b = i / kActRows, row = i - b * kActRows;
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + 1)));
-    for (int i = 2; i < 8; ++i)
+    for (int i = 2; i < 9; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + i)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -405,6 +414,14 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above overlapped the tail of k_actor_pack (programmatic dependent launch); its image and the
+  // observation rows of the env step before it are read only from here on
+  pdl_wait();
+  uint64_t *wbar = s_bar + 8;
+  if (tid == 0) {       // the packed weight image: one TMA bulk copy per CTA
+    mbar_expect_tx(wbar, (uint32_t)a.off_a1);
+    bulk_load_g2s(smem, a.image, (uint32_t)a.off_a1, wbar);
+  }
   // this slot's 256 TMEM columns: D1 -> A2 at [0, N1), D2 -> A3 at [N1, N1 + N2), D3 at [N1 + N2, +16)
   const uint32_t tmem = *s_tmem + (uint32_t)(slot * 256);
   const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2),
@@ -447,6 +464,7 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   // so every GEMM round trip is covered by the other tile's epilogue work.
   int tile_b = 2 * blockIdx.x + slot, tile_a = -1;
   if (tile_b < n_tiles) fetch(tile_b);
+  if (issuer) mbar_wait_bounded(wbar, 0);   // the weight image has landed (async proxy -> tensor core: no proxy fence)
   while (tile_b < n_tiles || tile_a >= 0) {
     const bool has_b = tile_b < n_tiles, has_a = tile_a >= 0;
     if (has_b) {   // ---- S1(b)

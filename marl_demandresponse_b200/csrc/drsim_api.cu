@@ -80,6 +80,7 @@ struct drsim_handle {
   double *h_env = nullptr;
   double *h_env_dev = nullptr;
   bool mirror_next = false;   // the next fused step writes its per-cluster results straight into h_env
+  unsigned char *actor_image = nullptr;   // packed weight operands of drsim_policy_step (k_actor_pack)
 
   template <typename T>
   T *at(size_t off) const {
@@ -444,6 +445,7 @@ extern "C" int drsim_destroy(drsim_t *h) {
   for (void *ptr : h->peer_mapped) cudaIpcCloseMemHandle(ptr);
   if (h->slab) cudaFree(h->slab);
   if (h->h_env) cudaFreeHost(h->h_env);
+  if (h->actor_image) cudaFree(h->actor_image);
   delete h;
   return 0;
 }
@@ -1253,8 +1255,12 @@ extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_
     a.off_bar = take(128);
     a.smem_bytes = off;
     if (a.smem_bytes > 227 * 1024) return fail(DRSIM_E_ARG, "drsim_policy_step: network / observation too wide for shared memory");
+    if (!h->actor_image) CU_TRY(cudaMalloc(&h->actor_image, 256 * 1024));
+    a.image = h->actor_image;
+    k_actor_pack<<<40, 512, 0, (cudaStream_t)stream>>>(a, h->actor_image);
     CU_TRY(cudaFuncSetAttribute(k_actor2, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
-    k_actor2<<<std::min((tiles + 1) / 2, h->sm_count), kAct2Threads, a.smem_bytes, (cudaStream_t)stream>>>(a);
+    launch_pdl(k_actor2, std::min((tiles + 1) / 2, h->sm_count), kAct2Threads, (size_t)a.smem_bytes, (cudaStream_t)stream, a);
+    h->launches++;
   }
   h->launches++;
   CU_TRY(cudaGetLastError());
