@@ -11,7 +11,6 @@ from typing import Any, Dict, Optional
 
 import numpy as np
 
-from . import _lib
 from .core import DrSim, comm_width, flatten_config, to_epoch
 from .properties import EnvironmentProperties, as_props
 

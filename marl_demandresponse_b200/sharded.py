@@ -18,7 +18,6 @@ from typing import Any, Dict, Optional
 
 import numpy as np
 
-from . import _lib
 from .batched import synthetic_state
 from .core import DrSim, flatten_config
 from .properties import as_props

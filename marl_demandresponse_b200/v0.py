@@ -36,7 +36,7 @@ from typing import Any, Dict, List
 import numpy as np
 
 from .core import DrSim, comm_width, flatten_config, to_epoch
-from .environment import Environment, _Perlin, build_comm_table, random_sample_ids
+from .environment import Environment, _Perlin, build_comm_table
 from .properties import EnvironmentProperties
 
 

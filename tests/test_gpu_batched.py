@@ -1,7 +1,5 @@
 """BatchedEnv / Philox / drop-in Environment on the GPU, against the NumPy oracle."""
 import copy
-import datetime as dt
-import random
 
 import numpy as np
 import pytest
