@@ -255,6 +255,10 @@ int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal,
 int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream);
 int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_gathered, int n_parts,
                       void *stream);
+/* drsim_step_begin + drsim_step_finish(h, args, NULL, -1 or 1, stream) in one call, for the peer-memory
+ * exchange (after drsim_ipc_attach) or a single rank: nothing is needed from the host in between. */
+int drsim_step_sharded(drsim_t *h, const drsim_step_args *args, void *stream);
+
 /* Same, for a sharded cluster whose observation rows carry ring-neighbour messages (cluster.py:91-111):
  * halo_gathered = the drsim_ptrs.halo_out blocks of all ranks, all-gathered in rank order
  * ([n_parts][R][nb_comm][DRSIM_HALO_FIELDS]); `rank` = this handle's position in that order.  The

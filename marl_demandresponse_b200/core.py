@@ -345,6 +345,11 @@ class DrSim:
         a = self._args()
         _lib.check(self._L.drsim_step_finish(self._h, C.byref(a), self._ptr(acc), int(n_parts), self._stream(stream)))
 
+    def step_sharded(self, actions=None, stream=None) -> None:
+        """``drsim_step_sharded``: both halves of a house-sharded step in one call (peer exchange / one rank)."""
+        a = self._args(actions)
+        _lib.check(self._L.drsim_step_sharded(self._h, C.byref(a), self._stream(stream)))
+
     def step_finish_gathered(self, acc, halo, n_parts: int, rank: int, stream=None) -> None:
         """Gathered partials ``[n_parts, R, N_ACC]`` + gathered halo records
         ``[n_parts, R, nb_comm, HALO_FIELDS]`` (or None when no halo is exchanged), rank order."""

@@ -1018,6 +1018,15 @@ extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const 
   return step_finish_impl(h, acc, nullptr, n_parts, -1, (cudaStream_t)stream);
 }
 
+// step_begin + step_finish(NULL, -1) in one call: the peer-memory exchange (or a single rank) needs nothing
+// from the host between the two halves, and a house-sharded step is launch-bound (4 small kernels), so
+// the second Python -> C round trip is worth saving
+extern "C" int drsim_step_sharded(drsim_t *h, const drsim_step_args *args, void *stream) {
+  int rc = drsim_step_begin(h, args, stream);
+  if (rc) return rc;
+  return step_finish_impl(h, nullptr, nullptr, h->peer_world > 1 ? -1 : 1, -1, (cudaStream_t)stream);
+}
+
 extern "C" int drsim_step_finish_gathered(drsim_t *h, const double *acc_gathered, const double *halo_gathered, int n_parts,
                                           int rank, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");

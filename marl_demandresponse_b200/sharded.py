@@ -108,11 +108,13 @@ class ShardedClusterEnv:
                 a = actions
             else:
                 self._v["actions"].copy_(actions)
+        if self.exchange == "peer" or self.world == 1:
+            # the exchange (if any) happens inside the kernels (NVLink peer stores): one call for both halves
+            sim.step_sharded(a)
+            return self._v["obs"], self._v["reward"]
         sim.step_begin(a)
         acc = self._v["acc"]
-        if self.exchange == "peer":
-            sim.step_finish(None, -1)          # the exchange happened inside the kernels (NVLink peer stores)
-        elif self.world > 1:
+        if self.world > 1:
             import torch.distributed as dist
 
             if self._gathered is None:
@@ -127,8 +129,6 @@ class ShardedClusterEnv:
                     self._halo_gathered = torch.empty((self.world,) + tuple(halo.shape), dtype=halo.dtype, device=halo.device)
                 dist.all_gather_into_tensor(self._halo_gathered, halo, group=self.group)
                 sim.step_finish_gathered(self._gathered, self._halo_gathered, self.world, self.rank)
-        else:
-            sim.step_finish(None, 1)
         return self._v["obs"], self._v["reward"]
 
     @property
