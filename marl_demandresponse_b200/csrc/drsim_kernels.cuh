@@ -996,29 +996,32 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
     }
   }
   __syncthreads();
+  __shared__ double s_row[kRed + 1];
   if (threadIdx.x == 0) {
     double a[kRed] = {0, 0, 0, 0, 0};
     double s = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { red_combine(a, wp[i]); s += wp[i][kRed]; }
     double *dst = pl.acc + (size_t)r * (kRed + 1);
-    for (int k = 0; k < kRed; ++k) dst[k] = a[k];
+    for (int k = 0; k < kRed; ++k) { dst[k] = a[k]; s_row[k] = a[k]; }
     dst[kRed] = s;
-    if (peer.world > 1) {
-      // the collective: this rank's row goes into slot [parity][rank][r] of EVERY rank's inbox
+    s_row[kRed] = s;
+  }
+  if (peer.world > 1) {
+    // the collective: this rank's row goes into slot [parity][rank][r] of EVERY rank's inbox -- one thread
+    // per destination, so the NVLink stores, their system-scope fences and the flag releases of the
+    // `world` peers overlap instead of queueing behind one thread
+    __syncthreads();
+    const int q = threadIdx.x;
+    if (q < peer.world) {
       const int parity = (int)(in.step & 1);
       const size_t row = (((size_t)parity * peer.world + peer.rank) * p.R + r);
-      for (int q = 0; q < peer.world; ++q) {
-        double *ib = peer.inbox[q] + row * (kRed + 1);
-        for (int k = 0; k < kRed; ++k) ib[k] = a[k];
-        ib[kRed] = s;
-      }
+      double *ib = peer.inbox[q] + row * (kRed + 1);
+      for (int k = 0; k <= kRed; ++k) ib[k] = s_row[k];
       __threadfence_system();
-      for (int q = 0; q < peer.world; ++q) {
-        unsigned long long *f = peer.flags[q] + row;
+      unsigned long long *f = peer.flags[q] + row;
 #if defined(__CUDA_ARCH__)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)(in.step + 1)) : "memory");
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)(in.step + 1)) : "memory");
 #endif
-      }
     }
   }
 }
