@@ -353,7 +353,7 @@ def run_gpu_arm(args, wl) -> None:
                                    "4 rotating fixed-seed Bernoulli(0.5) u8 tensors (policy cost excluded)")},
             "rollout_metrics": rollout,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0 if on_device_policy else total_houses,
-                    "d2h_bytes_per_step": world * R * 6 * 8, "ms_per_step": ms_e2e / e2e_steps,
+                    "d2h_bytes_per_step": world * R * 4 * 8, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "BatchedEnv.step_host -> drsim_step_host: pinned host actions in, per-replica results out, one stream "
                            "sync per step; on the staged fused path the kernel reads the action bytes in place over PCIe and "
                            "mirrors the results into mapped host memory (no copy-engine transfers)"},

@@ -280,7 +280,8 @@ int drsim_peer_status(drsim_t *h, void *stream);
  * `stream`; the call returns after the results have landed (stream synchronised).  When the step runs on
  * one of the staged fused kernels and `actions` is pinned (device-mapped) memory with N % 4 == 0, nothing
  * goes through the copy engines: the kernel reads the action bytes in place over PCIe, one tile ahead of
- * their use, and writes the results into a mapped buffer of the handle; otherwise explicit copies are used. */
+ * their use, and writes the [R][4] results itself -- straight into `env_out` when that is pinned memory too, else into a
+ * mapped buffer of the handle; otherwise explicit copies are used. */
 int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                     const int32_t *interp_ids, double *env_out, void *stream);
 

@@ -79,7 +79,7 @@ struct drsim_handle {
   // pinned staging for drsim_step_host; h_env_dev = the same memory as the device sees it (mapped)
   double *h_env = nullptr;
   double *h_env_dev = nullptr;
-  bool mirror_next = false;   // the next fused step writes its per-cluster results straight into h_env
+  double *mirror_next = nullptr;   // the next fused step writes its per-cluster results [R][4] straight to this mapped host buffer
   unsigned char *actor_image = nullptr;   // packed weight operands of drsim_policy_step (k_actor_pack)
 
   template <typename T>
@@ -905,7 +905,7 @@ static void launch_schedule(drsim_handle *h, cudaStream_t s) {
 static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp, cudaStream_t s) {
   StepIn in{};
   if (a) { in.actions = a->actions; in.od_noise = a->od_noise; in.perlin = a->perlin; in.interp_ids = a->interp_ids; }
-  in.host_env = h->mirror_next ? h->h_env_dev : nullptr;
+  in.host_env = h->mirror_next;
   in.step = h->step;
   in.advance = advance;
   in.do_interp = do_interp;
@@ -1090,21 +1090,36 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
     CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_ids, interp_ids, (size_t)p.R * p.interp_k * 4, cudaMemcpyHostToDevice, s));
     a.interp_ids = h->at<int32_t>(h->o_in_ids);
   }
-  const bool mirror = staged && env_out && h->h_env_dev;
+  // Results: on the staged path the kernel writes [R][4] itself -- into the caller's buffer when that is
+  // device-mapped pinned memory, else into the handle's mapped buffer (one small memcpy afterwards)
+  double *mirror = nullptr;
+  bool direct_out = false;
+  if (staged && env_out) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, env_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      mirror = static_cast<double *>(at.devicePointer);
+      direct_out = true;
+    } else {
+      cudaGetLastError();
+      mirror = h->h_env_dev;
+    }
+  }
   h->mirror_next = mirror;
   int rc = run_step(h, &a, 1, di, s);
-  h->mirror_next = false;
+  h->mirror_next = nullptr;
   if (rc) return rc;
   h->step++;
-  if (env_out) {
-    const size_t E8 = (size_t)p.R * 8;
-    if (!mirror) CU_TRY(cudaMemcpyAsync(h->h_env, h->slab + h->o_power, E8 * 6, cudaMemcpyDeviceToHost, s));
+  if (env_out && mirror) {
     CU_TRY(cudaStreamSynchronize(s));
-    // mirror: [R][6] records (power, signal, od, pen_sum, pen_max, rew_sig); copy: six [R] planes
-    const size_t sr = mirror ? 6 : 1, sk = mirror ? 1 : (size_t)p.R;
-    const double *v = h->h_env;
+    if (!direct_out) memcpy(env_out, h->h_env, (size_t)p.R * 4 * sizeof(double));
+  } else if (env_out) {
+    const size_t E8 = (size_t)p.R * 8;
+    CU_TRY(cudaMemcpyAsync(h->h_env, h->slab + h->o_power, E8 * 6, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const double *v = h->h_env;   // six [R] planes: power, signal, od, pen_sum, pen_max, rew_sig
+    const size_t sk = (size_t)p.R;
     for (int r = 0; r < p.R; ++r) {
-      const double *q = v + (size_t)r * sr;
+      const double *q = v + r;
       const double ps = q[3 * sk], pm = q[4 * sk];
       double pen = ps;  // mean individual penalty == common_L2 value
       if (p.penalty_mode == DRSIM_PEN_COMMON_MAX) pen = pm;

@@ -76,7 +76,7 @@ static_assert(sizeof(SchedRec) == 80, "SchedRec is copied in five 16-byte pieces
 
 struct StepIn {
   const SchedRec *sched_rec;  // this step's records [R], or NULL (inline evaluation)
-  double *host_env;           // drsim_step_host: mapped pinned mirror [R][6] of the per-cluster results, or NULL
+  double *host_env;           // drsim_step_host: mapped pinned [R][4] (power, signal, od_temp, mean reward) written by the kernel, or NULL
   // house-sharded ring cluster: message records of the L houses before / the H houses after this
   // shard, element (r, j) at base + (r * nb_comm + j) * kHaloFields (see k_reduce / k_obs)
   const double *halo_left, *halo_right;
@@ -1698,15 +1698,16 @@ DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, 
   if (p.base_mode != DRSIM_BASE_CONSTANT) pl.t_since_interp[r] = c.tsi;
   double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
   const double d = P - c.signal_prev;
+  const double mr = mean_reward(p, red[1], red[2], rew_sig);
   m[0] = st.m[0] + 1.0;
-  m[1] = st.m[1] + mean_reward(p, red[1], red[2], rew_sig);
+  m[1] = st.m[1] + mr;
   m[2] = st.m[2] + fabs(red[3]) * p.inv_n_global;
   m[3] = st.m[3] + red[4] * p.inv_n_global;
   m[4] = st.m[4] + fabs(d);
   m[5] = st.m[5] + d * d;
-  if (host_env) {  // zero-copy result mirror of drsim_step_host (posted writes over PCIe, no D2H copy)
-    double *o = host_env + (size_t)r * 6;
-    o[0] = P; o[1] = c.signal; o[2] = c.od; o[3] = red[1]; o[4] = red[2]; o[5] = rew_sig;
+  if (host_env) {  // drsim_step_host: the per-cluster results go straight to host memory (posted PCIe writes, no D2H copy)
+    double *o = host_env + (size_t)r * 4;
+    o[0] = P; o[1] = c.signal; o[2] = c.od; o[3] = mr;
   }
 }
 
