@@ -241,6 +241,13 @@ int drsim_set_interp_table(drsim_t *h, const double *sub_tables, void *stream);
 /* Environment.step (environment.py:72-108): one step of every replica on `stream`. */
 int drsim_step(drsim_t *h, const drsim_step_args *args, void *stream);
 
+/* `n_steps` consecutive Environment.step calls (environment.py:72-108) in one C call: a rollout under an
+ * on-device policy (args->actions NULL) or the replay of an action tape -- step k reads its actions at
+ * args->actions + k * action_stride bytes (stride 0: the same plane every step).  Injected noise and
+ * sampled ids are per-step inputs and are rejected when n_steps > 1.  Results are those of n_steps
+ * drsim_step calls. */
+int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, void *stream);
+
 /* PowerGrid.step at reset + get_obs (environment.py:66-70): recompute signal (optional) and the
  * observation / message gather from the current state without advancing time. */
 int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal, void *stream);
@@ -278,10 +285,14 @@ int drsim_peer_status(drsim_t *h, void *stream);
 /* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out
  * ([R][4] doubles: power, signal, od_temp, mean reward); transfers are inside the call and ordered on
  * `stream`; the call returns after the results have landed (stream synchronised).  When the step runs on
- * one of the staged fused kernels and `actions` is pinned (device-mapped) memory with N % 4 == 0, nothing
- * goes through the copy engines: the kernel reads the action bytes in place over PCIe, one tile ahead of
- * their use, and writes the [R][4] results itself -- straight into `env_out` when that is pinned memory too, else into a
- * mapped buffer of the handle; otherwise explicit copies are used. */
+ * one of the staged fused kernels and `actions` is pinned (device-mapped) memory with N % 4 == 0, the
+ * transfer overlaps the kernel: planes under 256 KB are read in place over PCIe by the kernel, one tile
+ * ahead of their use; larger ones travel as one linear copy-engine transfer (on a stream of the handle)
+ * into a staging plane the kernel consumes as it lands -- on that path an action byte must be 0 or 1
+ * (0xFF marks "not arrived yet"; a word that never arrives ends in DRSIM_E_STATE after ~2 s).  The kernel
+ * writes the [R][4] results itself -- straight into `env_out` when that is pinned memory too, else into a
+ * mapped buffer of the handle; otherwise explicit copies are used.  The environment variable
+ * DRSIM_HOST_ACTIONS = zerocopy | dma (read by drsim_create) forces one transfer mode. */
 int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                     const int32_t *interp_ids, double *env_out, void *stream);
 
@@ -314,6 +325,14 @@ int64_t drsim_launch_count(const drsim_t *h);
  * out[5] = resident CTAs per SM.  The environment variable DRSIM_TILE_ENVS (read by drsim_create)
  * caps the clusters per tile instead of the built-in round-count heuristic. */
 int drsim_fused_info(const drsim_t *h, int32_t out[6]);
+
+/* Per-cluster summary behind the reference's UI feed (ClientManagerService.update_data,
+ * server/app/services/client_manager_service.py:147-197; description values :64-118): one launch,
+ * d_out = device [R][DRSIM_SUMMARY_FIELDS] fp64 =
+ * { locked HVACs, sum Ta, sum (Ta - target), sum |Ta - target|, sum Tm, sum target, running HVACs, N }.
+ * Sums are taken in a fixed order (run-to-run identical). */
+#define DRSIM_SUMMARY_FIELDS 8
+int drsim_cluster_summary(drsim_t *h, double *d_out, void *stream);
 
 /* Host-side restatements of the env-level scalars, exported for CPU tests of the shared
  * __host__ __device__ code (utils/utils.py:42-117, environment.py:132-159). */

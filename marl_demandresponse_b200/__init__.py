@@ -7,6 +7,7 @@ Public surface
 ``BatchedEnv``      thousands of independent replicas with zero-copy torch tensor views.
 ``norm_state_dict`` the reference's observation normaliser, served from device tensors.
 ``MADemandResponseEnv`` / ``norm_state_dict_v0``  the legacy gym-style env of ``server/v0`` (``v0.py``).
+``ClientFeed``      the reference's UI feed payloads (``ClientManagerService``) from the simulator's tensors.
 ``DrSim``           thin owner of the C handle (``include/drsim.h``).
 
 The CUDA extension (``libdrsim.so``, sm_100a) is mandatory; there is no CPU fallback.
@@ -28,4 +29,8 @@ def __getattr__(name):
         from . import batched
 
         return getattr(batched, name)
+    if name in ("ClientFeed", "DESCRIPTION_KEYS"):
+        from . import ui_feed
+
+        return getattr(ui_feed, name)
     raise AttributeError(name)

@@ -16,6 +16,7 @@ INTERP_SUBTABLE_LEN = 25920
 N_METRICS = 6
 N_ACC = 6
 HALO_FIELDS = 8
+SUMMARY_FIELDS = 8
 
 F32, F64 = 0, 1
 PEN = {"individual_L2": 0, "common_L2": 1, "common_max_error": 2, "mixture": 3}
@@ -137,6 +138,7 @@ def lib():
         "drsim_set_comm_table": (C.c_int, [hp, C.c_void_p, C.c_int, C.c_void_p]),
         "drsim_set_interp_table": (C.c_int, [hp, C.c_void_p, C.c_void_p]),
         "drsim_step": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
+        "drsim_run": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_size_t, C.c_void_p]),
         "drsim_refresh": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_void_p]),
         "drsim_step_begin": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
         "drsim_step_finish": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p, C.c_int, C.c_void_p]),
@@ -149,6 +151,7 @@ def lib():
         "drsim_policy_step": (C.c_int, [hp, C.POINTER(ActorNet), _u64, C.c_void_p, C.c_void_p, C.c_void_p]),
         "drsim_launch_count": (C.c_int64, [hp]),
         "drsim_fused_info": (C.c_int, [hp, C.POINTER(_i32 * 6)]),
+        "drsim_cluster_summary": (C.c_int, [hp, C.c_void_p, C.c_void_p]),
         "drsim_host_solar_gain": (C.c_double, [_i64, _d, _d]),
         "drsim_host_od_temp": (C.c_double, [_i64, _d, _d, _d, _d]),
         "drsim_host_civil": (None, [_i64, C.POINTER(_i32 * 7)]),
@@ -173,8 +176,8 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
-    "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_refresh", "drsim_step_begin",
-    "drsim_step_finish", "drsim_step_sharded", "drsim_step_finish_gathered", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_host_solar_gain", "drsim_host_od_temp",
+    "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_run", "drsim_refresh", "drsim_step_begin",
+    "drsim_step_finish", "drsim_step_sharded", "drsim_step_finish_gathered", "drsim_step_host", "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_cluster_summary", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",
     "drsim_sizeof",
 ]

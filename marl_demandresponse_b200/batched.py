@@ -188,6 +188,24 @@ class BatchedEnv:
         sim.step(a, od_noise, perlin, interp_ids)
         return self._v["obs"], self._v["reward"]
 
+    def run(self, n_steps: int, action_tape=None):
+        """``n_steps`` steps in one C call (``drsim_run``): a rollout under an on-device policy
+        (``action_tape`` None) or the replay of recorded actions, ``action_tape`` u8 CUDA ``[n_steps, R, N]``
+        (or ``[R, N]``: the same actions every step).  Same results as ``n_steps`` calls of :meth:`step`."""
+        sim = self.sim
+        if action_tape is not None:
+            if action_tape.dtype != self._v["actions"].dtype:
+                action_tape = action_tape.to(self._v["actions"].dtype)
+            if sim.N != sim.Ns:   # pad the house axis to the plane stride
+                import torch
+
+                padded = torch.zeros(tuple(action_tape.shape[:-1]) + (sim.Ns,), dtype=action_tape.dtype, device=action_tape.device)
+                padded[..., :sim.N] = action_tape
+                action_tape = padded
+            action_tape = action_tape.contiguous()
+        sim.run(n_steps, action_tape)
+        return self._v["obs"], self._v["reward"]
+
     # ---- on-device MA-PPO actor (SURVEY 8f-2) ----------------------------------------------
     @staticmethod
     def actor_weights(actor) -> tuple:

@@ -332,6 +332,18 @@ class DrSim:
         a = self._args(actions, od_noise, perlin, interp_ids)
         _lib.check(self._L.drsim_step(self._h, C.byref(a), self._stream(stream)))
 
+    def run(self, n_steps: int, action_tape=None, stream=None) -> None:
+        """``drsim_run``: ``n_steps`` steps in one call.  ``action_tape``: u8 CUDA tensor ``[n_steps, R, Ns]``
+        (one plane per step), ``[R, Ns]`` (the same plane every step) or None (internal plane / on-device policy)."""
+        stride = 0
+        if action_tape is not None:
+            assert action_tape.is_contiguous() and tuple(action_tape.shape[-2:]) == (self.R, self.Ns)
+            if action_tape.dim() == 3:
+                assert action_tape.shape[0] >= n_steps
+                stride = self.R * self.Ns
+        a = self._args(action_tape)
+        _lib.check(self._L.drsim_run(self._h, C.byref(a), int(n_steps), stride, self._stream(stream)))
+
     def refresh(self, recompute_signal: bool, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
         a = self._args(None, od_noise, perlin, interp_ids)
         _lib.check(self._L.drsim_refresh(self._h, C.byref(a), int(recompute_signal), self._stream(stream)))
@@ -412,6 +424,18 @@ class DrSim:
         names = ("none", "chunked", "direct", "staged", "staged_rows")
         return {"variant": names[out[0]], "envs_per_tile": out[1], "tiles": out[2], "grid": out[3],
                 "smem_bytes": out[4], "ctas_per_sm": out[5]}
+
+    def cluster_summary(self, out=None, stream=None):
+        """``drsim_cluster_summary``: fp64 CUDA tensor ``[R, 8]`` = locked HVACs, sum Ta, sum (Ta - target),
+        sum |Ta - target|, sum Tm, sum target, running HVACs, N  (the UI feed's aggregates,
+        client_manager_service.py:64-118,178-197)."""
+        import torch
+
+        if out is None:
+            out = torch.empty((self.R, _lib.SUMMARY_FIELDS), dtype=torch.float64, device=f"cuda:{self.device}")
+        assert out.dtype == torch.float64 and out.is_contiguous() and out.numel() == self.R * _lib.SUMMARY_FIELDS
+        _lib.check(self._L.drsim_cluster_summary(self._h, self._ptr(out), self._stream(stream)))
+        return out
 
     # ---- zero-copy torch views ------------------------------------------------------------
     def views(self) -> Dict[str, Any]:

@@ -79,6 +79,13 @@ struct drsim_handle {
   // pinned staging for drsim_step_host; h_env_dev = the same memory as the device sees it (mapped)
   double *h_env = nullptr;
   double *h_env_dev = nullptr;
+  // copy-engine mode of drsim_step_host: poisoned device staging plane for the actions, its own
+  // non-blocking stream, and a mapped int the kernel sets when a poll times out
+  size_t o_act_stage = 0;
+  cudaStream_t copy_stream = nullptr;
+  int *h_poll_err = nullptr, *h_poll_err_dev = nullptr;
+  int host_actions_mode = 0;       // 0 auto, 1 always read in place (zero-copy), 2 always copy engine
+  bool act_poll_next = false;      // the next fused step polls its action words (see StepIn::act_poll_err)
   double *mirror_next = nullptr;   // the next fused step writes its per-cluster results [R][4] straight to this mapped host buffer
   unsigned char *actor_image = nullptr;   // packed weight operands of drsim_policy_step (k_actor_pack)
 
@@ -352,6 +359,7 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   h->o_reward = cv.take(HP * rb);
   h->o_obs = cv.take(HP * p.obs_dim * rb + 16);
   h->o_actions = cv.take(HP);
+  h->o_act_stage = cv.take(HP);
   const size_t E8 = (size_t)p.R * 8;
   h->o_epoch = cv.take(E8);
   // contiguous env-output block (one D2H copy in drsim_step_host): power, signal, od, pen_sum, pen_max, rew_sig
@@ -387,11 +395,23 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     return fail(DRSIM_E_CUDA, std::string("cudaMalloc of ") + std::to_string(cv.off) + " bytes: " + cudaGetErrorString(e));
   }
   cudaMemset(h->slab, 0, h->slab_bytes);
-  cudaHostAlloc(&h->h_env, E8 * 6, cudaHostAllocMapped);
+  cudaMemset(h->slab + h->o_act_stage, 0xFF, HP);
+  cudaHostAlloc(&h->h_env, E8 * 6 + 16, cudaHostAllocMapped);
   if (h->h_env && cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_env_dev), h->h_env, 0) != cudaSuccess) {
     h->h_env_dev = nullptr;
     cudaGetLastError();
   }
+  if (h->h_env && h->h_env_dev) {
+    h->h_poll_err = reinterpret_cast<int *>(h->h_env + (size_t)p.R * 6);
+    h->h_poll_err_dev = reinterpret_cast<int *>(h->h_env_dev + (size_t)p.R * 6);
+    *h->h_poll_err = 0;
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      h->copy_stream = nullptr;
+      cudaGetLastError();
+    }
+  }
+  if (const char *m = getenv("DRSIM_HOST_ACTIONS"))
+    h->host_actions_mode = !strcmp(m, "zerocopy") ? 1 : (!strcmp(m, "dma") ? 2 : 0);
   plan_fused(h);
   int rc = cfg->precision == DRSIM_F64 ? configure_kernels<double>(h) : configure_kernels<float>(h);
   if (rc) { drsim_destroy(h); return rc; }
@@ -444,6 +464,7 @@ extern "C" int drsim_destroy(drsim_t *h) {
   cudaSetDevice(h->device);
   for (void *ptr : h->peer_mapped) cudaIpcCloseMemHandle(ptr);
   if (h->slab) cudaFree(h->slab);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_env) cudaFreeHost(h->h_env);
   if (h->actor_image) cudaFree(h->actor_image);
   delete h;
@@ -906,6 +927,7 @@ static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, in
   StepIn in{};
   if (a) { in.actions = a->actions; in.od_noise = a->od_noise; in.perlin = a->perlin; in.interp_ids = a->interp_ids; }
   in.host_env = h->mirror_next;
+  in.act_poll_err = h->act_poll_next ? h->h_poll_err_dev : nullptr;
   in.step = h->step;
   in.advance = advance;
   in.do_interp = do_interp;
@@ -959,6 +981,29 @@ extern "C" int drsim_step(drsim_t *h, const drsim_step_args *args, void *stream)
   int rc = run_step(h, args, 1, di, (cudaStream_t)stream);
   if (!rc) h->step++;
   return rc;
+}
+
+// n_steps consecutive steps in one C call: a rollout under an on-device policy, or the replay of an
+// action tape, without a host-language round trip per step (a 10-house cluster steps in ~2 us of GPU
+// time; the per-call overhead of a scripting host is several times that)
+extern "C" int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  if (n_steps < 0) return fail(DRSIM_E_ARG, "n_steps must be >= 0");
+  if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "house-sharded cluster: use drsim_step_sharded");
+  drsim_step_args a{};
+  if (args) a = *args;
+  if (n_steps > 1 && (a.od_noise || a.perlin || a.interp_ids))
+    return fail(DRSIM_E_ARG, "drsim_run: injected noise / sampled ids are per-step inputs (n_steps must be 1)");
+  CU_TRY(cudaSetDevice(h->device));
+  const uint8_t *tape = a.actions;
+  for (int k = 0; k < n_steps; ++k) {
+    a.actions = tape ? tape + (size_t)k * action_stride : nullptr;
+    const int di = interp_decision(h);
+    const int rc = run_step(h, &a, 1, di, (cudaStream_t)stream);
+    if (rc) return rc;
+    h->step++;
+  }
+  return 0;
 }
 
 extern "C" int drsim_refresh(drsim_t *h, const drsim_step_args *args, int recompute_signal, void *stream) {
@@ -1045,11 +1090,14 @@ static bool staged_fast_step(const drsim_handle *h, int do_interp, bool injected
   return h->fused_direct && h->geom.use_tma;
 }
 
-// Host-buffer step.  On the staged fused path nothing is copied by the copy engines: the kernel reads
-// the action bytes in place from the caller's pinned (device-mapped) buffer -- the PCIe transfer then
-// overlaps the kernel's own HBM traffic instead of preceding it -- and writes the per-cluster results
-// straight into the handle's mapped result buffer.  Pageable buffers, padded rows (N % 4 != 0) and
-// every other step kind use explicit copies.
+// Host-buffer step.  On the staged fused path the action transfer overlaps the kernel instead of
+// preceding it: small planes (< 256 KB) are read in place from the caller's pinned (device-mapped)
+// buffer by the kernel itself; larger ones travel as ONE linear copy-engine DMA, issued next to the
+// kernel on the handle's own stream, into a poisoned staging plane that the kernel consumes word by
+// word as it lands (measured on B200: the copy engine moves 2 MB at 51 GB/s, in-place reads from the
+// SMs reach ~30 GB/s).  The per-cluster results are written by the kernel straight into the caller's
+// pinned result buffer.  Pageable buffers, padded rows (N % 4 != 0) and every other step kind use
+// explicit copies.
 extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                                const int32_t *interp_ids, double *env_out, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
@@ -1059,6 +1107,7 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
   drsim_step_args a{};
   const int di = interp_decision(h);
   const bool staged = staged_fast_step(h, di, od_noise || perlin);
+  bool dma_poll = false;
   if (actions) {
     const uint8_t *mapped = nullptr;
     if (staged && p.Ns == p.N && (p.policy == DRSIM_POLICY_EXTERNAL)) {
@@ -1068,7 +1117,19 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
       else
         cudaGetLastError();
     }
-    if (mapped) {
+    // Large action planes: ONE linear DMA into the poisoned staging plane on the handle's own stream,
+    // launched next to the kernel, which consumes the words as they land (the copy engine moves ~50 GB/s,
+    // in-place reads from the SMs ~30 GB/s).  Small ones are read in place (no copy start-up latency).
+    // Needs the stream sync this call ends with (env_out), so the next copy cannot overtake this kernel.
+    const size_t act_bytes = (size_t)p.R * p.N;
+    const bool can_dma = mapped && h->copy_stream && h->h_poll_err_dev && env_out && h->h_env_dev &&
+                         (!h->geom.use_rows || h->geom.in_stride > 0);
+    const bool want_dma = h->host_actions_mode == 2 || (h->host_actions_mode == 0 && act_bytes >= ((size_t)256 << 10));
+    if (can_dma && want_dma) {
+      CU_TRY(cudaMemcpyAsync(h->slab + h->o_act_stage, actions, act_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      a.actions = h->at<uint8_t>(h->o_act_stage);
+      dma_poll = true;
+    } else if (mapped) {
       a.actions = mapped;
     } else {
       if (p.Ns == p.N)  // contiguous rows: one linear DMA instead of R row descriptors
@@ -1105,12 +1166,26 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
     }
   }
   h->mirror_next = mirror;
+  h->act_poll_next = dma_poll;
   int rc = run_step(h, &a, 1, di, s);
   h->mirror_next = nullptr;
-  if (rc) return rc;
+  h->act_poll_next = false;
+  if (rc) {
+    if (dma_poll) {  // the kernel did not run: nothing consumed the copy, restore the poison
+      cudaStreamSynchronize(h->copy_stream);
+      cudaMemset(h->slab + h->o_act_stage, 0xFF, (size_t)p.R * p.Ns);
+    }
+    return rc;
+  }
   h->step++;
   if (env_out && mirror) {
     CU_TRY(cudaStreamSynchronize(s));
+    if (dma_poll && *h->h_poll_err) {
+      *h->h_poll_err = 0;
+      cudaStreamSynchronize(h->copy_stream);
+      cudaMemset(h->slab + h->o_act_stage, 0xFF, (size_t)p.R * p.Ns);
+      return fail(DRSIM_E_STATE, "drsim_step_host: the action copy did not arrive (poll timed out); action bytes must be 0 or 1");
+    }
     if (!direct_out) memcpy(env_out, h->h_env, (size_t)p.R * 4 * sizeof(double));
   } else if (env_out) {
     const size_t E8 = (size_t)p.R * 8;
@@ -1309,6 +1384,21 @@ extern "C" int drsim_fused_info(const drsim_t *h, int32_t out[6]) {
   out[4] = h->fused_ok ? h->geom.smem_bytes : 0;
   out[5] = h->fused_ok ? h->fused_per_sm : 0;
   return 0;
+}
+
+template <typename real>
+static int summary_impl(drsim_t *h, double *d_out, cudaStream_t st) {
+  const Planes<real> pl = make_planes<real>(h);
+  k_summary<real><<<h->p.R, 256, 0, st>>>(pl, h->p, d_out);
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int drsim_cluster_summary(drsim_t *h, double *d_out, void *stream) {
+  if (!h || !d_out) return fail(DRSIM_E_ARG, "null argument");
+  CU_TRY(cudaSetDevice(h->device));
+  return h->real_bytes == 8 ? summary_impl<double>(h, d_out, (cudaStream_t)stream)
+                            : summary_impl<float>(h, d_out, (cudaStream_t)stream);
 }
 
 // ---- host-side debug entry points ----------------------------------------------------------

@@ -81,6 +81,10 @@ struct StepIn {
   // shard, element (r, j) at base + (r * nb_comm + j) * kHaloFields (see k_reduce / k_obs)
   const double *halo_left, *halo_right;
   const uint8_t *actions;
+  // drsim_step_host, copy-engine mode: `actions` is a device staging plane that ONE linear DMA is filling
+  // while the kernel runs.  Consumed words are re-poisoned with 0xFFFFFFFF, so a word still holding the
+  // poison has not arrived yet and is polled (bounded; *act_poll_err is set on a time-out).  NULL otherwise.
+  int *act_poll_err;
   const double *od_noise;
   const double *perlin;
   const int32_t *interp_ids;
@@ -1756,6 +1760,24 @@ DRSIM_D void cp_async4(void *sdst, const void *gsrc) {
 #endif
 
 
+// Action word of a thread's four houses on the copy-engine path of drsim_step_host (see StepIn::act_poll_err)
+DRSIM_D uint32_t act_word_polled(const uint8_t *actions, size_t off, uint32_t staged, int *err) {
+  uint32_t v = staged;
+#if defined(__CUDA_ARCH__)
+  uint32_t *ga = reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(actions + off));
+  if (v == 0xFFFFFFFFu) {
+    for (int spin = 0;; ++spin) {
+      asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(ga) : "memory");
+      if (v != 0xFFFFFFFFu) break;
+      if (spin > (1 << 21)) { *err = 1; v = 0; break; }   // ~2 s: the copy never came
+      __nanosleep(100);
+    }
+  }
+  *ga = 0xFFFFFFFFu;   // poison for the next step's copy
+#endif
+  return v;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, DRSIM_FUSED_MINCTAS)
 k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
@@ -1934,6 +1956,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 #else
       w.flags = s_flags[threadIdx.x];
       w.act = ext ? s_act[threadIdx.x] : 0u;
+      if (ext && in.act_poll_err) w.act = act_word_polled(actions, base + s0, w.act, in.act_poll_err);
       if (fast) { const float2 v = s_os[threadIdx.x]; w.od = v.x; w.solar = v.y; }
       else { w.od = nx_od; w.solar = nx_solar; }
     }
@@ -2293,6 +2316,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       for (int q = 0; q < 6; ++q) ld(5 + q, w.c[q]);
       w.flags = s_flags[threadIdx.x];
       w.act = s_act[threadIdx.x];
+      if (in.act_poll_err) w.act = act_word_polled(actions, base + s0, w.act, in.act_poll_err);
       const float2 v = s_os[threadIdx.x];
       w.od = v.x; w.solar = v.y;
     }
@@ -2682,6 +2706,49 @@ __global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, i
   }
   __syncthreads();
   for (int i = threadIdx.x; i < p.N; i += blockDim.x) pl.actions[rb + idx[i]] = mark[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-cluster summary for the UI feed (client_manager_service.py:64-118 description values, :178-197
+// graph series): one CTA per replica, fp64 sums in a fixed order (thread-strided partials, butterfly
+// inside the warp, warps combined in index order) => run-to-run identical.
+//   out[r] = { locked HVACs, sum Ta, sum (Ta - target), sum |Ta - target|, sum Tm, sum target, running HVACs, N }
+// ------------------------------------------------------------------------------------------
+constexpr int kSummaryFields = 8;
+
+template <typename real>
+__global__ void __launch_bounds__(256) k_summary(Planes<real> pl, SimParams p, double *out) {
+  const int r = blockIdx.x;
+  const size_t rb = (size_t)r * p.Ns;
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    const double tgt = (double)pl.target[rb + i];
+    const double d = (double)Rep<real>::dev(pl.t_air[rb + i], pl.target[rb + i]);
+    const double dm = (double)Rep<real>::dev(pl.t_mass[rb + i], pl.target[rb + i]);
+    const uint32_t f = pl.flags[rb + i];
+    s[0] += (double)((f >> 1) & 1u);
+    s[1] += d + tgt;
+    s[2] += d;
+    s[3] += fabs(d);
+    s[4] += dm + tgt;
+    s[5] += tgt;
+    s[6] += (double)(f & 1u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  __shared__ double wp[8][7];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int k = 0; k < 7; ++k) wp[w][k] = s[k];
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    double t = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) t += wp[q][threadIdx.x];
+    out[(size_t)r * kSummaryFields + threadIdx.x] = t;
+  }
+  if (threadIdx.x == 7) out[(size_t)r * kSummaryFields + 7] = (double)p.N;
 }
 
 }  // namespace drsim

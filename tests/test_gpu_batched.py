@@ -208,12 +208,16 @@ def test_fused_kernel_variants_match_general_path(R, n, layout, tile_envs, varia
 
 @pytest.mark.parametrize("n,R,layout,base_mode", [(1000, 300, "tarmac", "constant"), (100, 2500, "hand_engineered", "constant"),
                                                  (100, 64, "tarmac", "interpolation"), (37, 9, "hand_engineered", "constant")])
-def test_step_host_zero_copy_equals_device_step(n, R, layout, base_mode):
-    """drsim_step_host with PINNED host buffers (actions read in place over PCIe by the staged fused
-    kernel, results mirrored into mapped memory -- no copy-engine transfers), with pageable buffers
+@pytest.mark.parametrize("host_actions", ["zerocopy", "dma"])
+def test_step_host_zero_copy_equals_device_step(n, R, layout, base_mode, host_actions, monkeypatch):
+    """drsim_step_host with PINNED host buffers (``zerocopy``: actions read in place over PCIe by the staged
+    fused kernel; ``dma``: one linear copy-engine transfer into the poisoned staging plane, consumed by the
+    kernel as it lands; results mirrored into mapped memory either way), with pageable buffers
     (explicit copies) and the device-resident step: identical state, identical per-replica results,
     including the steps on which the interpolator fires (general path) and padded rows (N % 4 != 0)."""
     import torch
+
+    monkeypatch.setenv("DRSIM_HOST_ACTIONS", host_actions)   # read by drsim_create
 
     from marl_demandresponse_b200 import BatchedEnv
     from marl_demandresponse_b200.batched import synthetic_state
@@ -376,6 +380,46 @@ def test_on_device_policies_match_oracle_controllers():
         for k in ("on", "lockout", "sso"):
             assert np.array_equal(got[k].astype(np.int64), orc.state[k].astype(np.int64)), (policy, n, cop, k)
         np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,policy,base_mode", [(10, "deadband_bangbang", "constant"), (130, "external", "interpolation"),
+                                                  (1000, "greedy_myopic", "constant"), (37, "external", "constant")])
+def test_run_equals_repeated_steps(n, policy, base_mode):
+    """``drsim_run`` (n steps in one C call, optionally replaying an action tape) == n ``drsim_step`` calls."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+
+    prop = _prop(n, **{"power_grid_prop/base_power_props/mode": base_mode, "cluster_prop/house_prop/deadband": 0.4,
+                       "power_grid_prop/signal_properties/mode": "sinusoidals"})
+    table = np.random.default_rng(3).uniform(0, 6000, 3 * 3 * 3 * 3 * 9 * 5 * 8 * 2 * 12 * 6) if base_mode == "interpolation" else None
+    R, T = 5, 90   # 90 steps: crosses a 64-step schedule block and (interpolation) the 75-step update
+    a = BatchedEnv(prop, R, policy=policy, noise="philox", seed=13, obs_layout="hand_engineered", interp_table=table)
+    a.reset()
+    b = copy.deepcopy(a)
+    tape = None
+    if policy == "external":
+        tape = (torch.rand((T, R, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) < 0.5).to(torch.uint8)
+    for t in range(T):
+        a.step(None if tape is None else tape[t])
+    b.run(40, None if tape is None else tape[:40])
+    b.run(T - 40, None if tape is None else tape[40:])
+    torch.cuda.synchronize()
+    for k in ("dt_air", "dt_mass", "sso", "flags", "reward", "obs", "signal", "power", "od_temp", "base_power", "metrics"):
+        assert torch.equal(a.state[k], b.state[k]), k
+    with pytest.raises(Exception):   # injected noise is a per-step input: rejected for n_steps > 1
+        _run_with_noise(b, R)
+
+
+def _run_with_noise(env, R):
+    import ctypes as C
+
+    import torch
+
+    from marl_demandresponse_b200 import _lib
+
+    args = env.sim._args(None, torch.zeros(R, dtype=torch.float64, device="cuda"))
+    _lib.check(env.sim._L.drsim_run(env.sim._h, C.byref(args), 2, 0, None))
 
 
 def test_clone_is_a_deep_copy():
