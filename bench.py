@@ -297,7 +297,7 @@ def run_gpu_arm(args, wl) -> None:
         ms = timed(step_dev, args.steps)
     launches = env.sim.launch_count - l0
     clocks = sampler.stop() if rank == 0 else {}
-    for i in range(max(50, args.warmup)):   # the first few hundred zero-copy steps run slower (host-page mappings warm up)
+    for i in range(max(50, args.warmup)):   # in-place reads of a pinned buffer run slower for the first few hundred steps (host-page mappings warm up)
         step_host(i)
     e2e_steps = max(3, min(args.steps, 500))
     ms_e2e = timed(step_host, e2e_steps)
@@ -363,8 +363,9 @@ def run_gpu_arm(args, wl) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0 if on_device_policy else total_houses,
                     "d2h_bytes_per_step": world * R * 4 * 8, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "BatchedEnv.step_host -> drsim_step_host: pinned host actions in, per-replica results out, one stream "
-                           "sync per step; on the staged fused path the kernel reads the action bytes in place over PCIe and "
-                           "mirrors the results into mapped host memory (no copy-engine transfers)"},
+                           "sync per step; on the staged fused path the action plane travels as one copy-engine DMA issued "
+                           "next to the kernel, which consumes the words as they land (planes under 256 KB: read in place "
+                           "over PCIe), and the kernel writes the results straight into the pinned result buffer"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_house+k_obs (general path)" if sharded else
                          {"staged": "k_fused_tma", "staged_rows": "k_fused_rows", "direct": "k_fused_direct", "chunked": "k_fused",

@@ -996,6 +996,28 @@ extern "C" int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, s
     return fail(DRSIM_E_ARG, "drsim_run: injected noise / sampled ids are per-step inputs (n_steps must be 1)");
   CU_TRY(cudaSetDevice(h->device));
   const uint8_t *tape = a.actions;
+  // On-device policy on the staged fused kernel with at most one tile per CTA: the step loop runs INSIDE
+  // the kernel (k_fused_tma<0>, StepIn::n_steps), one launch per block of scheduled records -- a small
+  // cluster then costs the in-kernel step latency instead of one dependent launch per step.
+  const SimParams &p = h->p;
+  const bool episode = !tape && h->fused_ok && h->real_bytes == 4 && h->fused_direct && h->geom.use_tma && !h->geom.use_rows &&
+                       p.policy != DRSIM_POLICY_EXTERNAL && p.policy != DRSIM_POLICY_GREEDY_MYOPIC &&
+                       p.base_mode == DRSIM_BASE_CONSTANT && h->geom.n_tiles <= h->fused_grid && !getenv("DRSIM_NO_EPISODE");
+  if (episode) {
+    int left = n_steps;
+    while (left > 0) {
+      StepIn in = make_in(h, &a, 1, 0, (cudaStream_t)stream);   // (re)generates the schedule block when the step leaves it
+      if (!in.sched_rec) break;                                  // no scheduled records (should not happen): per-step loop
+      const int k = (int)std::min<int64_t>(left, h->sched_base + drsim_handle::kSched - h->step);
+      in.n_steps = k;
+      const int rc = launch_fused<float>(h, in, (cudaStream_t)stream);
+      if (rc) return rc;
+      h->step += k;
+      left -= k;
+    }
+    if (left == 0) return 0;
+    n_steps = left;
+  }
   for (int k = 0; k < n_steps; ++k) {
     a.actions = tape ? tape + (size_t)k * action_stride : nullptr;
     const int di = interp_decision(h);

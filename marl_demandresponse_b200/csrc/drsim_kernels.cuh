@@ -94,6 +94,9 @@ struct StepIn {
   int64_t step;
   int do_interp;
   int advance;  // 1 = real step, 0 = refresh (recompute signal / obs without advancing time)
+  // in-kernel episode (drsim_run under an on-device policy, k_fused_tma<0> only): this launch advances
+  // n_steps consecutive steps; step k uses the schedule records sched_rec + k * R.  0 / 1 = one step.
+  int n_steps;
 };
 
 // Peer-memory exchange of the per-rank partial sums of ONE house-sharded cluster: every
@@ -1685,7 +1688,7 @@ DRSIM_D void env_stage_fetch(EnvStage *dst, const SchedRec *rec, const double *m
 // env_fast_store from a staged record: env planes + running metrics of cluster r after the step
 template <typename real>
 DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, const EnvStage &st, const double red[kRed],
-                             double *host_env = nullptr) {
+                             double *host_env = nullptr, double *m_next = nullptr) {
   const SchedRec &c = st.rec;
   const double P = red[0];
   const double rew_sig = signal_penalty(p, P, c.signal_prev);
@@ -1703,12 +1706,14 @@ DRSIM_D void env_stage_store(const Planes<real> &pl, const SimParams &p, int r, 
   double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
   const double d = P - c.signal_prev;
   const double mr = mean_reward(p, red[1], red[2], rew_sig);
-  m[0] = st.m[0] + 1.0;
-  m[1] = st.m[1] + mr;
-  m[2] = st.m[2] + fabs(red[3]) * p.inv_n_global;
-  m[3] = st.m[3] + red[4] * p.inv_n_global;
-  m[4] = st.m[4] + fabs(d);
-  m[5] = st.m[5] + d * d;
+  const double nm[DRSIM_N_METRICS] = {st.m[0] + 1.0, st.m[1] + mr, st.m[2] + fabs(red[3]) * p.inv_n_global,
+                                      st.m[3] + red[4] * p.inv_n_global, st.m[4] + fabs(d), st.m[5] + d * d};
+#pragma unroll
+  for (int q = 0; q < DRSIM_N_METRICS; ++q) m[q] = nm[q];
+  if (m_next) {  // in-kernel episode: the next step's staged record takes its running metrics from here
+#pragma unroll
+    for (int q = 0; q < DRSIM_N_METRICS; ++q) m_next[q] = nm[q];
+  }
   if (host_env) {  // drsim_step_host: the per-cluster results go straight to host memory (posted PCIe writes, no D2H copy)
     double *o = host_env + (size_t)r * 4;
     o[0] = P; o[1] = c.signal; o[2] = c.od; o[3] = mr;
@@ -1900,7 +1905,14 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (fast) fetch_env(blockIdx.x, 0);
   }
 
-  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
+  // In-kernel episode (MODE 0, host guarantees at most one tile per CTA and scheduled records for all
+  // n_steps): the step loop runs inside the tile loop; between steps the thread's updated state goes back
+  // into its own staging slots, the next step's (static) record is fetched while this one computes, and the
+  // running metrics travel through the staged record -- nothing is re-read from global memory.
+  const int n_epi = (MODE == 0 && in.n_steps > 1) ? in.n_steps : 1;
+  for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x)
+  for (int epi = 0; epi < n_epi; ++epi, parity ^= 1) {
+    const bool epi_more = MODE == 0 && epi + 1 < n_epi;
     const int r0 = tile * g.envs_per_tile;
     const int E = min(g.envs_per_tile, p.R - r0);
     const int slots = E * Ns;
@@ -1966,7 +1978,20 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       const int nt = tile + gridDim.x;
       if (nt < g.n_tiles) prefetch(nt, 3);
     }
+    if constexpr (MODE == 0) {
+      if (epi_more && active && fast)   // house-update inputs of the next step of the episode (static record)
+        cp_async8(s_os + threadIdx.x, &in.sched_rec[(size_t)(epi + 1) * p.R + r0 + e_loc].od_prev_f);
+    }
     if (active) house4_compute_f32<MODE != 0>(pl, p, w, base + s0, min(4, p.N - n0), h, red, pol_keep);
+    if constexpr (MODE == 0) {
+      if (epi_more && active) {   // the next step reads its state from the thread's own staging slots
+        float4 *o4 = reinterpret_cast<float4 *>(s_in) + threadIdx.x;
+        o4[0] = make_float4(h.ta[0], h.ta[1], h.ta[2], h.ta[3]);
+        o4[kTileSlots / 4] = make_float4(h.tm[0], h.tm[1], h.tm[2], h.tm[3]);
+        reinterpret_cast<int4 *>(s_in)[(size_t)2 * (kTileSlots / 4) + threadIdx.x] = make_int4(h.sso[0], h.sso[1], h.sso[2], h.sso[3]);
+        s_flags[threadIdx.x] = h.flags;
+      }
+    }
 #endif
     // the previous tile's row store must have drained the warp's staging rows before they are rewritten
     // (waited for here, after the house update, not at the top of the tile)
@@ -2052,6 +2077,14 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (fast) {
       const int nt = tile + gridDim.x;
       if (nt < g.n_tiles) fetch_env(nt, parity ^ 1);
+      if constexpr (MODE == 0) {
+        if (epi_more && (int)threadIdx.x < E) {   // record of the next step; its metrics part is filled by env_stage_store
+          const char *src = reinterpret_cast<const char *>(in.sched_rec + (size_t)(epi + 1) * p.R + r0 + threadIdx.x);
+          char *d = reinterpret_cast<char *>(s_stage_base + (size_t)(parity ^ 1) * g.envs_per_tile + threadIdx.x);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) cp_async16(d + 16 * q, src + 16 * q);
+        }
+      }
     }
 
     // ---- phase 2 -------------------------------------------------------------------------
@@ -2170,7 +2203,11 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     if (threadIdx.x < E && fast) {
       double a[kRed] = {0, 0, 0, 0, 0};
       combine(threadIdx.x, a, true);
-      env_stage_store<real>(pl, p, r0 + threadIdx.x, s_stage[threadIdx.x], a, in.host_env);
+      double *m_next = nullptr;
+      if constexpr (MODE == 0) {
+        if (epi_more) m_next = (s_stage_base + (size_t)(parity ^ 1) * g.envs_per_tile + threadIdx.x)->m;
+      }
+      env_stage_store<real>(pl, p, r0 + threadIdx.x, s_stage[threadIdx.x], a, in.host_env, m_next);
     }
   }
   // shared memory must outlive the reads of the last row store; its global writes complete with the grid

@@ -382,10 +382,16 @@ def test_on_device_policies_match_oracle_controllers():
         np.testing.assert_allclose(got["t_air"], orc.state["t_air"], rtol=0, atol=1e-9)
 
 
-@pytest.mark.parametrize("n,policy,base_mode", [(10, "deadband_bangbang", "constant"), (130, "external", "interpolation"),
-                                                  (1000, "greedy_myopic", "constant"), (37, "external", "constant")])
-def test_run_equals_repeated_steps(n, policy, base_mode):
-    """``drsim_run`` (n steps in one C call, optionally replaying an action tape) == n ``drsim_step`` calls."""
+@pytest.mark.parametrize("n,R,policy,base_mode,layout", [
+    (10, 5, "deadband_bangbang", "constant", "hand_engineered"),   # in-kernel episode, one tile
+    (1000, 7, "bangbang", "constant", "tarmac"),                   # in-kernel episode, one cluster per tile
+    (37, 300, "deadband_bangbang", "constant", "hand_engineered"), # in-kernel episode, 12 tiles of 25 clusters, padded rows
+    (100, 40, "deadband_bangbang", "interpolation", "tarmac"),     # interpolated base power: per-step loop
+    (130, 5, "external", "interpolation", "hand_engineered"), (1000, 5, "greedy_myopic", "constant", "hand_engineered"),
+    (37, 5, "external", "constant", "hand_engineered")])
+def test_run_equals_repeated_steps(n, R, policy, base_mode, layout):
+    """``drsim_run`` (n steps in one C call: in-kernel step loop under an on-device policy, per-step launches
+    otherwise, optionally replaying an action tape) == n ``drsim_step`` calls, bit for bit."""
     import torch
 
     from marl_demandresponse_b200 import BatchedEnv
@@ -393,8 +399,8 @@ def test_run_equals_repeated_steps(n, policy, base_mode):
     prop = _prop(n, **{"power_grid_prop/base_power_props/mode": base_mode, "cluster_prop/house_prop/deadband": 0.4,
                        "power_grid_prop/signal_properties/mode": "sinusoidals"})
     table = np.random.default_rng(3).uniform(0, 6000, 3 * 3 * 3 * 3 * 9 * 5 * 8 * 2 * 12 * 6) if base_mode == "interpolation" else None
-    R, T = 5, 90   # 90 steps: crosses a 64-step schedule block and (interpolation) the 75-step update
-    a = BatchedEnv(prop, R, policy=policy, noise="philox", seed=13, obs_layout="hand_engineered", interp_table=table)
+    T = 90   # 90 steps: crosses a 64-step schedule block and (interpolation) the 75-step update
+    a = BatchedEnv(prop, R, policy=policy, noise="philox", seed=13, obs_layout=layout, interp_table=table)
     a.reset()
     b = copy.deepcopy(a)
     tape = None
