@@ -289,6 +289,8 @@ static int configure_kernels(drsim_handle *h) {
       if (sizeof(real) == 4) {
         auto kern = h->geom.in_stride ? k_fused_rows<true> : k_fused_rows<false>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+        if (h->geom.in_stride)
+          CU_TRY(cudaFuncSetAttribute(k_fused_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, h->geom.smem_bytes));
       }
       CU_TRY(cudaFuncSetAttribute(k_fused<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -296,6 +298,9 @@ static int configure_kernels(drsim_handle *h) {
       CU_TRY(cudaFuncSetAttribute(k_fused_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaFuncSetAttribute(k_fused_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaFuncSetAttribute(k_fused_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
+      CU_TRY(cudaFuncSetAttribute(k_fused_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
       CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_tma<0>, kThreads, h->geom.smem_bytes));
     } else if (direct) {
       CU_TRY(cudaFuncSetAttribute(k_fused_direct<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->geom.smem_bytes));
@@ -857,17 +862,24 @@ static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const bool plain = p.own_dim == 10 && p.msg_dim == 4 && (p.obs_dim % 2) == 0 && p.obs_dim > 0;
   const bool common = plain && in.sched_od != nullptr && p.policy == DRSIM_POLICY_EXTERNAL &&
                       p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
-  if (common && !g.need_msg && g.envs_per_tile == 1)
-    launch_pdl(k_fused_tma<1>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
-  else if (common && g.need_msg && g.envs_per_tile > 1)
-    launch_pdl(k_fused_tma<2>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
-  else
-    launch_pdl(k_fused_tma<0>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+  const bool poll = in.act_poll_err != nullptr;   // copy-engine mode of drsim_step_host
+  if (common && !g.need_msg && g.envs_per_tile == 1) {
+    if (poll) launch_pdl(k_fused_tma<1, true>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    else launch_pdl(k_fused_tma<1>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+  } else if (common && g.need_msg && g.envs_per_tile > 1) {
+    if (poll) launch_pdl(k_fused_tma<2, true>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    else launch_pdl(k_fused_tma<2>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+  } else {
+    if (poll) launch_pdl(k_fused_tma<0, true>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    else launch_pdl(k_fused_tma<0>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+  }
 }
 
 static void launch_rows(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
-  if (h->geom.in_stride) launch_pdl(k_fused_rows<true>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+  if (h->geom.in_stride && in.act_poll_err)
+    launch_pdl(k_fused_rows<true, true>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+  else if (h->geom.in_stride) launch_pdl(k_fused_rows<true>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
   else launch_pdl(k_fused_rows<false>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
 }
 

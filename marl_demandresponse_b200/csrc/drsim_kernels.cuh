@@ -1783,7 +1783,9 @@ DRSIM_D uint32_t act_word_polled(const uint8_t *actions, size_t off, uint32_t st
   return v;
 }
 
-template <int MODE>
+// POLL = copy-engine mode of drsim_step_host (StepIn::act_poll_err): a separate instantiation, so the
+// device-resident step does not carry the branch (measured: 0.6 us of 39 on C4)
+template <int MODE, bool POLL = false>
 __global__ void __launch_bounds__(kThreads, DRSIM_FUSED_MINCTAS)
 k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   typedef float real;
@@ -1968,7 +1970,9 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 #else
       w.flags = s_flags[threadIdx.x];
       w.act = ext ? s_act[threadIdx.x] : 0u;
-      if (ext && in.act_poll_err) w.act = act_word_polled(actions, base + s0, w.act, in.act_poll_err);
+      if constexpr (POLL) {
+        if (ext) w.act = act_word_polled(actions, base + s0, w.act, in.act_poll_err);
+      }
       if (fast) { const float2 v = s_os[threadIdx.x]; w.od = v.x; w.solar = v.y; }
       else { w.od = nx_od; w.solar = nx_solar; }
     }
@@ -2242,7 +2246,7 @@ constexpr int kRowGroup = 16;  // rows per warp-level TMA store in k_fused_rows 
 
 // STAGED = inputs prefetched one tile ahead into thread-private shared-memory slots (needs 44 B of
 // shared memory per house slot); false = 128-bit register loads at the top of the tile (large clusters)
-template <bool STAGED>
+template <bool STAGED, bool POLL = false>
 __global__ void __launch_bounds__(kThreads, 2)
 k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   typedef float real;
@@ -2353,7 +2357,7 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       for (int q = 0; q < 6; ++q) ld(5 + q, w.c[q]);
       w.flags = s_flags[threadIdx.x];
       w.act = s_act[threadIdx.x];
-      if (in.act_poll_err) w.act = act_word_polled(actions, base + s0, w.act, in.act_poll_err);
+      if constexpr (POLL) w.act = act_word_polled(actions, base + s0, w.act, in.act_poll_err);
       const float2 v = s_os[threadIdx.x];
       w.od = v.x; w.solar = v.y;
     }
