@@ -150,6 +150,35 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def cpu_numpy_rate(n_houses: int, obs: str, target_house_steps: float = 2e6) -> dict:
+    """house-steps/s of the vectorised fp64 NumPy restatement (oracle/np_oracle.py) on one core: NOT how the
+    reference computes (it loops over Python objects), reported next to the port so the CPU side is not
+    only a slow baseline."""
+    import numpy as np
+
+    from marl_demandresponse_b200.batched import synthetic_state
+    from oracle.np_oracle import NpOracle, from_epoch
+
+    prop = env_prop_for(n_houses)
+    prop["power_grid_prop"] = {"signal_properties": {"mode": "perlin"}}
+    if obs == "tarmac":
+        prop["cluster_prop"]["agents_comm_prop"] = {"max_nb_agents_communication": 0}
+    R = max(1, min(64, int(65536 // n_houses)))
+    steps = max(2, int(target_house_steps / (R * n_houses)))
+    o = NpOracle(prop, R)
+    o.set_state(synthetic_state(prop, R, seed=1234, quirk_ua=False))
+    o.power_grid_step([from_epoch(e) for e in o.state["epoch"]], np.zeros(R))
+    acts = np.random.default_rng(0).random((steps, R, n_houses)) < 0.5
+    zero = np.zeros(R)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        o.step(acts[t], zero, zero)
+        o.obs_vectors()
+    dt = time.perf_counter() - t0
+    return {"value": R * n_houses * steps / dt, "unit": UNIT, "cores": 1, "kind": "vectorised NumPy restatement (not the reference's implementation)",
+            "sample": f"{R} replica(s) x {n_houses} houses x {steps} steps of oracle/np_oracle.py incl. observation vectors"}
+
+
 def cpu_port_rate(n_houses: int, obs: str, steps: int, procs: int) -> dict:
     """house-steps/s of the scalar port: ``procs`` independent single-cluster replicas."""
     if procs <= 1:
@@ -381,6 +410,10 @@ def run_gpu_arm(args, wl) -> None:
         }
         if cpu:
             line["cpu_baseline"] = cpu
+            try:
+                line["cpu_baseline"]["vectorised"] = cpu_numpy_rate(N if not sharded else min(N, 65536), wl["obs"])
+            except Exception as e:  # noqa: BLE001 -- an extra, never a reason to lose the line
+                line["cpu_baseline"]["vectorised"] = {"error": str(e)[:200]}
         if rollout_line:
             line["rollout"] = rollout_line
         print(json.dumps(line), flush=True)
