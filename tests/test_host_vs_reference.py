@@ -88,3 +88,18 @@ def test_default_property_tree_equals_reference_defaults():
                 assert str(a[k]) == str(v) or a[k] == v, (path + k, a[k], v)
 
     walk(ours, ref, "")
+
+
+def test_perlin_wrapper_equals_reference_octave_sum():
+    """``_Perlin`` (the drop-in's wrapper around the third-party generator) against the reference's
+    ``Perlin.calculate_noise`` (perlin.py:41-56, last-octave weight quirk Q7) on the same generator --
+    the deterministic stand-in both sides import here, since ``perlin_noise`` is absent from this image."""
+    ns = refenv.load()
+    from marl_demandresponse_b200.environment import _Perlin
+
+    for octaves, step, period, seed in ((5, 5, 300, 0.37), (3, 2, 120, 0.9), (1, 5, 300, 0.1), (6, 1, 50, 0.5)):
+        ours = _Perlin(octaves, step, period, seed)
+        ref = ns.perlin_mod.Perlin(1, octaves, step, period, seed)
+        assert ours.available
+        for x in (0.0, 1.0, 17.5, 299.0, 86399.0):
+            assert ours.calculate_noise(x) == ref.calculate_noise(x)
