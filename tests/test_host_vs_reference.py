@@ -103,3 +103,23 @@ def test_perlin_wrapper_equals_reference_octave_sum():
         assert ours.available
         for x in (0.0, 1.0, 17.5, 299.0, 86399.0):
             assert ours.calculate_noise(x) == ref.calculate_noise(x)
+
+
+def test_interpolation_grids_equal_the_reference_files():
+    """Key order and grids of the interpolation table: ``interp_dict_keys.csv:1`` /
+    ``interp_parameters_dict.json:1`` against the generator's (``montecarlo.GRID``) and the oracle's."""
+    import csv
+    import json
+    import os
+
+    from marl_demandresponse_b200 import montecarlo
+    from oracle.config import INTERP_GRIDS, INTERP_KEYS
+
+    mc = os.path.join(refenv.REFERENCE_ROOT, "server/v0/monteCarlo")
+    grids = json.load(open(os.path.join(mc, "interp_parameters_dict.json")))
+    keys = [k.strip() for k in next(csv.reader(open(os.path.join(mc, "interp_dict_keys.csv")))) if k.strip()]
+    assert keys == list(INTERP_KEYS) == list(montecarlo.KEYS)
+    for k in keys:
+        want = [float(v) for v in grids[k]]
+        assert [float(v) for v in INTERP_GRIDS[k]] == want, k
+        assert [float(v) for v in montecarlo.GRID[k]] == want, k
