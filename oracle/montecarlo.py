@@ -5,6 +5,10 @@ single-house cluster per grid point, BangBangController, 75 steps, mean of the l
 averages of the HVAC power.  The v0 and app environments share the thermal / HVAC model; the v0
 specifics (HVAC initially off with ``seconds_since_off = lockout_duration``, constant outdoor
 temperature, ``Ua`` multiplied rather than overwritten) are part of the injected initial state.
+
+Pinned: ``tests/test_montecarlo_vs_reference.py`` evaluates the reference's own
+``eval_parameters_bangbang_average_consumption`` (with the real legacy env and controller) on random grid
+points and compares it with :func:`table_entries` (rtol 1e-9).
 """
 from __future__ import annotations
 
