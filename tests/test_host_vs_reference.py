@@ -123,3 +123,30 @@ def test_interpolation_grids_equal_the_reference_files():
         want = [float(v) for v in grids[k]]
         assert [float(v) for v in INTERP_GRIDS[k]] == want, k
         assert [float(v) for v in montecarlo.GRID[k]] == want, k
+
+
+@pytest.mark.parametrize("n", [3, 17, 40, 128])
+def test_greedy_myopic_restatement_equals_reference_controller(n):
+    """``oracle.np_oracle.greedy_myopic`` (what ``k_greedy`` is compared with on the GPU) against the
+    reference's ``GreedyMyopic.get_action`` (greedy_myopic_controller.py:67-104: pandas sort, first clause
+    ignoring lock-out) on random observations with distinct temperatures (its sort is unstable on ties),
+    over regulation signals from "nobody" to "everybody"."""
+    from oracle.np_oracle import greedy_myopic
+
+    gm = refenv.load_controller_module("greedy_myopic_controller")
+    rng = np.random.default_rng(n)
+    for trial in range(6):
+        target = 20.0 + np.abs(rng.normal(0, 1, n))
+        t_air = target + rng.permutation(np.linspace(-3.0, 4.0, n))           # distinct differences
+        cap = rng.choice([12500.0, 15000.0, 17500.0], n)
+        cop = float(rng.choice([2.5, 2.3]))
+        lock = rng.random(n) < 0.3
+        signal = float(rng.uniform(0.0, 1.1) * (cap / cop).sum()) if trial else 0.0
+        obs = {i: {"indoor_temp": t_air[i], "target_temp": target[i], "cooling_capacity": cap[i], "cop": cop,
+                   "lockout": bool(lock[i]), "reg_signal": signal} for i in range(n)}
+        ctl = gm.GreedyMyopic({"id": 0}, None)
+        ctl.get_action(obs)
+        df = gm.GreedyMyopic.actions_df
+        want = np.array([bool(df.loc[i]["HVAC_status"]) for i in range(n)])
+        got = np.asarray(greedy_myopic(t_air, target, cap, cop, lock, signal)).astype(bool)
+        assert np.array_equal(got, want), (n, trial)
