@@ -150,3 +150,36 @@ def test_greedy_myopic_restatement_equals_reference_controller(n):
         want = np.array([bool(df.loc[i]["HVAC_status"]) for i in range(n)])
         got = np.asarray(greedy_myopic(t_air, target, cap, cop, lock, signal)).astype(bool)
         assert np.array_equal(got, want), (n, trial)
+
+
+def test_bangbang_rules_equal_reference_controllers():
+    """``deadband_bangbang`` / ``bangbang`` of the oracle (the on-device policies are compared with them)
+    against the reference's controller classes (bangbang_controllers.py:18-89), including the exact
+    boundary values of the dead band."""
+    import sys
+    import types
+
+    from oracle.np_oracle import bangbang, deadband_bangbang
+
+    if "app.services.parser_service" not in sys.modules:   # only the type annotation MarlConfig is taken from it
+        stub = types.ModuleType("app.services.parser_service")
+        stub.MarlConfig = object
+        sys.modules.setdefault("app.services", types.ModuleType("app.services"))
+        sys.modules["app.services.parser_service"] = stub
+    bb = refenv.load_controller_module("bangbang_controllers")
+    rng = np.random.default_rng(3)
+    n = 400
+    target = 20.0 + np.abs(rng.normal(0, 1, n))
+    db = rng.choice([0.0, 0.5, 1.0, 2.0], n)
+    t_air = target + rng.uniform(-2, 2, n)
+    t_air[:40] = target[:40] + db[:40] / 2        # on the upper edge
+    t_air[40:80] = target[40:80] - db[40:80] / 2  # on the lower edge
+    t_air[80:100] = target[80:100]                # exactly on target
+    on = rng.random(n) < 0.5
+    obs = {i: {"indoor_temp": t_air[i], "target_temp": target[i], "deadband": db[i], "turned_on": bool(on[i])} for i in range(n)}
+    for cls, ours in ((bb.DeadbandBangBangController, deadband_bangbang(t_air, target, db, on)),
+                      (bb.BasicController, deadband_bangbang(t_air, target, db, on)),
+                      (bb.BangBangController, bangbang(t_air, target)),
+                      (bb.AlwaysOnController, np.ones(n, dtype=bool))):
+        want = np.array([bool(cls({"id": i}, None).act(obs)) for i in range(n)])
+        assert np.array_equal(np.asarray(ours).astype(bool), want), cls.__name__
