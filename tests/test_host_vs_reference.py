@@ -183,3 +183,37 @@ def test_bangbang_rules_equal_reference_controllers():
                       (bb.AlwaysOnController, np.ones(n, dtype=bool))):
         want = np.array([bool(cls({"id": i}, None).act(obs)) for i in range(n)])
         assert np.array_equal(np.asarray(ours).astype(bool), want), cls.__name__
+
+
+def test_actor_architecture_is_the_reference_actor():
+    """The MA-PPO actor the tcgen05 kernel implements (Linear-ReLU-Linear-ReLU-Linear-softmax, probabilities
+    over {off, on}; ``test_on_device_actor_matches_torch_fp32`` compares the kernel with exactly this
+    computation) against the reference's ``Actor`` module (trainables/network.py:14-35) on its own weights."""
+    import importlib.util
+    import os
+    import sys
+    import types
+
+    import torch
+
+    if "app.utils.logger" not in sys.modules:   # pydantic BaseSettings moved: the logger module cannot load here
+        stub = types.ModuleType("app.utils.logger")
+        stub.logger = types.SimpleNamespace(info=lambda *a, **k: None, debug=lambda *a, **k: None)
+        sys.modules["app.utils.logger"] = stub
+    refenv.load()
+    path = os.path.join(refenv.REFERENCE_ROOT, "server/app/core/agents/trainables/network.py")
+    spec = importlib.util.spec_from_file_location("_ref_network", path)
+    net = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(net)
+    torch.manual_seed(0)
+    for D, layers in ((50, [100, 100]), (10, "[100, 100]"), (46, [64, 48])):
+        actor = net.Actor(D, 2, layers)
+        x = torch.randn(37, D)
+        with torch.no_grad():
+            want = actor(x)
+            w = [(l.weight, l.bias) for l in actor.fc]
+            assert len(w) == 3
+            h = torch.relu(x @ w[0][0].T + w[0][1])
+            h = torch.relu(h @ w[1][0].T + w[1][1])
+            got = torch.softmax(h @ w[2][0].T + w[2][1], dim=1)
+        assert got.shape == (37, 2) and torch.allclose(got, want, rtol=0, atol=1e-7)
