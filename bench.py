@@ -179,6 +179,17 @@ def cpu_numpy_rate(n_houses: int, obs: str, target_house_steps: float = 2e6) -> 
             "sample": f"{R} replica(s) x {n_houses} houses x {steps} steps of oracle/np_oracle.py incl. observation vectors"}
 
 
+def cpu_model() -> str:
+    """CPU model of the box the baseline ran on (SURVEY 8d asks for it next to the core count)."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_port_rate(n_houses: int, obs: str, steps: int, procs: int) -> dict:
     """house-steps/s of the scalar port: ``procs`` independent single-cluster replicas."""
     if procs <= 1:
@@ -192,7 +203,7 @@ def cpu_port_rate(n_houses: int, obs: str, steps: int, procs: int) -> dict:
             pool.map(_cpu_worker, [(n_houses, obs, steps, s) for s in range(procs)])
             wall = time.perf_counter() - t0
         rate = procs * n_houses * steps / wall
-    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "port", "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
             "sample": f"{procs} replica(s) x {n_houses} houses x {steps} steps of oracle/scalar_port.py "
                       f"(per-house Python loop restating the reference step)"}
 
