@@ -289,12 +289,21 @@ int drsim_peer_status(drsim_t *h, void *stream);
  * transfer overlaps the kernel: planes under 256 KB are read in place over PCIe by the kernel, one tile
  * ahead of their use; larger ones travel as one linear copy-engine transfer (on a stream of the handle)
  * into a staging plane the kernel consumes as it lands -- on that path an action byte must be 0 or 1
- * (0xFF marks "not arrived yet"; a word that never arrives ends in DRSIM_E_STATE after ~2 s).  The kernel
+ * (four 0xFF bytes in one aligned word mark "not arrived yet"; a word that never arrives ends in DRSIM_E_STATE
+ * after ~2 s, the step having been committed with those houses off: the handle then refuses every further step
+ * until drsim_set_state / drsim_reset re-injects a state).  The kernel
  * writes the [R][4] results itself -- straight into `env_out` when that is pinned memory too, else into a
  * mapped buffer of the handle; otherwise explicit copies are used.  The environment variable
  * DRSIM_HOST_ACTIONS = zerocopy | dma (read by drsim_create) forces one transfer mode. */
 int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                     const int32_t *interp_ids, double *env_out, void *stream);
+
+/* Environment.step with HOST buffers and the reference's full return value (environment.py:108: per-agent
+ * observations and rewards): drsim_step_host, then reward_out[R][N] and obs_out[R][N][obs_dim] (`real` = float or
+ * double as the handle was built; row-major, no padding; either may be NULL) are copied back behind the kernel,
+ * ahead of the call's one stream synchronisation.  On BASELINE config 4 that is 90 MB per step: PCIe-bound. */
+int drsim_step_host_full(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                         const int32_t *interp_ids, double *env_out, void *reward_out, void *obs_out, void *stream);
 
 /* MA-PPO actor of the reference (agents/trainables/network.py:14-35: Linear(obs_dim, h1) - ReLU -
  * Linear(h1, h2) - ReLU - Linear(h2, 2) - softmax), all DEVICE pointers in torch.nn.Linear layout

@@ -9,7 +9,6 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.environ.get("DRSIM_LIB") or os.path.join(PKG, "libdrsim.so")
 SOURCES = ["drsim_api.cu"]
-HEADERS = ["drsim_kernels.cuh", "drsim_device.cuh", os.path.join("..", "..", "include", "drsim.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xptxas=-v",
@@ -29,7 +28,9 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    # every source / header the translation unit can include: csrc/* and the public header
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(PKG, "..", "include", "drsim.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -247,11 +247,13 @@ class BatchedEnv:
         self.sim.step(None)
         return self._v["obs"], self._v["reward"], actions, prob
 
-    def step_host(self, actions_host, env_out=None):
-        """End-to-end step with HOST buffers: ``actions_host`` uint8 ``[R, N]`` (pinned torch CPU
-        tensor or numpy) is copied in, the per-replica results ``[R, 4]`` = (power, signal,
-        outdoor temperature, mean reward) are copied back."""
-        return self.sim.step_host(actions_host, env_out=env_out)
+    def step_host(self, actions_host, env_out=None, reward_out=None, obs_out=None):
+        """End-to-end step with HOST buffers: ``actions_host`` uint8 / bool ``[R, N]`` (pinned torch CPU
+        tensor or numpy, values 0 / 1) is copied in, the per-replica results ``[R, 4]`` = (power, signal,
+        outdoor temperature, mean reward) are copied back.  With ``reward_out [R, N]`` / ``obs_out [R, N, D]``
+        (host buffers of the build's dtype) the reference's full ``step`` result -- per-agent observations
+        and rewards, environment.py:108 -- comes back too (``drsim_step_host_full``)."""
+        return self.sim.step_host(actions_host, env_out=env_out, reward_out=reward_out, obs_out=obs_out)
 
     def clone(self) -> "BatchedEnv":
         other = object.__new__(BatchedEnv)

@@ -381,24 +381,56 @@ class DrSim:
     def peer_status(self, stream=None) -> None:
         _lib.check(self._L.drsim_peer_status(self._h, self._stream(stream)))
 
-    def step_host(self, actions: Optional[np.ndarray], od_noise=None, perlin=None, interp_ids=None,
-                  env_out: Optional[np.ndarray] = None, stream=None) -> Optional[np.ndarray]:
-        """Host-buffer step (``drsim_step_host``): numpy (or pinned torch CPU) buffers in and out."""
-        def hp(x, dtype):
-            if x is None:
-                return None
-            if hasattr(x, "data_ptr"):
-                return C.c_void_p(x.data_ptr())
-            x = np.ascontiguousarray(x, dtype=dtype)
+    def _host_buf(self, x, dtype, shape, keep: list, what: str, writable: bool = False):
+        """Pointer of a host buffer handed to the C ABI, after checking what the ABI cannot: dtype, shape and
+        contiguity (a wrong stride or a 4-byte dtype would be read as garbage actions)."""
+        if x is None:
+            return None
+        if hasattr(x, "data_ptr"):   # torch CPU tensor (pinned or pageable)
+            import torch
+
+            want = {np.uint8: (torch.uint8, torch.bool), np.float64: (torch.float64,), np.float32: (torch.float32,),
+                    np.int32: (torch.int32,)}[dtype]
+            if x.is_cuda or x.dtype not in want or not x.is_contiguous() or tuple(x.shape) != tuple(shape):
+                raise ValueError(f"{what}: expected a contiguous CPU tensor of dtype {want[0]} and shape {tuple(shape)}, "
+                                 f"got {x.dtype} {tuple(x.shape)} (cuda={x.is_cuda}, contiguous={x.is_contiguous()})")
+            return C.c_void_p(x.data_ptr())
+        if writable:
+            if not (isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.c_contiguous and x.shape == tuple(shape)):
+                raise ValueError(f"{what}: expected a C-contiguous numpy array of dtype {np.dtype(dtype)} and shape {tuple(shape)}")
             keep.append(x)
             return x.ctypes.data_as(C.c_void_p)
+        a = np.asarray(x)
+        if dtype == np.uint8 and a.dtype == np.bool_:
+            a = a.view(np.uint8)
+        if a.shape != tuple(shape):
+            raise ValueError(f"{what}: expected shape {tuple(shape)}, got {a.shape}")
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
 
+    def step_host(self, actions: Optional[np.ndarray], od_noise=None, perlin=None, interp_ids=None,
+                  env_out: Optional[np.ndarray] = None, reward_out=None, obs_out=None, stream=None) -> Optional[np.ndarray]:
+        """Host-buffer step (``drsim_step_host``): numpy (or pinned torch CPU) buffers in and out.
+        ``actions`` uint8 / bool ``[R, N]`` with values 0 / 1; ``env_out`` fp64 ``[R, 4]``.  With ``reward_out``
+        ``[R, N]`` and / or ``obs_out`` ``[R, N, D]`` (dtype of the build) the call is ``drsim_step_host_full``:
+        the reference's full ``step`` result comes back to the host."""
         keep: list = []
+        R, N = self.R, self.N
         if env_out is None:
-            env_out = np.zeros((self.R, 4), dtype=np.float64)
-        _lib.check(self._L.drsim_step_host(
-            self._h, hp(actions, np.uint8), hp(od_noise, np.float64), hp(perlin, np.float64),
-            hp(interp_ids, np.int32), hp(env_out, np.float64), self._stream(stream)))
+            env_out = np.zeros((R, 4), dtype=np.float64)
+        k = int(self.cfg.interp_nb_agents)
+        args = [self._host_buf(actions, np.uint8, (R, N), keep, "actions"),
+                self._host_buf(None if od_noise is None else np.reshape(od_noise, (R,)), np.float64, (R,), keep, "od_noise"),
+                self._host_buf(None if perlin is None else np.reshape(perlin, (R,)), np.float64, (R,), keep, "perlin"),
+                self._host_buf(None if interp_ids is None else np.reshape(interp_ids, (R, k)), np.int32, (R, k), keep, "interp_ids"),
+                self._host_buf(env_out, np.float64, (R, 4), keep, "env_out", writable=True)]
+        if reward_out is None and obs_out is None:
+            _lib.check(self._L.drsim_step_host(self._h, *args, self._stream(stream)))
+        else:
+            args += [self._host_buf(reward_out, self.real, (R, N), keep, "reward_out", writable=True),
+                     self._host_buf(obs_out, self.real, (R, N, self.D), keep, "obs_out", writable=True)]
+            _lib.check(self._L.drsim_step_host_full(self._h, *args, self._stream(stream)))
         return env_out
 
     def policy_step(self, weights, seed: int = 0, prob_drawn=None, prob_on=None, stream=None) -> None:

@@ -88,6 +88,7 @@ struct drsim_handle {
   bool act_poll_next = false;      // the next fused step polls its action words (see StepIn::act_poll_err)
   double *mirror_next = nullptr;   // the next fused step writes its per-cluster results [R][4] straight to this mapped host buffer
   unsigned char *actor_image = nullptr;   // packed weight operands of drsim_policy_step (k_actor_pack)
+  bool broken = false;             // a step was committed with missing inputs: refuse to step until state is re-injected
 
   template <typename T>
   T *at(size_t off) const {
@@ -683,6 +684,7 @@ extern "C" int drsim_set_state(drsim_t *h, const drsim_host_state *st, void *str
   if (!h || !st) return fail(DRSIM_E_ARG, "null argument");
   CU_TRY(cudaSetDevice(h->device));
   h->sched_valid = false;
+  h->broken = false;
   auto s = (cudaStream_t)stream;
   return h->real_bytes == 8 ? set_state_t<double>(h, st, s) : set_state_t<float>(h, st, s);
 }
@@ -969,6 +971,9 @@ static int interp_decision(drsim_handle *h) {
 }
 
 static int run_step(drsim_handle *h, const drsim_step_args *a, int advance, int do_interp, cudaStream_t s) {
+  if (h->broken)
+    return fail(DRSIM_E_STATE, "an earlier host-buffer step was committed with missing actions: re-inject the state "
+                               "(drsim_set_state / drsim_reset) before stepping again");
   const StepIn in = make_in(h, a, advance, do_interp, s);
   const bool dbl = h->real_bytes == 8;
   int rc;
@@ -1132,13 +1137,15 @@ static bool staged_fast_step(const drsim_handle *h, int do_interp, bool injected
 // SMs reach ~30 GB/s).  The per-cluster results are written by the kernel straight into the caller's
 // pinned result buffer.  Pageable buffers, padded rows (N % 4 != 0) and every other step kind use
 // explicit copies.
-extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
-                               const int32_t *interp_ids, double *env_out, void *stream) {
+static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                          const int32_t *interp_ids, double *env_out, void *reward_out, void *obs_out, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   CU_TRY(cudaSetDevice(h->device));
   auto s = (cudaStream_t)stream;
   const SimParams &p = h->p;
+  if (obs_out && !p.obs_dim) return fail(DRSIM_E_ARG, "drsim_step_host_full: obs_out given but the handle has obs_layout = none");
   drsim_step_args a{};
+  const int tsi_before = h->t_since_interp;
   const int di = interp_decision(h);
   const bool staged = staged_fast_step(h, di, od_noise || perlin);
   bool dma_poll = false;
@@ -1209,16 +1216,34 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
       cudaStreamSynchronize(h->copy_stream);
       cudaMemset(h->slab + h->o_act_stage, 0xFF, (size_t)p.R * p.Ns);
     }
+    h->t_since_interp = tsi_before;
     return rc;
   }
   h->step++;
+  // Environment.step returns the per-agent observations and rewards (environment.py:108): the full result goes
+  // back to the caller's host buffers behind the kernel, ahead of the one stream synchronisation below
+  if (reward_out) {
+    if (p.Ns == p.N) CU_TRY(cudaMemcpyAsync(reward_out, h->slab + h->o_reward, (size_t)p.R * p.N * h->real_bytes, cudaMemcpyDeviceToHost, s));
+    else CU_TRY(cudaMemcpy2DAsync(reward_out, (size_t)p.N * h->real_bytes, h->slab + h->o_reward, (size_t)p.Ns * h->real_bytes,
+                                  (size_t)p.N * h->real_bytes, p.R, cudaMemcpyDeviceToHost, s));
+  }
+  if (obs_out) {
+    const size_t row = (size_t)p.obs_dim * h->real_bytes;
+    if (p.Ns == p.N) CU_TRY(cudaMemcpyAsync(obs_out, h->slab + h->o_obs, (size_t)p.R * p.N * row, cudaMemcpyDeviceToHost, s));
+    else CU_TRY(cudaMemcpy2DAsync(obs_out, (size_t)p.N * row, h->slab + h->o_obs, (size_t)p.Ns * row, (size_t)p.N * row, p.R,
+                                  cudaMemcpyDeviceToHost, s));
+  }
   if (env_out && mirror) {
     CU_TRY(cudaStreamSynchronize(s));
     if (dma_poll && *h->h_poll_err) {
+      // the kernel substituted "off" for the words that never came: the state it committed is not the step the
+      // caller asked for.  The handle is marked broken (every later step fails) until state is injected again.
       *h->h_poll_err = 0;
       cudaStreamSynchronize(h->copy_stream);
       cudaMemset(h->slab + h->o_act_stage, 0xFF, (size_t)p.R * p.Ns);
-      return fail(DRSIM_E_STATE, "drsim_step_host: the action copy did not arrive (poll timed out); action bytes must be 0 or 1");
+      h->broken = true;
+      return fail(DRSIM_E_STATE, "drsim_step_host: the action copy did not arrive (poll timed out); the step was committed with "
+                                 "missing actions -- re-inject the state (drsim_set_state / drsim_reset) before stepping again");
     }
     if (!direct_out) memcpy(env_out, h->h_env, (size_t)p.R * 4 * sizeof(double));
   } else if (env_out) {
@@ -1243,6 +1268,16 @@ extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double 
     CU_TRY(cudaStreamSynchronize(s));
   }
   return 0;
+}
+
+extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                               const int32_t *interp_ids, double *env_out, void *stream) {
+  return step_host_impl(h, actions, od_noise, perlin, interp_ids, env_out, nullptr, nullptr, stream);
+}
+
+extern "C" int drsim_step_host_full(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                                    const int32_t *interp_ids, double *env_out, void *reward_out, void *obs_out, void *stream) {
+  return step_host_impl(h, actions, od_noise, perlin, interp_ids, env_out, reward_out, obs_out, stream);
 }
 
 template <typename real>
@@ -1278,6 +1313,7 @@ extern "C" int drsim_reset(drsim_t *h, const drsim_reset_args *ra, void *stream)
   a.std_target = ra->std_target_temp; a.f_lo = ra->factor_low; a.f_hi = ra->factor_high;
   for (int k = 0; k < 8; ++k) a.caps[k] = ra->caps[k];
   h->sched_valid = false;
+  h->broken = false;
   h->step = 0;
   h->t_since_interp = h->p.interp_period + 1;
   // artificial ratio: power_grid.py:46-49 draws ratio * range^(2u - 1); range == 1 in every shipped config

@@ -253,6 +253,40 @@ def test_step_host_zero_copy_equals_device_step(n, R, layout, base_mode, host_ac
             assert torch.equal(envs[0].state[k], e.state[k]), k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,R,layout", [(100, 9, "hand_engineered"), (1000, 3, "tarmac"), (10, 5, "hand_engineered")])
+def test_step_host_full_returns_obs_and_reward(n, R, layout):
+    """drsim_step_host_full: what Environment.step returns (environment.py:108) -- per-agent observations and
+    rewards -- lands in the caller's host buffers (pinned and pageable), identical to the device tensors of a
+    device-resident step; N = 10 exercises the padded rows (house stride 12)."""
+    import torch
+
+    prop = _prop(n)
+    st = synthetic_state(prop, R, seed=5)
+    acts = (np.random.default_rng(6).random((6, R, n)) < 0.5).astype(np.uint8)
+    envs = [BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=3) for _ in range(3)]
+    for e in envs:
+        e.reset(copy.deepcopy(st))
+    D = envs[0].sim.D
+    env_pin = torch.zeros((R, 4), dtype=torch.float64).pin_memory()
+    rew_pin = torch.zeros((R, n), dtype=torch.float32).pin_memory()
+    obs_pin = torch.zeros((R, n, D), dtype=torch.float32).pin_memory()
+    rew_np, obs_np = np.zeros((R, n), np.float32), np.zeros((R, n, D), np.float32)
+    for t in range(6):
+        obs_d, rew_d = envs[0].step(torch.as_tensor(acts[t], device="cuda"))
+        envs[1].step_host(torch.as_tensor(acts[t]).pin_memory(), env_pin, reward_out=rew_pin, obs_out=obs_pin)
+        envs[2].step_host(acts[t].astype(bool), None, reward_out=rew_np, obs_out=obs_np)
+        torch.cuda.synchronize()
+        for rew, obs in ((rew_pin.numpy(), obs_pin.numpy()), (rew_np, obs_np)):
+            assert np.array_equal(rew, rew_d.cpu().numpy()), t
+            assert np.array_equal(obs, obs_d.cpu().numpy()), t
+        assert np.array_equal(env_pin.numpy()[:, 0], envs[0].state["power"].cpu().numpy())
+    with pytest.raises(ValueError):
+        envs[1].step_host(torch.zeros((R, n), dtype=torch.int32), env_pin)      # a 4-byte dtype is not reinterpreted as bytes
+    with pytest.raises(ValueError):
+        envs[1].step_host(torch.zeros((R, n + 1), dtype=torch.uint8), env_pin)   # wrong shape
+
+
 def _torch_actor(D, h1, h2, seed):
     """The reference's Actor (network.py:14-35) restated in plain PyTorch fp32."""
     import torch
