@@ -263,7 +263,10 @@ int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *stream);
 int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const double *acc_gathered, int n_parts,
                       void *stream);
 /* drsim_step_begin + drsim_step_finish(h, args, NULL, -1 or 1, stream) in one call, for the peer-memory
- * exchange (after drsim_ipc_attach) or a single rank: nothing is needed from the host in between. */
+ * exchange (after drsim_ipc_attach / drsim_peer_attach_local) or a single rank: nothing is needed from the
+ * host in between.  Runs as ONE persistent kernel (house update, reduction, NVLink push of the partial sums
+ * and halo records, bounded wait, env epilogue, rewards, observations); results are bit-identical to the
+ * begin / finish pair.  Fails with DRSIM_E_STATE once an exchange wait has timed out on an earlier step. */
 int drsim_step_sharded(drsim_t *h, const drsim_step_args *args, void *stream);
 
 /* Same, for a sharded cluster whose observation rows carry ring-neighbour messages (cluster.py:91-111):
@@ -281,6 +284,11 @@ int drsim_step_finish_gathered(drsim_t *h, const double *acc_gathered, const dou
 int drsim_ipc_export(drsim_t *h, void *out96);
 int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *handles96, void *stream);
 int drsim_peer_status(drsim_t *h, void *stream);
+/* The same attachment for `world` handles of ONE process, in rank order (raw device pointers instead of
+ * IPC handles): several shards on one GPU -- their steps must then be issued on different streams, the
+ * kernels of the shards wait for one another -- or several GPUs driven by one process (peer access is
+ * enabled here).  Replaces nothing in the reference (cluster.py:73-89 is one Python loop). */
+int drsim_peer_attach_local(drsim_t *const *handles, int world, void *stream);
 
 /* Same step with HOST buffers (pinned or pageable): actions u8 [R][N] in, per-env results out
  * ([R][4] doubles: power, signal, od_temp, mean reward); transfers are inside the call and ordered on

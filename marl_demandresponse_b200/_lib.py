@@ -147,6 +147,7 @@ def lib():
         "drsim_ipc_export": (C.c_int, [hp, C.c_void_p]),
         "drsim_ipc_attach": (C.c_int, [hp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
         "drsim_peer_status": (C.c_int, [hp, C.c_void_p]),
+        "drsim_peer_attach_local": (C.c_int, [C.POINTER(hp), C.c_int, C.c_void_p]),
         "drsim_step_host": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "drsim_step_host_full": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
@@ -180,7 +181,7 @@ EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
     "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_run", "drsim_refresh", "drsim_step_begin",
     "drsim_step_finish", "drsim_step_sharded", "drsim_step_finish_gathered", "drsim_step_host", "drsim_step_host_full",
-    "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_cluster_summary", "drsim_host_solar_gain", "drsim_host_od_temp",
+    "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_peer_attach_local", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_cluster_summary", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",
     "drsim_sizeof",
 ]

@@ -381,6 +381,13 @@ class DrSim:
     def peer_status(self, stream=None) -> None:
         _lib.check(self._L.drsim_peer_status(self._h, self._stream(stream)))
 
+    @staticmethod
+    def peer_attach_local(sims: list, stream=None) -> None:
+        """``drsim_peer_attach_local``: the peer exchange between handles of THIS process, in rank order (raw
+        device pointers instead of IPC handles).  Shards that share a GPU must be stepped on different streams."""
+        arr = (C.c_void_p * len(sims))(*[s._h for s in sims])
+        _lib.check(sims[0]._L.drsim_peer_attach_local(arr, len(sims), sims[0]._stream(stream)))
+
     def _host_buf(self, x, dtype, shape, keep: list, what: str, writable: bool = False):
         """Pointer of a host buffer handed to the C ABI, after checking what the ABI cannot: dtype, shape and
         contiguity (a wrong stride or a 4-byte dtype would be read as garbage actions)."""

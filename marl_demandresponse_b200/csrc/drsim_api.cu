@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "drsim_kernels.cuh"
+#include "drsim_shard.cuh"
 #include "drsim_actor.cuh"
 
 using namespace drsim;
@@ -74,6 +75,14 @@ struct drsim_handle {
   int peer_world = 1, peer_rank = 0;
   size_t o_inbox = 0, o_pflags = 0, o_peer_tab = 0, o_peer_err = 0;
   std::vector<void *> peer_mapped;  // cudaIpcOpenMemHandle results to close
+  // sequence number of the house-sharded exchange (StepIn::xseq): +1 per sharded step, never reset
+  int64_t xseq = 0;
+  // single-kernel step of clusters larger than a tile / house-sharded clusters (drsim_shard.cuh)
+  ShardGeom shard{};
+  int shard_grid = 0, shard_capacity = 0;
+  bool shard_ok = false;
+  size_t o_sh_arrive = 0, o_sh_ready = 0, o_sh_envb = 0;
+  int *h_peer_err = nullptr, *h_peer_err_dev = nullptr;   // mapped: set by a kernel whose exchange wait timed out
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
   StepIn pending_in{};
   // pinned staging for drsim_step_host; h_env_dev = the same memory as the device sees it (mapped)
@@ -281,6 +290,9 @@ static void plan_fused(drsim_handle *h, int e_cap = 1 << 30) {
 }
 
 template <typename real>
+static int plan_shard(drsim_handle *h);
+
+template <typename real>
 static int configure_kernels(drsim_handle *h) {
   if (h->fused_ok) {
     const bool direct = h->geom.chunk_rows == h->geom.envs_per_tile * h->p.Ns || h->p.obs_dim == 0;
@@ -390,6 +402,9 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     h->o_halo_out = cv.take(halo);
     h->o_halo_in = cv.take(2 * halo);
     h->o_peer_err = cv.take(8);
+    h->o_sh_arrive = cv.take((size_t)p.R * 4);
+    h->o_sh_ready = cv.take((size_t)p.R * 8);
+    h->o_sh_envb = cv.take((size_t)p.R * 8 * 8);
   }
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
   h->o_sched_aux = cv.take(E8 * drsim_handle::kSched); h->o_sched_tsec = cv.take((size_t)p.R * 4 * drsim_handle::kSched);
@@ -411,6 +426,9 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     h->h_poll_err = reinterpret_cast<int *>(h->h_env + (size_t)p.R * 6);
     h->h_poll_err_dev = reinterpret_cast<int *>(h->h_env_dev + (size_t)p.R * 6);
     *h->h_poll_err = 0;
+    h->h_peer_err = h->h_poll_err + 1;
+    h->h_peer_err_dev = h->h_poll_err_dev + 1;
+    *h->h_peer_err = 0;
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
       h->copy_stream = nullptr;
       cudaGetLastError();
@@ -457,6 +475,8 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
       if (rc) { drsim_destroy(h); return rc; }
     }
   }
+  rc = cfg->precision == DRSIM_F64 ? plan_shard<double>(h) : plan_shard<float>(h);
+  if (rc) { drsim_destroy(h); return rc; }
   if (cfg->path == DRSIM_PATH_FUSED && !h->fused_ok) {
     drsim_destroy(h);
     return fail(DRSIM_E_ARG, "path=FUSED requested but the cluster does not fit a tile (N > 1024, sharded, or obs row too large)");
@@ -488,6 +508,7 @@ extern "C" int drsim_clone(const drsim_t *src, drsim_t **out) {
   h->t_since_interp = src->t_since_interp;
   h->sched_valid = src->sched_valid;
   h->sched_base = src->sched_base;
+  h->xseq = src->xseq;
   *out = h;
   return 0;
 }
@@ -804,7 +825,7 @@ static PeerCtx make_peer(const drsim_handle *h) {
   pc.inbox = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab);
   pc.flags = reinterpret_cast<unsigned long long *const *>(h->slab + h->o_peer_tab + 16 * 8);
   pc.halo = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab + 32 * 8);
-  pc.err = reinterpret_cast<int *>(h->slab + h->o_peer_err);
+  pc.err = h->h_peer_err_dev ? h->h_peer_err_dev : reinterpret_cast<int *>(h->slab + h->o_peer_err);
   return pc;
 }
 
@@ -853,6 +874,106 @@ static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc
   launch_pdl(k_obs<real>, p.R * h->obs_chunks, kObsChunk, (size_t)kObsChunk * p.obs_dim * sizeof(real), s, pl, p, in, h->obs_chunks);
   h->launches += 2;
   CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+
+// ---- single-kernel step of the general path (drsim_shard.cuh) ---------------------------------
+static bool shard_plain(const drsim_handle *h) {
+  return h->real_bytes == 4 && h->p.obs_dim == 10 && h->p.own_dim == 10;
+}
+
+template <typename real>
+static int plan_shard(drsim_handle *h) {
+  const SimParams &p = h->p;
+  ShardGeom g{};
+  h->shard_ok = false;
+  if (getenv("DRSIM_NO_SHARD_KERNEL")) return 0;
+  const int rb = (int)sizeof(real);
+  const bool plain = shard_plain(h);
+  g.chunks = h->chunks;
+  g.n_tiles = p.R * h->chunks;
+  const int min_ctas = FusedOcc<real>::min_ctas;
+  const size_t budget = min_ctas >= 2 ? 110 * 1024 : 200 * 1024;
+  const size_t group = (size_t)kShardGroup * p.obs_dim * rb;
+  g.nbuf = (size_t)(kThreads / 32) * 2 * group <= 48 * 1024 ? 2 : 1;
+  const size_t rows = plain ? (size_t)kTileSlots * 10 * 4 : std::max<size_t>(16, (size_t)(kThreads / 32) * g.nbuf * group);
+  if (rows + 1024 > budget) return 0;   // rows too wide: four-kernel path
+  g.tile_bytes = kTileSlots * (3 * rb + 5);
+  g.off_rows = 0;
+  g.off_saved = (int)((rows + 127) / 128 * 128);
+  const int cap0 = std::min(g.n_tiles, min_ctas * h->sm_count);
+  const int per_cta0 = (g.n_tiles + cap0 - 1) / cap0;
+  g.t_smem = (int)std::min<size_t>(per_cta0, (budget - g.off_saved) / g.tile_bytes);
+  if (const char *e = getenv("DRSIM_SHARD_TSMEM")) g.t_smem = std::max(0, std::min(g.t_smem, atoi(e)));
+  g.smem_bytes = g.off_saved + g.t_smem * g.tile_bytes;
+  int per_sm = 0;
+  if constexpr (sizeof(real) == 4) {
+    if (plain) {
+      CU_TRY(cudaFuncSetAttribute(k_shard<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard<float, true>, kThreads, g.smem_bytes));
+    }
+  }
+  if (!plain) {
+    CU_TRY(cudaFuncSetAttribute(k_shard<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard<real, false>, kThreads, g.smem_bytes));
+  }
+  if (per_sm < 1) return 0;
+  h->shard_capacity = per_sm * h->sm_count;
+  h->shard_grid = std::min(g.n_tiles, h->shard_capacity);
+  h->shard = g;
+  h->shard_ok = true;
+  return 0;
+}
+
+// can this step run as ONE k_shard launch?  (refreshes, the NCCL-gathered exchange and a halo without
+// attached peers stay on the four-kernel path)
+static bool shard_step_ok(const drsim_handle *h) {
+  if (!h->shard_ok) return false;
+  if (needs_halo(h->p) && h->peer_world < 2) return false;
+  return true;
+}
+
+template <typename real>
+static int launch_shard(drsim_handle *h, StepIn in, cudaStream_t s) {
+  const Planes<real> pl = make_planes<real>(h);
+  const SimParams &p = h->p;
+  if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
+    int n2 = 1;
+    while (n2 < p.N) n2 <<= 1;
+    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
+    h->launches++;
+  }
+  if (needs_halo(p)) {   // the peers push their edge-house records into this rank's halo inbox (reduce_cluster)
+    const int L = p.nb_comm / 2;
+    const size_t per_rank = (size_t)p.R * p.nb_comm * kHaloFields;
+    const double *inbox = h->at<double>(h->o_halo_in) + (size_t)(in.xseq & 1) * per_rank;
+    in.halo_left = inbox;
+    in.halo_right = inbox + (size_t)L * kHaloFields;
+  }
+  ShardCtx sc{};
+  sc.arrive = h->at<unsigned int>(h->o_sh_arrive);
+  sc.ready = h->at<unsigned long long>(h->o_sh_ready);
+  sc.envb = h->slab + h->o_sh_envb;
+  sc.err = h->h_peer_err_dev ? h->h_peer_err_dev : reinterpret_cast<int *>(h->slab + h->o_peer_err);
+  bool plain = false;
+  if constexpr (sizeof(real) == 4) {
+    if (shard_plain(h)) {
+      launch_pdl(k_shard<float, true>, h->shard_grid, kThreads, (size_t)h->shard.smem_bytes, s, pl, p, in, h->shard, sc, make_peer(h));
+      plain = true;
+    }
+  }
+  if (!plain)
+    launch_pdl(k_shard<real, false>, h->shard_grid, kThreads, (size_t)h->shard.smem_bytes, s, pl, p, in, h->shard, sc, make_peer(h));
+  h->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int exchange_error(const drsim_handle *h) {
+  if (h->h_peer_err && *reinterpret_cast<volatile int *>(h->h_peer_err))
+    return fail(DRSIM_E_STATE, "an in-kernel exchange wait timed out on an earlier step (a rank / CTA did not deliver its partial "
+                               "sums within ~2 s): power, signal and rewards since then are not valid");
   return 0;
 }
 
@@ -943,6 +1064,7 @@ static StepIn make_in(drsim_handle *h, const drsim_step_args *a, int advance, in
   in.host_env = h->mirror_next;
   in.act_poll_err = h->act_poll_next ? h->h_poll_err_dev : nullptr;
   in.step = h->step;
+  in.xseq = h->xseq;
   in.advance = advance;
   in.do_interp = do_interp;
   if (advance && !in.od_noise && !in.perlin) {
@@ -974,11 +1096,14 @@ static int run_step(drsim_handle *h, const drsim_step_args *a, int advance, int 
   if (h->broken)
     return fail(DRSIM_E_STATE, "an earlier host-buffer step was committed with missing actions: re-inject the state "
                                "(drsim_set_state / drsim_reset) before stepping again");
+  h->xseq++;
   const StepIn in = make_in(h, a, advance, do_interp, s);
   const bool dbl = h->real_bytes == 8;
   int rc;
   if (h->fused_ok && do_interp <= 0 && advance) {
     rc = dbl ? launch_fused<double>(h, in, s) : launch_fused<float>(h, in, s);
+  } else if (advance && h->p.N == h->p.n_global && shard_step_ok(h)) {
+    rc = dbl ? launch_shard<double>(h, in, s) : launch_shard<float>(h, in, s);   // one launch instead of four
   } else {
     if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "house-sharded cluster: use drsim_step_begin / drsim_step_finish");
     rc = dbl ? launch_house_phase<double>(h, in, s) : launch_house_phase<float>(h, in, s);
@@ -1059,6 +1184,7 @@ extern "C" int drsim_step_begin(drsim_t *h, const drsim_step_args *args, void *s
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   CU_TRY(cudaSetDevice(h->device));
   h->pending_interp = interp_decision(h);
+  h->xseq++;
   const StepIn in = make_in(h, args, 1, h->pending_interp, (cudaStream_t)stream);
   h->pending_in = in;
   return h->real_bytes == 8 ? launch_house_phase<double>(h, in, (cudaStream_t)stream)
@@ -1082,7 +1208,7 @@ static int step_finish_impl(drsim_handle *h, const double *acc, const double *ha
       in.halo_left = halo + (size_t)((rank + n_parts - 1) % n_parts) * per_rank + (size_t)H * kHaloFields;
       in.halo_right = halo + (size_t)((rank + 1) % n_parts) * per_rank;
     } else if (!acc && n_parts < 0) {
-      const double *inbox = h->at<double>(h->o_halo_in) + (size_t)(in.step & 1) * per_rank;   // pushed by the peers
+      const double *inbox = h->at<double>(h->o_halo_in) + (size_t)(in.xseq & 1) * per_rank;   // pushed by the peers
       in.halo_left = inbox;
       in.halo_right = inbox + (size_t)L * kHaloFields;
     } else {
@@ -1106,6 +1232,19 @@ extern "C" int drsim_step_finish(drsim_t *h, const drsim_step_args *args, const 
 // from the host between the two halves, and a house-sharded step is launch-bound (4 small kernels), so
 // the second Python -> C round trip is worth saving
 extern "C" int drsim_step_sharded(drsim_t *h, const drsim_step_args *args, void *stream) {
+  if (!h) return fail(DRSIM_E_ARG, "null handle");
+  if (int rc = exchange_error(h)) return rc;
+  if (shard_step_ok(h)) {
+    // house update, reduction, peer push, wait, epilogue, rewards and observations in ONE launch (k_shard)
+    CU_TRY(cudaSetDevice(h->device));
+    const int di = interp_decision(h);
+    h->xseq++;
+    const StepIn in = make_in(h, args, 1, di, (cudaStream_t)stream);
+    const int rc = h->real_bytes == 8 ? launch_shard<double>(h, in, (cudaStream_t)stream)
+                                      : launch_shard<float>(h, in, (cudaStream_t)stream);
+    if (!rc) h->step++;
+    return rc;
+  }
   int rc = drsim_step_begin(h, args, stream);
   if (rc) return rc;
   return step_finish_impl(h, nullptr, nullptr, h->peer_world > 1 ? -1 : 1, -1, (cudaStream_t)stream);
@@ -1370,11 +1509,52 @@ extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *han
   return 0;
 }
 
+// Same attachment for handles living in ONE process: raw device pointers instead of IPC handles (several
+// shards on one GPU -- the kernels of the shards must then run concurrently, i.e. on different streams --
+// or several GPUs driven by one process, peer access enabled here).
+extern "C" int drsim_peer_attach_local(drsim_t *const *handles, int world, void *stream) {
+  if (!handles) return fail(DRSIM_E_ARG, "null argument");
+  if (world < 1 || world > 16) return fail(DRSIM_E_ARG, "world must be in [1, 16]");
+  for (int q = 0; q < world; ++q)
+    if (!handles[q]) return fail(DRSIM_E_ARG, "null handle");
+  for (int i = 0; i < world; ++i) {
+    drsim_handle *h = handles[i];
+    CU_TRY(cudaSetDevice(h->device));
+    std::vector<uint64_t> tab(48, 0);
+    int same_device = 0;
+    for (int q = 0; q < world; ++q) {
+      const drsim_handle *o = handles[q];
+      if (o->p.R != h->p.R) return fail(DRSIM_E_ARG, "drsim_peer_attach_local: the shards must have the same number of replicas");
+      if (o->device == h->device) same_device++;
+      else {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(DRSIM_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      tab[q] = (uint64_t)(uintptr_t)(o->slab + o->o_inbox);
+      tab[16 + q] = (uint64_t)(uintptr_t)(o->slab + o->o_pflags);
+      tab[32 + q] = (uint64_t)(uintptr_t)(o->slab + o->o_halo_in);
+    }
+    auto s = (cudaStream_t)stream;
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 48 * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemsetAsync(h->slab + h->o_pflags, 0, (size_t)2 * 16 * h->p.R * 8, s));
+    CU_TRY(cudaMemsetAsync(h->slab + h->o_peer_err, 0, 8, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    h->peer_world = world;
+    h->peer_rank = i;
+    // shards that share a device share its SMs: every shard's persistent grid must be resident at once
+    if (h->shard_ok) h->shard_grid = std::max(1, std::min(h->shard.n_tiles, h->shard_capacity / same_device));
+  }
+  return 0;
+}
+
 extern "C" int drsim_peer_status(drsim_t *h, void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   int err = 0;
   CU_TRY(cudaMemcpyAsync(&err, h->slab + h->o_peer_err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (h->h_peer_err) err |= *reinterpret_cast<volatile int *>(h->h_peer_err);
   if (err) return fail(DRSIM_E_STATE, "a peer-exchange wait timed out (a rank did not deliver its partial sums)");
   return 0;
 }

@@ -92,6 +92,10 @@ struct StepIn {
   const double *sched_od, *sched_solar, *sched_aux;
   const int32_t *sched_tsec;
   int64_t step;
+  // house-sharded exchange: sequence number of this step's exchange on the handle -- starts at 1, grows by
+  // one per sharded step and is NEVER reset (drsim_reset / drsim_set_state keep it), so a flag left by an
+  // earlier episode can never equal the value a later step waits for; its low bit selects the inbox parity
+  int64_t xseq;
   int do_interp;
   int advance;  // 1 = real step, 0 = refresh (recompute signal / obs without advancing time)
   // in-kernel episode (drsim_run under an on-device policy, k_fused_tma<0> only): this launch advances
@@ -910,16 +914,42 @@ DRSIM_D real interp5(const real *sub, const real x[5]) {
 // General path, kernel 2: per-cluster reduction of the CTA partials (+ the interpolated base
 // power of the sampled houses this handle owns).  One CTA per cluster.
 // ------------------------------------------------------------------------------------------
+// loads that must observe what OTHER CTAs of the same launch wrote (k_shard): L2, never a stale L1 line
+template <typename T>
+DRSIM_D T ld_cg(const T *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+DRSIM_D uint8_t ld_cg(const uint8_t *p) {
+#if defined(__CUDA_ARCH__)
+  return (uint8_t)__ldcg(reinterpret_cast<const unsigned char *>(p));
+#else
+  return *p;
+#endif
+}
+
+constexpr int kReduceThreads = 128;  // threads that take part in reduce_cluster (fixes the combine order)
+
+// Reduction of cluster r: called by EVERY thread of the CTA (it contains CTA barriers); the first
+// kReduceThreads threads do the work, in an order that depends on nothing but `chunks`.
 template <typename real>
-__global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, StepIn in, int chunks, PeerCtx peer) {
-  pdl_wait();
-  pdl_trigger();
-  const int r = blockIdx.x;
+DRSIM_D void reduce_cluster(const Planes<real> &pl, const SimParams &p, const StepIn &in, int chunks, const PeerCtx &peer, int r) {
+  const bool worker = threadIdx.x < kReduceThreads;
   double red[kRed] = {0, 0, 0, 0, 0};
   // fixed assignment + fixed combine order => deterministic
-  for (int c = threadIdx.x; c < chunks; c += blockDim.x) red_combine(red, pl.partials + ((size_t)r * chunks + c) * kRed);
+  if (worker)
+    for (int c = threadIdx.x; c < chunks; c += kReduceThreads) {
+      const double *src = pl.partials + ((size_t)r * chunks + c) * kRed;
+      double t[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) t[k] = ld_cg(src + k);
+      red_combine(red, t);
+    }
   double isum = 0.0;
-  if (in.do_interp > 0) {
+  if (in.do_interp > 0 && worker) {
     const int k_all = p.n_global <= p.interp_k ? (int)p.n_global : p.interp_k;
     // the interpolator sees the NEW outdoor temperature and datetime (environment.py:94,104-106);
     // both are re-derived here exactly as the epilogue will derive them
@@ -936,7 +966,7 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
         od_new = od_temp_model(now, p.day_temp, p.night_temp, p.phase, noise);
       }
     }
-    for (int k = threadIdx.x; k < k_all; k += blockDim.x) {
+    for (int k = threadIdx.x; k < k_all; k += kReduceThreads) {
       int64_t id;
       if (p.n_global <= p.interp_k) id = k;                       // interpolation.py:220-222
       else if (in.interp_ids) id = in.interp_ids[(size_t)r * p.interp_k + k];
@@ -949,8 +979,8 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
       const size_t o = (size_t)r * p.Ns + id;
       const real tgt = pl.target[o];
       real x[5];
-      x[0] = Rep<real>::dev(pl.t_air[o], tgt);
-      x[1] = Rep<real>::dev(pl.t_mass[o], tgt);
+      x[0] = Rep<real>::dev(ld_cg(pl.t_air + o), tgt);
+      x[1] = Rep<real>::dev(ld_cg(pl.t_mass + o), tgt);
       x[2] = (real)od_new - tgt;
       if (p.solar_on) {
         x[3] = (real)(now.hour * 3600 + now.minute * 60 + now.second);
@@ -961,7 +991,7 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
       isum += (double)interp5<real>(pl.interp_table + (size_t)pl.interp_sub[o] * DRSIM_INTERP_SUBTABLE_LEN, x);
     }
   }
-  __shared__ double wp[4][kRed + 1];
+  __shared__ double wp[kReduceThreads / 32][kRed + 1];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double t[kRed];
@@ -971,7 +1001,7 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
     isum += __shfl_down_sync(0xffffffffu, isum, o);
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) {
+  if (lane == 0 && worker) {
     for (int k = 0; k < kRed; ++k) wp[w][k] = red[k];
     wp[w][kRed] = isum;
   }
@@ -985,16 +1015,16 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
     const KC<real> kc(p);
     const real pmax = qdiv(pl.cap[o], kc.cop, kc.inv_cop);
     double rec[kHaloFields];
-    rec[0] = (double)div5(Rep<real>::dev(pl.t_air[o], pl.target[o]));          // norm.py:39
-    rec[1] = (double)(real)fast_div((uint32_t)pl.sso[o], p.fd_dur);            // norm.py:40-43
-    rec[2] = (double)qdiv((pl.flags[o] & 1u) ? pmax : (real)0, kc.nrs, kc.inv_nrs);
+    rec[0] = (double)div5(Rep<real>::dev(ld_cg(pl.t_air + o), pl.target[o]));  // norm.py:39
+    rec[1] = (double)(real)fast_div((uint32_t)ld_cg(pl.sso + o), p.fd_dur);    // norm.py:40-43
+    rec[2] = (double)qdiv((ld_cg(pl.flags + o) & 1u) ? pmax : (real)0, kc.nrs, kc.inv_nrs);
     rec[3] = (double)qdiv(pmax, kc.nrs, kc.inv_nrs);
     for (int m = 0; m < 4; ++m) rec[4 + m] = p.msg_thermal ? (double)pl.ratio[m][o] : 0.0;
     double *mine = pl.halo_out + ((size_t)r * c + t) * kHaloFields;
     for (int m = 0; m < kHaloFields; ++m) mine[m] = rec[m];
     if (peer.world > 1) {
       // my first houses are the RIGHT halo of the previous rank, my last houses the LEFT halo of the next
-      const int parity = (int)(in.step & 1);
+      const int parity = (int)(in.xseq & 1);
       const int dst_rank = t < H ? (peer.rank + peer.world - 1) % peer.world : (peer.rank + 1) % peer.world;
       const int slot = t < H ? L + t : t - H;
       double *dst = peer.halo[dst_rank] + (((size_t)parity * p.R + r) * c + slot) * kHaloFields;
@@ -1007,7 +1037,7 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
   if (threadIdx.x == 0) {
     double a[kRed] = {0, 0, 0, 0, 0};
     double s = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { red_combine(a, wp[i]); s += wp[i][kRed]; }
+    for (int i = 0; i < kReduceThreads / 32; ++i) { red_combine(a, wp[i]); s += wp[i][kRed]; }
     double *dst = pl.acc + (size_t)r * (kRed + 1);
     for (int k = 0; k < kRed; ++k) { dst[k] = a[k]; s_row[k] = a[k]; }
     dst[kRed] = s;
@@ -1020,34 +1050,38 @@ __global__ void __launch_bounds__(128) k_reduce(Planes<real> pl, SimParams p, St
     __syncthreads();
     const int q = threadIdx.x;
     if (q < peer.world) {
-      const int parity = (int)(in.step & 1);
+      const int parity = (int)(in.xseq & 1);
       const size_t row = (((size_t)parity * peer.world + peer.rank) * p.R + r);
       double *ib = peer.inbox[q] + row * (kRed + 1);
       for (int k = 0; k <= kRed; ++k) ib[k] = s_row[k];
       __threadfence_system();
       unsigned long long *f = peer.flags[q] + row;
 #if defined(__CUDA_ARCH__)
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)(in.step + 1)) : "memory");
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)in.xseq) : "memory");
 #endif
     }
   }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kReduceThreads) k_reduce(Planes<real> pl, SimParams p, StepIn in, int chunks, PeerCtx peer) {
+  pdl_wait();
+  pdl_trigger();
+  reduce_cluster<real>(pl, p, in, chunks, peer, blockIdx.x);
 }
 
 // General path, kernel 3: env epilogue, one thread per cluster.  `acc` holds `n_parts` per-rank
 // partial results [n_parts][R][kRed + 1] (n_parts = 1: this handle's own); they are combined here in
 // rank order (sums; column 2 is a max), so every rank derives bit-identical cluster totals.
 template <typename real>
-__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc, int n_parts, PeerCtx peer) {
-  pdl_wait();
-  pdl_trigger();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= p.R) return;
+DRSIM_D EnvBroadcast<real> env_cluster(const Planes<real> &pl, const SimParams &p, const StepIn &in, const double *acc, int n_parts,
+                                       const PeerCtx &peer, int r) {
   double red[kRed] = {0, 0, 0, 0, 0};
   double isum = 0.0;
   if (peer.world > 1) {
     // wait (bounded) until every rank's row for this step has landed in the local inbox
-    const int parity = (int)(in.step & 1);
-    const unsigned long long want = (unsigned long long)(in.step + 1);
+    const int parity = (int)(in.xseq & 1);
+    const unsigned long long want = (unsigned long long)in.xseq;
     const long long t0 = clock64();
     for (int q = 0; q < peer.world; ++q) {
       const unsigned long long *f = peer.flags[peer.rank] + (((size_t)parity * peer.world + q) * p.R + r);
@@ -1064,10 +1098,22 @@ __global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc
   }
   for (int q = 0; q < n_parts; ++q) {
     const double *a = acc + ((size_t)q * p.R + r) * (kRed + 1);
-    red_combine(red, a);
-    isum += a[kRed];
+    double t[kRed + 1];
+#pragma unroll
+    for (int k = 0; k <= kRed; ++k) t[k] = ld_cg(a + k);
+    red_combine(red, t);
+    isum += t[kRed];
   }
-  env_epilogue<real>(pl, p, in, r, env_load(pl, in, r), red, isum);
+  return env_epilogue<real>(pl, p, in, r, env_load(pl, in, r), red, isum);
+}
+
+template <typename real>
+__global__ void k_env(Planes<real> pl, SimParams p, StepIn in, const double *acc, int n_parts, PeerCtx peer) {
+  pdl_wait();
+  pdl_trigger();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.R) return;
+  env_cluster<real>(pl, p, in, acc, n_parts, peer, r);
 }
 
 // General path, kernel 4: rewards + observation rows for a chunk of kObsChunk houses.

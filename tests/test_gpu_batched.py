@@ -261,6 +261,9 @@ def test_step_host_full_returns_obs_and_reward(n, R, layout):
     device-resident step; N = 10 exercises the padded rows (house stride 12)."""
     import torch
 
+    from marl_demandresponse_b200 import BatchedEnv
+    from marl_demandresponse_b200.batched import synthetic_state
+
     prop = _prop(n)
     st = synthetic_state(prop, R, seed=5)
     acts = (np.random.default_rng(6).random((6, R, n)) < 0.5).astype(np.uint8)
