@@ -81,7 +81,8 @@ struct drsim_handle {
   ShardGeom shard{};
   int shard_grid = 0, shard_capacity = 0;
   bool shard_ok = false;
-  size_t o_sh_arrive = 0, o_sh_ready = 0, o_sh_envb = 0;
+  size_t o_sh_partll = 0, o_sh_envll = 0;
+  unsigned long long *shard_dbg = nullptr;   // DRSIM_SHARD_DBG: per-CTA time stamps of the last k_shard launch
   int *h_peer_err = nullptr, *h_peer_err_dev = nullptr;   // mapped: set by a kernel whose exchange wait timed out
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
   StepIn pending_in{};
@@ -402,9 +403,8 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     h->o_halo_out = cv.take(halo);
     h->o_halo_in = cv.take(2 * halo);
     h->o_peer_err = cv.take(8);
-    h->o_sh_arrive = cv.take((size_t)p.R * 4);
-    h->o_sh_ready = cv.take((size_t)p.R * 8);
-    h->o_sh_envb = cv.take((size_t)p.R * 8 * 8);
+    h->o_sh_partll = cv.take((size_t)p.R * h->chunks * 16 * 8);
+    h->o_sh_envll = cv.take((size_t)p.R * 16 * 8);
   }
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
   h->o_sched_aux = cv.take(E8 * drsim_handle::kSched); h->o_sched_tsec = cv.take((size_t)p.R * 4 * drsim_handle::kSched);
@@ -493,6 +493,7 @@ extern "C" int drsim_destroy(drsim_t *h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_env) cudaFreeHost(h->h_env);
   if (h->actor_image) cudaFree(h->actor_image);
+  if (h->shard_dbg) cudaFree(h->shard_dbg);
   delete h;
   return 0;
 }
@@ -897,26 +898,36 @@ static int plan_shard(drsim_handle *h) {
   const size_t budget = min_ctas >= 2 ? 110 * 1024 : 200 * 1024;
   const size_t group = (size_t)kShardGroup * p.obs_dim * rb;
   g.nbuf = (size_t)(kThreads / 32) * 2 * group <= 48 * 1024 ? 2 : 1;
-  const size_t rows = plain ? (size_t)kTileSlots * 10 * 4 : std::max<size_t>(16, (size_t)(kThreads / 32) * g.nbuf * group);
+  // (also where the reducer parks the tile partials it collects: room for at least kReduceThreads of them)
+  const size_t rows = plain ? (size_t)kTileSlots * 10 * 4
+                            : std::max<size_t>((size_t)kReduceThreads * kRed * 8, (size_t)(kThreads / 32) * g.nbuf * group);
+  g.part_cap = (int)std::min<size_t>(32 * kThreads, rows / (kRed * 8) / kReduceThreads * kReduceThreads);
   if (rows + 1024 > budget) return 0;   // rows too wide: four-kernel path
   g.tile_bytes = kTileSlots * (3 * rb + 5);
   g.off_rows = 0;
   g.off_saved = (int)((rows + 127) / 128 * 128);
+  // tiles kept in shared memory between the phases: as many as a CTA owns, as long as min_ctas CTAs stay resident
+  // per SM (the occupancy query knows the kernel's static shared memory and the per-CTA reservation)
   const int cap0 = std::min(g.n_tiles, min_ctas * h->sm_count);
   const int per_cta0 = (g.n_tiles + cap0 - 1) / cap0;
   g.t_smem = (int)std::min<size_t>(per_cta0, (budget - g.off_saved) / g.tile_bytes);
   if (const char *e = getenv("DRSIM_SHARD_TSMEM")) g.t_smem = std::max(0, std::min(g.t_smem, atoi(e)));
-  g.smem_bytes = g.off_saved + g.t_smem * g.tile_bytes;
   int per_sm = 0;
-  if constexpr (sizeof(real) == 4) {
-    if (plain) {
-      CU_TRY(cudaFuncSetAttribute(k_shard<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard<float, true>, kThreads, g.smem_bytes));
+  for (;; --g.t_smem) {
+    g.smem_bytes = g.off_saved + g.t_smem * g.tile_bytes;
+    bool done = false;
+    if constexpr (sizeof(real) == 4) {
+      if (plain) {
+        CU_TRY(cudaFuncSetAttribute(k_shard<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard<float, true>, kThreads, g.smem_bytes));
+        done = true;
+      }
     }
-  }
-  if (!plain) {
-    CU_TRY(cudaFuncSetAttribute(k_shard<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard<real, false>, kThreads, g.smem_bytes));
+    if (!done) {
+      CU_TRY(cudaFuncSetAttribute(k_shard<real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shard<real, false>, kThreads, g.smem_bytes));
+    }
+    if (per_sm >= min_ctas || g.t_smem == 0) break;
   }
   if (per_sm < 1) return 0;
   h->shard_capacity = per_sm * h->sm_count;
@@ -952,10 +963,11 @@ static int launch_shard(drsim_handle *h, StepIn in, cudaStream_t s) {
     in.halo_right = inbox + (size_t)L * kHaloFields;
   }
   ShardCtx sc{};
-  sc.arrive = h->at<unsigned int>(h->o_sh_arrive);
-  sc.ready = h->at<unsigned long long>(h->o_sh_ready);
-  sc.envb = h->slab + h->o_sh_envb;
+  sc.partll = h->at<unsigned long long>(h->o_sh_partll);
+  sc.envll = h->at<unsigned long long>(h->o_sh_envll);
   sc.err = h->h_peer_err_dev ? h->h_peer_err_dev : reinterpret_cast<int *>(h->slab + h->o_peer_err);
+  if (!h->shard_dbg && getenv("DRSIM_SHARD_DBG")) cudaMalloc(&h->shard_dbg, (size_t)h->shard_capacity * 16 * 8);
+  sc.dbg = h->shard_dbg;
   bool plain = false;
   if constexpr (sizeof(real) == 4) {
     if (shard_plain(h)) {
@@ -1614,6 +1626,15 @@ extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_
   h->launches++;
   CU_TRY(cudaGetLastError());
   return 0;
+}
+
+// diagnostics, not part of the documented ABI: per-CTA globaltimer stamps [grid][16] of the last k_shard launch
+// (start, after the dependency wait, phase 1 done, arrival / reduction done, first broadcast values seen, end)
+extern "C" int drsim_debug_shard_times(drsim_t *h, unsigned long long *host_out, int max_ctas) {
+  if (!h || !h->shard_dbg || !host_out) return 0;
+  const int n = std::min(max_ctas, h->shard_grid);
+  cudaMemcpy(host_out, h->shard_dbg, (size_t)n * 128, cudaMemcpyDeviceToHost);
+  return n;
 }
 
 extern "C" int64_t drsim_launch_count(const drsim_t *h) { return h ? h->launches : 0; }

@@ -551,9 +551,18 @@ DRSIM_D double signal_penalty(const SimParams &p, double P, double s_old) {
   return p.alpha_sig * (dev * dev) * p.inv_norm_sig;
 }
 
+// what env_epilogue leaves in the env planes: computed first (env_epilogue_compute), stored afterwards
+// (env_epilogue_store), so that a caller with consumers waiting for the broadcast values (k_shard) can
+// publish them before paying for the stores
+struct EnvOut {
+  EnvRegs e;
+  double solar_cur, P, rew_sig, pen_sum, pen_max;
+  double mean_rew, abs_dt, sq_dt, p_minus_s;   // terms of the running-metric updates (valid when advance)
+};
+
 template <typename real>
-DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams &p, const StepIn &in,
-                                        int r, EnvRegs e, const double red[kRed], double interp_sum) {
+DRSIM_D EnvBroadcast<real> env_epilogue_compute(const Planes<real> &pl, const SimParams &p, const StepIn &in,
+                                                int r, EnvRegs e, const double red[kRed], double interp_sum, EnvOut &o) {
   const uint32_t env_global = (uint32_t)(p.rep_offset + r);
   double solar_cur, rew_sig = 0.0, P;
   const bool sched = in.advance && in.sched_od != nullptr;
@@ -563,13 +572,10 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
     P = red[0];
     rew_sig = signal_penalty(p, P, e.signal);                      // old signal (quirk Q6)
     // running rollout metrics (metrics_service.py:108-157 restated as per-cluster sums)
-    double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
-    m[0] += 1.0;
-    m[1] += mean_reward(p, red[1], red[2], rew_sig);
-    m[2] += fabs(red[3]) * p.inv_n_global;
-    m[3] += red[4] * p.inv_n_global;
-    m[4] += fabs(P - e.signal);
-    m[5] += (P - e.signal) * (P - e.signal);
+    o.mean_rew = mean_reward(p, red[1], red[2], rew_sig);
+    o.abs_dt = fabs(red[3]);
+    o.sq_dt = red[4];
+    o.p_minus_s = P - e.signal;
   } else {
     solar_cur = pl.solar_cur[r];
     // a refresh keeps the injected cluster power: the reference's reset observation carries the
@@ -615,17 +621,7 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
       e.signal = grid_signal(p, e.base_power, now, perlin, e.artificial_ratio, e.max_power);
     }
   }
-  pl.epoch[r] = e.epoch;
-  pl.od_temp[r] = e.od_temp;
-  pl.solar_next[r] = e.solar_next;
-  pl.solar_cur[r] = solar_cur;
-  pl.signal[r] = e.signal;
-  pl.base_power[r] = e.base_power;
-  if (in.advance) pl.power[r] = P;
-  pl.pen_sum[r] = red[1];
-  pl.pen_max[r] = red[2];
-  pl.rew_sig[r] = rew_sig;
-  pl.t_since_interp[r] = e.t_since_interp;
+  o.e = e; o.solar_cur = solar_cur; o.P = P; o.rew_sig = rew_sig; o.pen_sum = red[1]; o.pen_max = red[2];
   EnvBroadcast<real> b;
   b.power_n = (real)(P * p.inv_nrs);                               // norm.py:144-146
   b.signal_n = (real)(e.signal * p.inv_nrs * p.inv_n_global);      // norm.py:132-135
@@ -634,6 +630,40 @@ DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams 
   b.rew_sig = (real)rew_sig;
   b.pen_common = (real)red[1];
   b.pen_max = (real)red[2];
+  return b;
+}
+
+template <typename real>
+DRSIM_D void env_epilogue_store(const Planes<real> &pl, const SimParams &p, const StepIn &in, int r, const EnvOut &o) {
+  if (in.advance) {
+    // (multiply-adds as in env_stage_store: the contraction into FMAs is part of the result)
+    double *m = pl.metrics + (size_t)r * DRSIM_N_METRICS;
+    m[0] += 1.0;
+    m[1] += o.mean_rew;
+    m[2] += o.abs_dt * p.inv_n_global;
+    m[3] += o.sq_dt * p.inv_n_global;
+    m[4] += fabs(o.p_minus_s);
+    m[5] += o.p_minus_s * o.p_minus_s;
+  }
+  pl.epoch[r] = o.e.epoch;
+  pl.od_temp[r] = o.e.od_temp;
+  pl.solar_next[r] = o.e.solar_next;
+  pl.solar_cur[r] = o.solar_cur;
+  pl.signal[r] = o.e.signal;
+  pl.base_power[r] = o.e.base_power;
+  if (in.advance) pl.power[r] = o.P;
+  pl.pen_sum[r] = o.pen_sum;
+  pl.pen_max[r] = o.pen_max;
+  pl.rew_sig[r] = o.rew_sig;
+  pl.t_since_interp[r] = o.e.t_since_interp;
+}
+
+template <typename real>
+DRSIM_D EnvBroadcast<real> env_epilogue(const Planes<real> &pl, const SimParams &p, const StepIn &in,
+                                        int r, EnvRegs e, const double red[kRed], double interp_sum) {
+  EnvOut o;
+  const EnvBroadcast<real> b = env_epilogue_compute<real>(pl, p, in, r, e, red, interp_sum, o);
+  env_epilogue_store<real>(pl, p, in, r, o);
   return b;
 }
 
@@ -932,21 +962,139 @@ DRSIM_D uint8_t ld_cg(const uint8_t *p) {
 }
 
 constexpr int kReduceThreads = 128;  // threads that take part in reduce_cluster (fixes the combine order)
+constexpr int kReduceBatch = 2;      // tile partials a thread has in flight (register budget of the callers)
+
+// Tile partials as self-validating words (k_shard): [tile][16] u64, word 2k / 2k+1 = (tag << 32 | low / high half
+// of double k), k < kRed.  The producer needs no fence and no flag, the consumer has the value the moment the
+// tags match (the "LL" idea of NCCL's low-latency protocol, here inside one GPU).
+struct PartLL {
+  unsigned long long *words;   // NULL: the partials are plain doubles in Planes::partials
+  uint32_t tag;
+  int *err;
+  double *stage;               // shared memory: the reducer collects the partials here, [cap][kRed]
+  int cap;                     // tiles per collection pass, a multiple of kReduceThreads
+  unsigned long long *dbg;     // diagnostics: globaltimer stamps of thread 0 (slots 8..), or NULL
+};
+
+DRSIM_D void partll_store(const PartLL &ll, int tile, const double v[kRed]) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long *dst = ll.words + (size_t)tile * 16;
+  const unsigned long long tag = (unsigned long long)ll.tag << 32;
+#pragma unroll
+  for (int k = 0; k < kRed; ++k) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * k), "l"(tag | (bits & 0xffffffffull)),
+                 "l"(tag | (bits >> 32))
+                 : "memory");
+  }
+  // the record is one 128-byte line and ALL of it is written: a reader of a partially written 32-byte sector
+  // would make the L2 fetch the rest of the sector from HBM first (microseconds while the step is streaming)
+#pragma unroll
+  for (int k = kRed; k < 8; ++k)
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * k), "l"(tag), "l"(tag) : "memory");
+#endif
+}
+
+// the words of one tile's partial, requested (partll_issue) and examined (partll_check) separately so that a
+// thread can have the requests of several tiles in flight at once
+struct PartWords {
+  unsigned long long w[2 * kRed];
+};
+DRSIM_D void partll_issue(const PartLL &ll, int tile, PartWords &x) {
+#if defined(__CUDA_ARCH__)
+  const unsigned long long *src = ll.words + (size_t)tile * 16;
+#pragma unroll
+  for (int k = 0; k < kRed; ++k)
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(x.w[2 * k]), "=l"(x.w[2 * k + 1]) : "l"(src + 2 * k) : "memory");
+#endif
+}
+// true (and v filled) when every word carries this step's tag
+DRSIM_D bool partll_check(const PartLL &ll, const PartWords &x, double v[kRed]) {
+  bool ok = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int k = 0; k < 2 * kRed; ++k) ok = ok && (uint32_t)(x.w[k] >> 32) == ll.tag;
+#pragma unroll
+  for (int k = 0; k < kRed; ++k) v[k] = __longlong_as_double((long long)((x.w[2 * k + 1] << 32) | (x.w[2 * k] & 0xffffffffull)));
+#endif
+  return ok;
+}
 
 // Reduction of cluster r: called by EVERY thread of the CTA (it contains CTA barriers); the first
 // kReduceThreads threads do the work, in an order that depends on nothing but `chunks`.
+// Returns this rank's reduced row [kRed + 1] in shared memory (meaningful on thread 0 only).
 template <typename real>
-DRSIM_D void reduce_cluster(const Planes<real> &pl, const SimParams &p, const StepIn &in, int chunks, const PeerCtx &peer, int r) {
+DRSIM_D const double *reduce_cluster(const Planes<real> &pl, const SimParams &p, const StepIn &in, int chunks, const PeerCtx &peer, int r,
+                                     const PartLL ll = PartLL{nullptr, 0u, nullptr, nullptr, 0, nullptr}) {
   const bool worker = threadIdx.x < kReduceThreads;
   double red[kRed] = {0, 0, 0, 0, 0};
   // fixed assignment + fixed combine order => deterministic
-  if (worker)
-    for (int c = threadIdx.x; c < chunks; c += kReduceThreads) {
-      const double *src = pl.partials + ((size_t)r * chunks + c) * kRed;
-      double t[kRed];
+  if (ll.words) {
+    // Collection is decoupled from the fold: EVERY thread of the CTA polls the tiles it owns (a late tile does
+    // not hold up the ones behind it -- after the last producer only that tile is outstanding) and parks the
+    // values in shared memory; the workers then fold them in the fixed ascending order.
+    for (int base = 0; base < chunks; base += ll.cap) {
+      const int nb = min(ll.cap, chunks - base);
+      const int n_own = (int)threadIdx.x < nb ? (nb - (int)threadIdx.x + (int)blockDim.x - 1) / (int)blockDim.x : 0;   // <= 32
+      unsigned pending = n_own >= 32 ? 0xffffffffu : ((1u << n_own) - 1u);
+      const long long t0 = clock64();
+      if (ll.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[11] = t; ll.dbg[12] = 0; }
+      while (pending) {
+        if (ll.dbg && threadIdx.x == 0) ll.dbg[12] += 1;
+        // the requests of two outstanding tiles fly together (register budget of the callers)
+        for (int j0 = 0; j0 < n_own; j0 += 2) {
+          if (!((pending >> j0) & 0x3u)) continue;
+          PartWords x[2];
 #pragma unroll
-      for (int k = 0; k < kRed; ++k) t[k] = ld_cg(src + k);
-      red_combine(red, t);
+          for (int u = 0; u < 2; ++u)
+            if ((pending >> (j0 + u)) & 1u) partll_issue(ll, r * chunks + base + (int)threadIdx.x + (j0 + u) * (int)blockDim.x, x[u]);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (!((pending >> (j0 + u)) & 1u)) continue;
+            const int c = (int)threadIdx.x + (j0 + u) * (int)blockDim.x;
+            double t[kRed];
+            if (partll_check(ll, x[u], t)) {
+#pragma unroll
+              for (int k = 0; k < kRed; ++k) ll.stage[(size_t)c * kRed + k] = t[k];
+              pending &= ~(1u << (j0 + u));
+            }
+          }
+          if (ll.dbg && threadIdx.x == 0 && j0 == 0 && ll.dbg[12] == 1) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[13] = t; }
+        }
+        if (pending && clock64() - t0 > 4000000000ll) {   // ~2 s: give up, flag the error
+          *ll.err = 1;
+          for (int j = 0; j < n_own; ++j)
+            if ((pending >> j) & 1u)
+              for (int k = 0; k < kRed; ++k) ll.stage[(size_t)((int)threadIdx.x + j * (int)blockDim.x) * kRed + k] = 0.0;
+          pending = 0;
+        }
+      }
+      if (ll.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[8] = t; }
+      __syncthreads();
+      if (ll.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[9] = t; }
+      if (worker)
+        for (int c = threadIdx.x; c < nb; c += kReduceThreads) red_combine(red, ll.stage + (size_t)c * kRed);   // base % kReduceThreads == 0
+      __syncthreads();
+      if (ll.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[10] = t; }
+    }
+    // the interpolator / halo parts below read house state written by other CTAs before they stored their partial
+    if (in.do_interp > 0 || needs_halo(p)) __threadfence();
+  } else if (worker)
+    for (int c0 = threadIdx.x; c0 < chunks; c0 += kReduceBatch * kReduceThreads) {
+      // kReduceBatch tile partials in flight per thread; they are folded in ascending order (the order is part of the result)
+      double t[kReduceBatch][kRed];
+#pragma unroll
+      for (int u = 0; u < kReduceBatch; ++u) {
+        const int c = c0 + u * kReduceThreads;
+        if (c < chunks) {
+          const double *src = pl.partials + ((size_t)r * chunks + c) * kRed;
+#pragma unroll
+          for (int k = 0; k < kRed; ++k) t[u][k] = ld_cg(src + k);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kReduceBatch; ++u)
+        if (c0 + u * kReduceThreads < chunks) red_combine(red, t[u]);
     }
   double isum = 0.0;
   if (in.do_interp > 0 && worker) {
@@ -1061,6 +1209,7 @@ DRSIM_D void reduce_cluster(const Planes<real> &pl, const SimParams &p, const St
 #endif
     }
   }
+  return s_row;
 }
 
 template <typename real>
@@ -1073,9 +1222,11 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce(Planes<real> pl, SimP
 // General path, kernel 3: env epilogue, one thread per cluster.  `acc` holds `n_parts` per-rank
 // partial results [n_parts][R][kRed + 1] (n_parts = 1: this handle's own); they are combined here in
 // rank order (sums; column 2 is a max), so every rank derives bit-identical cluster totals.
+// `defer` != NULL: the env planes are NOT stored here; the caller runs env_epilogue_store(pl, in, r, *defer) later
 template <typename real>
 DRSIM_D EnvBroadcast<real> env_cluster(const Planes<real> &pl, const SimParams &p, const StepIn &in, const double *acc, int n_parts,
-                                       const PeerCtx &peer, int r) {
+                                       const PeerCtx &peer, int r, EnvOut *defer = nullptr, const EnvRegs *pre = nullptr,
+                                       const double *own_row = nullptr) {
   double red[kRed] = {0, 0, 0, 0, 0};
   double isum = 0.0;
   if (peer.world > 1) {
@@ -1096,6 +1247,11 @@ DRSIM_D EnvBroadcast<real> env_cluster(const Planes<real> &pl, const SimParams &
     acc = peer.inbox[peer.rank] + (size_t)parity * peer.world * p.R * (kRed + 1);
     n_parts = peer.world;
   }
+  if (own_row && peer.world <= 1) {   // this rank's row straight from the reducer's shared memory (one part)
+    red_combine(red, own_row);
+    isum += own_row[kRed];
+    n_parts = 0;
+  }
   for (int q = 0; q < n_parts; ++q) {
     const double *a = acc + ((size_t)q * p.R + r) * (kRed + 1);
     double t[kRed + 1];
@@ -1104,6 +1260,7 @@ DRSIM_D EnvBroadcast<real> env_cluster(const Planes<real> &pl, const SimParams &
     red_combine(red, t);
     isum += t[kRed];
   }
+  if (defer) return env_epilogue_compute<real>(pl, p, in, r, pre ? *pre : env_load(pl, in, r), red, isum, *defer);
   return env_epilogue<real>(pl, p, in, r, env_load(pl, in, r), red, isum);
 }
 

@@ -34,7 +34,8 @@
 namespace drsim {
 
 constexpr int kShardGroup = 32;    // rows per warp-level TMA store of the generic phase 2 (one row per lane)
-constexpr int kShardMaxRuns = 64;  // (cluster, tile-count) runs a CTA arrives with one batch of atomics
+constexpr int kShardBatch = 4;     // tiles whose partials a CTA publishes together (one CTA barrier per batch)
+constexpr int kShardFinish = 4;    // clusters a CTA completes at a time (reduce all, then one lane per cluster finishes)
 
 struct ShardGeom {
   int chunks;       // 1024-house tiles per cluster: the chunk geometry of k_house (fixes the partial sums)
@@ -44,14 +45,18 @@ struct ShardGeom {
   int tile_bytes;   // bytes of one saved tile
   int off_saved;    // [t_smem] saved tiles
   int off_rows;     // PLAIN: [1024][D] floats; generic: [warps][nbuf][kShardGroup][D] reals
+  int part_cap;     // tile partials the row staging area can park during the reduction (multiple of kReduceThreads)
   int smem_bytes;
 };
 
 struct ShardCtx {
-  unsigned int *arrive;        // [R] tiles of cluster r that finished phase 1 this step (reset by the last arrival)
-  unsigned long long *ready;   // [R] == StepIn::xseq once envb[r] holds this step's values
-  void *envb;                  // [R][8] reals: EnvBroadcast of cluster r
+  unsigned long long *partll;  // [R * chunks][16] tile partials as self-validating words (PartLL)
+  // [R][16] self-validating words: the 7 broadcast values of cluster r as doubles, each split into two
+  // (tag << 32 | 32 data bits) words, tag = low half of StepIn::xseq.  A consumer polls the 14 words with ONE
+  // coalesced load and has the values the moment all tags match -- no separate flag, no second round trip.
+  unsigned long long *envll;
   int *err;                    // set when a wait timed out
+  unsigned long long *dbg;     // diagnostics (DRSIM_SHARD_DBG): [grid][16] globaltimer stamps of thread 0, or NULL
 };
 
 template <typename real>
@@ -68,32 +73,59 @@ struct ShardSaved {
   }
 };
 
+// one thread: publish cluster r's broadcast values (reals are exactly representable as doubles)
 template <typename real>
 DRSIM_D void shard_publish(const ShardCtx &sc, const StepIn &in, int r, const EnvBroadcast<real> &e) {
-  real *dst = reinterpret_cast<real *>(sc.envb) + (size_t)r * 8;
-  dst[0] = e.power_n; dst[1] = e.signal_n; dst[2] = e.solar_n; dst[3] = e.od_n;
-  dst[4] = e.rew_sig; dst[5] = e.pen_common; dst[6] = e.pen_max;
-  __threadfence();
+  const double v[7] = {(double)e.power_n, (double)e.signal_n, (double)e.solar_n, (double)e.od_n,
+                       (double)e.rew_sig, (double)e.pen_common, (double)e.pen_max};
+  unsigned long long *dst = sc.envll + (size_t)r * 16;
+  const unsigned long long tag = (unsigned long long)(uint32_t)in.xseq << 32;
+  __threadfence();   // release: whatever the consumers read after seeing these words (other CTAs' state, halo) is ordered before them
 #if defined(__CUDA_ARCH__)
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(sc.ready + r), "l"((unsigned long long)in.xseq) : "memory");
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 2 * k), "l"(tag | (bits & 0xffffffffull)) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 2 * k + 1), "l"(tag | (bits >> 32)) : "memory");
+  }
+  // (whole 128-byte line written: no partially valid sector for the L2 to complete from HBM under the pollers)
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 14), "l"(tag) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(dst + 15), "l"(tag) : "memory");
 #endif
 }
 
-// thread 0: bounded wait for cluster r's broadcast values, copied into dst[8]
+// whole warp: bounded wait for cluster r's broadcast values
 template <typename real>
-DRSIM_D void shard_wait_env(const ShardCtx &sc, const StepIn &in, int r, real *dst) {
-  unsigned long long v = 0;
+DRSIM_D EnvBroadcast<real> shard_wait_env(const ShardCtx &sc, const StepIn &in, int r, int lane) {
+  const unsigned long long *src = sc.envll + (size_t)r * 16;
+  const uint32_t tag = (uint32_t)in.xseq;
+  unsigned long long w = 0;
   const long long t0 = clock64();
   for (;;) {
 #if defined(__CUDA_ARCH__)
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(sc.ready + r) : "memory");
+    if (lane < 14) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(src + lane) : "memory");
 #endif
-    if (v == (unsigned long long)in.xseq) break;
-    if (clock64() - t0 > 4000000000ll) { *sc.err = 1; break; }   // ~2 s: give up, flag the error
+    if (__all_sync(0xffffffffu, lane >= 14 || (uint32_t)(w >> 32) == tag)) break;
+    if (__any_sync(0xffffffffu, clock64() - t0 > 4000000000ll)) {   // ~2 s: give up, flag the error
+      if (lane == 0) *sc.err = 1;
+      break;
+    }
+#if defined(__CUDA_ARCH__)
+    __nanosleep(100);
+#endif
   }
-  const real *src = reinterpret_cast<const real *>(sc.envb) + (size_t)r * 8;
+  __threadfence();   // acquire side of the release in shard_publish
+  const uint32_t half = (uint32_t)w;
+  double v[7];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) dst[k] = ld_cg(src + k);
+  for (int k = 0; k < 7; ++k) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, half, 2 * k), hi = __shfl_sync(0xffffffffu, half, 2 * k + 1);
+    v[k] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+  }
+  EnvBroadcast<real> e;
+  e.power_n = (real)v[0]; e.signal_n = (real)v[1]; e.solar_n = (real)v[2]; e.od_n = (real)v[3];
+  e.rew_sig = (real)v[4]; e.pen_common = (real)v[5]; e.pen_max = (real)v[6];
+  return e;
 }
 
 DRSIM_D void ld4_cg(const float *p, float v[4]) {
@@ -115,11 +147,10 @@ __global__ void __launch_bounds__(kThreads, FusedOcc<real>::min_ctas)
 k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerCtx peer) {
   static_assert(!PLAIN || sizeof(real) == 4, "the plain variant is fp32 only");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double s_wp[kThreads / 32][kRed];
-  __shared__ int s_run_r[kShardMaxRuns], s_run_n[kShardMaxRuns], s_run_last[kShardMaxRuns];
-  __shared__ int s_n_runs, s_n_mine;
-  __shared__ int s_mine[kShardMaxRuns];
-  __shared__ real s_e[2][8];
+  __shared__ double s_wp[kShardBatch][kThreads / 32][kRed];   // warp partials of the tiles of one arrival batch
+  __shared__ EnvRegs s_er[kShardFinish];
+  __shared__ EnvStage s_st[kShardFinish];
+  __shared__ double s_rows[kShardFinish][kRed + 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Ns = p.Ns, D = p.obs_dim;
@@ -128,47 +159,70 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
   // this CTA's contiguous run of tiles (balanced: sizes differ by at most one)
   const int t_lo = (int)(((long long)blockIdx.x * g.n_tiles) / gridDim.x);
   const int t_hi = (int)(((long long)(blockIdx.x + 1) * g.n_tiles) / gridDim.x);
-  if (threadIdx.x == 0) { s_n_runs = 0; s_n_mine = 0; }
   pdl_trigger();
-  pdl_wait();
-
-  // arrival of the runs recorded so far: one fence, one atomic per cluster (issued by different threads, so
-  // their round trips overlap), then the reductions this CTA completed
-  auto flush = [&]() {
-    __threadfence();   // this thread's state (and partial) stores are visible device-wide before the arrivals below
-    __syncthreads();
-    const int nr = s_n_runs;
-    if ((int)threadIdx.x < nr) {
-      const int r = s_run_r[threadIdx.x], n = s_run_n[threadIdx.x];
-      const unsigned old = atomicAdd(sc.arrive + r, (unsigned)n);
-      const int last = old + (unsigned)n == (unsigned)g.chunks;
-      if (last) sc.arrive[r] = 0;   // every tile of the cluster has arrived: ready for the next step
-      __threadfence();
-      s_run_last[threadIdx.x] = last;
+  auto stamp = [&](int k) {
+#if defined(__CUDA_ARCH__)
+    if (sc.dbg && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      sc.dbg[(size_t)blockIdx.x * 16 + k] = t;
     }
-    __syncthreads();
-    for (int k = 0; k < nr; ++k) {
-      if (!s_run_last[k]) continue;   // CTA-uniform
-      const int r = s_run_r[k];
-      reduce_cluster<real>(pl, p, in, g.chunks, peer, r);
-      if (threadIdx.x == 0) {
-        if (peer.world > 1) s_mine[s_n_mine++] = r;   // the wait for the peers' rows is deferred: nothing left to contribute first
-        else shard_publish<real>(sc, in, r, env_cluster<real>(pl, p, in, pl.acc, 1, peer, r));
+#endif
+  };
+  stamp(0);
+  // PLAIN: the inputs of a tile are staged one tile ahead by thread-private cp.async copies (no registers held
+  // while they fly, completion = the thread's own wait_all): the state planes and the set-point go straight into
+  // the tile's SAVED slots (the update then overwrites them in place), capacity / coefficients / actions into
+  // the row staging area, which is idle during phase 1.  part 1 = launch-invariant planes (may run before
+  // pdl_wait), 2 = what an earlier kernel wrote.
+  float *s_in = reinterpret_cast<float *>(smem_raw + g.off_rows);            // [7][1024] cap, c0..c5 ; then [256] action words
+  uint32_t *s_act = reinterpret_cast<uint32_t *>(s_in + 7 * kTileSlots);
+  const bool ext = p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC;
+  auto prefetch = [&](int tile, int part) {
+    if constexpr (PLAIN) {
+      const int it = tile - t_lo;
+      const int r = tile / g.chunks, c = tile - r * g.chunks;
+      const int n0 = c * kTileSlots + s0;
+      if (n0 >= p.N) return;
+      const size_t off = (size_t)r * Ns + n0;
+      const ShardSaved<float> sv(smem_raw + g.off_saved + (size_t)it * g.tile_bytes);
+      if (part & 1) {
+        cp_async16(sv.tg + s0, pl.target + off);
+        cp_async16(s_in + s0, pl.cap + off);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cp_async16(s_in + (1 + k) * kTileSlots + s0, pl.coef[k] + off);
       }
-      __syncthreads();
+      if (part & 2) {
+        cp_async16(sv.ta + s0, pl.t_air + off);
+        cp_async16(sv.tm + s0, pl.t_mass + off);
+        cp_async16(sv.sso + s0, pl.sso + off);
+        cp_async4(sv.flags + s0, pl.flags + off);
+        if (ext) cp_async4(s_act + threadIdx.x, (in.actions ? in.actions : pl.actions) + off);
+      }
     }
-    if (threadIdx.x == 0) s_n_runs = 0;
-    if (peer.world > 1) {
-      __syncthreads();
-      const int nm = s_n_mine;
-      if (lane == 0)
-        for (int i = warp; i < nm; i += kThreads / 32) {
-          const int r = s_mine[i];
-          shard_publish<real>(sc, in, r, env_cluster<real>(pl, p, in, nullptr, 0, peer, r));
-        }
-      __syncthreads();
-      if (threadIdx.x == 0) s_n_mine = 0;
+  };
+  const bool staged0 = PLAIN && g.t_smem > 0 && t_hi > t_lo;
+  if (staged0) prefetch(t_lo, 1);
+  pdl_wait();
+  if (staged0) prefetch(t_lo, 2);
+  stamp(1);
+
+  // Tiles [f_lo, f_hi) (at most kShardBatch) are done: their partials are formed from the warp partials in warp
+  // order (the arithmetic of block_reduce in k_house) and published as self-validating words -- no atomic, and
+  // no fence unless a consumer of the partial will also read house STATE written by this CTA (`vis`).
+  // the reducer parks the collected partials in the (still unused) row staging area
+  const PartLL ll{sc.partll, (uint32_t)in.xseq, sc.err, reinterpret_cast<double *>(smem_raw + g.off_rows), g.part_cap,
+                  sc.dbg ? sc.dbg + (size_t)blockIdx.x * 16 : nullptr};
+  const bool vis = !PLAIN || in.do_interp > 0;
+  auto flush = [&](int f_lo, int f_hi) {
+    if (vis) __threadfence();   // this thread's state stores are visible device-wide before the partial that announces them
+    __syncthreads();
+    if ((int)threadIdx.x < f_hi - f_lo) {
+      double out[kRed] = {0, 0, 0, 0, 0};
+      for (int i = 0; i < kThreads / 32; ++i) red_combine(out, s_wp[threadIdx.x][i]);
+      partll_store(ll, f_lo + threadIdx.x, out);   // tile index == r * chunks + c
     }
+    __syncthreads();   // s_wp may be rewritten
   };
 
   // ---- phase 1: house update of every tile of this CTA ------------------------------------------
@@ -177,22 +231,40 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
     const int r = tile / g.chunks, c = tile - r * g.chunks;
     const int n0 = c * kTileSlots + s0;
     real red[kRed] = {0, 0, 0, 0, 0};
+    if constexpr (PLAIN) {
+      // a thread with no house in this tile (cluster tail) may own houses of the next one
+      if (n0 >= p.N && it + 1 < g.t_smem && tile + 1 < t_hi) { cp_async_wait_all(); prefetch(tile + 1, 3); }
+    }
     if (n0 < p.N) {
       House4<real> h;
       const size_t off = (size_t)r * Ns + n0;
       if constexpr (PLAIN) {
         Raw4f w;
-        load4(pl.t_air + off, w.ta);
-        load4(pl.t_mass + off, w.tm);
-        load4i(pl.sso + off, w.sso);
-        w.flags = load4b(pl.flags + off);
-        load4_ro(pl.target + off, w.target);
-        load4_ro(pl.cap + off, w.cap);
+        if (it < g.t_smem) {   // staged one tile ago
+          const ShardSaved<float> sv(smem_raw + g.off_saved + (size_t)it * g.tile_bytes);
+          cp_async_wait_all();
+          load4(sv.ta + s0, w.ta);
+          load4(sv.tm + s0, w.tm);
+          load4i(sv.sso + s0, w.sso);
+          w.flags = *reinterpret_cast<const uint32_t *>(sv.flags + s0);
+          load4(sv.tg + s0, w.target);
+          load4(s_in + s0, w.cap);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) load4_ro(pl.coef[k] + off, w.c[k]);
-        w.act = 0;
-        if (p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC)
-          w.act = load4b((in.actions ? in.actions : pl.actions) + off);
+          for (int k = 0; k < 6; ++k) load4(s_in + (1 + k) * kTileSlots + s0, w.c[k]);
+          w.act = ext ? s_act[threadIdx.x] : 0u;
+          // the thread holds its inputs in registers: its staging slots are free for the next tile's copies
+          if (it + 1 < g.t_smem && tile + 1 < t_hi) prefetch(tile + 1, 3);
+        } else {
+          load4(pl.t_air + off, w.ta);
+          load4(pl.t_mass + off, w.tm);
+          load4i(pl.sso + off, w.sso);
+          w.flags = load4b(pl.flags + off);
+          load4_ro(pl.target + off, w.target);
+          load4_ro(pl.cap + off, w.cap);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) load4_ro(pl.coef[k] + off, w.c[k]);
+          w.act = ext ? load4b((in.actions ? in.actions : pl.actions) + off) : 0u;
+        }
         w.od = (float)pl.od_temp[r];
         w.solar = (float)pl.solar_next[r];
         house4_compute_f32<false>(pl, p, w, off, min(4, p.N - n0), h, red);
@@ -208,30 +280,87 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
         *reinterpret_cast<uint32_t *>(sv.flags + s0) = h.flags;
       }
     }
-    double out[kRed];
-    block_reduce<real, kThreads / 32>(red, out, s_wp);
-    if (threadIdx.x == 0) {
-      double *dst = pl.partials + ((size_t)r * g.chunks + c) * kRed;
-      for (int k = 0; k < kRed; ++k) dst[k] = out[k];
-      const int nr = s_n_runs;
-      if (nr > 0 && s_run_r[nr - 1] == r) s_run_n[nr - 1]++;
-      else { s_run_r[nr] = r; s_run_n[nr] = 1; s_n_runs = nr + 1; }
+    // warp stage of block_reduce (k_house): shuffle tree in `real`, lane 0 keeps the warp partial as double
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      real t[kRed];
+#pragma unroll
+      for (int k = 0; k < kRed; ++k) t[k] = __shfl_down_sync(0xffffffffu, red[k], o);
+      red_combine(red, t);
     }
-    __syncthreads();   // s_wp is rewritten by the next tile; s_n_runs is read by everybody below
-    if (s_n_runs == kShardMaxRuns && tile + 1 < t_hi) flush();
+    if (lane == 0)
+      for (int k = 0; k < kRed; ++k) s_wp[it % kShardBatch][warp][k] = (double)red[k];
+    if ((it + 1) % kShardBatch == 0 && tile + 1 < t_hi) flush(tile + 1 - kShardBatch, tile + 1);
   }
-  flush();
+  stamp(2);
+  if (t_hi > t_lo) flush(t_lo + (t_hi - t_lo - 1) / kShardBatch * kShardBatch, t_hi);
+
+  // ---- reduce + env: this CTA completes the clusters whose FIRST tile it owns ---------------------
+  // Only now, with nothing left to contribute: every partial / push this CTA owes anybody is out, so the polls
+  // and peer waits below cannot deadlock (clusters are taken in ascending order on every rank).
+  {
+    // scheduled step of an unsharded cluster with constant base power, fp32: the packed records are exact
+    const bool fast_env = sizeof(real) == 4 && in.sched_rec != nullptr && p.base_mode == DRSIM_BASE_CONSTANT && peer.world <= 1 &&
+                          in.do_interp <= 0 && p.N == (int)p.n_global;
+    const int r_lo = (t_lo + g.chunks - 1) / g.chunks, r_hi = (t_hi + g.chunks - 1) / g.chunks;   // r * chunks in [t_lo, t_hi)
+    for (int rg = r_lo; rg < r_hi; rg += kShardFinish) {
+      const int ng = min(kShardFinish, r_hi - rg);
+      for (int k = 0; k < ng; ++k) {
+        const int r = rg + k;
+        // previous step's env scalars (or, on the scheduled path, this step's packed record + running metrics),
+        // fetched while the partials are being collected
+        if (threadIdx.x == kThreads - 32) {
+          if (fast_env) {
+            s_st[k].rec = in.sched_rec[r];
+            for (int q = 0; q < DRSIM_N_METRICS; ++q) s_st[k].m[q] = pl.metrics[(size_t)r * DRSIM_N_METRICS + q];
+          } else {
+            s_er[k] = env_load(pl, in, r);
+          }
+        }
+        const double *row = reduce_cluster<real>(pl, p, in, g.chunks, peer, r, ll);
+        if (threadIdx.x == 0) {
+#pragma unroll
+          for (int q = 0; q <= kRed; ++q) s_rows[k][q] = row[q];
+        }
+        __syncthreads();
+      }
+      stamp(6);
+      // lane 0 of warp k finishes cluster rg + k: wait for the peers' rows (house-sharded cluster), env epilogue,
+      // broadcast values to the consumers first, env planes / metrics afterwards
+      if (lane == 0 && warp < ng) {
+        const int r = rg + warp;
+        if (fast_env) {
+          // every env scalar that does not depend on the cluster power is in the step's record (k_schedule_pack):
+          // the consumers are two multiplications away from their values (expressions of the fused kernels)
+          const SchedRec &c = s_st[warp].rec;
+          const double *a = s_rows[warp];
+          EnvBroadcast<real> b;
+          b.power_n = (real)(a[0] * p.inv_nrs);
+          b.signal_n = c.signal_n; b.solar_n = c.solar_n; b.od_n = c.od_n;
+          b.rew_sig = (real)signal_penalty(p, a[0], c.signal_prev);
+          b.pen_common = (real)a[1];
+          b.pen_max = (real)a[2];
+          shard_publish<real>(sc, in, r, b);
+          stamp(7);
+          env_stage_store<real>(pl, p, r, s_st[warp], a);
+        } else {
+          EnvOut o;
+          shard_publish<real>(sc, in, r, env_cluster<real>(pl, p, in, nullptr, 0, peer, r, &o, &s_er[warp], s_rows[warp]));
+          stamp(7);
+          env_epilogue_store<real>(pl, p, in, r, o);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  stamp(3);
 
   // ---- phase 2: rewards + observation rows --------------------------------------------------------
-  int ebuf = 0, r_have = -1;
+  int r_have = -1;
   EnvBroadcast<real> e{};
-  auto env_of = [&](int r) {   // CTA-uniform: (re)fetch the broadcast values when the cluster changes
+  auto env_of = [&](int r) {   // warp-uniform: (re)fetch the broadcast values when the cluster changes
     if (r == r_have) return;
-    if (threadIdx.x == 0) shard_wait_env<real>(sc, in, r, s_e[ebuf]);
-    __syncthreads();
-    const real *v = s_e[ebuf];
-    e.power_n = v[0]; e.signal_n = v[1]; e.solar_n = v[2]; e.od_n = v[3]; e.rew_sig = v[4]; e.pen_common = v[5]; e.pen_max = v[6];
-    ebuf ^= 1;
+    e = shard_wait_env<real>(sc, in, r, lane);
     r_have = r;
   };
 
@@ -243,6 +372,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
       const int it = tile - t_lo;
       const int r = tile / g.chunks, c = tile - r * g.chunks;
       env_of(r);
+      if (tile == t_lo) stamp(4);
       const int n0 = c * kTileSlots + s0;
       const size_t rb = (size_t)r * Ns;
       const int slots = min(kTileSlots, Ns - c * kTileSlots);   // house slots of this tile (multiple of 4)
@@ -292,6 +422,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
     }
     // shared memory must outlive the reads of the last row stores; their global writes complete with the grid
     if (lane == 0 && store_pending) bulk_store_wait_read();
+    stamp(5);
   } else {
     real *rows_w = reinterpret_cast<real *>(smem_raw + g.off_rows) + (size_t)warp * g.nbuf * kShardGroup * D;
     const bool halo = needs_halo(p);
