@@ -266,8 +266,8 @@ def workload_config(wl: dict, world: int, obs_dim: int, exchange: str = "peer", 
             "parallelism": (f"house-sharded x{world}, per-step exchange of 48 B/rank via {exchange if world > 1 else 'none'}" if sharded
                             else f"replica-sharded x{world}, no per-step collective"),
             "l2": f"working set {ws / 1e6:.0f} MB per step per GPU vs 126 MB L2"
-                  + ("" if ws > 126e6 else "; L2 flushed between timed steps by a 256 MB write (flush time excluded)"
-                     if flush_l2 else "; fits L2 (latency-bound workload, see DESIGN.md)"),
+                  + ("" if ws > 126e6 else "; L2 flushed between timed steps by a 256 MB write (flush time excluded: one "
+                     "event pair per step)" if flush_l2 else "; fits L2 (latency-bound workload, see DESIGN.md)"),
             "actions": (f"on-device controller ({wl['policy']})" if on_device_policy else
                         "4 rotating fixed-seed Bernoulli(0.5) u8 tensors (policy cost excluded)")}
 
@@ -321,12 +321,163 @@ def run_reference_arm(args, wl) -> None:
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def run_gpu_arm(args, wl) -> None:
+def source_hash() -> str:
+    """sha256 over the CUDA sources + the public header: what a committed ncu capture must match to be current."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "marl_demandresponse_b200", "csrc")
+    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "drsim.h")]:
+        with open(os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(workload: str) -> dict:
+    """DRAM bytes per launch of the workload's dominant kernel from the committed ncu capture
+    (profiles/r2_traffic.json, written by profiles/tools/ncu_traffic.py); `traffic_stale` says whether the kernels
+    have changed since it was taken."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        t = d.get(workload)
+        if not t:
+            return {"traffic": None}
+        return {"traffic": t["dram_bytes_read"] + t["dram_bytes_write"], "traffic_read": t["dram_bytes_read"],
+                "traffic_write": t["dram_bytes_write"], "traffic_launches_averaged": t.get("launches"),
+                "traffic_stale": d.get("source_hash") != source_hash()}
+    except Exception:  # noqa: BLE001
+        return {"traffic": None}
+
+
+class GpuWorkload:
+    """One workload on this rank's GPU: environment, rotating action tape, timing helpers."""
+
+    def __init__(self, name: str, args, rank: int, world: int, local: int):
+        import numpy as np
+        import torch
+
+        from marl_demandresponse_b200 import BatchedEnv
+
+        self.wl = wl = WORKLOADS[name]
+        self.name, self.args, self.rank, self.world, self.local = name, args, rank, world, local
+        self.dev = dev = torch.device("cuda", local)
+        R, N = wl["rep_per_gpu"], wl["n_houses"]
+        self.R, self.N = R, N
+        self.sharded = bool(wl.get("sharded"))
+        if self.sharded:
+            from marl_demandresponse_b200.sharded import ShardedClusterEnv
+
+            self.env = ShardedClusterEnv(env_prop_for(N), R, rank=rank, world=world, device=local, precision="f32",
+                                         obs_layout=wl["obs"], noise="philox", seed=1234, exchange=args.exchange)
+            self.env.reset()
+            self.n_local = self.env.hi - self.env.lo
+        else:
+            table = None
+            if wl.get("base_mode") == "interpolation":
+                table = interp_table_for_bench()
+            self.env = BatchedEnv(env_prop_for(N, wl.get("base_mode", "constant")), R, device=local, precision="f32",
+                                  obs_layout=wl["obs"], policy=wl.get("policy", "external"), noise="philox", seed=1234,
+                                  rep_offset=rank * R, interp_table=table)
+            self.env.reset()
+            self.n_local = N
+        self.D = self.env.sim.D
+        self.on_device_policy = wl.get("policy", "external") != "external"
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        self.n_act = 4
+        Ns = self.env.sim.Ns
+        # rotating action tape [4][R][Ns] (house axis padded to the plane stride), fixed-seed Bernoulli(0.5)
+        self.tape = torch.zeros((self.n_act, R, Ns), dtype=torch.uint8, device=dev)
+        self.tape[:, :, :self.n_local] = (torch.rand((self.n_act, R, self.n_local), device=dev, generator=g) < 0.5).to(torch.uint8)
+        self.acts = [self.tape[i, :, :self.n_local] for i in range(self.n_act)]
+        self.total_houses = R * N if self.sharded else world * R * N
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
+
+    # -- timing ------------------------------------------------------------------------------
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, one_call=False):
+        """CUDA events around `steps` steps (barrier + synchronize on both sides), MAX over ranks, in ms.  With
+        --flush-l2 every step is bracketed by its own event pair and a 256 MB write runs between the pairs (its
+        time is not counted)."""
+        import torch
+        import torch.distributed as dist
+
+        self.barrier()
+        if self.flush_buf is not None and not one_call:
+            pairs = []
+            for i in range(steps):
+                self.flush_buf.fill_(i & 0xFF)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(i)
+                e1.record()
+                pairs.append((e0, e1))
+            self.barrier()
+            t = sum(a.elapsed_time(b) for a, b in pairs)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if one_call:
+                fn(steps)      # the whole run in one C call (drsim_run_tape)
+            else:
+                for i in range(steps):
+                    fn(i)
+            e1.record()
+            self.barrier()
+            t = e0.elapsed_time(e1)
+        ms = torch.tensor([t], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_dev(self, i):
+        self.env.step(None if self.on_device_policy else self.acts[i % self.n_act])
+
+    def run_dev(self, k):
+        """K device-resident steps enqueued by ONE C call: on-device controller, or the rotating action tape
+        (step k replays plane k % 4) -- no host-language round trip, no launch jitter inside the timed region."""
+        if self.on_device_policy:
+            self.env.run(k)
+        else:
+            self.env.run(k, self.tape, rotate=True)
+
+    def device_resident(self, steps, warmup):
+        """(ms per step, launches inside the timed region)"""
+        for i in range(max(3, warmup)):
+            self.step_dev(i)
+        one_call = self.flush_buf is None and (self.sharded is False or self.args.exchange == "peer" or self.world == 1)
+        if one_call:
+            self.run_dev(8)
+        l0 = self.env.sim.launch_count
+        ms = self.timed(self.run_dev, steps, one_call=True) if one_call else self.timed(self.step_dev, steps)
+        return ms / steps, self.env.sim.launch_count - l0, one_call
+
+
+def interp_table_for_bench():
+    """The interpolation table of BASELINE config 2: GENERATED by the Monte-Carlo table generator (SURVEY 8f-1,
+    v0/monteCarlo/monteCarlo.py:152-230 on the GPU) on a coarse sub-grid when the GPU is free for it, else the seeded
+    stand-in for the reference's missing mergedGridSearchResultFinal.npy."""
     import numpy as np
+
+    try:
+        from marl_demandresponse_b200.montecarlo import generate_table
+
+        return generate_table()
+    except Exception:  # noqa: BLE001
+        return np.random.default_rng(2024).uniform(0.0, 6000.0, 3 * 3 * 3 * 3 * 9 * 5 * 8 * 2 * 12 * 6)
+
+
+def run_gpu_arm(args, wl) -> None:
     import torch
     import torch.distributed as dist
-
-    from marl_demandresponse_b200 import BatchedEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -339,163 +490,132 @@ def run_gpu_arm(args, wl) -> None:
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    R, N = wl["rep_per_gpu"], wl["n_houses"]
-    sharded = bool(wl.get("sharded"))
-    if sharded:
-        from marl_demandresponse_b200.sharded import ShardedClusterEnv
+    w = GpuWorkload(args.workload, args, rank, world, local)
+    env, R, N, D = w.env, w.R, w.N, w.D
+    sharded, on_device_policy = w.sharded, w.on_device_policy
+    n_local = w.n_local
 
-        env = ShardedClusterEnv(env_prop_for(N), R, rank=rank, world=world, device=local, precision="f32",
-                                obs_layout=wl["obs"], noise="philox", seed=1234, exchange=args.exchange)
-        env.reset()
-        n_local = env.hi - env.lo
-    else:
-        table = None
-        if wl.get("base_mode") == "interpolation":
-            # seeded stand-in for the reference's missing mergedGridSearchResultFinal.npy,
-            # shape of interp_parameters_dict.json: 4,199,040 entries
-            table = np.random.default_rng(2024).uniform(0.0, 6000.0, 3 * 3 * 3 * 3 * 9 * 5 * 8 * 2 * 12 * 6)
-        env = BatchedEnv(env_prop_for(N, wl.get("base_mode", "constant")), R, device=local, precision="f32",
-                         obs_layout=wl["obs"], policy=wl.get("policy", "external"), noise="philox", seed=1234,
-                         rep_offset=rank * R, interp_table=table)
-        env.reset()
-        n_local = N
-    D = env.sim.D
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    n_act = 4
-    acts = [(torch.rand((R, n_local), device=dev, generator=g) < 0.5).to(torch.uint8).contiguous() for _ in range(n_act)]
-    acts_host = [a.cpu().pin_memory() for a in acts]
-    env_out = torch.zeros((R, 4), dtype=torch.float64).pin_memory()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, one_call=False):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if one_call:
-            fn(steps)      # the whole run in one C call (drsim_run)
-        else:
-            for i in range(steps):
-                fn(i)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    on_device_policy = wl.get("policy", "external") != "external"
-    step_dev = (lambda i: env.step(None)) if on_device_policy else (lambda i: env.step(acts[i % n_act]))
-    if sharded:
-        def step_host(i):  # host actions in (pinned), per-replica results out, around the sharded step
-            env.state["actions"].copy_(acts_host[i % n_act], non_blocking=True)
-            env.step(None)
-            env_out[:, 0].copy_(env.state["power"], non_blocking=True)
-            torch.cuda.synchronize()
-    elif on_device_policy:
-        step_host = lambda i: env.step_host(None, env_out)   # no actions to send: per-replica results out, sync
-    else:
-        step_host = lambda i: env.step_host(acts_host[i % n_act], env_out)
-
+    # ---- device-resident: `value` -------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()   # nvidia-smi needs ~0.1 s to deliver its first sample: start it before the warm-up
-    for i in range(max(3, args.warmup)):
-        step_dev(i)
-    l0 = env.sim.launch_count
-    if on_device_policy and not sharded:
-        # no per-step input from the host: the K steps go down in one C call (drsim_run), so a latency-bound
-        # 10-house cluster is not timed through K Python -> C round trips
-        ms = timed(lambda k: env.run(k), args.steps, one_call=True)
-    else:
-        ms = timed(step_dev, args.steps)
-    launches = env.sim.launch_count - l0
+    ms_step, launches, one_call = w.device_resident(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- end to end through the host-buffer C-ABI entry: `e2e` (full result) and `e2e_summary` -------------
+    acts_host = [a.contiguous().cpu().pin_memory() for a in w.acts]
+    env_out = torch.zeros((R, 4), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 300))
+    e2e = None
+    if sharded:
+        def step_host(i):  # host actions in (pinned), per-replica results out, around the sharded step
+            env.state["actions"].copy_(acts_host[i % w.n_act], non_blocking=True)
+            env.step(None)
+            env_out[:, 0].copy_(env.state["power"], non_blocking=True)
+            torch.cuda.synchronize()
+        step_full = None
+    elif on_device_policy:
+        step_host = lambda i: env.step_host(None, env_out)   # no actions to send: per-replica results out, sync
+        step_full = None
+    else:
+        step_host = lambda i: env.step_host(acts_host[i % w.n_act], env_out)
+        rew_host = torch.zeros((R, N), dtype=torch.float32).pin_memory()
+        obs_host = torch.zeros((R, N, D), dtype=torch.float32).pin_memory() if D else None
+        step_full = lambda i: env.step_host(acts_host[i % w.n_act], env_out, reward_out=rew_host, obs_out=obs_host)
     for i in range(max(50, args.warmup)):   # in-place reads of a pinned buffer run slower for the first few hundred steps (host-page mappings warm up)
         step_host(i)
-    e2e_steps = max(3, min(args.steps, 500))
-    ms_e2e = timed(step_host, e2e_steps)
+    ms_sum = w.timed(step_host, e2e_steps) / e2e_steps
+    h2d = 0 if on_device_policy else w.total_houses
+    summary = {"value": w.total_houses / (ms_sum * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": world * R * 4 * 8, "ms_per_step": ms_sum,
+               "returns": "per-replica [R][4] doubles: cluster power, signal, outdoor temperature, mean reward"}
+    if step_full is not None:
+        for i in range(5):
+            step_full(i)
+        ms_full = w.timed(step_full, e2e_steps) / e2e_steps
+        e2e = {"value": w.total_houses / (ms_full * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": world * (R * 4 * 8 + R * N * 4 + R * N * D * 4), "ms_per_step": ms_full,
+               "returns": "what Environment.step returns (environment.py:108): per-agent observation rows [R][N][D] f32 + "
+                          "rewards [R][N] f32 into pinned host buffers, plus the [R][4] summary",
+               "api": "BatchedEnv.step_host(actions, env_out, reward_out, obs_out) -> drsim_step_host_full: pinned host "
+                      "actions in, full result out, one stream sync per step"}
+    else:
+        e2e = dict(summary)
+        e2e["note"] = ("on-device controller: no actions to send, the [R][4] summary is the step's result" if on_device_policy else
+                       "house-sharded cluster: actions H2D + step + cluster power D2H + sync through the torch views")
 
+    # ---- the whole rollout transition on the device (nothing crosses PCIe) ---------------------
     rollout_line = None
-    if args.rollout and not sharded and not on_device_policy:
-        # the whole rollout transition on the device -- MA-PPO actor (reference default
-        # [D -> 100 -> 100 -> 2], random-init weights) + categorical draw + environment step
+    if not args.no_rollout and not sharded and not on_device_policy and 1 <= D <= 64:
         torch.manual_seed(4 + rank)
         fc = torch.nn.ModuleList([torch.nn.Linear(D, 100), torch.nn.Linear(100, 100), torch.nn.Linear(100, 2)]).to(dev)
-        weights = BatchedEnv.actor_weights(fc)
+        weights = type(env).actor_weights(fc)
         for i in range(5):
             env.rollout_step(weights)
-        r_steps = max(3, min(args.steps, 500))
-        ms_pol = timed(lambda i: env.policy_step(weights), r_steps)
-        ms_roll = timed(lambda i: env.rollout_step(weights), r_steps)
+        r_steps = max(3, min(args.steps, 300))
+        ms_pol = w.timed(lambda i: env.policy_step(weights), r_steps)
+        ms_roll = w.timed(lambda i: env.rollout_step(weights), r_steps)
         flops = 2.0 * R * N * (D * 100 + 100 * 100 + 100 * 2)
-        rollout_line = {"agent_steps_per_s": world * R * N * r_steps / (ms_roll * 1e-3), "us_per_transition": 1e3 * ms_roll / r_steps,
-                        "actor_us": 1e3 * ms_pol / r_steps, "actor_tflops": flops * r_steps / (ms_pol * 1e-3) / 1e12,
+        rollout_line = {"value": world * R * N * r_steps / (ms_roll * 1e-3), "unit": "agent-steps/s",
+                        "us_per_transition": 1e3 * ms_roll / r_steps, "actor_us": 1e3 * ms_pol / r_steps,
+                        "actor_tflops": flops * r_steps / (ms_pol * 1e-3) / 1e12,
+                        "what": "device-resident rollout transition: MA-PPO actor (mappo.py:83-97) + categorical draw + "
+                                "environment step, policy and observations never leave the GPU",
                         "actor": f"tcgen05 TF32, [{D} -> 100 -> 100 -> 2], random-init weights", "steps": r_steps}
 
-    total_houses = R * N if sharded else world * R * N
-    value = total_houses * args.steps / (ms * 1e-3)
-    e2e_value = total_houses * e2e_steps / (ms_e2e * 1e-3)
+    # ---- BASELINE config 5 next to the main workload: ONE 1M-house cluster split by houses over the ranks ----
+    sharded_line = None
+    if not sharded and not args.no_c5:
+        try:
+            del w.tape, w.acts
+            c5 = GpuWorkload("c5", args, rank, world, local)
+            c5_steps = max(3, min(args.steps, 2000))
+            ms5, l5, oc5 = c5.device_resident(c5_steps, args.warmup)
+            b5 = algorithmic_bytes_per_house_step(4, c5.D)
+            c5.env.sim.peer_status()
+            sharded_line = {"workload": c5.wl["name"], "value": c5.total_houses / (ms5 * 1e-3), "unit": UNIT, "us_per_step": ms5 * 1e3,
+                            "houses_per_gpu": c5.n_local, "scaling": "strong", "exchange": args.exchange if world > 1 else "none",
+                            "kernel": "k_shard (one persistent kernel per step: update, reduction, NVLink push of the "
+                                      "partial sums, wait, epilogue, rewards, rows)",
+                            "launches_per_step": l5 / c5_steps, "steps": c5_steps,
+                            "roofline_frac_per_gpu": c5.R * c5.n_local * b5 / (ms5 * 1e-3) / 1e9 / peak_gbs()}
+            del c5
+        except Exception as e:  # noqa: BLE001 -- an extra, never a reason to lose the line
+            sharded_line = {"error": str(e)[:300]}
+
+    value = w.total_houses / (ms_step * 1e-3)
     # end-of-rollout metric reduction (one all-reduce of a handful of fp64 sums)
     from marl_demandresponse_b200.distributed import reduce_rollout_metrics
 
     rollout = reduce_rollout_metrics(env.state["metrics"])
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak = peak_gbs()
         bytes_hs = algorithmic_bytes_per_house_step(4, D)
-        launch_ms = ms / args.steps   # one fused launch per step (+ one k_schedule every 64 steps, included)
-        achieved = R * n_local * bytes_hs / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        try:   # DRAM bytes of one launch from the committed ncu capture of this workload
-            t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
-            if t:
-                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-        except Exception:  # noqa: BLE001
-            pass
-        if sharded:  # the general path runs k_house + k_reduce + k_env + k_obs per step
-            achieved = R * n_local * bytes_hs / ((ms / args.steps) * 1e-3) / 1e9
+        achieved = R * n_local * bytes_hs / (ms_step * 1e-3) / 1e9
+        variant = env.sim.fused_info()["variant"]
+        kernel = ("k_shard" if (sharded or variant == "none") else
+                  {"staged": "k_fused_tma", "staged_rows": "k_fused_rows", "direct": "k_fused_direct", "chunked": "k_fused"}[variant])
         cpu = cpu_port_rate(N, wl["obs"], max(1, int(1e6 / N)), 1) if world == 1 and not args.no_cpu else None   # ~10 s of CPU work
+        cfg = workload_config(wl, world, D, args.exchange, args.flush_l2)
+        cfg["timed_region"] = (f"{args.steps} steps enqueued by one drsim_run_tape call (rotating 4-plane action tape)" if one_call
+                               else f"{args.steps} Python -> C step calls")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "replicas_per_gpu": R, "houses_per_cluster": N, "obs_dim": D,
-                       "parallelism": (f"house-sharded x{world}, per-step exchange of 48 B/rank via {args.exchange if world > 1 else 'none'}" if sharded
-                                       else f"replica-sharded x{world}, no per-step collective"),
-                       "l2": f"working set {R * n_local * bytes_hs / 1e6:.0f} MB per step per GPU vs 126 MB L2"
-                             + ("" if R * n_local * bytes_hs > 126e6 else "; L2 flushed between steps by a 256 MB write"
-                                if args.flush_l2 else "; fits L2 (latency-bound workload, see DESIGN.md)"),
-                       "actions": (f"on-device controller ({wl['policy']})" if on_device_policy else
-                                   "4 rotating fixed-seed Bernoulli(0.5) u8 tensors (policy cost excluded)")},
+            "config": cfg,
             "rollout_metrics": rollout,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0 if on_device_policy else total_houses,
-                    "d2h_bytes_per_step": world * R * 4 * 8, "ms_per_step": ms_e2e / e2e_steps,
-                    "api": "BatchedEnv.step_host -> drsim_step_host: pinned host actions in, per-replica results out, one stream "
-                           "sync per step; on the staged fused path the action plane travels as one copy-engine DMA issued "
-                           "next to the kernel, which consumes the words as they land (planes under 256 KB: read in place "
-                           "over PCIe), and the kernel writes the results straight into the pinned result buffer"},
+            "e2e": e2e, "e2e_summary": summary,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_house+k_obs (general path)" if sharded else
-                         {"staged": "k_fused_tma", "staged_rows": "k_fused_rows", "direct": "k_fused_direct", "chunked": "k_fused",
-                          "none": "k_house+k_reduce+k_env+k_obs"}[env.sim.fused_info()["variant"]],
+            "roofline": {"bound": "hbm", "kernel": kernel,
                          "achieved": achieved, "peak": peak,
                          **({"note": "latency-bound workload (one small cluster): the fraction is reported for completeness"}
                             if R * n_local < 100000 else {}),
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "unit": "GB/s", "frac": achieved / peak, **committed_traffic(args.workload),
                          "algorithmic_bytes_per_launch": R * n_local * bytes_hs,
                          "bytes_per_house_step": bytes_hs,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650"},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback 6650"},
             "clocks": clocks,
         }
         if cpu:
@@ -506,9 +626,18 @@ def run_gpu_arm(args, wl) -> None:
                 line["cpu_baseline"]["vectorised"] = {"error": str(e)[:200]}
         if rollout_line:
             line["rollout"] = rollout_line
+        if sharded_line:
+            line["sharded_cluster"] = sharded_line
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def peak_gbs() -> float:
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:  # noqa: BLE001
+        return 6650.0
 
 
 def main():
@@ -520,8 +649,12 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--flush-l2", action="store_true", help="write a 256 MB buffer between timed steps")
-    ap.add_argument("--rollout", action="store_true",
-                    help="also time the on-device rollout transition (MA-PPO actor + draw + env step) -> \"rollout\" key")
+    ap.add_argument("--no-rollout", action="store_true",
+                    help="skip the device-resident rollout transition (MA-PPO actor + draw + env step), the \"rollout\" key")
+    ap.add_argument("--rollout", action="store_true", help="(accepted for compatibility: the rollout line is on by default)")
+    ap.add_argument("--no-c5", action="store_true",
+                    help="skip the house-sharded 1M-house cluster (BASELINE config 5) timed next to the main workload, the "
+                         "\"sharded_cluster\" key")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="c5 only: per-step exchange of the aggregate-power partials (peer-memory stores vs NCCL all-gather)")
     args = ap.parse_args()

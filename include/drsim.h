@@ -247,6 +247,12 @@ int drsim_step(drsim_t *h, const drsim_step_args *args, void *stream);
  * sampled ids are per-step inputs and are rejected when n_steps > 1.  Results are those of n_steps
  * drsim_step calls. */
 int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, void *stream);
+/* The same with a ROTATING action tape of `tape_planes` planes: step k reads plane k % tape_planes
+ * (tape_planes = 0: no wrap, drsim_run).  Also accepts a house-sharded handle (every step is then a
+ * drsim_step_sharded: all ranks must run the same number of steps), so that a rollout of one cluster split
+ * across GPUs is enqueued by one C call per rank instead of one host-language call per step. */
+int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, int tape_planes,
+                   void *stream);
 
 /* PowerGrid.step at reset + get_obs (environment.py:66-70): recompute signal (optional) and the
  * observation / message gather from the current state without advancing time. */

@@ -139,6 +139,7 @@ def lib():
         "drsim_set_interp_table": (C.c_int, [hp, C.c_void_p, C.c_void_p]),
         "drsim_step": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
         "drsim_run": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_size_t, C.c_void_p]),
+        "drsim_run_tape": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_size_t, C.c_int, C.c_void_p]),
         "drsim_refresh": (C.c_int, [hp, C.POINTER(StepArgs), C.c_int, C.c_void_p]),
         "drsim_step_begin": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p]),
         "drsim_step_finish": (C.c_int, [hp, C.POINTER(StepArgs), C.c_void_p, C.c_int, C.c_void_p]),
@@ -179,7 +180,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
-    "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_run", "drsim_refresh", "drsim_step_begin",
+    "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_run", "drsim_run_tape", "drsim_refresh", "drsim_step_begin",
     "drsim_step_finish", "drsim_step_sharded", "drsim_step_finish_gathered", "drsim_step_host", "drsim_step_host_full",
     "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_peer_attach_local", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_cluster_summary", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",

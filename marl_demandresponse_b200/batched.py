@@ -188,10 +188,11 @@ class BatchedEnv:
         sim.step(a, od_noise, perlin, interp_ids)
         return self._v["obs"], self._v["reward"]
 
-    def run(self, n_steps: int, action_tape=None):
+    def run(self, n_steps: int, action_tape=None, rotate: bool = False):
         """``n_steps`` steps in one C call (``drsim_run``): a rollout under an on-device policy
         (``action_tape`` None) or the replay of recorded actions, ``action_tape`` u8 CUDA ``[n_steps, R, N]``
-        (or ``[R, N]``: the same actions every step).  Same results as ``n_steps`` calls of :meth:`step`."""
+        (or ``[R, N]``: the same actions every step; ``rotate=True``: ``[T, R, N]``, step k replays plane
+        ``k % T``).  Same results as ``n_steps`` calls of :meth:`step`."""
         sim = self.sim
         if action_tape is not None:
             if action_tape.dtype != self._v["actions"].dtype:
@@ -203,7 +204,7 @@ class BatchedEnv:
                 padded[..., :sim.N] = action_tape
                 action_tape = padded
             action_tape = action_tape.contiguous()
-        sim.run(n_steps, action_tape)
+        sim.run(n_steps, action_tape, rotate=rotate)
         return self._v["obs"], self._v["reward"]
 
     # ---- on-device MA-PPO actor ----------------------------------------------

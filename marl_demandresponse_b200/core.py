@@ -332,17 +332,19 @@ class DrSim:
         a = self._args(actions, od_noise, perlin, interp_ids)
         _lib.check(self._L.drsim_step(self._h, C.byref(a), self._stream(stream)))
 
-    def run(self, n_steps: int, action_tape=None, stream=None) -> None:
-        """``drsim_run``: ``n_steps`` steps in one call.  ``action_tape``: u8 CUDA tensor ``[n_steps, R, Ns]``
-        (one plane per step), ``[R, Ns]`` (the same plane every step) or None (internal plane / on-device policy)."""
-        stride = 0
+    def run(self, n_steps: int, action_tape=None, stream=None, rotate: bool = False) -> None:
+        """``drsim_run`` / ``drsim_run_tape``: ``n_steps`` steps in one call.  ``action_tape``: u8 CUDA tensor
+        ``[T, R, Ns]`` (one plane per step; ``rotate=True``: step k reads plane ``k % T``), ``[R, Ns]`` (the same
+        plane every step) or None (internal plane / on-device policy)."""
+        stride, planes = 0, 0
         if action_tape is not None:
             assert action_tape.is_contiguous() and tuple(action_tape.shape[-2:]) == (self.R, self.Ns)
             if action_tape.dim() == 3:
-                assert action_tape.shape[0] >= n_steps
+                assert rotate or action_tape.shape[0] >= n_steps
                 stride = self.R * self.Ns
+                planes = int(action_tape.shape[0]) if rotate else 0
         a = self._args(action_tape)
-        _lib.check(self._L.drsim_run(self._h, C.byref(a), int(n_steps), stride, self._stream(stream)))
+        _lib.check(self._L.drsim_run_tape(self._h, C.byref(a), int(n_steps), stride, planes, self._stream(stream)))
 
     def refresh(self, recompute_signal: bool, od_noise=None, perlin=None, interp_ids=None, stream=None) -> None:
         a = self._args(None, od_noise, perlin, interp_ids)

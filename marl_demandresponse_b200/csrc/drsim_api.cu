@@ -81,7 +81,7 @@ struct drsim_handle {
   ShardGeom shard{};
   int shard_grid = 0, shard_capacity = 0;
   bool shard_ok = false;
-  size_t o_sh_partll = 0, o_sh_envll = 0;
+  size_t o_sh_partll = 0, o_sh_envll = 0, o_sh_pearly = 0, o_pinbox = 0, o_rowll = 0;
   unsigned long long *shard_dbg = nullptr;   // DRSIM_SHARD_DBG: per-CTA time stamps of the last k_shard launch
   int *h_peer_err = nullptr, *h_peer_err_dev = nullptr;   // mapped: set by a kernel whose exchange wait timed out
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
@@ -398,12 +398,15 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
     const int wmax = 16;  // ranks of one box
     h->o_inbox = cv.take((size_t)2 * wmax * p.R * DRSIM_N_ACC * 8);
     h->o_pflags = cv.take((size_t)2 * wmax * p.R * 8);
-    h->o_peer_tab = cv.take((size_t)3 * wmax * 8);
+    h->o_peer_tab = cv.take((size_t)5 * wmax * 8);
     const size_t halo = needs_halo(p) ? (size_t)p.R * p.nb_comm * kHaloFields * 8 : 0;
     h->o_halo_out = cv.take(halo);
     h->o_halo_in = cv.take(2 * halo);
     h->o_peer_err = cv.take(8);
     h->o_sh_partll = cv.take((size_t)p.R * h->chunks * 16 * 8);
+    h->o_sh_pearly = cv.take((size_t)p.R * h->chunks * 4 * 8);
+    h->o_pinbox = cv.take((size_t)2 * wmax * p.R * 4 * 8);
+    h->o_rowll = cv.take((size_t)2 * wmax * p.R * 16 * 8);
     h->o_sh_envll = cv.take((size_t)p.R * 16 * 8);
   }
   h->o_sched_od = cv.take(E8 * drsim_handle::kSched); h->o_sched_solar = cv.take(E8 * drsim_handle::kSched);
@@ -826,6 +829,8 @@ static PeerCtx make_peer(const drsim_handle *h) {
   pc.inbox = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab);
   pc.flags = reinterpret_cast<unsigned long long *const *>(h->slab + h->o_peer_tab + 16 * 8);
   pc.halo = reinterpret_cast<double *const *>(h->slab + h->o_peer_tab + 32 * 8);
+  pc.pinbox = reinterpret_cast<unsigned long long *const *>(h->slab + h->o_peer_tab + 48 * 8);
+  pc.rowll = nullptr;   // (k_shard without halo records switches the word protocol on, see launch_shard)
   pc.err = h->h_peer_err_dev ? h->h_peer_err_dev : reinterpret_cast<int *>(h->slab + h->o_peer_err);
   return pc;
 }
@@ -931,7 +936,9 @@ static int plan_shard(drsim_handle *h) {
   }
   if (per_sm < 1) return 0;
   h->shard_capacity = per_sm * h->sm_count;
-  h->shard_grid = std::min(g.n_tiles, h->shard_capacity);
+  // one cluster on the plain path: one more CTA, which owns no tile and only reduces (see `dedicated` in k_shard)
+  const int extra = (plain && p.R == 1 && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2) ? 1 : 0;
+  h->shard_grid = std::min(g.n_tiles + extra, h->shard_capacity);
   h->shard = g;
   h->shard_ok = true;
   return 0;
@@ -964,19 +971,22 @@ static int launch_shard(drsim_handle *h, StepIn in, cudaStream_t s) {
   }
   ShardCtx sc{};
   sc.partll = h->at<unsigned long long>(h->o_sh_partll);
+  sc.pearly = h->at<unsigned long long>(h->o_sh_pearly);
   sc.envll = h->at<unsigned long long>(h->o_sh_envll);
   sc.err = h->h_peer_err_dev ? h->h_peer_err_dev : reinterpret_cast<int *>(h->slab + h->o_peer_err);
   if (!h->shard_dbg && getenv("DRSIM_SHARD_DBG")) cudaMalloc(&h->shard_dbg, (size_t)h->shard_capacity * 16 * 8);
   sc.dbg = h->shard_dbg;
+  PeerCtx pc = make_peer(h);
+  if (!needs_halo(p)) pc.rowll = reinterpret_cast<unsigned long long *const *>(h->slab + h->o_peer_tab + 64 * 8);
   bool plain = false;
   if constexpr (sizeof(real) == 4) {
     if (shard_plain(h)) {
-      launch_pdl(k_shard<float, true>, h->shard_grid, kThreads, (size_t)h->shard.smem_bytes, s, pl, p, in, h->shard, sc, make_peer(h));
+      launch_pdl(k_shard<float, true>, h->shard_grid, kThreads, (size_t)h->shard.smem_bytes, s, pl, p, in, h->shard, sc, pc);
       plain = true;
     }
   }
   if (!plain)
-    launch_pdl(k_shard<real, false>, h->shard_grid, kThreads, (size_t)h->shard.smem_bytes, s, pl, p, in, h->shard, sc, make_peer(h));
+    launch_pdl(k_shard<real, false>, h->shard_grid, kThreads, (size_t)h->shard.smem_bytes, s, pl, p, in, h->shard, sc, pc);
   h->launches++;
   CU_TRY(cudaGetLastError());
   return 0;
@@ -1141,9 +1151,30 @@ extern "C" int drsim_step(drsim_t *h, const drsim_step_args *args, void *stream)
 // action tape, without a host-language round trip per step (a 10-house cluster steps in ~2 us of GPU
 // time; the per-call overhead of a scripting host is several times that)
 extern "C" int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, void *stream) {
+  return drsim_run_tape(h, args, n_steps, action_stride, 0, stream);
+}
+
+extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, int tape_planes,
+                              void *stream) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   if (n_steps < 0) return fail(DRSIM_E_ARG, "n_steps must be >= 0");
-  if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "house-sharded cluster: use drsim_step_sharded");
+  if (tape_planes < 0) return fail(DRSIM_E_ARG, "tape_planes must be >= 0");
+  if (h->p.N != h->p.n_global) {
+    // house-sharded cluster: every step is drsim_step_sharded (peer exchange inside the kernel, or one rank)
+    if (h->peer_world < 2 && needs_halo(h->p))
+      return fail(DRSIM_E_STATE, "house-sharded cluster with a halo: attach the peers first (drsim_ipc_attach)");
+    drsim_step_args a{};
+    if (args) a = *args;
+    if (n_steps > 1 && (a.od_noise || a.perlin || a.interp_ids))
+      return fail(DRSIM_E_ARG, "drsim_run: injected noise / sampled ids are per-step inputs (n_steps must be 1)");
+    const uint8_t *tape = a.actions;
+    for (int k = 0; k < n_steps; ++k) {
+      a.actions = tape ? tape + (size_t)(tape_planes > 0 ? k % tape_planes : k) * action_stride : nullptr;
+      const int rc = drsim_step_sharded(h, &a, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   drsim_step_args a{};
   if (args) a = *args;
   if (n_steps > 1 && (a.od_noise || a.perlin || a.interp_ids))
@@ -1173,7 +1204,7 @@ extern "C" int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, s
     n_steps = left;
   }
   for (int k = 0; k < n_steps; ++k) {
-    a.actions = tape ? tape + (size_t)k * action_stride : nullptr;
+    a.actions = tape ? tape + (size_t)(tape_planes > 0 ? k % tape_planes : k) * action_stride : nullptr;
     const int di = interp_decision(h);
     const int rc = run_step(h, &a, 1, di, (cudaStream_t)stream);
     if (rc) return rc;
@@ -1483,7 +1514,7 @@ extern "C" int drsim_ipc_export(drsim_t *h, void *out96) {
   CU_TRY(cudaIpcGetMemHandle(&mh, h->slab));
   unsigned char *o = static_cast<unsigned char *>(out96);
   memcpy(o, &mh, 64);
-  const uint64_t off[4] = {(uint64_t)h->o_inbox, (uint64_t)h->o_pflags, (uint64_t)h->o_halo_in, 0};
+  const uint64_t off[4] = {(uint64_t)h->o_inbox, (uint64_t)h->o_pflags, (uint64_t)h->o_halo_in, (uint64_t)h->o_pinbox};
   memcpy(o + 64, off, 32);
   return 0;
 }
@@ -1493,7 +1524,7 @@ extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *han
   if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(DRSIM_E_ARG, "rank / world");
   CU_TRY(cudaSetDevice(h->device));
   const unsigned char *in = static_cast<const unsigned char *>(handles96);
-  std::vector<uint64_t> tab(48, 0);
+  std::vector<uint64_t> tab(80, 0);
   for (int q = 0; q < world; ++q) {
     cudaIpcMemHandle_t mh;
     uint64_t off[4];
@@ -1510,9 +1541,11 @@ extern "C" int drsim_ipc_attach(drsim_t *h, int rank, int world, const void *han
     tab[q] = (uint64_t)(uintptr_t)(base + off[0]);
     tab[16 + q] = (uint64_t)(uintptr_t)(base + off[1]);
     tab[32 + q] = (uint64_t)(uintptr_t)(base + off[2]);
+    tab[48 + q] = (uint64_t)(uintptr_t)(base + off[3]);
+    tab[64 + q] = (uint64_t)(uintptr_t)(base + off[3] + (h->o_rowll - h->o_pinbox));   // same slab layout on every rank (same R)
   }
   auto s = (cudaStream_t)stream;
-  CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 48 * 8, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 80 * 8, cudaMemcpyHostToDevice, s));
   CU_TRY(cudaMemsetAsync(h->slab + h->o_pflags, 0, (size_t)2 * 16 * h->p.R * 8, s));
   CU_TRY(cudaMemsetAsync(h->slab + h->o_peer_err, 0, 8, s));
   CU_TRY(cudaStreamSynchronize(s));
@@ -1532,7 +1565,7 @@ extern "C" int drsim_peer_attach_local(drsim_t *const *handles, int world, void 
   for (int i = 0; i < world; ++i) {
     drsim_handle *h = handles[i];
     CU_TRY(cudaSetDevice(h->device));
-    std::vector<uint64_t> tab(48, 0);
+    std::vector<uint64_t> tab(80, 0);
     int same_device = 0;
     for (int q = 0; q < world; ++q) {
       const drsim_handle *o = handles[q];
@@ -1547,16 +1580,18 @@ extern "C" int drsim_peer_attach_local(drsim_t *const *handles, int world, void 
       tab[q] = (uint64_t)(uintptr_t)(o->slab + o->o_inbox);
       tab[16 + q] = (uint64_t)(uintptr_t)(o->slab + o->o_pflags);
       tab[32 + q] = (uint64_t)(uintptr_t)(o->slab + o->o_halo_in);
+      tab[48 + q] = (uint64_t)(uintptr_t)(o->slab + o->o_pinbox);
+      tab[64 + q] = (uint64_t)(uintptr_t)(o->slab + o->o_rowll);
     }
     auto s = (cudaStream_t)stream;
-    CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 48 * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(h->slab + h->o_peer_tab, tab.data(), 80 * 8, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemsetAsync(h->slab + h->o_pflags, 0, (size_t)2 * 16 * h->p.R * 8, s));
     CU_TRY(cudaMemsetAsync(h->slab + h->o_peer_err, 0, 8, s));
     CU_TRY(cudaStreamSynchronize(s));
     h->peer_world = world;
     h->peer_rank = i;
     // shards that share a device share its SMs: every shard's persistent grid must be resident at once
-    if (h->shard_ok) h->shard_grid = std::max(1, std::min(h->shard.n_tiles, h->shard_capacity / same_device));
+    if (h->shard_ok) h->shard_grid = std::max(1, std::min(h->shard_grid, h->shard_capacity / same_device));
   }
   return 0;
 }

@@ -114,8 +114,68 @@ struct PeerCtx {
   double *const *inbox;               // [world] base of each rank's inbox (peer-mapped)
   unsigned long long *const *flags;   // [world] base of each rank's flags [2][world][R]
   double *const *halo;                // [world] base of each rank's halo inbox [2][R][nb_comm][kHaloFields]
+  unsigned long long *const *pinbox;  // [world] base of each rank's EARLY cluster-power inbox [2][world][R][4] (PowerLL words)
+  // [world] base of each rank's row inbox as self-validating words [2][world][R][16], or NULL: rows travel as plain
+  // doubles + release flag (needed when halo records travel with them: those announce house state)
+  unsigned long long *const *rowll;
   int *err;                           // local: set when a wait timed out
 };
+
+// a rank's reduced row (kRed + 1 doubles) as one 128-byte line of self-validating words, system scope
+DRSIM_D void rowll_store(unsigned long long *dst, uint32_t tag32, const double *v) {
+#if defined(__CUDA_ARCH__)
+  const unsigned long long tag = (unsigned long long)tag32 << 32;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const unsigned long long bits = k <= kRed ? (unsigned long long)__double_as_longlong(v[k]) : 0ull;
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * k), "l"(tag | (bits & 0xffffffffull)),
+                 "l"(tag | (bits >> 32))
+                 : "memory");
+  }
+#endif
+}
+// one poll of a row: true (and v filled) when all its words carry this step's tag
+DRSIM_D bool rowll_try(const unsigned long long *src, uint32_t tag32, double v[kRed + 1]) {
+  bool ok = true;
+#if defined(__CUDA_ARCH__)
+  unsigned long long w[2 * (kRed + 1)];
+#pragma unroll
+  for (int k = 0; k <= kRed; ++k)
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2 * k]), "=l"(w[2 * k + 1]) : "l"(src + 2 * k) : "memory");
+#pragma unroll
+  for (int k = 0; k < 2 * (kRed + 1); ++k) ok = ok && (uint32_t)(w[k] >> 32) == tag32;
+#pragma unroll
+  for (int k = 0; k <= kRed; ++k) v[k] = __longlong_as_double((long long)((w[2 * k + 1] << 32) | (w[2 * k] & 0xffffffffull)));
+#endif
+  return ok;
+}
+
+// One double as a self-validating 32-byte record: words 0 / 1 = (tag << 32 | low / high half), words 2 / 3 = tag
+// only (the whole sector is written, so no reader makes the L2 complete a partial sector from HBM).
+DRSIM_D void powll_store(unsigned long long *rec, uint32_t tag32, double v, bool sys) {
+#if defined(__CUDA_ARCH__)
+  const unsigned long long tag = (unsigned long long)tag32 << 32;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  if (sys) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(rec), "l"(tag | (bits & 0xffffffffull)), "l"(tag | (bits >> 32)) : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(rec + 2), "l"(tag), "l"(tag) : "memory");
+  } else {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(rec), "l"(tag | (bits & 0xffffffffull)), "l"(tag | (bits >> 32)) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(rec + 2), "l"(tag), "l"(tag) : "memory");
+  }
+#endif
+}
+DRSIM_D void powll_issue(const unsigned long long *rec, unsigned long long w[2]) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(rec) : "memory");
+#endif
+}
+DRSIM_D bool powll_check(const unsigned long long w[2], uint32_t tag32, double &v) {
+#if defined(__CUDA_ARCH__)
+  v = __longlong_as_double((long long)((w[1] << 32) | (w[0] & 0xffffffffull)));
+#endif
+  return (uint32_t)(w[0] >> 32) == tag32 && (uint32_t)(w[1] >> 32) == tag32;
+}
 
 // a house-sharded cluster whose observation rows carry ring-neighbour messages exchanges the message
 // records of the shard's edge houses every step ("halo")
@@ -1041,7 +1101,7 @@ DRSIM_D const double *reduce_cluster(const Planes<real> &pl, const SimParams &p,
       if (ll.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[11] = t; ll.dbg[12] = 0; }
       while (pending) {
         if (ll.dbg && threadIdx.x == 0) ll.dbg[12] += 1;
-        // the requests of two outstanding tiles fly together (register budget of the callers)
+        // the requests of two outstanding tiles fly together (four would spill: 80 registers of words)
         for (int j0 = 0; j0 < n_own; j0 += 2) {
           if (!((pending >> j0) & 0x3u)) continue;
           PartWords x[2];
@@ -1061,6 +1121,9 @@ DRSIM_D const double *reduce_cluster(const Planes<real> &pl, const SimParams &p,
           }
           if (ll.dbg && threadIdx.x == 0 && j0 == 0 && ll.dbg[12] == 1) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ll.dbg[13] = t; }
         }
+#if defined(__CUDA_ARCH__)
+        if (pending) __nanosleep(200);   // the pollers share their SM (issue slots, LSU) with CTAs that still compute
+#endif
         if (pending && clock64() - t0 > 4000000000ll) {   // ~2 s: give up, flag the error
           *ll.err = 1;
           for (int j = 0; j < n_own; ++j)
@@ -1197,7 +1260,10 @@ DRSIM_D const double *reduce_cluster(const Planes<real> &pl, const SimParams &p,
     // `world` peers overlap instead of queueing behind one thread
     __syncthreads();
     const int q = threadIdx.x;
-    if (q < peer.world) {
+    if (q < peer.world && peer.rowll) {
+      const size_t row = (((size_t)(in.xseq & 1) * peer.world + peer.rank) * p.R + r);
+      rowll_store(peer.rowll[q] + row * 16, (uint32_t)in.xseq, s_row);   // no fence, no flag: the words validate themselves
+    } else if (q < peer.world) {
       const int parity = (int)(in.xseq & 1);
       const size_t row = (((size_t)parity * peer.world + peer.rank) * p.R + r);
       double *ib = peer.inbox[q] + row * (kRed + 1);
@@ -1229,7 +1295,25 @@ DRSIM_D EnvBroadcast<real> env_cluster(const Planes<real> &pl, const SimParams &
                                        const double *own_row = nullptr) {
   double red[kRed] = {0, 0, 0, 0, 0};
   double isum = 0.0;
-  if (peer.world > 1) {
+  if (peer.world > 1 && peer.rowll) {
+    // rows as self-validating words: poll each rank's line (bounded), fold in rank order
+    const long long t0 = clock64();
+    for (int q = 0; q < peer.world; ++q) {
+      const unsigned long long *src = peer.rowll[peer.rank] + ((((size_t)(in.xseq & 1) * peer.world + q) * p.R + r) * 16);
+      double t[kRed + 1];
+      while (!rowll_try(src, (uint32_t)in.xseq, t)) {
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s: give up, flag the error
+          *peer.err = 1;
+          for (int k = 0; k <= kRed; ++k) t[k] = 0.0;
+          break;
+        }
+      }
+      red_combine(red, t);
+      isum += t[kRed];
+    }
+    n_parts = 0;
+    own_row = nullptr;
+  } else if (peer.world > 1) {
     // wait (bounded) until every rank's row for this step has landed in the local inbox
     const int parity = (int)(in.xseq & 1);
     const unsigned long long want = (unsigned long long)in.xseq;

@@ -51,6 +51,7 @@ struct ShardGeom {
 
 struct ShardCtx {
   unsigned long long *partll;  // [R * chunks][16] tile partials as self-validating words (PartLL)
+  unsigned long long *pearly;  // [R * chunks][4] EARLY tile power (see the pre-pass in k_shard), one 32-byte record each
   // [R][16] self-validating words: the 7 broadcast values of cluster r as doubles, each split into two
   // (tag << 32 | 32 data bits) words, tag = low half of StepIn::xseq.  A consumer polls the 14 words with ONE
   // coalesced load and has the values the moment all tags match -- no separate flag, no second round trip.
@@ -156,9 +157,22 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
   const int Ns = p.Ns, D = p.obs_dim;
   const int s0 = threadIdx.x * kHousesPerThread;
   const KC<real> kc(p);
+  // EARLY CLUSTER POWER.  Rewards and rows need the cluster power, and the power needs every house -- but only its
+  // lock-out state machine (hvac.py:43-64), not its thermal update.  On the plain fp32 path with the individual
+  // penalty a PRE-PASS over flags / sso / action / capacity (10 of the 103 bytes per house) forms the tile powers
+  // with the arithmetic of the main pass, the reducer combines and publishes them while everybody runs the main
+  // house update, and nobody waits between the two phases.  The other reduced quantities (penalty sums for the
+  // running metrics, env planes) follow after phase 1, off the critical path.
+  const bool early = PLAIN && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2 && in.do_interp <= 0;
+  // one cluster: CTA 0 owns no tile and only reduces (it polls while the others compute; the host adds it to the grid)
+  const bool dedicated = early && p.R == 1 && gridDim.x > 1;
+  const int n_work = dedicated ? (int)gridDim.x - 1 : (int)gridDim.x, wid = dedicated ? (int)blockIdx.x - 1 : (int)blockIdx.x;
   // this CTA's contiguous run of tiles (balanced: sizes differ by at most one)
-  const int t_lo = (int)(((long long)blockIdx.x * g.n_tiles) / gridDim.x);
-  const int t_hi = (int)(((long long)(blockIdx.x + 1) * g.n_tiles) / gridDim.x);
+  const int t_lo = wid < 0 ? 0 : (int)(((long long)wid * g.n_tiles) / n_work);
+  const int t_hi = wid < 0 ? 0 : (int)(((long long)(wid + 1) * g.n_tiles) / n_work);
+  // clusters this CTA completes: those whose first tile it owns (or all of them: dedicated reducer)
+  const int r_lo = dedicated ? 0 : (t_lo + g.chunks - 1) / g.chunks;
+  const int r_hi = dedicated ? (blockIdx.x == 0 ? p.R : 0) : (t_hi + g.chunks - 1) / g.chunks;
   pdl_trigger();
   auto stamp = [&](int k) {
 #if defined(__CUDA_ARCH__)
@@ -202,9 +216,11 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
     }
   };
   const bool staged0 = PLAIN && g.t_smem > 0 && t_hi > t_lo;
-  if (staged0) prefetch(t_lo, 1);
+  // (a CTA that reduces early parks the tile powers in the row staging area: its first copies wait until then)
+  const bool stage_late = early && r_hi > r_lo;
+  if (staged0 && !stage_late) prefetch(t_lo, 1);
   pdl_wait();
-  if (staged0) prefetch(t_lo, 2);
+  if (staged0 && !stage_late) prefetch(t_lo, 2);
   stamp(1);
 
   // Tiles [f_lo, f_hi) (at most kShardBatch) are done: their partials are formed from the warp partials in warp
@@ -224,6 +240,134 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
     }
     __syncthreads();   // s_wp may be rewritten
   };
+
+  // ---- early cluster power: pre-pass + reduction + publication ----------------------------------------
+  if constexpr (PLAIN) {
+    if (early) {
+      const uint32_t tag = (uint32_t)in.xseq;
+      const int dt = p.dt, dur = p.lockout_duration;
+      const float half_db = p.hf.half_db;
+      const int policy = p.policy;
+      const bool need_ta = policy == DRSIM_POLICY_DEADBAND_BANGBANG || policy == DRSIM_POLICY_BANGBANG;
+      for (int b0 = t_lo; b0 < t_hi; b0 += kShardBatch) {
+        const int b1 = min(t_hi, b0 + kShardBatch);
+        for (int tile = b0; tile < b1; ++tile) {
+          const int r = tile / g.chunks, c = tile - r * g.chunks;
+          const int n0 = c * kTileSlots + s0;
+          float P = 0.f;
+          if (n0 < p.N) {
+            const size_t off = (size_t)r * Ns + n0;
+            const int valid = min(4, p.N - n0);
+            const uint32_t flags = load4b(pl.flags + off);
+            int sso[4];
+            float cap[4], ta[4] = {0.f, 0.f, 0.f, 0.f};
+            load4i(pl.sso + off, sso);
+            load4_ro(pl.cap + off, cap);
+            if (need_ta) load4(pl.t_air + off, ta);
+            const uint32_t act = ext ? load4b((in.actions ? in.actions : pl.actions) + off) : 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // the state machine and the power term of house4_compute_f32, nothing else
+              const bool on = (flags >> (8 * j)) & 1u;
+              bool a = (act >> (8 * j)) & 0xffu;
+              if (policy == DRSIM_POLICY_DEADBAND_BANGBANG) a = ta[j] < -half_db ? false : (ta[j] > half_db ? true : on);
+              else if (policy == DRSIM_POLICY_BANGBANG) a = ta[j] > 0.f;
+              else if (policy == DRSIM_POLICY_ALWAYS_ON) a = true;
+              const int s = sso[j] + (on ? 0 : dt);
+              const bool on_n = !(!on && s < dur) && a;
+              const float m = j < valid ? 1.f : 0.f;
+              P = fmaf(on_n ? m : 0.f, cap[j] * p.hf.inv_cop, P);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) P += __shfl_down_sync(0xffffffffu, P, o);
+          if (lane == 0) s_wp[tile - b0][warp][0] = (double)P;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < b1 - b0) {
+          double out = 0.0;
+          for (int i = 0; i < kThreads / 32; ++i) out += s_wp[threadIdx.x][i][0];
+          powll_store(sc.pearly + (size_t)(b0 + threadIdx.x) * 4, tag, out, false);
+        }
+        __syncthreads();
+      }
+      // the reducer of cluster r: collect the tile powers (all requests of a thread in flight together), fold them in
+      // the order of reduce_cluster, exchange with the peers (house-sharded cluster), publish
+      double *stage = reinterpret_cast<double *>(smem_raw + g.off_rows);
+      for (int r = r_lo; r < r_hi; ++r) {
+        if (threadIdx.x == kThreads - 32) s_er[0] = env_load(pl, in, r);   // fetched under the poll
+        double red0 = 0.0;
+        for (int base = 0; base < g.chunks; base += g.part_cap) {
+          const int nb = min(g.part_cap, g.chunks - base);
+          const int n_own = (int)threadIdx.x < nb ? (nb - (int)threadIdx.x + kThreads - 1) / kThreads : 0;   // <= 32
+          unsigned pending = n_own >= 32 ? 0xffffffffu : ((1u << n_own) - 1u);
+          const long long t0 = clock64();
+          while (pending) {
+            for (int j0 = 0; j0 < n_own; j0 += 4) {
+              if (!((pending >> j0) & 0xfu)) continue;
+              unsigned long long w[4][2];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if ((pending >> (j0 + u)) & 1u)
+                  powll_issue(sc.pearly + (size_t)(r * g.chunks + base + (int)threadIdx.x + (j0 + u) * kThreads) * 4, w[u]);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                double v;
+                if (((pending >> (j0 + u)) & 1u) && powll_check(w[u], tag, v)) {
+                  stage[(int)threadIdx.x + (j0 + u) * kThreads] = v;
+                  pending &= ~(1u << (j0 + u));
+                }
+              }
+            }
+            if (pending) __nanosleep(200);   // the pollers share their SM (issue slots, LSU) with a CTA that computes
+            if (pending && clock64() - t0 > 4000000000ll) {   // ~2 s: give up, flag the error
+              *sc.err = 1;
+              for (int j = 0; j < n_own; ++j)
+                if ((pending >> j) & 1u) stage[(int)threadIdx.x + j * kThreads] = 0.0;
+              pending = 0;
+            }
+          }
+          __syncthreads();
+          if (threadIdx.x < kReduceThreads)
+            for (int c = threadIdx.x; c < nb; c += kReduceThreads) red0 += stage[c];
+          __syncthreads();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) red0 += __shfl_down_sync(0xffffffffu, red0, o);
+        if (lane == 0 && threadIdx.x < kReduceThreads) s_rows[0][warp] = red0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double P_rank = 0.0;
+          for (int i = 0; i < kReduceThreads / 32; ++i) P_rank += s_rows[0][i];
+          double P_total = 0.0;
+          if (peer.world > 1) {
+            const int parity = (int)(in.xseq & 1);
+            for (int q = 0; q < peer.world; ++q)
+              powll_store(peer.pinbox[q] + ((((size_t)parity * peer.world + peer.rank) * p.R + r) * 4), tag, P_rank, true);
+            const long long t0 = clock64();
+            for (int q = 0; q < peer.world; ++q) {   // rank order: the order env_cluster folds the late rows in
+              const unsigned long long *rec = peer.pinbox[peer.rank] + ((((size_t)parity * peer.world + q) * p.R + r) * 4);
+              double v = 0.0;
+              for (;;) {
+                unsigned long long w[2];
+                powll_issue(rec, w);
+                if (powll_check(w, tag, v)) break;
+                if (clock64() - t0 > 4000000000ll) { *peer.err = 1; v = 0.0; break; }
+              }
+              P_total += v;
+            }
+          } else {
+            P_total += P_rank;
+          }
+          const double red5[kRed] = {P_total, 0.0, 0.0, 0.0, 0.0};
+          EnvOut o;
+          shard_publish<real>(sc, in, r, env_epilogue_compute<real>(pl, p, in, r, s_er[0], red5, 0.0, o));
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (staged0 && stage_late) prefetch(t_lo, 3);
+  stamp(14);
 
   // ---- phase 1: house update of every tile of this CTA ------------------------------------------
   for (int tile = t_lo; tile < t_hi; ++tile) {
@@ -302,7 +446,6 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
     // scheduled step of an unsharded cluster with constant base power, fp32: the packed records are exact
     const bool fast_env = sizeof(real) == 4 && in.sched_rec != nullptr && p.base_mode == DRSIM_BASE_CONSTANT && peer.world <= 1 &&
                           in.do_interp <= 0 && p.N == (int)p.n_global;
-    const int r_lo = (t_lo + g.chunks - 1) / g.chunks, r_hi = (t_hi + g.chunks - 1) / g.chunks;   // r * chunks in [t_lo, t_hi)
     for (int rg = r_lo; rg < r_hi; rg += kShardFinish) {
       const int ng = min(kShardFinish, r_hi - rg);
       for (int k = 0; k < ng; ++k) {
@@ -340,12 +483,13 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
           b.rew_sig = (real)signal_penalty(p, a[0], c.signal_prev);
           b.pen_common = (real)a[1];
           b.pen_max = (real)a[2];
-          shard_publish<real>(sc, in, r, b);
+          if (!early) shard_publish<real>(sc, in, r, b);   // (early: the consumers have had these values since the pre-pass)
           stamp(7);
           env_stage_store<real>(pl, p, r, s_st[warp], a);
         } else {
           EnvOut o;
-          shard_publish<real>(sc, in, r, env_cluster<real>(pl, p, in, nullptr, 0, peer, r, &o, &s_er[warp], s_rows[warp]));
+          const EnvBroadcast<real> b = env_cluster<real>(pl, p, in, nullptr, 0, peer, r, &o, &s_er[warp], s_rows[warp]);
+          if (!early) shard_publish<real>(sc, in, r, b);
           stamp(7);
           env_epilogue_store<real>(pl, p, in, r, o);
         }

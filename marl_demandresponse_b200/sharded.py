@@ -131,6 +131,19 @@ class ShardedClusterEnv:
                 sim.step_finish_gathered(self._gathered, self._halo_gathered, self.world, self.rank)
         return self._v["obs"], self._v["reward"]
 
+    def run(self, n_steps: int, action_tape=None, rotate: bool = False):
+        """``n_steps`` sharded steps enqueued by ONE C call (``drsim_run_tape``): peer exchange or a single rank
+        only (the NCCL exchange needs the host between the two halves of every step).  ``action_tape``: u8 CUDA
+        ``[T, R, n_local]`` (``rotate``: step k replays plane ``k % T``) / ``[R, n_local]`` / None; every rank must
+        run the same number of steps."""
+        if not (self.exchange == "peer" or self.world == 1):
+            raise ValueError("ShardedClusterEnv.run needs the peer exchange (or one rank)")
+        sim = self.sim
+        if action_tape is not None and sim.N != sim.Ns:
+            raise ValueError("run(): shard sizes are multiples of 4 except on the last rank; pad the tape to the plane stride")
+        sim.run(n_steps, action_tape, rotate=rotate)
+        return self._v["obs"], self._v["reward"]
+
     @property
     def state(self):
         return self._v

@@ -39,6 +39,9 @@ for k, nm in enumerate(names):
 others = np.sort((np.delete(t[:, 3], int(np.argmax(t[:, 3]))) - t0) / 1e3)
 print("partials published by the non-reducing CTAs (all warps done), us: p50 %.2f p90 %.2f p99 %.2f max %.2f" %
       (np.percentile(others, 50), np.percentile(others, 90), np.percentile(others, 99), others[-1]))
+for k, nm in ((2, "phase-1 stamp"), (3, "partials out"), (5, "end")):
+    order = np.argsort(-t[:, k])[:8]
+    print(f"   latest {nm}: " + ", ".join(f"CTA {int(i)} {(t[i, k] - t0) / 1e3:.1f}" for i in order))
 last = int(np.argmax(t[:, 3] - t[:, 2]))
 print(f"   collection entered {(t[last, 11] - t0) / 1e3:.2f}, first pair of polls answered {(t[last, 13] - t0) / 1e3:.2f}, sweeps of thread 0: {t[last, 12]}")
 for c in (0, 77, 155, 232, 148):
