@@ -972,6 +972,7 @@ static int launch_shard(drsim_handle *h, StepIn in, cudaStream_t s) {
   ShardCtx sc{};
   sc.partll = h->at<unsigned long long>(h->o_sh_partll);
   sc.pearly = h->at<unsigned long long>(h->o_sh_pearly);
+  sc.pinbox = h->at<unsigned long long>(h->o_pinbox);
   sc.envll = h->at<unsigned long long>(h->o_sh_envll);
   sc.err = h->h_peer_err_dev ? h->h_peer_err_dev : reinterpret_cast<int *>(h->slab + h->o_peer_err);
   if (!h->shard_dbg && getenv("DRSIM_SHARD_DBG")) cudaMalloc(&h->shard_dbg, (size_t)h->shard_capacity * 16 * 8);
@@ -1285,6 +1286,8 @@ extern "C" int drsim_step_sharded(drsim_t *h, const drsim_step_args *args, void 
     const StepIn in = make_in(h, args, 1, di, (cudaStream_t)stream);
     const int rc = h->real_bytes == 8 ? launch_shard<double>(h, in, (cudaStream_t)stream)
                                       : launch_shard<float>(h, in, (cudaStream_t)stream);
+    // the packed schedule records chain each step to the one before it: a step off the schedule ends their validity
+    if (!(in.sched_rec && di <= 0)) h->sched_valid = false;
     if (!rc) h->step++;
     return rc;
   }

@@ -52,6 +52,7 @@ struct ShardGeom {
 struct ShardCtx {
   unsigned long long *partll;  // [R * chunks][16] tile partials as self-validating words (PartLL)
   unsigned long long *pearly;  // [R * chunks][4] EARLY tile power (see the pre-pass in k_shard), one 32-byte record each
+  unsigned long long *pinbox;  // this handle's own early cluster-power inbox [2][world][R][4] (what PeerCtx::pinbox[rank] points at)
   // [R][16] self-validating words: the 7 broadcast values of cluster r as doubles, each split into two
   // (tag << 32 | 32 data bits) words, tag = low half of StepIn::xseq.  A consumer polls the 14 words with ONE
   // coalesced load and has the values the moment all tags match -- no separate flag, no second round trip.
@@ -129,6 +130,43 @@ DRSIM_D EnvBroadcast<real> shard_wait_env(const ShardCtx &sc, const StepIn &in, 
   return e;
 }
 
+// whole warp, scheduled step with constant base power: the cluster power straight from the early inbox -- lane q
+// polls rank q's record, the ranks are folded in rank order (the order of env_cluster) -- and every other
+// broadcast value from the step's packed record.  No reducer-side combine / publish hop in between.
+template <typename real>
+DRSIM_D EnvBroadcast<real> shard_wait_power(const ShardCtx &sc, const SimParams &p, const StepIn &in, int world, int r, int lane) {
+  const uint32_t tag = (uint32_t)in.xseq;
+  const unsigned long long *rec = sc.pinbox + ((((size_t)(in.xseq & 1) * world + min(lane, world - 1)) * p.R + r) * 4);
+  const SchedRec &c = in.sched_rec[r];
+  const float sn = c.signal_n, so = c.solar_n, on = c.od_n;
+  const double sprev = c.signal_prev;
+  double v = 0.0;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long w[2];
+    powll_issue(rec, w);
+    const bool ok = powll_check(w, tag, v);
+    if (__all_sync(0xffffffffu, ok || lane >= world)) break;
+    if (__any_sync(0xffffffffu, clock64() - t0 > 4000000000ll)) {   // ~2 s: give up, flag the error
+      if (lane == 0) *sc.err = 1;
+      v = 0.0;
+      break;
+    }
+#if defined(__CUDA_ARCH__)
+    __nanosleep(100);
+#endif
+  }
+  double P = 0.0;
+  for (int q = 0; q < world; ++q) P += __shfl_sync(0xffffffffu, v, q);
+  EnvBroadcast<real> e;
+  e.power_n = (real)(P * p.inv_nrs);
+  e.signal_n = (real)sn; e.solar_n = (real)so; e.od_n = (real)on;
+  e.rew_sig = (real)signal_penalty(p, P, sprev);
+  e.pen_common = (real)0;   // individual_L2 (the early path's condition): not consumed
+  e.pen_max = (real)0;
+  return e;
+}
+
 DRSIM_D void ld4_cg(const float *p, float v[4]) {
 #if defined(__CUDA_ARCH__)
   const float4 t = __ldcg(reinterpret_cast<const float4 *>(p));
@@ -166,6 +204,10 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
   const bool early = PLAIN && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2 && in.do_interp <= 0;
   // one cluster: CTA 0 owns no tile and only reduces (it polls while the others compute; the host adds it to the grid)
   const bool dedicated = early && p.R == 1 && gridDim.x > 1;
+  // scheduled step with constant base power (fp32): the step's packed record (k_schedule_pack) holds every env
+  // scalar that does not depend on the cluster power, exactly as the epilogue would compute it
+  const bool fast_env = sizeof(real) == 4 && in.sched_rec != nullptr && p.base_mode == DRSIM_BASE_CONSTANT && in.do_interp <= 0;
+  const bool direct = early && fast_env;   // the consumers take the cluster power straight from the early inbox
   const int n_work = dedicated ? (int)gridDim.x - 1 : (int)gridDim.x, wid = dedicated ? (int)blockIdx.x - 1 : (int)blockIdx.x;
   // this CTA's contiguous run of tiles (balanced: sizes differ by at most one)
   const int t_lo = wid < 0 ? 0 : (int)(((long long)wid * g.n_tiles) / n_work);
@@ -294,7 +336,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
       // the order of reduce_cluster, exchange with the peers (house-sharded cluster), publish
       double *stage = reinterpret_cast<double *>(smem_raw + g.off_rows);
       for (int r = r_lo; r < r_hi; ++r) {
-        if (threadIdx.x == kThreads - 32) s_er[0] = env_load(pl, in, r);   // fetched under the poll
+        if (threadIdx.x == kThreads - 32 && !direct) s_er[0] = env_load(pl, in, r);   // fetched under the poll
         double red0 = 0.0;
         for (int base = 0; base < g.chunks; base += g.part_cap) {
           const int nb = min(g.part_cap, g.chunks - base);
@@ -339,10 +381,16 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
           double P_rank = 0.0;
           for (int i = 0; i < kReduceThreads / 32; ++i) P_rank += s_rows[0][i];
           double P_total = 0.0;
+          const int parity = (int)(in.xseq & 1);
           if (peer.world > 1) {
-            const int parity = (int)(in.xseq & 1);
             for (int q = 0; q < peer.world; ++q)
               powll_store(peer.pinbox[q] + ((((size_t)parity * peer.world + peer.rank) * p.R + r) * 4), tag, P_rank, true);
+          } else {
+            powll_store(sc.pinbox + (((size_t)parity * p.R + r) * 4), tag, P_rank, false);
+          }
+          if (direct) {
+            // nothing else to do here: every consumer folds the inbox itself (shard_wait_power)
+          } else if (peer.world > 1) {
             const long long t0 = clock64();
             for (int q = 0; q < peer.world; ++q) {   // rank order: the order env_cluster folds the late rows in
               const unsigned long long *rec = peer.pinbox[peer.rank] + ((((size_t)parity * peer.world + q) * p.R + r) * 4);
@@ -358,9 +406,11 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
           } else {
             P_total += P_rank;
           }
-          const double red5[kRed] = {P_total, 0.0, 0.0, 0.0, 0.0};
-          EnvOut o;
-          shard_publish<real>(sc, in, r, env_epilogue_compute<real>(pl, p, in, r, s_er[0], red5, 0.0, o));
+          if (!direct) {
+            const double red5[kRed] = {P_total, 0.0, 0.0, 0.0, 0.0};
+            EnvOut o;
+            shard_publish<real>(sc, in, r, env_epilogue_compute<real>(pl, p, in, r, s_er[0], red5, 0.0, o));
+          }
         }
         __syncthreads();
       }
@@ -443,9 +493,8 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
   // Only now, with nothing left to contribute: every partial / push this CTA owes anybody is out, so the polls
   // and peer waits below cannot deadlock (clusters are taken in ascending order on every rank).
   {
-    // scheduled step of an unsharded cluster with constant base power, fp32: the packed records are exact
-    const bool fast_env = sizeof(real) == 4 && in.sched_rec != nullptr && p.base_mode == DRSIM_BASE_CONSTANT && peer.world <= 1 &&
-                          in.do_interp <= 0 && p.N == (int)p.n_global;
+    // (several ranks: the late rows are combined by env_cluster, which also runs the full epilogue -- off the critical path)
+    const bool fast_late = fast_env && peer.world <= 1;
     for (int rg = r_lo; rg < r_hi; rg += kShardFinish) {
       const int ng = min(kShardFinish, r_hi - rg);
       for (int k = 0; k < ng; ++k) {
@@ -453,7 +502,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
         // previous step's env scalars (or, on the scheduled path, this step's packed record + running metrics),
         // fetched while the partials are being collected
         if (threadIdx.x == kThreads - 32) {
-          if (fast_env) {
+          if (fast_late) {
             s_st[k].rec = in.sched_rec[r];
             for (int q = 0; q < DRSIM_N_METRICS; ++q) s_st[k].m[q] = pl.metrics[(size_t)r * DRSIM_N_METRICS + q];
           } else {
@@ -472,7 +521,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
       // broadcast values to the consumers first, env planes / metrics afterwards
       if (lane == 0 && warp < ng) {
         const int r = rg + warp;
-        if (fast_env) {
+        if (fast_late) {
           // every env scalar that does not depend on the cluster power is in the step's record (k_schedule_pack):
           // the consumers are two multiplications away from their values (expressions of the fused kernels)
           const SchedRec &c = s_st[warp].rec;
@@ -504,7 +553,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
   EnvBroadcast<real> e{};
   auto env_of = [&](int r) {   // warp-uniform: (re)fetch the broadcast values when the cluster changes
     if (r == r_have) return;
-    e = shard_wait_env<real>(sc, in, r, lane);
+    e = direct ? shard_wait_power<real>(sc, p, in, peer.world, r, lane) : shard_wait_env<real>(sc, in, r, lane);
     r_have = r;
   };
 
