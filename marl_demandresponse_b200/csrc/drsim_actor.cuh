@@ -119,166 +119,6 @@ DRSIM_D void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
   asm volatile("trap;");
 }
 
-__global__ void __launch_bounds__(kActThreads, 1) k_actor(ActorArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *s_w1 = smem + a.off_w1, *s_w2 = smem + a.off_w2, *s_a1 = smem + a.off_a1, *s_a2 = smem + a.off_a2;
-  float *s_b1 = reinterpret_cast<float *>(smem + a.off_vec);   // [N1]
-  float *s_b2 = s_b1 + a.N1;                                     // [N2]
-  float *s_w3 = s_b2 + a.N2;                                     // [2][N2]
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
-
-  // ---- once per CTA: weights into the canonical operand layout (padding rows / columns = 0) ----------
-  for (int i = tid; i < a.N1 * a.K1; i += kActThreads) {
-    const int n = i / a.K1, k = i - n * a.K1;
-    *reinterpret_cast<float *>(s_w1 + umma_kmajor_off(a.N1, n, k)) = (n < a.h1 && k < a.D) ? to_tf32(a.w1[(size_t)n * a.D + k]) : 0.f;
-  }
-  for (int i = tid; i < a.N2 * a.K2; i += kActThreads) {
-    const int n = i / a.K2, k = i - n * a.K2;
-    *reinterpret_cast<float *>(s_w2 + umma_kmajor_off(a.N2, n, k)) = (n < a.h2 && k < a.h1) ? to_tf32(a.w2[(size_t)n * a.h1 + k]) : 0.f;
-  }
-  for (int i = tid; i < a.N1; i += kActThreads) s_b1[i] = i < a.h1 ? a.b1[i] : 0.f;
-  for (int i = tid; i < a.N2; i += kActThreads) {
-    s_b2[i] = i < a.h2 ? a.b2[i] : 0.f;
-    s_w3[i] = i < a.h2 ? a.w3[i] : 0.f;
-    s_w3[a.N2 + i] = i < a.h2 ? a.w3[a.h2 + i] : 0.f;
-  }
-  // padding columns [D, K1) of the observation tile stay zero for the whole kernel
-  for (int i = tid; i < kActRows * (a.K1 - a.D); i += kActThreads) {
-    const int row = i / (a.K1 - a.D), k = a.D + i % (a.K1 - a.D);
-    *reinterpret_cast<float *>(s_a1 + umma_kmajor_off(kActRows, row, k)) = 0.f;
-  }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
-                 "r"((uint32_t)kActTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2);
-  const uint32_t a1_addr = (uint32_t)__cvta_generic_to_shared(s_a1), a2_addr = (uint32_t)__cvta_generic_to_shared(s_a2);
-  const uint32_t w1_addr = (uint32_t)__cvta_generic_to_shared(s_w1), w2_addr = (uint32_t)__cvta_generic_to_shared(s_w2);
-  const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128;
-  const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's TMEM lane quadrant
-  uint32_t phase = 0;
-
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = (long long)tile * kActRows;
-    // ---- observation tile -> A1 (coalesced over the flat [128 * D] run, scattered into core matrices) ----
-    const int n_valid = (int)min((long long)kActRows, a.rows - row0);
-    const float *src = a.obs + (size_t)row0 * a.D;
-    if ((a.D & 1) == 0) {
-      const int half = a.D >> 1;
-      for (int i = tid; i < kActRows * half; i += kActThreads) {
-        const int row = i / half, k = (i - row * half) * 2;
-        const float2 v = row < n_valid ? reinterpret_cast<const float2 *>(src)[i] : make_float2(0.f, 0.f);
-        *reinterpret_cast<float2 *>(s_a1 + umma_kmajor_off(kActRows, row, k)) = make_float2(to_tf32(v.x), to_tf32(v.y));
-      }
-    } else {
-      for (int i = tid; i < kActRows * a.D; i += kActThreads) {
-        const int row = i / a.D, k = i - row * a.D;
-        *reinterpret_cast<float *>(s_a1 + umma_kmajor_off(kActRows, row, k)) = row < n_valid ? to_tf32(src[i]) : 0.f;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 1: D1[128 x N1] = A1 . W1^T, K1 / 8 instructions issued by one thread ----------------
-    if (tid == 0) {
-      tc_fence_after();
-      for (int ks = 0; ks < a.K1 / 8; ++ks)
-        umma_tf32_ss(tmem, umma_smem_desc(a1_addr + ks * 2 * lbo_a, lbo_a, 128),
-                     umma_smem_desc(w1_addr + ks * 2 * lbo_w1, lbo_w1, 128), idesc1, ks > 0);
-      umma_commit(s_bar);
-    }
-    mbar_wait_bounded(s_bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    // ---- epilogue 1: + b1, ReLU, hidden row -> A2 (row = this thread; 16-byte chunk stores) -----------
-    for (int c0 = 0; c0 < a.N1; c0 += 16) {
-      float v[16];
-      tmem_ld16(lane_addr + (uint32_t)c0, v);
-      if (c0 < a.K2) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = c0 + 4 * q;
-          if (k < a.K2) {
-            float4 hq;
-            hq.x = to_tf32(fmaxf(v[4 * q] + s_b1[k], 0.f));
-            hq.y = to_tf32(fmaxf(v[4 * q + 1] + s_b1[k + 1], 0.f));
-            hq.z = to_tf32(fmaxf(v[4 * q + 2] + s_b1[k + 2], 0.f));
-            hq.w = to_tf32(fmaxf(v[4 * q + 3] + s_b1[k + 3], 0.f));
-            *reinterpret_cast<float4 *>(s_a2 + umma_kmajor_off(kActRows, tid, k)) = hq;
-          }
-        }
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 2: D2[128 x N2] = A2 . W2^T -------------------------------------------------------------
-    if (tid == 0) {
-      tc_fence_after();
-      for (int ks = 0; ks < a.K2 / 8; ++ks)
-        umma_tf32_ss(tmem + (uint32_t)a.N1, umma_smem_desc(a2_addr + ks * 2 * lbo_a, lbo_a, 128),
-                     umma_smem_desc(w2_addr + ks * 2 * lbo_w2, lbo_w2, 128), idesc2, ks > 0);
-      umma_commit(s_bar);
-    }
-    mbar_wait_bounded(s_bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    // ---- epilogue 2: + b2, ReLU, output layer (2 x h2) on the CUDA cores, softmax, categorical draw ----
-    float l0 = a.b3[0], l1 = a.b3[1];
-    for (int c0 = 0; c0 < a.N2; c0 += 16) {
-      float v[16];
-      tmem_ld16(lane_addr + (uint32_t)(a.N1 + c0), v);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float h = fmaxf(v[j] + s_b2[c0 + j], 0.f);
-        l0 = fmaf(h, s_w3[c0 + j], l0);
-        l1 = fmaf(h, s_w3[a.N2 + c0 + j], l1);
-      }
-    }
-    const long long row = row0 + tid;
-    if (row < a.rows) {
-      const long long r = row / a.Ns;
-      const int n = (int)(row - r * a.Ns);
-      uint8_t act = 0;
-      float p_draw = 0.f, p1 = 0.f;
-      if (n < a.N) {
-        const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
-        const float e0 = __expf(l0 - m), e1 = __expf(l1 - m);
-        const float p0 = e0 / (e0 + e1);
-        p1 = 1.f - p0;
-        // Categorical(action_prob).sample() (mappo.py:91-92) as an inverse-CDF draw from a Philox uniform
-        const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + r), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
-        const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
-        act = uf < p0 ? 0 : 1;
-        p_draw = act ? p1 : p0;
-      }
-      a.actions[row] = act;
-      if (a.prob) a.prob[row] = p_draw;
-      if (a.prob_on) a.prob_on[row] = p1;
-    }
-    tc_fence_before();
-    __syncthreads();   // every lane has drained D1 / D2 and A1 / A2 before the next tile overwrites them
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kActTmemCols) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------
 // k_actor2: the production variant.  Same network, but
 //   * two tiles in flight per CTA: 512 threads = two groups of 8 warps; group g owns tile slot g (its own

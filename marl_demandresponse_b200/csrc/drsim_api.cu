@@ -1629,18 +1629,7 @@ extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_
   auto take = [&](int b) { int o = off; off += (b + 127) / 128 * 128; return o; };
   a.seed = seed; a.step = h->step; a.rep_offset = p.rep_offset;
   const int tiles = (int)((a.rows + kActRows - 1) / kActRows);
-  const char *v1 = getenv("DRSIM_ACTOR_V1");   // single-tile variant: hidden layer staged in shared memory, biases in the epilogues
-  if (v1 && v1[0] == '1') {
-    a.K1 = (a.D + 7) / 8 * 8; a.N1 = (a.h1 + 15) / 16 * 16;
-    a.K2 = (a.h1 + 7) / 8 * 8; a.N2 = (a.h2 + 15) / 16 * 16;
-    a.off_w1 = take(a.N1 * a.K1 * 4); a.off_w2 = take(a.N2 * a.K2 * 4);
-    a.off_a1 = take(kActRows * a.K1 * 4); a.off_a2 = take(kActRows * a.K2 * 4);
-    a.off_vec = take((a.N1 + 3 * a.N2) * 4); a.off_bar = take(16);
-    a.smem_bytes = off;
-    if (a.smem_bytes > 227 * 1024) return fail(DRSIM_E_ARG, "drsim_policy_step: network / observation too wide for shared memory");
-    CU_TRY(cudaFuncSetAttribute(k_actor, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
-    k_actor<<<std::min(tiles, h->sm_count), kActThreads, a.smem_bytes, (cudaStream_t)stream>>>(a);
-  } else {
+  {
     // one spare K column per layer carries the bias (constant-one column in A), one spare output row regenerates the one
     a.K1 = (a.D + 1 + 7) / 8 * 8; a.N1 = (a.h1 + 1 + 15) / 16 * 16;
     a.K2 = (a.h1 + 1 + 7) / 8 * 8; a.N2 = (a.h2 + 1 + 15) / 16 * 16;

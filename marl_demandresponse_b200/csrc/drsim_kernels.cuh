@@ -2047,9 +2047,6 @@ DRSIM_D void cp_async4(void *sdst, const void *gsrc) {
 #endif
 }
 
-#ifndef DRSIM_STAGE_BULK
-#define DRSIM_STAGE_BULK 0  // 1: inputs staged by per-warp TMA bulk loads; 0: by thread-private cp.async copies
-#endif
 
 
 // Action word of a thread's four houses on the copy-engine path of drsim_step_host (see StepIn::act_poll_err)
@@ -2086,7 +2083,6 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   EnvStage *s_stage_base = reinterpret_cast<EnvStage *>(smem_raw + g.off_stage);  // [2][E] schedule record + metrics
   real *s_tile = reinterpret_cast<real *>(smem_raw + g.off_tile);
   float *s_in = reinterpret_cast<float *>(smem_raw + g.off_in);        // [kInPlanes][kTileSlots]
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + g.off_bar);  // [warps]
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int Ns = p.Ns, D = p.obs_dim;
@@ -2102,22 +2098,9 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   bool store_pending = false;
   int parity = 0;
-  uint32_t ld_phase = 0;  // phase of the warp's load mbarrier (flips only on tiles the warp takes part in)
   const int s0 = threadIdx.x * kHousesPerThread;
   const int w0 = warp * 128;
 
-#if DRSIM_STAGE_BULK
-  // plane base pointers in shared memory so that lane k can fetch "its" plane without a local array
-  const float **s_planes = reinterpret_cast<const float **>(s_bar + kThreads / 32);
-  if (threadIdx.x == 0) {
-    s_planes[0] = pl.t_air; s_planes[1] = pl.t_mass; s_planes[2] = reinterpret_cast<const float *>(pl.sso);
-    s_planes[3] = pl.target; s_planes[4] = pl.cap;
-    for (int k = 0; k < 6; ++k) s_planes[5 + k] = pl.coef[k];
-  }
-  if (lane == 0) mbar_init(&s_bar[warp], 1);
-  fence_proxy_async_smem();
-  __syncthreads();
-#endif
   // the spare staging plane holds the thread-private small inputs: flags word, action word, (od, solar)
   uint32_t *s_flags = reinterpret_cast<uint32_t *>(s_in + (size_t)11 * kTileSlots);
   uint32_t *s_act = s_flags + kThreads;
@@ -2128,35 +2111,14 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   // own staging slots with cp.async: no registers are held while the copies fly, nobody else reads the
   // slots, so completion is one cp.async.wait_all of the thread itself -- no barrier, no mbarrier, and
   // none of the per-copy issue latency of 512-byte TMA bulk loads (measured: 20 % of the stall samples)
-  uint32_t nx_flags = 0, nx_act = 0;
   float nx_od = 0.f, nx_solar = 0.f;
   // `part`: 1 = launch-invariant static planes only (may run before pdl_wait), 2 = the rest, 3 = both
   auto prefetch = [&](int t, int part) {
     const int tr0 = t * g.envs_per_tile;
     const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
     const size_t tbase = (size_t)tr0 * Ns;
-#if DRSIM_STAGE_BULK
-    if (part == 1) return;
-    const int nw = min(128, tslots - w0);
-    if (nw > 0) {
-      // lane 0 arms the barrier with the byte count, lanes 0..10 issue one plane each (the
-      // transaction count may go transiently negative; the phase cannot complete before lane 0's arrive)
-      if (lane == 0) mbar_expect_tx(&s_bar[warp], (uint32_t)(11 * nw * 4));
-      if (lane < 11)
-        bulk_load_g2s_hint(s_in + (size_t)lane * kTileSlots + w0, s_planes[lane] + tbase + w0, (uint32_t)(nw * 4),
-                           &s_bar[warp], pol_keep);
-    }
-#endif
     if (s0 < tslots) {
       const int r = tr0 + (one_env ? 0 : (int)fast_div((uint32_t)s0, p.fd_ns));
-#if DRSIM_STAGE_BULK
-      nx_flags = load4b(pl.flags + tbase + s0);
-      if (ext) nx_act = load4b(actions + tbase + s0);
-      if (fast) {  // fp32 house-update inputs straight from the step's record (no fp64 conversion)
-        const float2 v = *reinterpret_cast<const float2 *>(&in.sched_rec[r].od_prev_f);
-        nx_od = v.x; nx_solar = v.y;
-      }
-#else
       const size_t o = tbase + s0;
       float *d = s_in + s0;
       if (part & 1) {
@@ -2173,7 +2135,6 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         if (ext) cp_async4(s_act + threadIdx.x, actions + o);
         if (fast) cp_async8(s_os + threadIdx.x, &in.sched_rec[r].od_prev_f);
       }
-#endif
       if (!fast && (part & 2)) {
         nx_od = (float)pl.od_temp[r];
         nx_solar = (float)pl.solar_next[r];
@@ -2223,11 +2184,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     const int n0 = s0 - e_loc * Ns;
     House4<real> h;
     real red[kRed] = {0, 0, 0, 0, 0};
-#if DRSIM_STAGE_BULK
-    if (w0 < slots) { mbar_wait(&s_bar[warp], ld_phase); ld_phase ^= 1u; }   // this tile's planes have landed
-#else
     cp_async_wait_all();   // the thread's own staging copies of this tile have landed
-#endif
     Raw4f w;
     if (active) {
       const float4 *in4 = reinterpret_cast<const float4 *>(s_in) + threadIdx.x;
@@ -2243,18 +2200,6 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       ld(3, w.target); ld(4, w.cap);
 #pragma unroll
       for (int k = 0; k < 6; ++k) ld(5 + k, w.c[k]);
-#if DRSIM_STAGE_BULK
-      w.flags = nx_flags; w.act = nx_act; w.od = nx_od; w.solar = nx_solar;
-      house4_compute_f32<MODE != 0>(pl, p, w, base + s0, min(4, p.N - n0), h, red, pol_keep);
-    }
-    // every lane of the warp has consumed its staged inputs: prefetch the next tile into them
-    fence_proxy_async_smem();
-    __syncwarp();
-    {
-      const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) prefetch(nt, 3);
-    }
-#else
       w.flags = s_flags[threadIdx.x];
       w.act = ext ? s_act[threadIdx.x] : 0u;
       if constexpr (POLL) {
@@ -2283,7 +2228,6 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         s_flags[threadIdx.x] = h.flags;
       }
     }
-#endif
     // the previous tile's row store must have drained the warp's staging rows before they are rewritten
     // (waited for here, after the house update, not at the top of the tile)
     if (lane == 0 && store_pending) bulk_store_wait_read();

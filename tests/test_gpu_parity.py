@@ -3,12 +3,13 @@ trajectories recorded from the reference and against the NumPy oracle.
 
 Tolerances (BASELINE.json north_star): discrete state (on / lockout / seconds_since_off, epoch)
 bit-exact; continuous quantities within rtol 1e-5 (fp32 build) or 1e-12 (fp64 build) of their
-natural scale (temperatures 20 degC, powers 6 kW x N, rewards and normalised observations 1).
+natural scale (temperatures 20 degC, powers 6 kW x N; normalised observations and rewards 1 in fp32, 4 = 20 degC / 5
+and 40 = 2 x 20 degC in fp64 -- see golden_util.scales_for).  DRSIM_PARITY_OUT=<file> collects the worst errors per case.
 """
 import numpy as np
 import pytest
 
-from golden_util import GoldenCase, case_names, replay
+from golden_util import GoldenCase, case_names, record_worst, replay
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +32,7 @@ def test_golden_trajectory(name, precision, path):
     st = _stepper(case, precision, path)
     worst = replay(case, st, rtol=RTOL[precision], precision=precision)
     print(name, precision, path, {k: f"{v:.2e}" for k, v in worst.items()})
+    record_worst(name, precision, path, worst)
 
 
 @pytest.mark.parametrize("name", ["c1_default_n10_bangbang", "random_n24_sinus_commonL2"])
