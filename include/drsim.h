@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DRSIM_ABI_VERSION 2
+#define DRSIM_ABI_VERSION 3
 #define DRSIM_MAX_SIGNAL_TERMS 8
 #define DRSIM_INTERP_SUBTABLES 162      /* 3*3*3*3*2 nearest-neighbour cells            */
 #define DRSIM_INTERP_SUBTABLE_LEN 25920 /* 9*5*8*12*6 values of the 5-D multilinear part */
@@ -149,6 +149,11 @@ typedef struct drsim_host_state {
    * (set_state only).  When NULL the library derives it from Ua, Ca, Cm, Hm with libm; a caller
    * that wants the constants of building.py:196-206 bit-identical to NumPy's passes its own. */
   double *thermal_coefs;
+  /* optional [n_rep][n_house]: per-HVAC lock-out duration in seconds (the legacy env draws
+   * lockout_duration + randint(-lockout_noise, lockout_noise) per HVAC, v0/env/MA_DemandResponse.py:397-403).
+   * NULL = the handle's common drsim_config.lockout_duration.  A handle that has been given durations differing
+   * from the common one steps on the general path (the fused tile kernels share one duration) until drsim_reset. */
+  int32_t *lockout_duration;
 } drsim_host_state;
 
 /* Device pointers of a handle (zero-copy views for torch / cupy).  `real` planes are float
@@ -356,6 +361,18 @@ int drsim_fused_info(const drsim_t *h, int32_t out[6]);
  * Sums are taken in a fixed order (run-to-run identical). */
 #define DRSIM_SUMMARY_FIELDS 8
 int drsim_cluster_summary(drsim_t *h, double *d_out, void *stream);
+
+/* Metrics.update (server/app/services/metrics_service.py:108-157) LITERALLY, for every cluster, after a step:
+ * d_acc = device [R][DRSIM_REF_METRIC_FIELDS] fp64 running values =
+ * { cumul_avg_reward, cumul_temp_offset, cumul_temp_error, max_temp_error, cumul_signal_offset, cumul_signal_error,
+ *   cumul_squared_error_temp, cumul_OD_temp, cumul_signal, cumul_cons, cumul_squared_error_sig,
+ *   cumul_squared_max_error_temp } (zero them = Metrics.initialize, :70-107); d_prev = device [R][3] fp64 =
+ * { reg_signal, OD_temp, cluster_hvac_power } of the observation BEFORE the step (what the reference reads from
+ * obs_dict, :150-152; the caller snapshots them); collect_squares = (time_step >= start_stats_from), :139,:154.
+ * The reference's own expressions are kept, precedence slips included (temp_error = indoor_temp - target_temp /
+ * nb_agents; signal error / nb_agents**2 once per agent), so the logged values are the reference's. */
+#define DRSIM_REF_METRIC_FIELDS 12
+int drsim_metrics_update(drsim_t *h, const double *d_prev, double *d_acc, int collect_squares, void *stream);
 
 /* Host-side restatements of the env-level scalars, exported for CPU tests of the shared
  * __host__ __device__ code (utils/utils.py:42-117, environment.py:132-159). */

@@ -9,7 +9,7 @@ import os
 
 from . import _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_SIGNAL_TERMS = 8
 INTERP_SUBTABLES = 162
 INTERP_SUBTABLE_LEN = 25920
@@ -17,6 +17,7 @@ N_METRICS = 6
 N_ACC = 6
 HALO_FIELDS = 8
 SUMMARY_FIELDS = 8
+REF_METRIC_FIELDS = 12
 
 F32, F64 = 0, 1
 PEN = {"individual_L2": 0, "common_L2": 1, "common_max_error": 2, "mixture": 3}
@@ -70,7 +71,7 @@ class HostState(C.Structure):
         ("on", _pu8), ("lockout", _pu8), ("sso", _pi32), ("epoch", _pi64),
         ("od_temp", _pd), ("signal", _pd), ("base_power", _pd), ("power", _pd), ("solar", _pd),
         ("artificial_ratio", _pd), ("max_power", _pd), ("t_since_interp", _pi32),
-        ("thermal_coefs", _pd),
+        ("thermal_coefs", _pd), ("lockout_duration", _pi32),
     ]
 
 
@@ -156,6 +157,7 @@ def lib():
         "drsim_launch_count": (C.c_int64, [hp]),
         "drsim_fused_info": (C.c_int, [hp, C.POINTER(_i32 * 6)]),
         "drsim_cluster_summary": (C.c_int, [hp, C.c_void_p, C.c_void_p]),
+        "drsim_metrics_update": (C.c_int, [hp, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
         "drsim_host_solar_gain": (C.c_double, [_i64, _d, _d]),
         "drsim_host_od_temp": (C.c_double, [_i64, _d, _d, _d, _d]),
         "drsim_host_civil": (None, [_i64, C.POINTER(_i32 * 7)]),
@@ -182,7 +184,7 @@ EXPORTED_SYMBOLS = [
     "drsim_create", "drsim_destroy", "drsim_clone", "drsim_buffers", "drsim_set_state", "drsim_get_state", "drsim_reset",
     "drsim_set_comm_table", "drsim_set_interp_table", "drsim_step", "drsim_run", "drsim_run_tape", "drsim_refresh", "drsim_step_begin",
     "drsim_step_finish", "drsim_step_sharded", "drsim_step_finish_gathered", "drsim_step_host", "drsim_step_host_full",
-    "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_peer_attach_local", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_cluster_summary", "drsim_host_solar_gain", "drsim_host_od_temp",
+    "drsim_ipc_export", "drsim_ipc_attach", "drsim_peer_status", "drsim_peer_attach_local", "drsim_policy_step", "drsim_launch_count", "drsim_fused_info", "drsim_cluster_summary", "drsim_metrics_update", "drsim_host_solar_gain", "drsim_host_od_temp",
     "drsim_host_civil", "drsim_host_thermal_coefs", "drsim_host_philox", "drsim_last_error", "drsim_abi_version",
     "drsim_sizeof",
 ]

@@ -233,6 +233,8 @@ class DrSim:
                 put(k, np.asarray(st[k]).astype(bool), np.uint8, (R, N), _lib._pu8)
         if "sso" in st:
             put("sso", st["sso"], np.int32, (R, N), _lib._pi32)
+        if "lockout_duration" in st:   # per-HVAC durations (legacy lockout_noise): general path only
+            put("lockout_duration", st["lockout_duration"], np.int32, (R, N), _lib._pi32)
         if "epoch" in st:
             put("epoch", st["epoch"], np.int64, (R,), _lib._pi64)
         for k in _ENV_F64:
@@ -267,6 +269,8 @@ class DrSim:
                 get(k, np.uint8, (R, N), _lib._pu8)
         if "sso" in want:
             get("sso", np.int32, (R, N), _lib._pi32)
+        if "lockout_duration" in want:
+            get("lockout_duration", np.int32, (R, N), _lib._pi32)
         if "epoch" in want:
             get("epoch", np.int64, (R,), _lib._pi64)
         for k in _ENV_F64:

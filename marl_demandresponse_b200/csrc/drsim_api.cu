@@ -63,6 +63,8 @@ struct drsim_handle {
   bool sched_valid = false;
   int64_t sched_base = 0;
   bool has_ratio = false, has_interp = false, has_comm = false;
+  bool has_dur = false;   // per-HVAC lock-out durations were injected (plane o_dur is live): general path only
+  size_t o_dur = 0;
   int chunks = 1;       // CTAs per cluster in the general path
   int obs_chunks = 1;   // k_obs CTAs per cluster
   bool fused_ok = false, fused_direct = false;
@@ -119,6 +121,7 @@ static Planes<real> make_planes(const drsim_handle *h) {
   for (int k = 0; k < NCoef<real>::n; ++k) pl.coef[k] = h->at<real>(h->o_coef[k]);
   for (int k = 0; k < 4; ++k) pl.ratio[k] = h->has_ratio ? h->at<real>(h->o_ratio[k]) : nullptr;
   pl.interp_sub = h->has_interp ? h->at<uint8_t>(h->o_sub) : nullptr;
+  pl.dur = h->has_dur ? h->at<int32_t>(h->o_dur) : nullptr;
   pl.reward = h->at<real>(h->o_reward);
   pl.obs = h->p.obs_dim ? h->at<real>(h->o_obs) : nullptr;
   pl.actions = h->at<uint8_t>(h->o_actions);
@@ -376,6 +379,7 @@ extern "C" int drsim_create(const drsim_config *cfg, int device, drsim_t **out) 
   if (h->has_ratio) for (int k = 0; k < 4; ++k) h->o_ratio[k] = cv.take(HP * rb);
   if (h->has_interp) { h->o_sub = cv.take(HP); h->o_interp = cv.take((size_t)DRSIM_INTERP_SUBTABLES * DRSIM_INTERP_SUBTABLE_LEN * rb); }
   h->o_reward = cv.take(HP * rb);
+  h->o_dur = cv.take(HP * 4);
   h->o_obs = cv.take(HP * p.obs_dim * rb + 16);
   h->o_actions = cv.take(HP);
   h->o_act_stage = cv.take(HP);
@@ -513,6 +517,8 @@ extern "C" int drsim_clone(const drsim_t *src, drsim_t **out) {
   h->sched_valid = src->sched_valid;
   h->sched_base = src->sched_base;
   h->xseq = src->xseq;
+  if (src->has_dur) { h->has_dur = true; h->fused_ok = false; }
+  h->shard = src->shard; h->shard_grid = src->shard_grid; h->shard_ok = src->shard_ok;
   *out = h;
   return 0;
 }
@@ -628,6 +634,21 @@ static int set_state_t(drsim_handle *h, const drsim_host_state *st, cudaStream_t
   }
   UP_HOUSE(cap, real, h->o_cap)
   UP_HOUSE(sso, int32_t, h->o_sso)
+  if (st->lockout_duration) {
+    // per-HVAC lock-out durations (v0/env/MA_DemandResponse.py:397-403): live only when some house differs from
+    // the common duration -- the fused tile kernels and the plain k_shard variant share one duration
+    bool differs = false;
+    for (size_t i = 0; i < (size_t)p.R * p.N; ++i) {
+      if (st->lockout_duration[i] < 1) return fail(DRSIM_E_ARG, "set_state: lockout_duration must be >= 1 s");
+      differs = differs || st->lockout_duration[i] != p.lockout_duration;
+    }
+    UP_HOUSE(lockout_duration, int32_t, h->o_dur)
+    if (differs != h->has_dur) {
+      h->has_dur = differs;
+      if (differs) h->fused_ok = false;
+      if ((rc = plan_shard<real>(h))) return rc;   // (the plain variant is out while the plane is live)
+    }
+  }
 #undef UP_HOUSE
   if (st->on || st->lockout) {
     if (!(st->on && st->lockout)) return fail(DRSIM_E_ARG, "set_state: on and lockout must be given together");
@@ -778,6 +799,15 @@ static int get_state_t(drsim_handle *h, drsim_host_state *st, cudaStream_t s) {
     const int32_t *src = reinterpret_cast<const int32_t *>(env(h->o_tsi));
     for (int r = 0; r < p.R; ++r) st->t_since_interp[r] = src[r];
   }
+  if (st->lockout_duration) {
+    std::vector<int32_t> d(HP, p.lockout_duration);
+    if (h->has_dur) {
+      CU_TRY(cudaMemcpyAsync(d.data(), h->slab + h->o_dur, HP * 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+    }
+    for (int r = 0; r < p.R; ++r)
+      for (int n = 0; n < p.N; ++n) st->lockout_duration[(size_t)r * p.N + n] = d[(size_t)r * p.Ns + n];
+  }
   return 0;
 }
 
@@ -886,7 +916,7 @@ static int launch_env_phase(drsim_handle *h, const StepIn &in, const double *acc
 
 // ---- single-kernel step of the general path (drsim_shard.cuh) ---------------------------------
 static bool shard_plain(const drsim_handle *h) {
-  return h->real_bytes == 4 && h->p.obs_dim == 10 && h->p.own_dim == 10;
+  return h->real_bytes == 4 && h->p.obs_dim == 10 && h->p.own_dim == 10 && !h->has_dur;
 }
 
 template <typename real>
@@ -1501,6 +1531,11 @@ extern "C" int drsim_reset(drsim_t *h, const drsim_reset_args *ra, void *stream)
   h->broken = false;
   h->step = 0;
   h->t_since_interp = h->p.interp_period + 1;
+  if (h->has_dur) {   // the device reset draws no lock-out noise: back to the common duration
+    h->has_dur = false;
+    const int rc = h->real_bytes == 8 ? plan_shard<double>(h) : plan_shard<float>(h);
+    if (rc) return rc;
+  }
   // artificial ratio: power_grid.py:46-49 draws ratio * range^(2u - 1); range == 1 in every shipped config
   {
     std::vector<double> ar(h->p.R, h->cfg_artificial_ratio);
@@ -1697,6 +1732,23 @@ extern "C" int drsim_cluster_summary(drsim_t *h, double *d_out, void *stream) {
   CU_TRY(cudaSetDevice(h->device));
   return h->real_bytes == 8 ? summary_impl<double>(h, d_out, (cudaStream_t)stream)
                             : summary_impl<float>(h, d_out, (cudaStream_t)stream);
+}
+
+template <typename real>
+static int metrics_ref_impl(drsim_t *h, const double *prev, double *acc, int collect_sq, cudaStream_t st) {
+  const Planes<real> pl = make_planes<real>(h);
+  k_metrics_ref<real><<<h->p.R, 256, 0, st>>>(pl, h->p, prev, acc, collect_sq);
+  h->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int drsim_metrics_update(drsim_t *h, const double *d_prev, double *d_acc, int collect_squares, void *stream) {
+  if (!h || !d_prev || !d_acc) return fail(DRSIM_E_ARG, "null argument");
+  if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "drsim_metrics_update: not available on a house-sharded cluster");
+  CU_TRY(cudaSetDevice(h->device));
+  return h->real_bytes == 8 ? metrics_ref_impl<double>(h, d_prev, d_acc, collect_squares, (cudaStream_t)stream)
+                            : metrics_ref_impl<float>(h, d_prev, d_acc, collect_squares, (cudaStream_t)stream);
 }
 
 // ---- host-side debug entry points ----------------------------------------------------------

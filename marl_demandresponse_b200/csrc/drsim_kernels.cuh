@@ -41,6 +41,7 @@ struct Planes {
   const real *coef[9];       // fp32: c0..c5 ; fp64: Ua, Ca, Hm, r1, r2, A3, A4, e1, e2
   const real *ratio[4];      // Ua, Ca, Cm, Hm over the defaults (only if an obs flag needs them)
   const uint8_t *interp_sub; // nearest-neighbour cell of the interpolation table
+  const int32_t *dur;        // per-HVAC lock-out duration [R][Ns], or NULL: SimParams::lockout_duration for all
   // per-house outputs
   real *reward;
   real *obs;
@@ -381,7 +382,7 @@ DRSIM_D void house4_step(const Planes<real> &pl, const SimParams &p, const KC<re
       const bool ext = (act >> (8 * j)) & 0xffu;
       const bool a = Rep<real>::act(p.policy, h.ta[j], h.target[j], db, f & 1u, ext);
       if (advance) {
-        hvac_fsm(f, h.sso[j], a, p.dt, p.lockout_duration);
+        hvac_fsm(f, h.sso[j], a, p.dt, pl.dur ? __ldg(pl.dur + off + j) : p.lockout_duration);
         const real q = (f & 1u) ? hvac_heat(h.cap[j], kc.one_plus_latent, kc.neg_inv_opl) : (real)0;
         real c[NC];
 #pragma unroll
@@ -892,6 +893,14 @@ DRSIM_D int neighbour_of(const SimParams &p, const int32_t *table, int r, int n,
   return __ldg(table + base + (size_t)n * p.nb_comm + k);
 }
 
+// int(seconds_since_off / lockout_duration) of the house's OWN hvac (norm.py:79-82); messages use the default
+// duration (norm.py:40-43) and keep fast_div
+template <typename real>
+DRSIM_D real own_sso_norm(const Planes<real> &pl, const SimParams &p, size_t o, int sso) {
+  if (pl.dur) return (real)(sso / max(1, __ldg(pl.dur + o)));
+  return (real)fast_div((uint32_t)sso, p.fd_dur);
+}
+
 // own-state part of the observation row (utils/norm.py:71-146).  `what` selects the columns
 // written: bit0 = those that depend on the house only, bit1 = those that need the env epilogue
 // (cluster power, signal, solar gain, outdoor temperature).
@@ -1390,7 +1399,7 @@ __global__ void __launch_bounds__(kObsChunk) k_obs(Planes<real> pl, SimParams p,
         if (p.st_thermal)
           for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][o];
         const uint32_t f = pl.flags[o];
-        int i = obs_own<real>(row, p, f, (real)fast_div((uint32_t)pl.sso[o], p.fd_dur), Rep<real>::minus20(ta, tgt),
+        int i = obs_own<real>(row, p, f, own_sso_norm<real>(pl, p, o, pl.sso[o]), Rep<real>::minus20(ta, tgt),
                               Rep<real>::minus20(tm, tgt), tgt - (real)20, e, ratio);
         if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
           const bool halo = needs_halo(p);
@@ -3021,6 +3030,74 @@ __global__ void __launch_bounds__(256) k_summary(Planes<real> pl, SimParams p, d
     out[(size_t)r * kSummaryFields + threadIdx.x] = t;
   }
   if (threadIdx.x == 7) out[(size_t)r * kSummaryFields + 7] = (double)p.N;
+}
+
+// ------------------------------------------------------------------------------------------
+// The reference's running metrics, LITERALLY (server/app/services/metrics_service.py:108-157):
+// one launch after a step accumulates, per cluster, the twelve cumulative fields of `Metrics.update` with its
+// own expressions -- `temp_error = indoor_temp - target_temp / nb_agents` (:131-134: the division binds to the
+// set-point only), `signal_error = (reg_signal - cluster_hvac_power) / nb_agents**2` added once per agent
+// (:143-148) -- so that the logged values of a rollout on the device are the reference's, slips included.
+//   acc[r] = { cumul_avg_reward, cumul_temp_offset, cumul_temp_error, max_temp_error, cumul_signal_offset,
+//              cumul_signal_error, cumul_squared_error_temp, cumul_OD_temp, cumul_signal, cumul_cons,
+//              cumul_squared_error_sig, cumul_squared_max_error_temp }
+//   prev[r] = { reg_signal, OD_temp, cluster_hvac_power } of the observation BEFORE the step (obs_dict)
+// Fixed-order fp64 sums (strided per thread, butterfly inside the warp, warps in index order).
+// ------------------------------------------------------------------------------------------
+constexpr int kRefMetricFields = 12;
+
+template <typename real>
+__global__ void __launch_bounds__(256) k_metrics_ref(Planes<real> pl, SimParams p, const double *prev, double *acc, int collect_sq) {
+  const int r = blockIdx.x;
+  const size_t rb = (size_t)r * p.Ns;
+  const double n = (double)p.N;
+  double s[4] = {0, 0, 0, 0};   // sum temp_error, sum |temp_error|, sum temp_error^2, sum reward / n
+  double mx = acc[(size_t)r * kRefMetricFields + 3];
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    const double tgt = (double)pl.target[rb + i];
+    const double ta = (double)Rep<real>::dev(pl.t_air[rb + i], pl.target[rb + i]) + tgt;
+    const double te = ta - tgt / n;
+    s[0] += te;
+    s[1] += fabs(te);
+    s[2] += te * te;
+    s[3] += (double)pl.reward[rb + i] / n;
+    mx = fmax(mx, te);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ double wp[8][5];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    for (int k = 0; k < 4; ++k) wp[w][k] = s[k];
+    wp[w][4] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0};
+    double m = wp[0][4];
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
+      for (int k = 0; k < 4; ++k) t[k] += wp[q][k];
+      m = fmax(m, wp[q][4]);
+    }
+    double *a = acc + (size_t)r * kRefMetricFields;
+    const double sig_old = prev[(size_t)r * 3], od_old = prev[(size_t)r * 3 + 1], p_old = prev[(size_t)r * 3 + 2];
+    const double se = (sig_old - pl.power[r]) / (n * n);
+    a[0] += t[3];
+    a[1] += t[0];
+    a[2] += t[1];
+    a[3] = m;
+    a[4] += n * se;
+    a[5] += n * fabs(se);
+    if (collect_sq) a[6] += t[2];
+    a[7] += od_old;
+    a[8] += sig_old;
+    a[9] += p_old;
+    if (collect_sq) { a[10] += sig_old * sig_old; a[11] = m * m; }
+  }
 }
 
 }  // namespace drsim

@@ -655,7 +655,7 @@ k_shard(Planes<real> pl, SimParams p, StepIn in, ShardGeom g, ShardCtx sc, PeerC
             real ratio[4] = {0, 0, 0, 0};
             if (p.st_thermal)
               for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][o];
-            int i = obs_own<real>(row, p, f, (real)fast_div((uint32_t)sso, p.fd_dur), Rep<real>::minus20(ta, tgt),
+            int i = obs_own<real>(row, p, f, own_sso_norm<real>(pl, p, o, sso), Rep<real>::minus20(ta, tgt),
                                   Rep<real>::minus20(tm, tgt), tgt - (real)20, e, ratio);
             if (p.obs_layout == DRSIM_OBS_HAND_ENGINEERED) {
               for (int k = 0; k < p.nb_comm; ++k) {

@@ -24,7 +24,8 @@ reproduced here, is everything around the step:
 
 ``random.seed(s)`` before construction therefore reproduces the legacy trajectory
 (``tests/test_gpu_v0.py`` against ``tests/golden/v0_*.npz`` recorded from the reference).  Per-HVAC
-``lockout_noise != 0`` is not supported (the kernels share one lock-out duration); the draw is still consumed.
+``lockout_noise != 0`` gives every HVAC its own lock-out duration (:397-403): the durations travel to the device as
+a per-house plane and the step then runs on the general path (the fused tile kernels share one duration).
 """
 from __future__ import annotations
 
@@ -217,9 +218,10 @@ class MADemandResponseEnv(Environment):
         self.time_step = p.time_step
         # ClusterHouses.__init__ (:714-759): HVACs (lock-out noise draw), phase, first outdoor temperature, links
         ln = hv.noise_prop.lockout_noise
-        for i in range(n):
-            if random.randint(-ln, ln) != 0:
-                raise NotImplementedError("per-HVAC lockout_noise is not supported by the batched kernels")
+        # per-HVAC lock-out duration = lockout_duration + randint(-lockout_noise, lockout_noise) (:397-403)
+        self._durations = [hv.lockout_duration + random.randint(-ln, ln) for _ in range(n)]
+        if min(self._durations) < 1:
+            raise ValueError("lockout_duration - lockout_noise must stay >= 1 s")
         tp = p.temp_prop
         phase = random.random() * 24 if tp.random_phase_offset else 0.0
         tp.phase = phase
@@ -248,7 +250,8 @@ class MADemandResponseEnv(Environment):
                 self._sim.set_interp_table(self._interp_table)
         st["on"] = np.zeros((1, n), dtype=np.uint8)      # HVACs start OFF, free to start (:401-403)
         st["lockout"] = np.zeros((1, n), dtype=np.uint8)
-        st["sso"] = np.full((1, n), hv.lockout_duration, dtype=np.int32)
+        st["sso"] = np.asarray([self._durations], dtype=np.int32)     # seconds_since_off = the HVAC's own duration
+        st["lockout_duration"] = np.asarray([self._durations], dtype=np.int32)
         st.update(epoch=[to_epoch(self.date_time)], od_temp=[float(od)], signal=[0.0], base_power=[0.0],
                   artificial_ratio=[self._artificial_ratio], max_power=[self._max_power], solar=[0.0], power=[0.0],
                   t_since_interp=[gp.base_power_props.interp_update_period + 1])
@@ -304,7 +307,7 @@ class MADemandResponseEnv(Environment):
                  "hvac_seconds_since_off": sso[i],
                  "hvac_curr_consumption": hv.max_consumption if on[i] else 0,
                  "hvac_max_consumption": hv.max_consumption,
-                 "hvac_lockout_duration": hv.lockout_duration}
+                 "hvac_lockout_duration": self._durations[i]}
             if mp.thermal:
                 m.update(house_Ua=b.Ua, house_Cm=b.Cm, house_Ca=b.Ca, house_Hm=b.Hm)
             if mp.hvac:
@@ -324,7 +327,7 @@ class MADemandResponseEnv(Environment):
                 "house_solar_gain": solar,
                 "hvac_COP": hv.cop, "hvac_cooling_capacity": hv.cooling_capacity,
                 "hvac_latent_cooling_fraction": hv.latent_cooling_fraction,
-                "hvac_lockout_duration": hv.lockout_duration,
+                "hvac_lockout_duration": self._durations[i],
                 "message": [dict(msgs[j]) for j in table[i]],
                 "reg_signal": signal, "cluster_hvac_power": power,
             }

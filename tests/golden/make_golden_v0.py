@@ -84,6 +84,12 @@ CASES = [
         "default_env_prop/cluster_prop/agents_comm_mode": "random_fixed",
         "default_env_prop/cluster_prop/nb_agents_comm": 3,
         "default_env_prop/power_grid_prop/artificial_signal_ratio_range": 2}),
+    # per-HVAC lock-out durations: lockout_duration 24 s + randint(-12, 12) (MA_DemandResponse.py:397-403)
+    dict(name="v0_n14_lockout_noise", n=14, T=70, seed=24, over={
+        "default_env_prop/power_grid_prop/base_power_mode": "constant",
+        "default_env_prop/power_grid_prop/signal_mode": "sinusoidals",
+        "default_hvac_prop/lockout_duration": 24,
+        "default_hvac_prop/lockout_noise": 12}),
 ]
 
 SCALARS = ["house_temp", "house_mass_temp", "hvac_turned_on", "hvac_seconds_since_off", "hvac_lockout",

@@ -12,7 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["v0_n12_steps_constant", "v0_n20_sinus_mixture_flags", "v0_n9_random_fixed_flat"]
+CASES = ["v0_n12_steps_constant", "v0_n20_sinus_mixture_flags", "v0_n9_random_fixed_flat", "v0_n14_lockout_noise"]
 
 
 def _actions_for(t, n):
