@@ -324,6 +324,26 @@ int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, 
 int drsim_step_host_full(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
                          const int32_t *interp_ids, double *env_out, void *reward_out, void *obs_out, void *stream);
 
+/* What Environment.get_obs (environment.py:110-130, cluster.py:113-121, building.py:79-100, hvac.py:72-83) builds
+ * its 21-key per-agent dicts from, in ONE call: a kernel writes the house state (absolute temperatures and rewards
+ * as fp64, seconds_since_off, the two flags) and the env scalars straight into pinned host memory of the handle,
+ * the observation rows follow by one copy, the stream is synchronised once.  The pointers stay valid until the
+ * next snapshot of the handle (copy what must outlive it).
+ * env[r] = { OD_temp, reg_signal, cluster_hvac_power, solar_gain, base_power, epoch, time_since_last_interp, max_power }. */
+typedef struct drsim_snapshot_view {
+  int32_t n_rep, n_house, obs_dim, real_bytes;
+  const double *t_air, *t_mass, *reward; /* [R][N] */
+  const int32_t *sso;                    /* [R][N] */
+  const uint8_t *on, *lockout;           /* [R][N] */
+  const double *env;                     /* [R][8] */
+  const void *obs;                       /* [R][N][obs_dim] float | double as the handle was built, or NULL */
+} drsim_snapshot_view;
+int drsim_snapshot(drsim_t *h, drsim_snapshot_view *out, void *stream);
+/* Environment.step for the dict API: drsim_step_host (host action / noise buffers in) followed by the snapshot,
+ * with ONE stream synchronisation for both. */
+int drsim_step_host_snapshot(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                             const int32_t *interp_ids, drsim_snapshot_view *out, void *stream);
+
 /* MA-PPO actor of the reference (agents/trainables/network.py:14-35: Linear(obs_dim, h1) - ReLU -
  * Linear(h1, h2) - ReLU - Linear(h2, 2) - softmax), all DEVICE pointers in torch.nn.Linear layout
  * (weight [out][in], row-major fp32). */

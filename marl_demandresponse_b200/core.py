@@ -399,6 +399,9 @@ class DrSim:
         contiguity (a wrong stride or a 4-byte dtype would be read as garbage actions)."""
         if x is None:
             return None
+        if type(x) is np.ndarray and x.dtype == dtype and x.shape == tuple(shape) and x.flags.c_contiguous:
+            keep.append(x)           # already what the ABI wants: no conversion
+            return C.c_void_p(x.__array_interface__["data"][0])
         if hasattr(x, "data_ptr"):   # torch CPU tensor (pinned or pageable)
             import torch
 
@@ -445,6 +448,43 @@ class DrSim:
                      self._host_buf(obs_out, self.real, (R, N, self.D), keep, "obs_out", writable=True)]
             _lib.check(self._L.drsim_step_host_full(self._h, *args, self._stream(stream)))
         return env_out
+
+    def _snapshot_arrays(self, v: "_lib.SnapshotView") -> Dict[str, np.ndarray]:
+        """numpy views of the handle's pinned snapshot (valid until the next snapshot of this handle)."""
+        key = (C.cast(v.t_air, C.c_void_p).value, C.cast(v.env, C.c_void_p).value)
+        if getattr(self, "_snap_key", None) == key:      # the pinned buffers do not move: reuse the views
+            return self._snap_arrays
+        R, N, D = self.R, self.N, self.D
+        as_arr = np.ctypeslib.as_array
+        out = {"t_air": as_arr(v.t_air, (R, N)), "t_mass": as_arr(v.t_mass, (R, N)), "reward": as_arr(v.reward, (R, N)),
+               "sso": as_arr(v.sso, (R, N)), "on": as_arr(v.on, (R, N)), "lockout": as_arr(v.lockout, (R, N)),
+               "env": as_arr(v.env, (R, 8)), "obs": None}
+        if D and v.obs:
+            ct = C.c_double if self.ptrs.real_bytes == 8 else C.c_float
+            out["obs"] = as_arr(C.cast(v.obs, C.POINTER(ct)), (R, N, D))
+        self._snap_key, self._snap_arrays = key, out
+        return out
+
+    def snapshot(self, stream=None) -> Dict[str, np.ndarray]:
+        """``drsim_snapshot``: what the dict API is built from (absolute temperatures, rewards, seconds_since_off,
+        flags, env scalars ``[R, 8]`` = od_temp, signal, power, solar, base_power, epoch, t_since_interp, max_power,
+        observation rows) in ONE call / one synchronisation, as numpy views of pinned host memory."""
+        v = _lib.SnapshotView()
+        _lib.check(self._L.drsim_snapshot(self._h, C.byref(v), self._stream(stream)))
+        return self._snapshot_arrays(v)
+
+    def step_host_snapshot(self, actions, od_noise=None, perlin=None, interp_ids=None, stream=None) -> Dict[str, np.ndarray]:
+        """``drsim_step_host_snapshot``: the host-buffer step followed by the snapshot, one synchronisation."""
+        keep: list = []
+        R, N = self.R, self.N
+        k = int(self.cfg.interp_nb_agents)
+        args = [self._host_buf(actions, np.uint8, (R, N), keep, "actions"),
+                self._host_buf(None if od_noise is None else np.reshape(od_noise, (R,)), np.float64, (R,), keep, "od_noise"),
+                self._host_buf(None if perlin is None else np.reshape(perlin, (R,)), np.float64, (R,), keep, "perlin"),
+                self._host_buf(None if interp_ids is None else np.reshape(interp_ids, (R, k)), np.int32, (R, k), keep, "interp_ids")]
+        v = _lib.SnapshotView()
+        _lib.check(self._L.drsim_step_host_snapshot(self._h, *args, C.byref(v), self._stream(stream)))
+        return self._snapshot_arrays(v)
 
     def policy_step(self, weights, seed: int = 0, prob_drawn=None, prob_on=None, stream=None) -> None:
         """``drsim_policy_step``: the reference's MA-PPO actor + categorical draw on the observation rows.

@@ -84,6 +84,12 @@ struct drsim_handle {
   int shard_grid = 0, shard_capacity = 0;
   bool shard_ok = false;
   size_t o_sh_partll = 0, o_sh_envll = 0, o_sh_pearly = 0, o_pinbox = 0, o_rowll = 0;
+  // small host inputs of drsim_step_host (actions / noise / ids of a small cluster) are staged in pinned mapped
+  // memory and READ IN PLACE by the kernel: no copy-engine call for a handful of bytes
+  unsigned char *h_in = nullptr, *h_in_dev = nullptr;
+  // pinned + mapped snapshot for the dict API (drsim_snapshot)
+  unsigned char *h_snap = nullptr, *h_snap_dev = nullptr;
+  size_t snap_bytes = 0, snap_obs_off = 0;
   unsigned long long *shard_dbg = nullptr;   // DRSIM_SHARD_DBG: per-CTA time stamps of the last k_shard launch
   int *h_peer_err = nullptr, *h_peer_err_dev = nullptr;   // mapped: set by a kernel whose exchange wait timed out
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
@@ -501,6 +507,8 @@ extern "C" int drsim_destroy(drsim_t *h) {
   if (h->h_env) cudaFreeHost(h->h_env);
   if (h->actor_image) cudaFree(h->actor_image);
   if (h->shard_dbg) cudaFree(h->shard_dbg);
+  if (h->h_snap) cudaFreeHost(h->h_snap);
+  if (h->h_in) cudaFreeHost(h->h_in);
   delete h;
   return 0;
 }
@@ -1352,8 +1360,69 @@ static bool staged_fast_step(const drsim_handle *h, int do_interp, bool injected
 // SMs reach ~30 GB/s).  The per-cluster results are written by the kernel straight into the caller's
 // pinned result buffer.  Pageable buffers, padded rows (N % 4 != 0) and every other step kind use
 // explicit copies.
+// ---- snapshot for the dict API ---------------------------------------------------------------
+static size_t snap_layout(const drsim_handle *h, size_t off[8]) {
+  const size_t HN = (size_t)h->p.R * h->p.N;
+  size_t o = 0;
+  auto take = [&](size_t b) { const size_t r = o; o += (b + 255) / 256 * 256; return r; };
+  off[0] = take(HN * 8); off[1] = take(HN * 8); off[2] = take(HN * 8); off[3] = take(HN * 4); off[4] = take(HN);
+  off[5] = take(HN); off[6] = take((size_t)h->p.R * kSnapEnv * 8); off[7] = take(HN * h->p.obs_dim * h->real_bytes);
+  return o;
+}
+
+// enqueues the snapshot kernel + the observation-row copy on `s`; the caller synchronises
+static int enqueue_snapshot(drsim_handle *h, cudaStream_t s) {
+  size_t off[8];
+  const size_t bytes = snap_layout(h, off);
+  if (bytes > ((size_t)512 << 20)) return fail(DRSIM_E_ARG, "drsim_snapshot: more than 512 MB -- use the tensor views for clusters this large");
+  if (!h->h_snap) {
+    CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h->h_snap), bytes, cudaHostAllocMapped));
+    CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_snap_dev), h->h_snap, 0));
+    h->snap_bytes = bytes;
+  }
+  SnapPtrs o{};
+  unsigned char *d = h->h_snap_dev;
+  o.t_air = reinterpret_cast<double *>(d + off[0]); o.t_mass = reinterpret_cast<double *>(d + off[1]);
+  o.reward = reinterpret_cast<double *>(d + off[2]); o.sso = reinterpret_cast<int32_t *>(d + off[3]);
+  o.on = d + off[4]; o.lockout = d + off[5]; o.env = reinterpret_cast<double *>(d + off[6]);
+  const SimParams &p = h->p;
+  const long long n = std::max<long long>((long long)p.R * p.N, p.R);
+  if (h->real_bytes == 8) k_snapshot<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(make_planes<double>(h), p, o);
+  else k_snapshot<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(make_planes<float>(h), p, o);
+  h->launches++;
+  if (p.obs_dim) {
+    const size_t row = (size_t)p.obs_dim * h->real_bytes;
+    if (p.Ns == p.N) CU_TRY(cudaMemcpyAsync(h->h_snap + off[7], h->slab + h->o_obs, (size_t)p.R * p.N * row, cudaMemcpyDeviceToHost, s));
+    else CU_TRY(cudaMemcpy2DAsync(h->h_snap + off[7], (size_t)p.N * row, h->slab + h->o_obs, (size_t)p.Ns * row, (size_t)p.N * row, p.R,
+                                  cudaMemcpyDeviceToHost, s));
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+static void fill_snapshot_view(const drsim_handle *h, drsim_snapshot_view *v) {
+  size_t off[8];
+  snap_layout(h, off);
+  const unsigned char *b = h->h_snap;
+  v->n_rep = h->p.R; v->n_house = h->p.N; v->obs_dim = h->p.obs_dim; v->real_bytes = h->real_bytes;
+  v->t_air = reinterpret_cast<const double *>(b + off[0]); v->t_mass = reinterpret_cast<const double *>(b + off[1]);
+  v->reward = reinterpret_cast<const double *>(b + off[2]); v->sso = reinterpret_cast<const int32_t *>(b + off[3]);
+  v->on = b + off[4]; v->lockout = b + off[5]; v->env = reinterpret_cast<const double *>(b + off[6]);
+  v->obs = h->p.obs_dim ? b + off[7] : nullptr;
+}
+
+extern "C" int drsim_snapshot(drsim_t *h, drsim_snapshot_view *out, void *stream) {
+  if (!h || !out) return fail(DRSIM_E_ARG, "null argument");
+  CU_TRY(cudaSetDevice(h->device));
+  if (int rc = enqueue_snapshot(h, (cudaStream_t)stream)) return rc;
+  CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  fill_snapshot_view(h, out);
+  return 0;
+}
+
 static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
-                          const int32_t *interp_ids, double *env_out, void *reward_out, void *obs_out, void *stream) {
+                          const int32_t *interp_ids, double *env_out, void *reward_out, void *obs_out, void *stream,
+                          drsim_snapshot_view *snap = nullptr) {
   if (!h) return fail(DRSIM_E_ARG, "null handle");
   CU_TRY(cudaSetDevice(h->device));
   auto s = (cudaStream_t)stream;
@@ -1364,7 +1433,23 @@ static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_n
   const int di = interp_decision(h);
   const bool staged = staged_fast_step(h, di, od_noise || perlin);
   bool dma_poll = false;
-  if (actions) {
+  // small inputs: staged in the handle's pinned mapped page and read in place by the kernels (the call ends with a
+  // stream synchronisation, so the page is free again when it returns)
+  constexpr size_t kInAct = 8192, kInOd = 2048, kInIds = 4096;
+  const bool small_in = (size_t)p.R * p.Ns <= kInAct && (size_t)p.R * 8 <= kInOd && (size_t)p.R * std::max(1, p.interp_k) * 4 <= kInIds;
+  if (small_in && !h->h_in) {
+    if (cudaHostAlloc(reinterpret_cast<void **>(&h->h_in), kInAct + 2 * kInOd + kInIds, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_in_dev), h->h_in, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (h->h_in) cudaFreeHost(h->h_in);
+      h->h_in = h->h_in_dev = nullptr;
+    }
+  }
+  const bool in_place = small_in && h->h_in_dev;
+  if (actions && in_place) {
+    for (int r = 0; r < p.R; ++r) memcpy(h->h_in + (size_t)r * p.Ns, actions + (size_t)r * p.N, p.N);
+    a.actions = h->h_in_dev;
+  } else if (actions) {
     const uint8_t *mapped = nullptr;
     if (staged && p.Ns == p.N && (p.policy == DRSIM_POLICY_EXTERNAL)) {
       cudaPointerAttributes at{};
@@ -1395,15 +1480,24 @@ static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_n
       a.actions = h->at<uint8_t>(h->o_actions);
     }
   }
-  if (od_noise) {
+  if (od_noise && in_place) {
+    memcpy(h->h_in + kInAct, od_noise, (size_t)p.R * 8);
+    a.od_noise = reinterpret_cast<const double *>(h->h_in_dev + kInAct);
+  } else if (od_noise) {
     CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_od, od_noise, (size_t)p.R * 8, cudaMemcpyHostToDevice, s));
     a.od_noise = h->at<double>(h->o_in_od);
   }
-  if (perlin) {
+  if (perlin && in_place) {
+    memcpy(h->h_in + kInAct + kInOd, perlin, (size_t)p.R * 8);
+    a.perlin = reinterpret_cast<const double *>(h->h_in_dev + kInAct + kInOd);
+  } else if (perlin) {
     CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_perlin, perlin, (size_t)p.R * 8, cudaMemcpyHostToDevice, s));
     a.perlin = h->at<double>(h->o_in_perlin);
   }
-  if (interp_ids) {
+  if (interp_ids && in_place) {
+    memcpy(h->h_in + kInAct + 2 * kInOd, interp_ids, (size_t)p.R * p.interp_k * 4);
+    a.interp_ids = reinterpret_cast<const int32_t *>(h->h_in_dev + kInAct + 2 * kInOd);
+  } else if (interp_ids) {
     CU_TRY(cudaMemcpyAsync(h->slab + h->o_in_ids, interp_ids, (size_t)p.R * p.interp_k * 4, cudaMemcpyHostToDevice, s));
     a.interp_ids = h->at<int32_t>(h->o_in_ids);
   }
@@ -1448,6 +1542,9 @@ static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_n
     else CU_TRY(cudaMemcpy2DAsync(obs_out, (size_t)p.N * row, h->slab + h->o_obs, (size_t)p.Ns * row, (size_t)p.N * row, p.R,
                                   cudaMemcpyDeviceToHost, s));
   }
+  if (snap) {
+    if (int rc2 = enqueue_snapshot(h, s)) return rc2;
+  }
   if (env_out && mirror) {
     CU_TRY(cudaStreamSynchronize(s));
     if (dma_poll && *h->h_poll_err) {
@@ -1482,7 +1579,14 @@ static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_n
   } else {
     CU_TRY(cudaStreamSynchronize(s));
   }
+  if (snap) fill_snapshot_view(h, snap);
   return 0;
+}
+
+extern "C" int drsim_step_host_snapshot(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,
+                                        const int32_t *interp_ids, drsim_snapshot_view *out, void *stream) {
+  if (!out) return fail(DRSIM_E_ARG, "null argument");
+  return step_host_impl(h, actions, od_noise, perlin, interp_ids, nullptr, nullptr, nullptr, stream, out);
 }
 
 extern "C" int drsim_step_host(drsim_t *h, const uint8_t *actions, const double *od_noise, const double *perlin,

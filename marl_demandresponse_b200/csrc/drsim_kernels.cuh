@@ -3100,4 +3100,41 @@ __global__ void __launch_bounds__(256) k_metrics_ref(Planes<real> pl, SimParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Snapshot for the dict API (Environment.get_obs, environment.py:110-130): everything the per-agent observation
+// dicts are built from, written by ONE launch straight into mapped pinned host memory -- absolute temperatures
+// as fp64 (the fp32 build keeps deviations), rewards as fp64, seconds_since_off, the two flags, the env scalars.
+// The observation rows follow by one copy-engine transfer; the caller synchronises once.
+// ------------------------------------------------------------------------------------------
+struct SnapPtrs {
+  double *t_air, *t_mass, *reward;   // [R][N]
+  int32_t *sso;                      // [R][N]
+  uint8_t *on, *lockout;             // [R][N]
+  double *env;                       // [R][kSnapEnv]
+};
+constexpr int kSnapEnv = 8;   // od_temp, signal, power, solar, base_power, epoch, t_since_interp, max_power
+
+template <typename real>
+__global__ void k_snapshot(Planes<real> pl, SimParams p, SnapPtrs o) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)p.R * p.N) {
+    const int r = (int)(i / p.N), n = (int)(i - (long long)r * p.N);
+    const size_t s = (size_t)r * p.Ns + n;
+    const double tgt = (double)pl.target[s];
+    const bool dev = sizeof(real) == 4;
+    o.t_air[i] = (double)pl.t_air[s] + (dev ? tgt : 0.0);
+    o.t_mass[i] = (double)pl.t_mass[s] + (dev ? tgt : 0.0);
+    o.reward[i] = (double)pl.reward[s];
+    o.sso[i] = pl.sso[s];
+    const uint32_t f = pl.flags[s];
+    o.on[i] = (uint8_t)(f & 1u);
+    o.lockout[i] = (uint8_t)((f >> 1) & 1u);
+  }
+  if (i < p.R) {
+    double *e = o.env + (size_t)i * kSnapEnv;
+    e[0] = pl.od_temp[i]; e[1] = pl.signal[i]; e[2] = pl.power[i]; e[3] = pl.solar_cur[i];
+    e[4] = pl.base_power[i]; e[5] = (double)pl.epoch[i]; e[6] = (double)pl.t_since_interp[i]; e[7] = pl.max_power[i];
+  }
+}
+
 }  // namespace drsim

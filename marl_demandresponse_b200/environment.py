@@ -163,9 +163,95 @@ class _PowerGridView:
 
 
 class ObsDict(dict):
-    """The per-agent observation dicts, plus the device-computed normalised vectors."""
+    """The per-agent observation dicts of ``Environment.get_obs`` (environment.py:110-130), plus the
+    device-computed normalised vectors (``vectors``, what ``norm_state_dict`` returns).
+
+    A real ``dict`` whose entries are MATERIALISED ON ACCESS: ``obs[i]`` builds house i's 21-key dict (and the
+    message dicts of its neighbours) from the step's snapshot the first time it is asked for; anything that needs
+    all of them (iteration, ``keys`` / ``items`` / ``values``, comparison, copy, pickling, ``dict(obs)``) fills the
+    rest in id order first.  A policy that consumes ``norm_state_dict(obs, props)`` -- the vectors the GPU already
+    gathered -- never pays for the 1000 x (21 + 10 x 5) Python objects of a large cluster.
+
+    One caveat: C-level consumers that walk the dict storage directly (``json.dumps(obs)``) see only what has been
+    materialised; hand them ``obs.materialize()`` (or build the environment with ``lazy_obs=False``)."""
 
     vectors: Optional[np.ndarray] = None
+
+    def __init__(self, build=None, n: int = 0):
+        super().__init__()
+        self._build, self._n, self._full = build, int(n), build is None
+
+    def __missing__(self, i):
+        if self._build is None or isinstance(i, bool) or not isinstance(i, (int, np.integer)) or not 0 <= i < self._n:
+            raise KeyError(i)
+        d = self._build(int(i))
+        dict.__setitem__(self, int(i), d)
+        return d
+
+    def _fill(self) -> None:
+        if self._full:
+            return
+        have = {k: dict.__getitem__(self, k) for k in dict.keys(self)}
+        dict.clear(self)
+        for i in range(self._n):                       # id order, like the reference's loop (cluster.py:113-121)
+            dict.__setitem__(self, i, have[i] if i in have else self._build(i))
+        self._full = True
+
+    def materialize(self) -> "ObsDict":
+        """Build every entry now (id order); returns self."""
+        self._fill()
+        return self
+
+    def __len__(self):
+        return dict.__len__(self) if self._full else self._n
+
+    def __contains__(self, i):
+        if self._full:
+            return dict.__contains__(self, i)
+        return isinstance(i, (int, np.integer)) and not isinstance(i, bool) and 0 <= i < self._n
+
+    def __iter__(self):
+        self._fill()
+        return dict.__iter__(self)
+
+    def keys(self):
+        self._fill()
+        return dict.keys(self)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+    def get(self, i, default=None):
+        return self[i] if i in self else default
+
+    def __eq__(self, other):
+        self._fill()
+        if isinstance(other, ObsDict):
+            other._fill()
+        return dict.__eq__(self, other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._fill()
+        return dict.__repr__(self)
+
+    def copy(self):
+        self._fill()
+        return dict(self)
+
+    def __reduce__(self):
+        self._fill()
+        return (dict, (dict(dict.items(self)),))
+
+    def __deepcopy__(self, memo):
+        self._fill()
+        return copy.deepcopy(dict(dict.items(self)), memo)
 
 
 def norm_state_dict(obs_dicts: ObsDict, env_props: Any = None) -> List[np.ndarray]:
@@ -181,14 +267,16 @@ class Environment:
     """GPU-backed stand-in for the reference ``Environment``."""
 
     def __init__(self, env_props: Any, device: int = 0, precision: str = "f64",
-                 interp_table: Optional[np.ndarray] = None) -> None:
+                 interp_table: Optional[np.ndarray] = None, lazy_obs: bool = True) -> None:
         self.init_props: EnvironmentProperties = as_props(env_props)  # deepcopy, environment.py:46
+        self._lazy_obs = bool(lazy_obs)
         self.n = int(self.init_props.cluster_prop.nb_agents)
         self._device, self._precision = device, precision
         self._interp_table = interp_table
         if self.init_props.power_grid_prop.base_power_props.mode == "interpolation" and interp_table is None:
             self._interp_table = np.load(self.init_props.power_grid_prop.base_power_props.path_datafile)
         self._sim: Optional[DrSim] = None
+        self._ids = list(range(self.n))
         self.reset()
 
     # ---- reset (environment.py:49-70, draw order of SURVEY appendix B) --------------------
@@ -312,27 +400,39 @@ class Environment:
         if self._width > 0:
             self._sim.set_comm_table(self._table)
         self._sim.refresh(recompute_signal, None, self._upload(perlin, np.float64), self._upload(ids, np.int32))
-        self._pull()
+        self._take(self._sim.snapshot())
 
-    def _pull(self) -> None:
-        import torch
-
-        self._snap = self._sim.get_state()
-        self._tsi = int(self._snap["t_since_interp"][0])
-        torch.cuda.synchronize(self._device)
-        v = self._sim.views()
-        self._vectors = v["obs"][0].double().cpu().numpy() if v["obs"] is not None else None
-        self.current_od_temp = float(self._snap["od_temp"][0])
+    def _take(self, snap: Dict[str, np.ndarray]) -> None:
+        """Keep the step's snapshot (``drsim_snapshot``: one kernel writing pinned host memory + one copy of the
+        observation rows, ONE synchronisation): the pinned buffers are reused by the next step, callers hold on
+        to observation dicts of earlier steps, so everything is copied out here -- a few KB."""
+        env = snap["env"][0].copy()
+        if getattr(self, "_targets_of", None) is not self._house_props:     # static per reset
+            self._targets = np.asarray([[b.target_temp for b in self._house_props]], dtype=np.float64)
+            self._caps = np.asarray([[h.cooling_capacity for h in self._hvac_props]], dtype=np.float64)
+            self._targets_of = self._house_props
+        self._snap = {"target": self._targets, "cap": self._caps, "epoch": np.asarray([int(env[5])], dtype=np.int64),
+                      "t_air": snap["t_air"].copy(), "t_mass": snap["t_mass"].copy(), "sso": snap["sso"].copy(),
+                      "on": snap["on"].copy(), "lockout": snap["lockout"].copy(),
+                      "od_temp": env[0:1], "signal": env[1:2], "power": env[2:3], "solar": env[3:4], "base_power": env[4:5]}
+        self._reward = snap["reward"][0].copy()
+        self._tsi = int(env[6])
+        self._vectors = None if snap["obs"] is None else snap["obs"][0].astype(np.float64)
+        self.current_od_temp = float(env[0])
 
     # ---- step (environment.py:72-108) -----------------------------------------------------
     def step(self, action_dict: Dict[int, bool]):
         p = self.init_props
         mode = p.cluster_prop.agents_comm_prop.mode
         self.date_time += p.time_step
-        actions = np.zeros((1, self.n), dtype=np.uint8)
-        for i in range(self.n):                                 # missing action -> False (cluster.py:83-86)
-            if i in action_dict and action_dict[i]:
-                actions[0, i] = 1
+        n = self.n
+        if len(action_dict) == n and list(action_dict) == self._ids:      # the usual case: one command per house, id order
+            actions = np.fromiter(action_dict.values(), dtype=np.bool_, count=n).view(np.uint8).reshape(1, n)
+        else:
+            actions = np.zeros((1, n), dtype=np.uint8)
+            for i in range(n):                                  # missing action -> False (cluster.py:83-86)
+                if i in action_dict and action_dict[i]:
+                    actions[0, i] = 1
         if mode == "random_sample":
             self._draw_sample_table()                           # discarded get_obs of cluster.py:89 (quirk Q4)
         od_noise = np.asarray([random.gauss(0, p.temp_prop.temp_std)])
@@ -341,46 +441,57 @@ class Environment:
         if mode == "random_sample":
             self._draw_sample_table()
             self._sim.set_comm_table(self._table)
-        self._sim.step_host(actions, od_noise, perlin, None if ids is None else ids)
-        self._pull()
-        rew = self._sim.views()["reward"][0].double().cpu().numpy()
-        return self.get_obs(), {i: float(rew[i]) for i in range(self.n)}
+        self._take(self._sim.step_host_snapshot(actions, od_noise, perlin, None if ids is None else ids))
+        return self.get_obs(), dict(enumerate(self._reward.tolist()))
 
     # ---- observations (environment.py:110-130, cluster.py:91-121, building.py:79-139) ------
     def get_obs(self) -> ObsDict:
         s = self._snap
         mp = self.init_props.cluster_prop.message_prop
         n = self.n
-        # plain Python lists: per-element numpy indexing would dominate the dict building
-        sso, on = s["sso"][0].tolist(), [bool(x) for x in s["on"][0].tolist()]
-        lock = [bool(x) for x in s["lockout"][0].tolist()]
-        ta, tm = s["t_air"][0].tolist(), s["t_mass"][0].tolist()
+        hvac_props, house_props = self._hvac_props, self._house_props
+        table = self._table
+        date_time, od_temp = self.date_time, self.current_od_temp
         solar, power, signal = float(s["solar"][0]), float(s["power"][0]), float(s["signal"][0])
-        msgs = []
-        for i in range(n):
-            hp_i, b = self._hvac_props[i], self._house_props[i]
-            pmax = hp_i.max_consumption
-            m = {
-                "seconds_since_off": sso[i],
-                "curr_consumption": pmax if on[i] else 0.0,
-                "max_consumption": pmax,
-                "lockout_duration": hp_i.lockout_duration,
-                "current_temp_diff_to_target": ta[i] - b.target_temp,
-            }
-            if mp.hvac:
-                m.update(cop=hp_i.cop, latent_cooling_fraction=hp_i.latent_cooling_fraction,
-                         cooling_capacity=hp_i.cooling_capacity)
-            if mp.thermal:
-                m.update(Ca=b.Ca, Ua=b.Ua, Cm=b.Cm, Hm=b.Hm)
-            msgs.append(m)
-        table = self._table.tolist() if self._table.shape[1] else [[] for _ in range(n)]
-        out = ObsDict()
-        for i in range(n):
-            hp_i, b = self._hvac_props[i], self._house_props[i]
-            out[i] = {
-                "turned_on": on[i],
-                "seconds_since_off": sso[i],
-                "lockout": lock[i],
+        lists: Dict[str, list] = {}
+        msgs: Dict[int, dict] = {}
+
+        def col(k):
+            # plain Python lists (per-element numpy indexing would dominate the dict building), made on first use
+            v = lists.get(k)
+            if v is None:
+                v = s[k][0].tolist()
+                if k in ("on", "lockout"):
+                    v = [bool(x) for x in v]
+                lists[k] = v
+            return v
+
+        def message(j):                                         # Building.message (building.py:102-139)
+            m = msgs.get(j)
+            if m is None:
+                hp_j, b = hvac_props[j], house_props[j]
+                pmax = hp_j.max_consumption
+                m = {
+                    "seconds_since_off": col("sso")[j],
+                    "curr_consumption": pmax if col("on")[j] else 0.0,
+                    "max_consumption": pmax,
+                    "lockout_duration": hp_j.lockout_duration,
+                    "current_temp_diff_to_target": col("t_air")[j] - b.target_temp,
+                }
+                if mp.hvac:
+                    m.update(cop=hp_j.cop, latent_cooling_fraction=hp_j.latent_cooling_fraction,
+                             cooling_capacity=hp_j.cooling_capacity)
+                if mp.thermal:
+                    m.update(Ca=b.Ca, Ua=b.Ua, Cm=b.Cm, Hm=b.Hm)
+                msgs[j] = m
+            return m
+
+        def build(i):
+            hp_i, b = hvac_props[i], house_props[i]
+            return {
+                "turned_on": col("on")[i],
+                "seconds_since_off": col("sso")[i],
+                "lockout": col("lockout")[i],
                 "cop": hp_i.cop,
                 "cooling_capacity": hp_i.cooling_capacity,
                 "latent_cooling_fraction": hp_i.latent_cooling_fraction,
@@ -388,16 +499,20 @@ class Environment:
                 "target_temp": b.target_temp,
                 "deadband": b.deadband,
                 "Ua": b.Ua, "Ca": b.Ca, "Cm": b.Cm, "Hm": b.Hm,
-                "indoor_temp": ta[i],
-                "mass_temp": tm[i],
+                "indoor_temp": col("t_air")[i],
+                "mass_temp": col("t_mass")[i],
                 "solar_gain": solar,
                 "cluster_hvac_power": power,
-                "message": [dict(msgs[j]) for j in table[i]],
-                "OD_temp": self.current_od_temp,
-                "datetime": self.date_time,
+                "message": [dict(message(int(j))) for j in table[i]] if table.shape[1] else [],
+                "OD_temp": od_temp,
+                "datetime": date_time,
                 "reg_signal": signal,
             }
+
+        out = ObsDict(build, n)
         out.vectors = self._vectors
+        if not getattr(self, "_lazy_obs", True):
+            out.materialize()
         return out
 
     # ---- deepcopy (training_manager.py:269) -----------------------------------------------

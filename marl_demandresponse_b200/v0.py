@@ -283,9 +283,8 @@ class MADemandResponseEnv(Environment):
             self._sim.set_comm_table(self._table)
         ids = self._draw_interp_ids(self._interp_will_fire())
         perlin = self._perlin_value()
-        self._sim.step_host(actions, od_noise, perlin, None if ids is None else ids)
-        self._pull()
-        rew = self._sim.views()["reward"][0].double().cpu().numpy()
+        self._take(self._sim.step_host_snapshot(actions, od_noise, perlin, None if ids is None else ids))
+        rew = self._reward
         obs = self.get_obs()
         rewards = {i: float(rew[i]) for i in range(self.n)}
         dones = {i: False for i in range(self.n)}       # :342-358
