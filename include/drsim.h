@@ -363,6 +363,29 @@ typedef struct drsim_actor_net {
 int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_t seed, float *prob_drawn, float *prob_on,
                       void *stream);
 
+/* One transition of an MA-PPO rollout ENTIRELY on the device, stored where the caller wants it:
+ * MAPPO.select_actions (mappo.py:83-97) on state_t, Environment.step (environment.py:72-108) on the drawn actions and
+ * MAPPO.store_transition (mappo.py:105-127; training_manager.py:224-240) in one call.  All DEVICE pointers, plane
+ * layout of the handle (row stride = house_stride); obs / reward / next_obs 16-byte aligned, actions / prob 4-byte
+ * aligned; the step kernels write the slot directly:
+ *   obs      [R][stride][obs_dim] f32  state_t the actor reads (NULL: the handle's own rows = the last step's result)
+ *   actions  [R][stride] u8            a_t drawn by the actor, consumed by the step            (Transition.action)
+ *   prob     [R][stride] f32           probability of a_t under the actor (mappo.py:95)        (Transition.a_log_prob)
+ *   reward   [R][stride] f32           r_t                                                       (Transition.reward)
+ *   next_obs [R][stride][obs_dim] f32  state_{t+1}: pass it as `obs` of the next transition     (Transition.next_state)
+ * Transition.others_actions is the `actions` plane without the agent's own entry; `done` is the caller's
+ * (training_manager.py:233: end of the episode).  The reference does not evaluate its critic during the rollout
+ * (mappo.py:99-103 is commented out): Critic(cat(state, others_actions)) runs in update() on these buffers. */
+typedef struct drsim_rollout_slot {
+  const void *obs;
+  uint8_t *actions;
+  float *prob;
+  void *reward;
+  void *next_obs;
+} drsim_rollout_slot;
+int drsim_rollout_transition(drsim_t *h, const drsim_actor_net *net, uint64_t seed, const drsim_rollout_slot *slot,
+                             void *stream);
+
 /* number of kernels launched by this handle since creation (bench.py "gpu_launches") */
 int64_t drsim_launch_count(const drsim_t *h);
 

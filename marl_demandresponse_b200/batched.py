@@ -248,6 +248,13 @@ class BatchedEnv:
         self.sim.step(None)
         return self._v["obs"], self._v["reward"], actions, prob
 
+    def collect(self, weights, buf, n_steps=None, seed: Optional[int] = None, done_last: bool = False):
+        """A rollout segment entirely on the device, stored in a :class:`~.rollout.RolloutBuffer` (SURVEY 8f-2:
+        ``select_actions`` + ``env.step`` + ``store_transition`` of mappo.py:83-127 per transition, one C call)."""
+        from .rollout import collect
+
+        return collect(self, weights, buf, n_steps, seed, done_last)
+
     def step_host(self, actions_host, env_out=None, reward_out=None, obs_out=None):
         """End-to-end step with HOST buffers: ``actions_host`` uint8 / bool ``[R, N]`` (pinned torch CPU
         tensor or numpy, values 0 / 1) is copied in, the per-replica results ``[R, 4]`` = (power, signal,

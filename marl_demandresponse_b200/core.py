@@ -555,7 +555,8 @@ class DrSim:
         v["flags"] = t(p.flags, (R, Ns), "|u1")[:, :N]
         v["actions"] = t(p.actions, (R, Ns), "|u1")[:, :N]
         v["actions_padded"] = t(p.actions, (R, Ns), "|u1")
-        v["obs"] = t(p.obs, (R, Ns, D), rt)[:, :N, :] if D else None
+        v["obs_padded"] = t(p.obs, (R, Ns, D), rt) if D else None
+        v["obs"] = v["obs_padded"][:, :N, :] if D else None
         v["epoch"] = t(p.epoch, (R,), "<i8")
         for k in ("od_temp", "signal", "base_power", "power", "solar", "pen_sum", "pen_max", "rew_sig"):
             v[k] = t(getattr(p, k), (R,), "<f8")

@@ -84,6 +84,8 @@ struct drsim_handle {
   int shard_grid = 0, shard_capacity = 0;
   bool shard_ok = false;
   size_t o_sh_partll = 0, o_sh_envll = 0, o_sh_pearly = 0, o_pinbox = 0, o_rowll = 0;
+  // drsim_rollout_transition: the step writes rewards / observation rows into the caller's transition slot
+  void *obs_override = nullptr, *reward_override = nullptr;
   // small host inputs of drsim_step_host (actions / noise / ids of a small cluster) are staged in pinned mapped
   // memory and READ IN PLACE by the kernel: no copy-engine call for a handful of bytes
   unsigned char *h_in = nullptr, *h_in_dev = nullptr;
@@ -128,8 +130,8 @@ static Planes<real> make_planes(const drsim_handle *h) {
   for (int k = 0; k < 4; ++k) pl.ratio[k] = h->has_ratio ? h->at<real>(h->o_ratio[k]) : nullptr;
   pl.interp_sub = h->has_interp ? h->at<uint8_t>(h->o_sub) : nullptr;
   pl.dur = h->has_dur ? h->at<int32_t>(h->o_dur) : nullptr;
-  pl.reward = h->at<real>(h->o_reward);
-  pl.obs = h->p.obs_dim ? h->at<real>(h->o_obs) : nullptr;
+  pl.reward = h->reward_override ? static_cast<real *>(h->reward_override) : h->at<real>(h->o_reward);
+  pl.obs = !h->p.obs_dim ? nullptr : (h->obs_override ? static_cast<real *>(h->obs_override) : h->at<real>(h->o_obs));
   pl.actions = h->at<uint8_t>(h->o_actions);
   pl.epoch = h->at<int64_t>(h->o_epoch);
   pl.od_temp = h->at<double>(h->o_od);
@@ -1748,8 +1750,42 @@ extern "C" int drsim_peer_status(drsim_t *h, void *stream) {
   return 0;
 }
 
+static int policy_step_impl(drsim_t *h, const drsim_actor_net *net, uint64_t seed, const float *obs_in, uint8_t *actions_out,
+                            float *prob_drawn, float *prob_on, void *stream);
+
 extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_t seed, float *prob_drawn, float *prob_on,
                                  void *stream) {
+  return policy_step_impl(h, net, seed, nullptr, nullptr, prob_drawn, prob_on, stream);
+}
+
+// MAPPO.select_actions + Environment.step + MAPPO.store_transition (mappo.py:83-127, training_manager.py:224-240) for
+// every agent of every replica, with the transition landing in the caller's device buffers: the actor reads
+// state_t from slot->obs and writes a_t / p(a_t) into the slot, the step consumes a_t from there and writes r_t and
+// state_{t+1} straight into the slot -- nothing is copied, nothing leaves the device.
+extern "C" int drsim_rollout_transition(drsim_t *h, const drsim_actor_net *net, uint64_t seed, const drsim_rollout_slot *slot,
+                                        void *stream) {
+  if (!h || !net || !slot) return fail(DRSIM_E_ARG, "null argument");
+  if (!slot->actions || !slot->prob || !slot->reward || !slot->next_obs)
+    return fail(DRSIM_E_ARG, "drsim_rollout_transition: actions, prob, reward and next_obs are required");
+  if (h->p.N != h->p.n_global) return fail(DRSIM_E_STATE, "drsim_rollout_transition: not available on a house-sharded cluster");
+  auto misaligned = [](const void *q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) != 0; };
+  if (misaligned(slot->obs, 16) || misaligned(slot->reward, 16) || misaligned(slot->next_obs, 16) || misaligned(slot->actions, 4) ||
+      misaligned(slot->prob, 4))
+    return fail(DRSIM_E_ARG, "drsim_rollout_transition: obs / reward / next_obs must be 16-byte aligned, actions / prob 4-byte aligned");
+  int rc = policy_step_impl(h, net, seed, static_cast<const float *>(slot->obs), slot->actions, slot->prob, nullptr, stream);
+  if (rc) return rc;
+  drsim_step_args a{};
+  a.actions = slot->actions;
+  h->obs_override = slot->next_obs;
+  h->reward_override = slot->reward;
+  rc = drsim_step(h, &a, stream);
+  h->obs_override = nullptr;
+  h->reward_override = nullptr;
+  return rc;
+}
+
+static int policy_step_impl(drsim_t *h, const drsim_actor_net *net, uint64_t seed, const float *obs_in, uint8_t *actions_out,
+                            float *prob_drawn, float *prob_on, void *stream) {
   if (!h || !net) return fail(DRSIM_E_ARG, "null argument");
   const SimParams &p = h->p;
   if (h->real_bytes != 4) return fail(DRSIM_E_ARG, "drsim_policy_step needs the fp32 build (observation rows are its input)");
@@ -1758,9 +1794,9 @@ extern "C" int drsim_policy_step(drsim_t *h, const drsim_actor_net *net, uint64_
   if (!net->w1 || !net->b1 || !net->w2 || !net->b2 || !net->w3 || !net->b3) return fail(DRSIM_E_ARG, "drsim_policy_step: null weight pointer");
   CU_TRY(cudaSetDevice(h->device));
   ActorArgs a{};
-  a.obs = h->at<float>(h->o_obs);
+  a.obs = obs_in ? obs_in : h->at<float>(h->o_obs);
   a.w1 = net->w1; a.b1 = net->b1; a.w2 = net->w2; a.b2 = net->b2; a.w3 = net->w3; a.b3 = net->b3;
-  a.actions = h->at<uint8_t>(h->o_actions);
+  a.actions = actions_out ? actions_out : h->at<uint8_t>(h->o_actions);
   a.prob = prob_drawn; a.prob_on = prob_on;
   a.rows = (long long)p.R * p.Ns;
   a.Ns = p.Ns; a.N = p.N; a.D = p.obs_dim; a.h1 = net->h1; a.h2 = net->h2;
