@@ -554,14 +554,22 @@ def run_gpu_arm(args, wl) -> None:
 
         seg = 8   # transitions per collected segment
         buf = RolloutBuffer(env, seg)
-        env.collect(weights, buf)
-        r_steps = max(seg, min(args.steps, 304) // seg * seg)
-        ms_pol = w.timed(lambda i: env.policy_step(weights), r_steps)
-        ms_roll = w.timed(lambda i: env.collect(weights, buf), r_steps // seg)
+        r_steps = max(seg, min(args.steps, 160) // seg * seg)
         flops = 2.0 * R * N * (D * 100 + 100 * 100 + 100 * 2)
-        rollout_line = {"value": world * R * N * r_steps / (ms_roll * 1e-3), "unit": "agent-steps/s",
-                        "us_per_transition": 1e3 * ms_roll / r_steps, "actor_us": 1e3 * ms_pol / r_steps,
-                        "actor_tflops": flops * r_steps / (ms_pol * 1e-3) / 1e12,
+        per = {}
+        for prec in ("tf32x3", "tf32"):   # fp32-grade probabilities (three passes per product) / one TF32 pass
+            env.collect(weights, buf, precision=prec)
+            ms_pol = w.timed(lambda i: env.policy_step(weights, precision=prec), r_steps)
+            ms_roll = w.timed(lambda i: env.collect(weights, buf, precision=prec), r_steps // seg)
+            per[prec] = {"us_per_transition": 1e3 * ms_roll / r_steps, "actor_us": 1e3 * ms_pol / r_steps,
+                         "actor_tflops": (3 if prec == "tf32x3" else 1) * flops * r_steps / (ms_pol * 1e-3) / 1e12,
+                         "value": world * R * N * r_steps / (ms_roll * 1e-3)}
+        rollout_line = {"value": per["tf32x3"]["value"], "unit": "agent-steps/s",
+                        "us_per_transition": per["tf32x3"]["us_per_transition"], "actor_us": per["tf32x3"]["actor_us"],
+                        "actor_tflops": per["tf32x3"]["actor_tflops"],
+                        "actor_precision": "tf32x3: every operand split into hi + lo TF32 halves, three tcgen05 passes per "
+                                           "product, probabilities within ~1e-6 of an fp32 forward (the parity-grade default)",
+                        "single_pass_tf32": per["tf32"],
                         "what": "device-resident rollout: MAPPO.select_actions (actor + categorical draw, mappo.py:83-97), "
                                 "Environment.step and MAPPO.store_transition (mappo.py:105-127) per transition in one C call "
                                 "(drsim_rollout_transition); state / action / probability / reward / next state land in a "

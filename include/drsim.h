@@ -352,6 +352,10 @@ typedef struct drsim_actor_net {
   const float *w2, *b2; /* [h2][h1], [h2] */
   const float *w3, *b3; /* [2][h2], [2] */
   int32_t h1, h2;       /* 1 .. 111 each */
+  /* 0 = one TF32 pass per product (|dp| <= 5e-3 against an fp32 forward), 1 = "3xTF32": every operand split into
+   * hi + lo TF32 halves, three tensor-core passes per product, fp32-grade probabilities (|dp| ~ 1e-6) */
+  int32_t precision;
+  int32_t pad_;
 } drsim_actor_net;
 
 /* MAPPO.select_actions (mappo.py:83-97) for every house of every replica, on the device:

@@ -92,7 +92,8 @@ class ActorNet(C.Structure):
     """Mirror of ``drsim_actor_net``."""
 
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
-                ("w3", C.c_void_p), ("b3", C.c_void_p), ("h1", C.c_int32), ("h2", C.c_int32)]
+                ("w3", C.c_void_p), ("b3", C.c_void_p), ("h1", C.c_int32), ("h2", C.c_int32),
+                ("precision", C.c_int32), ("pad_", C.c_int32)]
 
 
 class Ptrs(C.Structure):

@@ -225,7 +225,7 @@ class BatchedEnv:
                     b.detach().to(device="cuda", dtype=torch.float32).contiguous()]
         return tuple(out)
 
-    def policy_step(self, weights, seed: Optional[int] = None, want_prob: bool = True):
+    def policy_step(self, weights, seed: Optional[int] = None, want_prob: bool = True, precision: str = "tf32x3"):
         """``MAPPO.select_actions`` (mappo.py:83-97) for all ``R * N`` agents in one kernel: actor
         forward on the current observation rows (tcgen05 TF32 GEMMs), softmax, categorical draw from a
         Philox uniform keyed (seed, replica, house, step).  The drawn actions land in the action plane
@@ -238,22 +238,23 @@ class BatchedEnv:
             if getattr(self, "_prob", None) is None:
                 self._prob = torch.zeros((sim.R, sim.Ns), dtype=torch.float32, device=f"cuda:{self.device}")
             prob = self._prob
-        sim.policy_step(weights, self.seed if seed is None else seed, prob_drawn=prob)
+        sim.policy_step(weights, self.seed if seed is None else seed, prob_drawn=prob, precision=precision)
         return self._v["actions"], (prob[:, :sim.N] if prob is not None else None)
 
-    def rollout_step(self, weights, seed: Optional[int] = None):
+    def rollout_step(self, weights, seed: Optional[int] = None, precision: str = "tf32x3"):
         """One transition of a rollout entirely on the device: actor + draw, then the environment
         step on the drawn actions.  Returns ``(obs', reward, actions, prob_of_drawn_action)``."""
-        actions, prob = self.policy_step(weights, seed)
+        actions, prob = self.policy_step(weights, seed, precision=precision)
         self.sim.step(None)
         return self._v["obs"], self._v["reward"], actions, prob
 
-    def collect(self, weights, buf, n_steps=None, seed: Optional[int] = None, done_last: bool = False):
+    def collect(self, weights, buf, n_steps=None, seed: Optional[int] = None, done_last: bool = False,
+                precision: str = "tf32x3"):
         """A rollout segment entirely on the device, stored in a :class:`~.rollout.RolloutBuffer` (SURVEY 8f-2:
         ``select_actions`` + ``env.step`` + ``store_transition`` of mappo.py:83-127 per transition, one C call)."""
         from .rollout import collect
 
-        return collect(self, weights, buf, n_steps, seed, done_last)
+        return collect(self, weights, buf, n_steps, seed, done_last, precision=precision)
 
     def step_host(self, actions_host, env_out=None, reward_out=None, obs_out=None):
         """End-to-end step with HOST buffers: ``actions_host`` uint8 / bool ``[R, N]`` (pinned torch CPU

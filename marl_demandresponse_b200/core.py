@@ -486,14 +486,23 @@ class DrSim:
         _lib.check(self._L.drsim_step_host_snapshot(self._h, *args, C.byref(v), self._stream(stream)))
         return self._snapshot_arrays(v)
 
-    def policy_step(self, weights, seed: int = 0, prob_drawn=None, prob_on=None, stream=None) -> None:
-        """``drsim_policy_step``: the reference's MA-PPO actor + categorical draw on the observation rows.
-        ``weights`` = (w1, b1, w2, b2, w3, b3) contiguous fp32 CUDA tensors in ``torch.nn.Linear`` layout;
-        ``prob_drawn`` / ``prob_on``: optional fp32 CUDA tensors ``[R, Ns]``."""
+    ACTOR_PRECISION = {"tf32": 0, "tf32x3": 1}
+
+    def actor_net(self, weights, precision: str = "tf32x3") -> "_lib.ActorNet":
         w1, b1, w2, b2, w3, b3 = weights
         net = _lib.ActorNet()
         net.w1, net.b1, net.w2, net.b2, net.w3, net.b3 = (self._ptr(t) for t in (w1, b1, w2, b2, w3, b3))
         net.h1, net.h2 = int(w1.shape[0]), int(w2.shape[0])
+        net.precision = self.ACTOR_PRECISION[precision]
+        return net
+
+    def policy_step(self, weights, seed: int = 0, prob_drawn=None, prob_on=None, stream=None, precision: str = "tf32x3") -> None:
+        """``drsim_policy_step``: the reference's MA-PPO actor + categorical draw on the observation rows.
+        ``weights`` = (w1, b1, w2, b2, w3, b3) contiguous fp32 CUDA tensors in ``torch.nn.Linear`` layout;
+        ``prob_drawn`` / ``prob_on``: optional fp32 CUDA tensors ``[R, Ns]``; ``precision``: "tf32x3" (three
+        tensor-core passes per product on hi / lo operand halves: fp32-grade probabilities) or "tf32" (one pass)."""
+        w1, b1, w2, b2, w3, b3 = weights
+        net = self.actor_net(weights, precision)
         assert tuple(w1.shape) == (net.h1, self.D) and tuple(w2.shape) == (net.h2, net.h1) and tuple(w3.shape) == (2, net.h2)
         _lib.check(self._L.drsim_policy_step(self._h, C.byref(net), int(seed) & (2 ** 64 - 1), self._ptr(prob_drawn),
                                              self._ptr(prob_on), self._stream(stream)))

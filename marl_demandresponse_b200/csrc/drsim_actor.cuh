@@ -406,6 +406,249 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"((uint32_t)kAct2TmemCols) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------
+// k_actor3x: the same network at fp32-grade accuracy on the same tensor cores ("3xTF32").
+//
+// A TF32 operand keeps 10 mantissa bits; splitting every operand into hi = tf32(x) and lo = tf32(x - hi) and
+// accumulating  A_hi W_hi + A_lo W_hi + A_hi W_lo  in the fp32 accumulator recovers ~21 bits per product (the
+// dropped A_lo W_lo term is 2^-22 relative): probabilities agree with a plain fp32 forward to ~1e-6 instead of
+// the 5e-3 of the single-pass kernel.  The hidden activations still never leave tensor memory -- each epilogue
+// writes BOTH halves: hi in place, lo into a second column range -- which is why this variant runs ONE tile
+// slot per CTA: R1 | L1 | R2 | L2 | R3 = 2 (N1 + N2) + 16 = 464 of the 512 TMEM columns.  All 512 threads serve
+// that slot (four threads per row, a quarter of the columns each), the two-tile software pipeline of k_actor2 is
+// unchanged.  Weight image: hi operands of the three layers, then the lo operands (k_actor_pack3x).
+// ------------------------------------------------------------------------------------------------
+DRSIM_D void pack_weights_split(unsigned char *dst_hi, unsigned char *dst_lo, const float *w, const float *b, int n_out, int n_in,
+                                int Np, int Kp, bool gen_one, int tid, int nthreads) {
+  for (int e = tid; e < Np * Kp; e += nthreads) {
+    const int n = e / Kp, k = e - n * Kp;
+    float v = 0.f;
+    if (n < n_out) v = k < n_in ? __ldg(w + (size_t)n * n_in + k) : (k == n_in ? __ldg(b + n) : 0.f);
+    else if (n == n_out && gen_one && k == n_in) v = 1.f;
+    const float hi = to_tf32(v);
+    const int off = umma_kmajor_off(Np, n, k);
+    *reinterpret_cast<float *>(dst_hi + off) = hi;
+    *reinterpret_cast<float *>(dst_lo + off) = to_tf32(v - hi);
+  }
+}
+
+// image = [w1_hi | w2_hi | w3_hi | w1_lo | w2_lo | w3_lo]; the lo block starts at a.off_a1 / 2
+__global__ void k_actor_pack3x(ActorArgs a, unsigned char *image) {
+  pdl_trigger();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  unsigned char *lo = image + a.off_a1 / 2;
+  pack_weights_split(image + a.off_w1, lo + a.off_w1, a.w1, a.b1, a.h1, a.D, a.N1, a.K1, true, tid, nt);
+  pack_weights_split(image + a.off_w2, lo + a.off_w2, a.w2, a.b2, a.h2, a.h1, a.N2, a.K2, true, tid, nt);
+  pack_weights_split(image + a.off_vec, lo + a.off_vec, a.w3, a.b3, 2, a.h2, kActN3, a.K3, false, tid, nt);
+}
+
+// ReLU of the accumulator columns [c_begin, c_end) of this thread's TMEM lane, split into hi (in place) and lo
+DRSIM_D void tmem_relu_split(uint32_t lane_hi, uint32_t lane_lo, int c_begin, int c_end) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    uint32_t r[16], l[16];
+    tmem_ld16_issue(lane_hi + (uint32_t)c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x = fmaxf(__uint_as_float(r[j]), 0.f);
+      const float hi = to_tf32(x);
+      r[j] = __float_as_uint(hi);
+      l[j] = __float_as_uint(to_tf32(x - hi));
+    }
+    tmem_st16(lane_hi + (uint32_t)c0, r);
+    tmem_st16(lane_lo + (uint32_t)c0, l);
+  }
+  tmem_wait_st();
+}
+
+__global__ void __launch_bounds__(kAct2Threads, 1) k_actor3x(ActorArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int w_bytes = a.off_a1 / 2;   // size of one (hi or lo) weight block
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // 0 GEMM1, 1 bulk copy, 2 GEMM2, 3 GEMM3, 4 weights
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 6);
+  // t = row of the tile (= TMEM lane); part = which quarter of the row's columns this thread handles
+  const int tid = threadIdx.x, warp = tid >> 5, t = tid & 127, part = tid >> 7;
+  const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
+  const int a1_bytes = kActRows * a.K1 * 4;
+  const int k3 = a.K3;
+  unsigned char *s_a1h = smem + a.off_a1, *s_a1l = s_a1h + a1_bytes;   // observation operand, hi and lo
+  uint64_t *wbar = s_bar + 4;
+
+  for (int row = tid; row < kActRows; row += kAct2Threads)              // constant-one column (hi only), zero padding
+    for (int k = a.D; k < a.K1; ++k) {
+      *reinterpret_cast<float *>(s_a1h + umma_kmajor_off(kActRows, row, k)) = k == a.D ? 1.f : 0.f;
+      *reinterpret_cast<float *>(s_a1l + umma_kmajor_off(kActRows, row, k)) = 0.f;
+    }
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + i)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_tmem)),
+                 "r"((uint32_t)kAct2TmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  if (tid == 0) {       // the packed weight image (hi + lo): one TMA bulk copy per CTA
+    mbar_expect_tx(wbar, (uint32_t)a.off_a1);
+    bulk_load_g2s(smem, a.image, (uint32_t)a.off_a1, wbar);
+  }
+  const uint32_t tmem = *s_tmem;
+  const uint32_t R1 = tmem, L1 = tmem + (uint32_t)a.N1, R2 = tmem + (uint32_t)(2 * a.N1), L2 = R2 + (uint32_t)a.N2,
+                 R3 = R2 + (uint32_t)(2 * a.N2);
+  const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2),
+                 idesc3 = umma_instr_desc_tf32(kActRows, kActN3);
+  const uint32_t w1h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w1), w2h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w2),
+                 w3h = (uint32_t)__cvta_generic_to_shared(smem + a.off_vec);
+  const uint32_t w1l = w1h + (uint32_t)w_bytes, w2l = w2h + (uint32_t)w_bytes, w3l = w3h + (uint32_t)w_bytes;
+  const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128, lbo_w3 = (kActN3 / 8) * 128;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lane quadrant
+  const uint32_t a1h = (uint32_t)__cvta_generic_to_shared(s_a1h), a1l = (uint32_t)__cvta_generic_to_shared(s_a1l);
+  uint64_t *bar1 = s_bar, *bar2 = s_bar + 2, *bar3 = s_bar + 3;
+  uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
+  const bool issuer = tid == 0;
+
+  // The weight halves leave no room for a staging buffer of the next tile's rows (D = 50: 2 x 78 KB of weights +
+  // 2 x 28 KB of operand): every thread instead keeps ITS quarter of its row of the next tile in registers, loaded
+  // one pipeline round ahead (the rows were just written by the env step: L2 hits).
+  constexpr int kPre = 16;                                   // ceil(64 / 4)
+  const int kq = (a.D + 3) / 4, k_lo = min(a.D, part * kq), k_hi = min(a.D, k_lo + kq);
+  float pre[kPre];
+  auto fetch = [&](int tile) {
+    const long long row = (long long)tile * kActRows + t;
+    const bool live = row < a.rows;
+    const float *g = a.obs + (size_t)row * a.D;
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) pre[j] = (live && k_lo + j < k_hi) ? __ldg(g + k_lo + j) : 0.f;
+  };
+  // the three passes of one K step: hi.hi, lo.hi, hi.lo (operand A from shared memory / from tensor memory)
+  auto mma3_ss = [&](uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t lbo_b, uint32_t idesc, int ksteps) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint64_t dah = umma_smem_desc(ah + ks * 2 * lbo_a, lbo_a, 128), dal = umma_smem_desc(al + ks * 2 * lbo_a, lbo_a, 128);
+      const uint64_t dbh = umma_smem_desc(bh + ks * 2 * lbo_b, lbo_b, 128), dbl = umma_smem_desc(bl + ks * 2 * lbo_b, lbo_b, 128);
+      umma_tf32_ss(d, dah, dbh, idesc, ks > 0);
+      umma_tf32_ss(d, dal, dbh, idesc, 1);
+      umma_tf32_ss(d, dah, dbl, idesc, 1);
+    }
+  };
+  auto mma3_ts = [&](uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t lbo_b, uint32_t idesc, int ksteps) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const uint64_t dbh = umma_smem_desc(bh + ks * 2 * lbo_b, lbo_b, 128), dbl = umma_smem_desc(bl + ks * 2 * lbo_b, lbo_b, 128);
+      umma_tf32_ts(d, ah + (uint32_t)(ks * 8), dbh, idesc, ks > 0);
+      umma_tf32_ts(d, al + (uint32_t)(ks * 8), dbh, idesc, 1);
+      umma_tf32_ts(d, ah + (uint32_t)(ks * 8), dbl, idesc, 1);
+    }
+  };
+  // this thread's quarter of `cols` columns, in 16-column granules
+  auto quarter = [&](int cols, int &lo, int &hi) {
+    const int q = ((cols + 3) / 4 + 15) & ~15;
+    lo = min(cols, part * q);
+    hi = min(cols, lo + q);
+  };
+
+  const int stride = gridDim.x;
+  int tile_b = blockIdx.x, tile_a = -1;
+  if (tile_b < n_tiles) fetch(tile_b);
+  if (issuer) mbar_wait_bounded(wbar, 0);
+  while (tile_b < n_tiles || tile_a >= 0) {
+    const bool has_b = tile_b < n_tiles, has_a = tile_a >= 0;
+    if (has_b) {   // ---- S1(b): re-tile the observation rows into hi / lo operands, GEMM1 -> R1
+      const int row_off = umma_kmajor_off(kActRows, t, 0);
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        const int k = k_lo + j;
+        if (k < k_hi) {
+          const float v = pre[j], hi = to_tf32(v);
+          const int off = row_off + (k >> 2) * (int)((kActRows / 8) * 128) + (k & 3) * 4;
+          *reinterpret_cast<float *>(s_a1h + off) = hi;
+          *reinterpret_cast<float *>(s_a1l + off) = to_tf32(v - hi);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncthreads();
+      if (tile_b + stride < n_tiles) fetch(tile_b + stride);   // in flight during the next stages
+      if (issuer) {
+        tc_fence_after();
+        mma3_ss(R1, a1h, a1l, w1h, w1l, lbo_w1, idesc1, a.K1 / 8);
+        umma_commit(bar1);
+      }
+    }
+    if (has_a) {   // ---- S2(a): A3 = relu(D2) as hi (in place) + lo, GEMM3 -> R3
+      mbar_wait_bounded(bar2, ph2);
+      ph2 ^= 1u;
+      tc_fence_after();
+      int c0, c1;
+      quarter(k3, c0, c1);
+      tmem_relu_split(R2 + lane_off, L2 + lane_off, c0, c1);
+      tc_fence_before();
+      __syncthreads();
+      if (issuer) {
+        tc_fence_after();
+        mma3_ts(R3, R2, L2, w3h, w3l, lbo_w3, idesc3, k3 / 8);
+        umma_commit(bar3);
+      }
+    }
+    if (has_b) {   // ---- S3(b): A2 = relu(D1) as hi + lo, GEMM2 -> R2
+      mbar_wait_bounded(bar1, ph1);
+      ph1 ^= 1u;
+      tc_fence_after();
+      int c0, c1;
+      quarter(a.K2, c0, c1);
+      tmem_relu_split(R1 + lane_off, L1 + lane_off, c0, c1);
+      tc_fence_before();
+      __syncthreads();
+      if (issuer) {
+        tc_fence_after();
+        mma3_ts(R2, R1, L1, w2h, w2l, lbo_w2, idesc2, a.K2 / 8);
+        umma_commit(bar2);
+      }
+    }
+    if (has_a) {   // ---- S4(a): softmax + categorical draw
+      mbar_wait_bounded(bar3, ph3);
+      ph3 ^= 1u;
+      tc_fence_after();
+      uint32_t lg[16];
+      tmem_ld16_issue(R3 + lane_off, lg);
+      tmem_wait_ld();
+      const float l0 = __uint_as_float(lg[0]), l1 = __uint_as_float(lg[1]);
+      const long long row = (long long)tile_a * kActRows + t;
+      if (row < a.rows && part == 0) {
+        const long long rr = row / a.Ns;
+        const int n = (int)(row - rr * a.Ns);
+        uint8_t act = 0;
+        float p_draw = 0.f, p1 = 0.f;
+        if (n < a.N) {
+          const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
+          const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+          const float p0 = e0 / (e0 + e1);
+          p1 = e1 / (e0 + e1);
+          const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + rr), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
+          const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
+          act = uf < p0 ? 0 : 1;
+          p_draw = act ? p1 : p0;
+        }
+        a.actions[row] = act;
+        if (a.prob) a.prob[row] = p_draw;
+        if (a.prob_on) a.prob_on[row] = p1;
+      }
+    }
+    tile_a = has_b ? tile_b : -1;
+    tile_b += stride;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"((uint32_t)kAct2TmemCols) : "memory");
+}
 #endif  // __CUDACC__
 
 }  // namespace drsim

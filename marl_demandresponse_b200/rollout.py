@@ -81,7 +81,7 @@ class RolloutBuffer:
 
 
 def collect(env, weights, buf: RolloutBuffer, n_steps: Optional[int] = None, seed: Optional[int] = None,
-            done_last: bool = False, stream=None) -> RolloutBuffer:
+            done_last: bool = False, stream=None, precision: str = "tf32x3") -> RolloutBuffer:
     """``n_steps`` (default: the buffer's horizon) rollout transitions on the device, stored in ``buf``:
     per transition ONE C call (``drsim_rollout_transition``: actor + categorical draw, then the environment step
     writing reward and next observation rows straight into the buffer)."""
@@ -89,10 +89,7 @@ def collect(env, weights, buf: RolloutBuffer, n_steps: Optional[int] = None, see
     T = buf.T if n_steps is None else int(n_steps)
     if T > buf.T:
         raise ValueError("n_steps exceeds the buffer's horizon")
-    w1, b1, w2, b2, w3, b3 = weights
-    net = _lib.ActorNet()
-    net.w1, net.b1, net.w2, net.b2, net.w3, net.b3 = (sim._ptr(t) for t in (w1, b1, w2, b2, w3, b3))
-    net.h1, net.h2 = int(w1.shape[0]), int(w2.shape[0])
+    net = sim.actor_net(weights, precision)
     buf.obs[0].copy_(sim.views()["obs_padded"])     # state_0 = the rows of the last step / reset (one copy per segment)
     seed = env.seed if seed is None else int(seed)
     st = sim._stream(stream)

@@ -290,6 +290,16 @@ def test_step_host_full_returns_obs_and_reward(n, R, layout):
         envs[1].step_host(torch.zeros((R, n + 1), dtype=torch.uint8), env_pin)   # wrong shape
 
 
+def _forward64(fc, x):
+    """The same network evaluated in fp64 (the yardstick both fp32 evaluations are measured against)."""
+    import torch
+
+    x = x.double()
+    x = torch.relu(x @ fc[0].weight.double().T + fc[0].bias.double())
+    x = torch.relu(x @ fc[1].weight.double().T + fc[1].bias.double())
+    return x @ fc[2].weight.double().T + fc[2].bias.double()
+
+
 def _torch_actor(D, h1, h2, seed):
     """The reference's Actor (network.py:14-35) restated in plain PyTorch fp32."""
     import torch
@@ -335,7 +345,16 @@ def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
         p_ref = forward(obs.reshape(-1, D)).reshape(R, n, 2)
     prob_on = torch.zeros((R, env.sim.Ns), dtype=torch.float32, device="cuda")
     prob = torch.zeros_like(prob_on)
-    env.sim.policy_step(weights, seed=99, prob_drawn=prob, prob_on=prob_on)
+    # "tf32x3" (default): operands split into hi + lo TF32 halves, three passes per product -> fp32-grade
+    env.sim.policy_step(weights, seed=99, prob_on=prob_on, precision="tf32x3")
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        p_ref64 = torch.softmax(_forward64(fc, obs.reshape(-1, D)), dim=1).reshape(R, n, 2)
+    err3 = float((prob_on[:, :n].double() - p_ref64[..., 1]).abs().max())
+    ref_err = float((p_ref.double() - p_ref64).abs().max())     # what a plain fp32 forward is off by itself
+    assert err3 <= 2e-6 + 2 * ref_err, (err3, ref_err)
+    # "tf32": one pass, 10-bit operands
+    env.sim.policy_step(weights, seed=99, prob_drawn=prob, prob_on=prob_on, precision="tf32")
     torch.cuda.synchronize()
     act = env.state["actions"][:, :n].clone()
     p_on = prob_on[:, :n]
