@@ -8,6 +8,9 @@ Public surface
 ``norm_state_dict`` the reference's observation normaliser, served from device tensors.
 ``MADemandResponseEnv`` / ``norm_state_dict_v0``  the legacy gym-style env of ``server/v0`` (``v0.py``).
 ``ClientFeed``      the reference's UI feed payloads (``ClientManagerService``) from the simulator's tensors.
+``ReferenceMetrics`` the reference's ``Metrics.update`` (metrics_service.py:108-157), literally, on the device.
+``RolloutBuffer``   device-resident MA-PPO transition storage filled by ``BatchedEnv.collect`` (mappo.py:83-127).
+``ShardedClusterEnv`` one very large cluster split by houses across the GPUs of a box.
 ``DrSim``           thin owner of the C handle (``include/drsim.h``).
 
 The CUDA extension (``libdrsim.so``, sm_100a) is mandatory; there is no CPU fallback.
@@ -33,4 +36,16 @@ def __getattr__(name):
         from . import ui_feed
 
         return getattr(ui_feed, name)
+    if name == "ReferenceMetrics":
+        from . import metrics
+
+        return metrics.ReferenceMetrics
+    if name == "RolloutBuffer":
+        from . import rollout
+
+        return rollout.RolloutBuffer
+    if name == "ShardedClusterEnv":
+        from . import sharded
+
+        return sharded.ShardedClusterEnv
     raise AttributeError(name)

@@ -1,0 +1,15 @@
+# run on the GPU box (1 GPU): the round-2 evidence set -> gpurun_out/
+set -x
+python bench.py > gpurun_out/r2_bench_c4_1gpu.json 2> gpurun_out/r2_bench_c4_1gpu.err
+for wl in c3 c5 c2 c1; do
+  python bench.py --workload $wl --no-c5 > gpurun_out/r2_bench_${wl}_1gpu.json 2> gpurun_out/r2_bench_${wl}_1gpu.err
+done
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null
+bash profiles/tools/capture_traffic.sh > gpurun_out/capture_traffic.log 2>&1
+python profiles/tools/time_dropin.py 10 100 1000 > gpurun_out/r2_dropin_times.txt 2>&1
+python profiles/tools/time_actor.py > gpurun_out/r2_actor_times.txt 2>&1
+python profiles/tools/shard_phases.py 1000000 1 > gpurun_out/r2_shard_phases_1gpu.txt 2>&1
+# one full ncu capture of each dominant kernel (source-level), after the plain runs above exited 0
+ncu --set full --clock-control none --import-source on -k regex:k_shard -s 30 -c 1 -o gpurun_out/r2_kshard_c5 -f python bench.py --workload c5 --steps 60 --no-cpu > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_fused_tma -s 30 -c 1 -o gpurun_out/r2_kfused_c4 -f python bench.py --workload c4 --steps 60 --no-cpu --no-c5 --no-rollout > /dev/null 2>&1
+ls -la gpurun_out | tail -30
