@@ -41,6 +41,7 @@ struct ActorArgs {
   int Ns, N, D, h1, h2;
   int K1, N1, K2, N2, K3;  // padded: K multiple of 8 (UMMA_K of tf32), N multiple of 16 (K3: k_actor2's output layer)
   int off_w1, off_w2, off_a1, off_a2, off_vec, off_bar, smem_bytes;
+  int off_w3, w_bytes;     // k_actor3x: the fp32 output layer in the image; size of one (hi or lo) weight block
   unsigned long long seed;
   long long step, rep_offset;
 };
@@ -413,12 +414,26 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
 // A TF32 operand keeps 10 mantissa bits; splitting every operand into hi = tf32(x) and lo = tf32(x - hi) and
 // accumulating  A_hi W_hi + A_lo W_hi + A_hi W_lo  in the fp32 accumulator recovers ~21 bits per product (the
 // dropped A_lo W_lo term is 2^-22 relative): probabilities agree with a plain fp32 forward to ~1e-6 instead of
-// the 5e-3 of the single-pass kernel.  The hidden activations still never leave tensor memory -- each epilogue
-// writes BOTH halves: hi in place, lo into a second column range -- which is why this variant runs ONE tile
-// slot per CTA: R1 | L1 | R2 | L2 | R3 = 2 (N1 + N2) + 16 = 464 of the 512 TMEM columns.  All 512 threads serve
-// that slot (four threads per row, a quarter of the columns each), the two-tile software pipeline of k_actor2 is
-// unchanged.  Weight image: hi operands of the three layers, then the lo operands (k_actor_pack3x).
+// the 5e-3 of the single-pass kernel.
+//
+// Structure: ONE CTA per SM, three warp-specialised roles decoupled by mbarriers (no CTA barrier in the loop):
+//   * producers (warps 0-7, two threads per row): the observation rows of the NEXT tile wait in registers; they
+//     are split into the hi / lo operands of layer 1 in shared memory (16-byte stores, canonical K-major layout),
+//     and after GEMM1 the accumulator R1 is turned into the layer-2 operand IN tensor memory: ReLU, hi in place,
+//     lo into a second column range L1.  This pass is pipelined with GEMM2 by 32-column chunks: a chunk's K steps
+//     are issued as soon as all rows have published it, so the tensor pipe idles for the first chunk only;
+//   * the MMA warp (warp 12, one thread): GEMM1 (shared x shared) and GEMM2 (A from tensor memory), three passes
+//     per K step, completion by tcgen05.commit on mbarriers;
+//   * consumers (warps 8-11, one thread per row): the layer-2 accumulator R2 is DOUBLE-buffered in tensor memory, so tile i's
+//     epilogue overlaps tile i+1's GEMMs: ReLU + the 2-wide output layer in plain fp32 FMAs straight from the
+//     tcgen05.ld registers (no third GEMM, no split, no write-back), softmax, Philox draw.
+// Tensor memory: R1 | L1 | R2[0] | R2[1] = 2 N1 + 2 N2 <= 512 columns.  Weight image (k_actor_pack3x):
+// [w1_hi | w2_hi | w1_lo | w2_lo | w3 fp32 [2][N2] zero-padded, b3[2]], one TMA bulk copy per CTA.
 // ------------------------------------------------------------------------------------------------
+constexpr int kAct3Threads = 416;    // 8 producer warps + 4 consumer warps + the MMA warp (13 warps: 128 registers each)
+constexpr int kAct3MaxChunks = 5;    // 32-column chunks of the layer-2 operand (N1 <= 144)
+constexpr int kAct3PreChunks = 9;    // 16-byte K chunks in HALF an observation row (K1 <= 72)
+
 DRSIM_D void pack_weights_split(unsigned char *dst_hi, unsigned char *dst_lo, const float *w, const float *b, int n_out, int n_in,
                                 int Np, int Kp, bool gen_one, int tid, int nthreads) {
   for (int e = tid; e < Np * Kp; e += nthreads) {
@@ -433,56 +448,54 @@ DRSIM_D void pack_weights_split(unsigned char *dst_hi, unsigned char *dst_lo, co
   }
 }
 
-// image = [w1_hi | w2_hi | w3_hi | w1_lo | w2_lo | w3_lo]; the lo block starts at a.off_a1 / 2
 __global__ void k_actor_pack3x(ActorArgs a, unsigned char *image) {
   pdl_trigger();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
-  unsigned char *lo = image + a.off_a1 / 2;
+  unsigned char *lo = image + a.w_bytes;
   pack_weights_split(image + a.off_w1, lo + a.off_w1, a.w1, a.b1, a.h1, a.D, a.N1, a.K1, true, tid, nt);
-  pack_weights_split(image + a.off_w2, lo + a.off_w2, a.w2, a.b2, a.h2, a.h1, a.N2, a.K2, true, tid, nt);
-  pack_weights_split(image + a.off_vec, lo + a.off_vec, a.w3, a.b3, 2, a.h2, kActN3, a.K3, false, tid, nt);
-}
-
-// ReLU of the accumulator columns [c_begin, c_end) of this thread's TMEM lane, split into hi (in place) and lo
-DRSIM_D void tmem_relu_split(uint32_t lane_hi, uint32_t lane_lo, int c_begin, int c_end) {
-  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-    uint32_t r[16], l[16];
-    tmem_ld16_issue(lane_hi + (uint32_t)c0, r);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float x = fmaxf(__uint_as_float(r[j]), 0.f);
-      const float hi = to_tf32(x);
-      r[j] = __float_as_uint(hi);
-      l[j] = __float_as_uint(to_tf32(x - hi));
-    }
-    tmem_st16(lane_hi + (uint32_t)c0, r);
-    tmem_st16(lane_lo + (uint32_t)c0, l);
+  pack_weights_split(image + a.off_w2, lo + a.off_w2, a.w2, a.b2, a.h2, a.h1, a.N2, a.K2, false, tid, nt);
+  float *w3 = reinterpret_cast<float *>(image + a.off_w3);     // output layer in plain fp32: [2][N2], then b3
+  for (int e = tid; e < 2 * a.N2 + 2; e += nt) {
+    const int n = e / a.N2, k = e - n * a.N2;
+    w3[e] = e >= 2 * a.N2 ? __ldg(a.b3 + (e - 2 * a.N2)) : (k < a.h2 ? __ldg(a.w3 + (size_t)n * a.h2 + k) : 0.f);
   }
-  tmem_wait_st();
 }
 
-__global__ void __launch_bounds__(kAct2Threads, 1) k_actor3x(ActorArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const int w_bytes = a.off_a1 / 2;   // size of one (hi or lo) weight block
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);   // 0 GEMM1, 1 bulk copy, 2 GEMM2, 3 GEMM3, 4 weights
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 6);
-  // t = row of the tile (= TMEM lane); part = which quarter of the row's columns this thread handles
-  const int tid = threadIdx.x, warp = tid >> 5, t = tid & 127, part = tid >> 7;
-  const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
-  const int a1_bytes = kActRows * a.K1 * 4;
-  const int k3 = a.K3;
-  unsigned char *s_a1h = smem + a.off_a1, *s_a1l = s_a1h + a1_bytes;   // observation operand, hi and lo
-  uint64_t *wbar = s_bar + 4;
+DRSIM_D void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// tcgen05.wait::ld that also DEFINES the registers of the load it completes: nothing computed from them can be
+// scheduled above it
+DRSIM_D void tmem_wait_ld_dep(uint32_t r[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
-  for (int row = tid; row < kActRows; row += kAct2Threads)              // constant-one column (hi only), zero padding
-    for (int k = a.D; k < a.K1; ++k) {
-      *reinterpret_cast<float *>(s_a1h + umma_kmajor_off(kActRows, row, k)) = k == a.D ? 1.f : 0.f;
-      *reinterpret_cast<float *>(s_a1l + umma_kmajor_off(kActRows, row, k)) = 0.f;
-    }
+__global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // mbarriers: 0 a1_ready (256) | 1 GEMM1 done | 2..6 a2_ready[chunk] (256) | 7, 8 GEMM2 done [slot] |
+  //            9, 10 R2 slot drained (128) | 11 weight image
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);
+  uint64_t *a1_ready = s_bar, *bar1 = s_bar + 1, *a2_ready = s_bar + 2, *bar2 = s_bar + 7, *r2_free = s_bar + 9, *wbar = s_bar + 11;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 12);
+  const int tid = threadIdx.x, warp = tid >> 5, role = warp < 8 ? 0 : (warp < 12 ? 1 : 2);   // producer, consumer, MMA warp
+  const int t = tid & 127, part = (tid >> 7) & 1;                   // row of the tile (= TMEM lane), column half
+  const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
+  const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  unsigned char *s_a1h = smem + a.off_a1, *s_a1l = s_a1h + kActRows * a.K1 * 4;   // observation operand, hi and lo
+
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_bar + i)));
+    mbar_init(a1_ready, 256);
+    mbar_init(bar1, 1);
+    for (int k = 0; k < kAct3MaxChunks; ++k) mbar_init(a2_ready + k, 256);
+    mbar_init(bar2, 1);
+    mbar_init(bar2 + 1, 1);
+    mbar_init(r2_free, 128);
+    mbar_init(r2_free + 1, 128);
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -492,157 +505,204 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor3x(ActorArgs a) {
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();
-  if (tid == 0) {       // the packed weight image (hi + lo): one TMA bulk copy per CTA
+  pdl_trigger();   // the env step behind us may become resident (it waits for our completion before it reads actions)
+  pdl_wait();      // the packed image, the observation rows; the action plane may still be read by the step before us
+  if (tid == 0) {  // the packed weight image (hi + lo + output layer): one TMA bulk copy per CTA
     mbar_expect_tx(wbar, (uint32_t)a.off_a1);
     bulk_load_g2s(smem, a.image, (uint32_t)a.off_a1, wbar);
   }
   const uint32_t tmem = *s_tmem;
-  const uint32_t R1 = tmem, L1 = tmem + (uint32_t)a.N1, R2 = tmem + (uint32_t)(2 * a.N1), L2 = R2 + (uint32_t)a.N2,
-                 R3 = R2 + (uint32_t)(2 * a.N2);
-  const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2),
-                 idesc3 = umma_instr_desc_tf32(kActRows, kActN3);
-  const uint32_t w1h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w1), w2h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w2),
-                 w3h = (uint32_t)__cvta_generic_to_shared(smem + a.off_vec);
-  const uint32_t w1l = w1h + (uint32_t)w_bytes, w2l = w2h + (uint32_t)w_bytes, w3l = w3h + (uint32_t)w_bytes;
-  const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128, lbo_w3 = (kActN3 / 8) * 128;
+  const uint32_t R1 = tmem, L1 = tmem + (uint32_t)a.N1, R2 = tmem + (uint32_t)(2 * a.N1);   // R2 slot s at R2 + s * N2
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;   // this warp's TMEM lane quadrant
-  const uint32_t a1h = (uint32_t)__cvta_generic_to_shared(s_a1h), a1l = (uint32_t)__cvta_generic_to_shared(s_a1l);
-  uint64_t *bar1 = s_bar, *bar2 = s_bar + 2, *bar3 = s_bar + 3;
-  uint32_t ph1 = 0, ph2 = 0, ph3 = 0;
-  const bool issuer = tid == 0;
+  const int ng = (a.K2 + 15) >> 4, nchunk = (ng + 1) >> 1;       // 16-column granules / 32-column chunks of the layer-2 operand
 
-  // The weight halves leave no room for a staging buffer of the next tile's rows (D = 50: 2 x 78 KB of weights +
-  // 2 x 28 KB of operand): every thread instead keeps ITS quarter of its row of the next tile in registers, loaded
-  // one pipeline round ahead (the rows were just written by the env step: L2 hits).
-  constexpr int kPre = 16;                                   // ceil(64 / 4)
-  const int kq = (a.D + 3) / 4, k_lo = min(a.D, part * kq), k_hi = min(a.D, k_lo + kq);
-  float pre[kPre];
-  auto fetch = [&](int tile) {
-    const long long row = (long long)tile * kActRows + t;
-    const bool live = row < a.rows;
-    const float *g = a.obs + (size_t)row * a.D;
+  if (role == 0) {
+    // ---------------------------------------------------------------- producers
+    const int nch = a.K1 >> 2, c_lo = part ? nch / 2 : 0, c_hi = part ? nch : nch / 2;   // this thread's 16-byte K chunks
+    float pre[kAct3PreChunks * 4];
+    auto fetch = [&](int tile) {
+      const long long row = (long long)tile * kActRows + t;
+      const bool live = row < a.rows;
+      const float *g = a.obs + (size_t)(live ? row : 0) * a.D;
+      if ((a.D & 1) == 0) {
 #pragma unroll
-    for (int j = 0; j < kPre; ++j) pre[j] = (live && k_lo + j < k_hi) ? __ldg(g + k_lo + j) : 0.f;
-  };
-  // the three passes of one K step: hi.hi, lo.hi, hi.lo (operand A from shared memory / from tensor memory)
-  auto mma3_ss = [&](uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t lbo_b, uint32_t idesc, int ksteps) {
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint64_t dah = umma_smem_desc(ah + ks * 2 * lbo_a, lbo_a, 128), dal = umma_smem_desc(al + ks * 2 * lbo_a, lbo_a, 128);
-      const uint64_t dbh = umma_smem_desc(bh + ks * 2 * lbo_b, lbo_b, 128), dbl = umma_smem_desc(bl + ks * 2 * lbo_b, lbo_b, 128);
-      umma_tf32_ss(d, dah, dbh, idesc, ks > 0);
-      umma_tf32_ss(d, dal, dbh, idesc, 1);
-      umma_tf32_ss(d, dah, dbl, idesc, 1);
-    }
-  };
-  auto mma3_ts = [&](uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t lbo_b, uint32_t idesc, int ksteps) {
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint64_t dbh = umma_smem_desc(bh + ks * 2 * lbo_b, lbo_b, 128), dbl = umma_smem_desc(bl + ks * 2 * lbo_b, lbo_b, 128);
-      umma_tf32_ts(d, ah + (uint32_t)(ks * 8), dbh, idesc, ks > 0);
-      umma_tf32_ts(d, al + (uint32_t)(ks * 8), dbh, idesc, 1);
-      umma_tf32_ts(d, ah + (uint32_t)(ks * 8), dbl, idesc, 1);
-    }
-  };
-  // this thread's quarter of `cols` columns, in 16-column granules
-  auto quarter = [&](int cols, int &lo, int &hi) {
-    const int q = ((cols + 3) / 4 + 15) & ~15;
-    lo = min(cols, part * q);
-    hi = min(cols, lo + q);
-  };
-
-  const int stride = gridDim.x;
-  int tile_b = blockIdx.x, tile_a = -1;
-  if (tile_b < n_tiles) fetch(tile_b);
-  if (issuer) mbar_wait_bounded(wbar, 0);
-  while (tile_b < n_tiles || tile_a >= 0) {
-    const bool has_b = tile_b < n_tiles, has_a = tile_a >= 0;
-    if (has_b) {   // ---- S1(b): re-tile the observation rows into hi / lo operands, GEMM1 -> R1
-      const int row_off = umma_kmajor_off(kActRows, t, 0);
+        for (int j = 0; j < kAct3PreChunks * 2; ++j) {
+          const int k = c_lo * 4 + 2 * j;
+          float2 v = make_float2(0.f, 0.f);
+          if (live && k < c_hi * 4 && k < a.D) v = __ldg(reinterpret_cast<const float2 *>(g + k));
+          pre[2 * j] = v.x;
+          pre[2 * j + 1] = v.y;
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < kPre; ++j) {
-        const int k = k_lo + j;
-        if (k < k_hi) {
-          const float v = pre[j], hi = to_tf32(v);
-          const int off = row_off + (k >> 2) * (int)((kActRows / 8) * 128) + (k & 3) * 4;
-          *reinterpret_cast<float *>(s_a1h + off) = hi;
-          *reinterpret_cast<float *>(s_a1l + off) = to_tf32(v - hi);
+        for (int j = 0; j < kAct3PreChunks * 4; ++j) {
+          const int k = c_lo * 4 + j;
+          pre[j] = (live && k < c_hi * 4 && k < a.D) ? __ldg(g + k) : 0.f;
+        }
+      }
+    };
+    if (n_my > 0) fetch((int)blockIdx.x);
+    for (int it = 0; it < n_my; ++it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      // layer-1 operand: [obs | 1 | 0 ...] as hi + lo, one 16-byte store per K chunk (consecutive rows are contiguous:
+      // conflict-free).  The previous tile's GEMM1 has completed (bar1 was waited for below).
+#pragma unroll
+      for (int j = 0; j < kAct3PreChunks; ++j) {
+        const int c = c_lo + j;
+        if (c < c_hi) {
+          float v[4], h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[i] = (4 * c + i == a.D) ? 1.f : pre[4 * j + i];
+            h[i] = to_tf32(v[i]);
+            l[i] = to_tf32(v[i] - h[i]);
+          }
+          const int off = c * (kActRows * 16) + t * 16;   // = umma_kmajor_off(kActRows, t, 4 c)
+          *reinterpret_cast<float4 *>(s_a1h + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4 *>(s_a1l + off) = make_float4(l[0], l[1], l[2], l[3]);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();
-      __syncthreads();
-      if (tile_b + stride < n_tiles) fetch(tile_b + stride);   // in flight during the next stages
-      if (issuer) {
-        tc_fence_after();
-        mma3_ss(R1, a1h, a1l, w1h, w1l, lbo_w1, idesc1, a.K1 / 8);
-        umma_commit(bar1);
-      }
-    }
-    if (has_a) {   // ---- S2(a): A3 = relu(D2) as hi (in place) + lo, GEMM3 -> R3
-      mbar_wait_bounded(bar2, ph2);
-      ph2 ^= 1u;
+      mbar_arrive(a1_ready);
+      if (it + 1 < n_my) fetch(tile + (int)gridDim.x);   // in flight during the rest of the round
+      // layer-2 operand: A2 = relu(D1) as hi (in place) + lo, published chunk by chunk.  bar1 also covers GEMM2 of the
+      // previous tile (commit tracks everything issued before it): L1 is free to overwrite.
+      mbar_wait_bounded(bar1, (uint32_t)(it & 1));
       tc_fence_after();
-      int c0, c1;
-      quarter(k3, c0, c1);
-      tmem_relu_split(R2 + lane_off, L2 + lane_off, c0, c1);
-      tc_fence_before();
-      __syncthreads();
-      if (issuer) {
-        tc_fence_after();
-        mma3_ts(R3, R2, L2, w3h, w3l, lbo_w3, idesc3, k3 / 8);
-        umma_commit(bar3);
-      }
-    }
-    if (has_b) {   // ---- S3(b): A2 = relu(D1) as hi + lo, GEMM2 -> R2
-      mbar_wait_bounded(bar1, ph1);
-      ph1 ^= 1u;
-      tc_fence_after();
-      int c0, c1;
-      quarter(a.K2, c0, c1);
-      tmem_relu_split(R1 + lane_off, L1 + lane_off, c0, c1);
-      tc_fence_before();
-      __syncthreads();
-      if (issuer) {
-        tc_fence_after();
-        mma3_ts(R2, R1, L1, w2h, w2l, lbo_w2, idesc2, a.K2 / 8);
-        umma_commit(bar2);
-      }
-    }
-    if (has_a) {   // ---- S4(a): softmax + categorical draw
-      mbar_wait_bounded(bar3, ph3);
-      ph3 ^= 1u;
-      tc_fence_after();
-      uint32_t lg[16];
-      tmem_ld16_issue(R3 + lane_off, lg);
-      tmem_wait_ld();
-      const float l0 = __uint_as_float(lg[0]), l1 = __uint_as_float(lg[1]);
-      const long long row = (long long)tile_a * kActRows + t;
-      if (row < a.rows && part == 0) {
-        const long long rr = row / a.Ns;
-        const int n = (int)(row - rr * a.Ns);
-        uint8_t act = 0;
-        float p_draw = 0.f, p1 = 0.f;
-        if (n < a.N) {
-          const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
-          const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-          const float p0 = e0 / (e0 + e1);
-          p1 = e1 / (e0 + e1);
-          const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + rr), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
-          const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
-          act = uf < p0 ? 0 : 1;
-          p_draw = act ? p1 : p0;
+      uint32_t r[2][16];
+      if (part < ng) tmem_ld16_issue(R1 + lane_off + (uint32_t)(16 * part), r[0]);
+#pragma unroll
+      for (int k = 0; k < kAct3MaxChunks; ++k) {
+        if (k < nchunk) {
+          const int g = 2 * k + part;                    // granule g of chunk k belongs to column half g & 1
+          if (g < ng) {
+            tmem_wait_ld_dep(r[k & 1]);
+            if (k + 1 < nchunk && g + 2 < ng) tmem_ld16_issue(R1 + lane_off + (uint32_t)(16 * (g + 2)), r[(k + 1) & 1]);
+            uint32_t l[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = fmaxf(__uint_as_float(r[k & 1][j]), 0.f);
+              const float hi = to_tf32(x);
+              r[k & 1][j] = __float_as_uint(hi);
+              l[j] = __float_as_uint(to_tf32(x - hi));
+            }
+            tmem_st16(R1 + lane_off + (uint32_t)(16 * g), r[k & 1]);
+            tmem_st16(L1 + lane_off + (uint32_t)(16 * g), l);
+            tmem_wait_st();
+          }
+          tc_fence_before();
+          mbar_arrive(a2_ready + k);
         }
-        a.actions[row] = act;
-        if (a.prob) a.prob[row] = p_draw;
-        if (a.prob_on) a.prob_on[row] = p1;
       }
     }
-    tile_a = has_b ? tile_b : -1;
-    tile_b += stride;
+  } else if (role == 2) {
+    // ---------------------------------------------------------------- MMA warp: one thread issues everything
+    if ((tid & 31) == 0 && n_my > 0) {
+      const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2);
+      const uint32_t w1h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w1), w2h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w2);
+      const uint32_t w1l = w1h + (uint32_t)a.w_bytes, w2l = w2h + (uint32_t)a.w_bytes;
+      const uint32_t a1h = (uint32_t)__cvta_generic_to_shared(s_a1h), a1l = (uint32_t)__cvta_generic_to_shared(s_a1l);
+      const uint32_t lbo_a = (kActRows / 8) * 128, lbo_w1 = (a.N1 / 8) * 128, lbo_w2 = (a.N2 / 8) * 128;
+      const int ks1 = a.K1 >> 3, ks2 = a.K2 >> 3;
+      mbar_wait_bounded(wbar, 0);   // the weight image has landed (async proxy -> tensor core: no proxy fence)
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it & 1;
+        const uint32_t d2 = R2 + (uint32_t)(s * a.N2);
+        mbar_wait_bounded(a1_ready, (uint32_t)(it & 1));
+        tc_fence_after();
+        for (int ks = 0; ks < ks1; ++ks) {      // layer 1: D1[128 x N1] = [obs | 1] . [W1 | b1]^T -- hi.hi, lo.hi, hi.lo
+          const uint64_t dah = umma_smem_desc(a1h + ks * 2 * lbo_a, lbo_a, 128), dal = umma_smem_desc(a1l + ks * 2 * lbo_a, lbo_a, 128);
+          const uint64_t dbh = umma_smem_desc(w1h + ks * 2 * lbo_w1, lbo_w1, 128), dbl = umma_smem_desc(w1l + ks * 2 * lbo_w1, lbo_w1, 128);
+          umma_tf32_ss(R1, dah, dbh, idesc1, ks > 0);
+          umma_tf32_ss(R1, dal, dbh, idesc1, 1);
+          umma_tf32_ss(R1, dah, dbl, idesc1, 1);
+        }
+        umma_commit(bar1);
+        for (int k = 0; k < nchunk; ++k) {      // layer 2: D2[128 x N2] = A2 (tensor memory) . [W2 | b2]^T, chunk by chunk
+          mbar_wait_bounded(a2_ready + k, (uint32_t)(it & 1));
+          if (k == 0 && it >= 2) mbar_wait_bounded(r2_free + s, (uint32_t)(((it >> 1) & 1) ^ 1));   // tile it - 2 has left the slot
+          tc_fence_after();
+          const int ke = min(4 * k + 4, ks2);
+          for (int ks = 4 * k; ks < ke; ++ks) {
+            const uint64_t dbh = umma_smem_desc(w2h + ks * 2 * lbo_w2, lbo_w2, 128), dbl = umma_smem_desc(w2l + ks * 2 * lbo_w2, lbo_w2, 128);
+            umma_tf32_ts(d2, R1 + (uint32_t)(ks * 8), dbh, idesc2, ks > 0);
+            umma_tf32_ts(d2, L1 + (uint32_t)(ks * 8), dbh, idesc2, 1);
+            umma_tf32_ts(d2, R1 + (uint32_t)(ks * 8), dbl, idesc2, 1);
+          }
+        }
+        umma_commit(bar2 + s);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- consumers
+    const float *w3 = reinterpret_cast<const float *>(smem + a.off_w3);   // [2][N2] zero-padded, then b3[2]
+    const int ng2 = (a.h2 + 15) >> 4;
+    if (n_my > 0) mbar_wait_bounded(wbar, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it & 1;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const uint32_t src = R2 + (uint32_t)(s * a.N2) + lane_off;
+      float acc0 = w3[2 * a.N2], acc1 = w3[2 * a.N2 + 1];
+      mbar_wait_bounded(bar2 + s, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      for (int g = 0; g < ng2; g += 2) {
+        uint32_t r[2][16];
+        const bool two = g + 1 < ng2;
+        tmem_ld16_issue(src + (uint32_t)(16 * g), r[0]);
+        if (two) tmem_ld16_issue(src + (uint32_t)(16 * g + 16), r[1]);
+        tmem_wait_ld_dep(r[0]);
+        if (two) tmem_wait_ld_dep(r[1]);
+        if (g + 2 >= ng2) {        // the slot's last read: GEMM2 of tile it + 2 may overwrite it
+          tc_fence_before();
+          mbar_arrive(r2_free + s);
+        }
+        const float4 *wa = reinterpret_cast<const float4 *>(w3 + 16 * g), *wb = reinterpret_cast<const float4 *>(w3 + a.N2 + 16 * g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 u = wa[q], v = wb[q];
+          const float x0 = fmaxf(__uint_as_float(r[0][4 * q]), 0.f), x1 = fmaxf(__uint_as_float(r[0][4 * q + 1]), 0.f),
+                      x2 = fmaxf(__uint_as_float(r[0][4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(r[0][4 * q + 3]), 0.f);
+          acc0 = fmaf(x0, u.x, acc0); acc0 = fmaf(x1, u.y, acc0); acc0 = fmaf(x2, u.z, acc0); acc0 = fmaf(x3, u.w, acc0);
+          acc1 = fmaf(x0, v.x, acc1); acc1 = fmaf(x1, v.y, acc1); acc1 = fmaf(x2, v.z, acc1); acc1 = fmaf(x3, v.w, acc1);
+        }
+        if (two) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 u = wa[4 + q], v = wb[4 + q];
+            const float x0 = fmaxf(__uint_as_float(r[1][4 * q]), 0.f), x1 = fmaxf(__uint_as_float(r[1][4 * q + 1]), 0.f),
+                        x2 = fmaxf(__uint_as_float(r[1][4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(r[1][4 * q + 3]), 0.f);
+            acc0 = fmaf(x0, u.x, acc0); acc0 = fmaf(x1, u.y, acc0); acc0 = fmaf(x2, u.z, acc0); acc0 = fmaf(x3, u.w, acc0);
+            acc1 = fmaf(x0, v.x, acc1); acc1 = fmaf(x1, v.y, acc1); acc1 = fmaf(x2, v.z, acc1); acc1 = fmaf(x3, v.w, acc1);
+          }
+        }
+      }
+      {
+        const float l0 = acc0, l1 = acc1;
+        const long long row = (long long)tile * kActRows + t;
+        if (row < a.rows) {
+          const long long rr = row / a.Ns;
+          const int n = (int)(row - rr * a.Ns);
+          uint8_t act = 0;
+          float p_draw = 0.f, p1 = 0.f;
+          if (n < a.N) {
+            const float m = fmaxf(l0, l1);                      // F.softmax(dim=1), network.py:34
+            const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+            const float p0 = e0 / (e0 + e1);
+            p1 = e1 / (e0 + e1);
+            const U4 u = philox4x32_10(a.seed, (uint32_t)(a.rep_offset + rr), (uint32_t)n, (uint32_t)a.step, PURPOSE_POLICY);
+            const float uf = (float)(u.x >> 8) * 5.9604644775390625e-8f;   // 24 random bits: [0, 1) exactly
+            act = uf < p0 ? 0 : 1;
+            p_draw = act ? p1 : p0;
+          }
+          a.actions[row] = act;
+          if (a.prob) a.prob[row] = p_draw;
+          if (a.prob_on) a.prob_on[row] = p1;
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

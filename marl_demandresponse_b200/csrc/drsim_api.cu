@@ -1805,18 +1805,19 @@ static int policy_step_impl(drsim_t *h, const drsim_actor_net *net, uint64_t see
   a.seed = seed; a.step = h->step; a.rep_offset = p.rep_offset;
   const int tiles = (int)((a.rows + kActRows - 1) / kActRows);
   if (net->precision == 1) {
-    // 3xTF32: hi + lo operands, one tile slot per CTA (see k_actor3x)
+    // 3xTF32: hi + lo operands, one CTA per SM, warp-specialised (see k_actor3x); the output layer runs in fp32 FMAs
     a.K1 = (a.D + 1 + 7) / 8 * 8; a.N1 = (a.h1 + 1 + 15) / 16 * 16;
-    a.K2 = (a.h1 + 1 + 7) / 8 * 8; a.N2 = (a.h2 + 1 + 15) / 16 * 16;
-    a.K3 = (a.h2 + 1 + 7) / 8 * 8;
-    if (2 * (a.N1 + a.N2) + kActN3 > 512)
+    a.K2 = (a.h1 + 1 + 7) / 8 * 8; a.N2 = (a.h2 + 15) / 16 * 16;
+    a.K3 = a.N2;
+    if (2 * (a.N1 + a.N2) > 512)
       return fail(DRSIM_E_ARG, "drsim_policy_step: h1 + h2 too wide for the split activations in tensor memory");
     a.off_w1 = take(a.N1 * a.K1 * 4); a.off_w2 = take(a.N2 * a.K2 * 4);
-    a.off_vec = take(kActN3 * a.K3 * 4);
-    const int w_bytes = off;                      // one (hi or lo) weight block
-    off = 2 * w_bytes;
-    a.off_a1 = take(2 * kActRows * a.K1 * 4);     // observation operand, hi and lo
-    a.off_a1 = 2 * w_bytes;
+    a.w_bytes = off;                              // one (hi or lo) weight block
+    off = 2 * a.w_bytes;
+    a.off_w3 = take((2 * a.N2 + 2) * 4);          // output layer, plain fp32
+    a.off_vec = a.off_w3;
+    a.off_a1 = off;                               // = size of the packed image
+    take(2 * kActRows * a.K1 * 4);                // observation operand, hi and lo
     a.off_a2 = off;                               // (no staging buffer: the next tile's rows wait in registers)
     a.off_bar = take(128);
     a.smem_bytes = off;
@@ -1827,7 +1828,7 @@ static int policy_step_impl(drsim_t *h, const drsim_actor_net *net, uint64_t see
     a.image = h->actor_image;
     k_actor_pack3x<<<40, 512, 0, (cudaStream_t)stream>>>(a, h->actor_image);
     CU_TRY(cudaFuncSetAttribute(k_actor3x, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
-    launch_pdl(k_actor3x, std::min(tiles, h->sm_count), kAct2Threads, (size_t)a.smem_bytes, (cudaStream_t)stream, a);
+    launch_pdl(k_actor3x, std::min(tiles, h->sm_count), kAct3Threads, (size_t)a.smem_bytes, (cudaStream_t)stream, a);
     h->launches++;
   } else {
     // one spare K column per layer carries the bias (constant-one column in A), one spare output row regenerates the one

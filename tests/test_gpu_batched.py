@@ -316,7 +316,8 @@ def _torch_actor(D, h1, h2, seed):
 
 
 @pytest.mark.parametrize("R,n,layout,h1,h2", [(300, 100, "hand_engineered", 100, 100), (7, 1000, "tarmac", 100, 100),
-                                              (33, 37, "hand_engineered", 64, 48), (5, 9, "tarmac", 111, 96)])
+                                              (33, 37, "hand_engineered", 64, 48), (5, 9, "tarmac", 111, 96),
+                                              (520, 100, "hand_engineered", 100, 100), (1100, 100, "tarmac", 32, 16)])
 def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
     """the tcgen05 actor + categorical draw against a plain PyTorch fp32 forward of the same
     weights.  Probabilities: TF32 operands (10-bit mantissa, rounded to nearest), fp32 accumulation -> |dp| <= 5e-3
@@ -346,13 +347,23 @@ def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
     prob_on = torch.zeros((R, env.sim.Ns), dtype=torch.float32, device="cuda")
     prob = torch.zeros_like(prob_on)
     # "tf32x3" (default): operands split into hi + lo TF32 halves, three passes per product -> fp32-grade
-    env.sim.policy_step(weights, seed=99, prob_on=prob_on, precision="tf32x3")
+    env.sim.policy_step(weights, seed=99, prob_drawn=prob, prob_on=prob_on, precision="tf32x3")
     torch.cuda.synchronize()
     with torch.no_grad():
         p_ref64 = torch.softmax(_forward64(fc, obs.reshape(-1, D)), dim=1).reshape(R, n, 2)
     err3 = float((prob_on[:, :n].double() - p_ref64[..., 1]).abs().max())
     ref_err = float((p_ref.double() - p_ref64).abs().max())     # what a plain fp32 forward is off by itself
     assert err3 <= 2e-6 + 2 * ref_err, (err3, ref_err)
+    # its draw and the probability it reports for the drawn action (same rule as below, on its own probabilities)
+    act3, p_on3 = env.state["actions"][:, :n].clone(), prob_on[:, :n].clone()
+    torch.testing.assert_close(prob[:, :n], torch.where(act3.bool(), p_on3, 1.0 - p_on3), rtol=0, atol=1e-6)
+    u3 = np.stack([(np.asarray(philox.philox4x32_10(99, 40 + r, np.arange(n), 1, 6)[0], dtype=np.uint64) >> np.uint64(8))
+                   .astype(np.float64) * 2.0 ** -24 for r in range(R)])
+    p03 = (1.0 - p_on3).double().cpu().numpy()
+    clear3 = np.abs(u3 - p03) > 1e-6
+    assert np.array_equal(act3.cpu().numpy()[clear3], (u3 >= p03).astype(np.uint8)[clear3])
+    assert clear3.mean() > 0.999
+    assert int(env.state["actions"][:, n:].sum()) == 0           # padding slots get action 0
     # "tf32": one pass, 10-bit operands
     env.sim.policy_step(weights, seed=99, prob_drawn=prob, prob_on=prob_on, precision="tf32")
     torch.cuda.synchronize()
