@@ -41,6 +41,7 @@ struct ActorArgs {
   int Ns, N, D, h1, h2;
   int K1, N1, K2, N2, K3;  // padded: K multiple of 8 (UMMA_K of tf32), N multiple of 16 (K3: k_actor2's output layer)
   int off_w1, off_w2, off_a1, off_a2, off_vec, off_bar, smem_bytes;
+  unsigned long long *dbg; // DRSIM_ACTOR_DBG: clock64 stamps [tile < 8][role][16] of CTA 0 (k_actor3x)
   int off_w3, w_bytes;     // k_actor3x: the fp32 output layer in the image; size of one (hi or lo) weight block
   unsigned long long seed;
   long long step, rep_offset;
@@ -82,12 +83,11 @@ DRSIM_D void umma_commit(uint64_t *bar) {
                    (uint32_t)__cvta_generic_to_shared(bar))
                : "memory");
 }
-// round-to-nearest TF32 (the tensor core would otherwise truncate the 13 low mantissa bits)
-DRSIM_D float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round-to-nearest (ties away from zero) TF32: the tensor core would otherwise truncate the 13 low mantissa bits.
+// Two integer instructions on the sign-magnitude bit pattern; `cvt.rna.tf32.f32` gives the same value for every
+// finite input but compiles to a six-instruction sequence with Inf / NaN handling on sm_100a, which made the
+// operand split of k_actor3x ALU-bound (activations and weights are finite).
+DRSIM_D float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 DRSIM_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 DRSIM_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 DRSIM_D void tmem_ld16(uint32_t taddr, float v[16]) {
@@ -461,6 +461,12 @@ __global__ void k_actor_pack3x(ActorArgs a, unsigned char *image) {
   }
 }
 
+// one lane of a converged warp (elect.sync): the form the compiler recognises as a single-thread region
+DRSIM_D bool elect_one_lane() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 DRSIM_D void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
@@ -474,6 +480,13 @@ DRSIM_D void tmem_wait_ld_dep(uint32_t r[16]) {
                : "memory");
 }
 
+// phase stamps of CTA 0 (first 8 tiles; producer warp 0, consumer warp 8, MMA warp), read back by drsim_debug_actor_times
+#define ACT3_STAMP(slot)                                                                          \
+  do {                                                                                            \
+    if (a.dbg && blockIdx.x == 0 && it < 8 && (tid & 31) == 0 && (warp == 0 || warp == 8 || warp == 12)) \
+      a.dbg[(it * 3 + role) * 16 + (slot)] = (unsigned long long)clock64();                       \
+  } while (0)
+
 __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // mbarriers: 0 a1_ready (256) | 1 GEMM1 done | 2..6 a2_ready[chunk] (256) | 7, 8 GEMM2 done [slot] |
@@ -481,7 +494,10 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + a.off_bar);
   uint64_t *a1_ready = s_bar, *bar1 = s_bar + 1, *a2_ready = s_bar + 2, *bar2 = s_bar + 7, *r2_free = s_bar + 9, *wbar = s_bar + 11;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 12);
-  const int tid = threadIdx.x, warp = tid >> 5, role = warp < 8 ? 0 : (warp < 12 ? 1 : 2);   // producer, consumer, MMA warp
+  // the warp index through a shuffle: provably warp-uniform, so the role branches and the MMA warp's descriptor arithmetic
+  // stay on the uniform datapath (a divergent single-lane issuer costs ~100 cycles per tcgen05.mma: R2UR + an elect loop
+  // around every instruction, twice the 56 cycles the tensor pipe needs for it)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), role = warp < 8 ? 0 : (warp < 12 ? 1 : 2);   // producer, consumer, MMA warp
   const int t = tid & 127, part = (tid >> 7) & 1;                   // row of the tile (= TMEM lane), column half
   const int n_tiles = (int)((a.rows + kActRows - 1) / kActRows);
   const int n_my = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -547,6 +563,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
     if (n_my > 0) fetch((int)blockIdx.x);
     for (int it = 0; it < n_my; ++it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      ACT3_STAMP(0);
       // layer-1 operand: [obs | 1 | 0 ...] as hi + lo, one 16-byte store per K chunk (consecutive rows are contiguous:
       // conflict-free).  The previous tile's GEMM1 has completed (bar1 was waited for below).
 #pragma unroll
@@ -567,11 +584,14 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a1_ready);
+      ACT3_STAMP(1);
       if (it + 1 < n_my) fetch(tile + (int)gridDim.x);   // in flight during the rest of the round
+      ACT3_STAMP(2);
       // layer-2 operand: A2 = relu(D1) as hi (in place) + lo, published chunk by chunk.  bar1 also covers GEMM2 of the
       // previous tile (commit tracks everything issued before it): L1 is free to overwrite.
       mbar_wait_bounded(bar1, (uint32_t)(it & 1));
       tc_fence_after();
+      ACT3_STAMP(3);
       uint32_t r[2][16];
       if (part < ng) tmem_ld16_issue(R1 + lane_off + (uint32_t)(16 * part), r[0]);
 #pragma unroll
@@ -595,12 +615,13 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
           }
           tc_fence_before();
           mbar_arrive(a2_ready + k);
+          ACT3_STAMP(4 + k);
         }
       }
     }
   } else if (role == 2) {
     // ---------------------------------------------------------------- MMA warp: one thread issues everything
-    if ((tid & 31) == 0 && n_my > 0) {
+    if (n_my > 0 && elect_one_lane()) {
       const uint32_t idesc1 = umma_instr_desc_tf32(kActRows, a.N1), idesc2 = umma_instr_desc_tf32(kActRows, a.N2);
       const uint32_t w1h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w1), w2h = (uint32_t)__cvta_generic_to_shared(smem + a.off_w2);
       const uint32_t w1l = w1h + (uint32_t)a.w_bytes, w2l = w2h + (uint32_t)a.w_bytes;
@@ -613,6 +634,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
         const uint32_t d2 = R2 + (uint32_t)(s * a.N2);
         mbar_wait_bounded(a1_ready, (uint32_t)(it & 1));
         tc_fence_after();
+        ACT3_STAMP(0);
         for (int ks = 0; ks < ks1; ++ks) {      // layer 1: D1[128 x N1] = [obs | 1] . [W1 | b1]^T -- hi.hi, lo.hi, hi.lo
           const uint64_t dah = umma_smem_desc(a1h + ks * 2 * lbo_a, lbo_a, 128), dal = umma_smem_desc(a1l + ks * 2 * lbo_a, lbo_a, 128);
           const uint64_t dbh = umma_smem_desc(w1h + ks * 2 * lbo_w1, lbo_w1, 128), dbl = umma_smem_desc(w1l + ks * 2 * lbo_w1, lbo_w1, 128);
@@ -621,10 +643,12 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
           umma_tf32_ss(R1, dah, dbl, idesc1, 1);
         }
         umma_commit(bar1);
+        ACT3_STAMP(1);
         for (int k = 0; k < nchunk; ++k) {      // layer 2: D2[128 x N2] = A2 (tensor memory) . [W2 | b2]^T, chunk by chunk
           mbar_wait_bounded(a2_ready + k, (uint32_t)(it & 1));
           if (k == 0 && it >= 2) mbar_wait_bounded(r2_free + s, (uint32_t)(((it >> 1) & 1) ^ 1));   // tile it - 2 has left the slot
           tc_fence_after();
+          ACT3_STAMP(2 + k);
           const int ke = min(4 * k + 4, ks2);
           for (int ks = 4 * k; ks < ke; ++ks) {
             const uint64_t dbh = umma_smem_desc(w2h + ks * 2 * lbo_w2, lbo_w2, 128), dbl = umma_smem_desc(w2l + ks * 2 * lbo_w2, lbo_w2, 128);
@@ -634,6 +658,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
           }
         }
         umma_commit(bar2 + s);
+        ACT3_STAMP(7);
       }
     }
   } else {
@@ -646,8 +671,10 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const uint32_t src = R2 + (uint32_t)(s * a.N2) + lane_off;
       float acc0 = w3[2 * a.N2], acc1 = w3[2 * a.N2 + 1];
+      ACT3_STAMP(0);
       mbar_wait_bounded(bar2 + s, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      ACT3_STAMP(1);
       for (int g = 0; g < ng2; g += 2) {
         uint32_t r[2][16];
         const bool two = g + 1 < ng2;
@@ -658,6 +685,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
         if (g + 2 >= ng2) {        // the slot's last read: GEMM2 of tile it + 2 may overwrite it
           tc_fence_before();
           mbar_arrive(r2_free + s);
+          ACT3_STAMP(2);
         }
         const float4 *wa = reinterpret_cast<const float4 *>(w3 + 16 * g), *wb = reinterpret_cast<const float4 *>(w3 + a.N2 + 16 * g);
 #pragma unroll
@@ -702,6 +730,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
           if (a.prob_on) a.prob_on[row] = p1;
         }
       }
+      ACT3_STAMP(3);
     }
   }
   tc_fence_before();
@@ -709,6 +738,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"((uint32_t)kAct2TmemCols) : "memory");
 }
+#undef ACT3_STAMP
 #endif  // __CUDACC__
 
 }  // namespace drsim

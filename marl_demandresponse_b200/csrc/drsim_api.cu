@@ -92,6 +92,7 @@ struct drsim_handle {
   // pinned + mapped snapshot for the dict API (drsim_snapshot)
   unsigned char *h_snap = nullptr, *h_snap_dev = nullptr;
   size_t snap_bytes = 0, snap_obs_off = 0;
+  unsigned long long *actor_dbg = nullptr;   // DRSIM_ACTOR_DBG: phase stamps of CTA 0 of the last k_actor3x launch
   unsigned long long *shard_dbg = nullptr;   // DRSIM_SHARD_DBG: per-CTA time stamps of the last k_shard launch
   int *h_peer_err = nullptr, *h_peer_err_dev = nullptr;   // mapped: set by a kernel whose exchange wait timed out
   int pending_interp = 0;  // decision of drsim_step_begin, consumed by drsim_step_finish
@@ -509,6 +510,7 @@ extern "C" int drsim_destroy(drsim_t *h) {
   if (h->h_env) cudaFreeHost(h->h_env);
   if (h->actor_image) cudaFree(h->actor_image);
   if (h->shard_dbg) cudaFree(h->shard_dbg);
+  if (h->actor_dbg) cudaFree(h->actor_dbg);
   if (h->h_snap) cudaFreeHost(h->h_snap);
   if (h->h_in) cudaFreeHost(h->h_in);
   delete h;
@@ -1826,6 +1828,11 @@ static int policy_step_impl(drsim_t *h, const drsim_actor_net *net, uint64_t see
                                "(hi + lo weight halves); use precision = 0");
     if (!h->actor_image) CU_TRY(cudaMalloc(&h->actor_image, 256 * 1024));
     a.image = h->actor_image;
+    if (!h->actor_dbg && getenv("DRSIM_ACTOR_DBG")) {
+      CU_TRY(cudaMalloc(&h->actor_dbg, 8 * 3 * 16 * 8));
+      CU_TRY(cudaMemset(h->actor_dbg, 0, 8 * 3 * 16 * 8));
+    }
+    a.dbg = h->actor_dbg;
     k_actor_pack3x<<<40, 512, 0, (cudaStream_t)stream>>>(a, h->actor_image);
     CU_TRY(cudaFuncSetAttribute(k_actor3x, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
     launch_pdl(k_actor3x, std::min(tiles, h->sm_count), kAct3Threads, (size_t)a.smem_bytes, (cudaStream_t)stream, a);
@@ -1863,6 +1870,14 @@ extern "C" int drsim_debug_shard_times(drsim_t *h, unsigned long long *host_out,
   const int n = std::min(max_ctas, h->shard_grid);
   cudaMemcpy(host_out, h->shard_dbg, (size_t)n * 128, cudaMemcpyDeviceToHost);
   return n;
+}
+
+// diagnostics, not part of the documented ABI: clock64 stamps [tile < 8][producer, consumer, MMA warp][16] of CTA 0 of the
+// last k_actor3x launch (DRSIM_ACTOR_DBG=1)
+extern "C" int drsim_debug_actor_times(drsim_t *h, unsigned long long *host_out) {
+  if (!h || !h->actor_dbg || !host_out) return 0;
+  cudaMemcpy(host_out, h->actor_dbg, 8 * 3 * 16 * 8, cudaMemcpyDeviceToHost);
+  return 8 * 3 * 16;
 }
 
 extern "C" int64_t drsim_launch_count(const drsim_t *h) { return h ? h->launches : 0; }
