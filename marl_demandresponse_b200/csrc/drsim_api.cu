@@ -1246,7 +1246,33 @@ extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_ste
     if (left == 0) return 0;
     n_steps = left;
   }
-  for (int k = 0; k < n_steps; ++k) {
+  // Action tape on the staged fused kernel with at least two tiles per CTA: the step loop runs INSIDE the kernel
+  // (StepIn::stream_steps), one launch per block of scheduled records.  Nothing a CTA reads of step k + 1 comes from
+  // another CTA, so the steps of a block have no boundary between them (no launch ramp / tail, no grid-wide wait).
+  const bool taped = tape && n_steps > 1 && h->fused_ok && h->real_bytes == 4 && h->fused_direct && h->geom.use_tma &&
+                      !h->geom.use_rows && p.policy == DRSIM_POLICY_EXTERNAL && p.base_mode == DRSIM_BASE_CONSTANT &&
+                      h->geom.n_tiles >= 2 * h->fused_grid && !h->mirror_next && !h->act_poll_next && !h->obs_override &&
+                      !h->reward_override && !h->broken && !getenv("DRSIM_NO_STREAM");
+  int first = 0;
+  if (taped) {
+    a.actions = tape;
+    while (first < n_steps) {
+      h->xseq++;
+      StepIn in = make_in(h, &a, 1, 0, (cudaStream_t)stream);   // (re)generates the schedule block when the step leaves it
+      if (!in.sched_rec) break;                                  // no scheduled records (should not happen): per-step loop
+      const int k = (int)std::min<int64_t>(n_steps - first, h->sched_base + drsim_handle::kSched - h->step);
+      in.stream_steps = k;
+      in.tape_planes = tape_planes;
+      in.tape_first = first;
+      in.tape_stride = action_stride;
+      if (k == 1) in.actions = tape + (size_t)(tape_planes > 0 ? first % tape_planes : first) * action_stride;
+      const int rc = launch_fused<float>(h, in, (cudaStream_t)stream);
+      if (rc) return rc;
+      h->step += k;
+      first += k;
+    }
+  }
+  for (int k = first; k < n_steps; ++k) {
     a.actions = tape ? tape + (size_t)(tape_planes > 0 ? k % tape_planes : k) * action_stride : nullptr;
     const int di = interp_decision(h);
     const int rc = run_step(h, &a, 1, di, (cudaStream_t)stream);

@@ -102,6 +102,14 @@ struct StepIn {
   // in-kernel episode (drsim_run under an on-device policy, k_fused_tma<0> only): this launch advances
   // n_steps consecutive steps; step k uses the schedule records sched_rec + k * R.  0 / 1 = one step.
   int n_steps;
+  // in-kernel step loop over an action tape (drsim_run_tape on k_fused_tma, every CTA owning at least two tiles):
+  // this launch advances stream_steps consecutive steps, a CTA taking (step 0: its tiles), (step 1: its tiles) ...
+  // Every byte a CTA reads of step k + 1 was written by the same thread of the same CTA in step k (state planes,
+  // running metrics) or is an input of the call (tape, schedule records), so no step boundary exists between CTAs:
+  // no launch ramp and tail, no grid-wide dependency.  Step k reads the records sched_rec + k * R and the action
+  // plane `actions + ((tape_first + k) % tape_planes) * tape_stride` (tape_planes 0: no rotation).  0 / 1 = one step.
+  int stream_steps, tape_planes, tape_first;
+  size_t tape_stride;
 };
 
 // Peer-memory exchange of the per-rank partial sums of ONE house-sharded cluster: every
@@ -2122,7 +2130,13 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   // none of the per-copy issue latency of 512-byte TMA bulk loads (measured: 20 % of the stall samples)
   float nx_od = 0.f, nx_solar = 0.f;
   // `part`: 1 = launch-invariant static planes only (may run before pdl_wait), 2 = the rest, 3 = both
-  auto prefetch = [&](int t, int part) {
+  const int n_stream = in.stream_steps > 1 ? in.stream_steps : 1;   // in-kernel step loop over an action tape
+  auto step_actions = [&](int st) -> const uint8_t * {
+    if (n_stream == 1 || !in.actions) return actions;
+    const int j = in.tape_first + st;
+    return in.actions + (size_t)(in.tape_planes > 0 ? j % in.tape_planes : j) * in.tape_stride;
+  };
+  auto prefetch = [&](int t, int st, int part) {
     const int tr0 = t * g.envs_per_tile;
     const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
     const size_t tbase = (size_t)tr0 * Ns;
@@ -2141,8 +2155,8 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
         cp_async16_hint(d + kTileSlots, pl.t_mass + o, pol_keep);
         cp_async16_hint(d + 2 * kTileSlots, pl.sso + o, pol_keep);
         cp_async4(s_flags + threadIdx.x, pl.flags + o);
-        if (ext) cp_async4(s_act + threadIdx.x, actions + o);
-        if (fast) cp_async8(s_os + threadIdx.x, &in.sched_rec[r].od_prev_f);
+        if (ext) cp_async4(s_act + threadIdx.x, step_actions(st) + o);
+        if (fast) cp_async8(s_os + threadIdx.x, &in.sched_rec[(size_t)st * p.R + r].od_prev_f);
       }
       if (!fast && (part & 2)) {
         nx_od = (float)pl.od_temp[r];
@@ -2151,17 +2165,18 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     }
   };
   // schedule record + running metrics of tile t's clusters -> shared memory (threads e < E, cp.async)
-  auto fetch_env = [&](int t, int par) {
+  auto fetch_env = [&](int t, int st, int par) {
     const int tr0 = t * g.envs_per_tile;
     if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
-      env_stage_fetch(s_stage_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
+      env_stage_fetch(s_stage_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec + (size_t)st * p.R, pl.metrics,
+                      tr0 + threadIdx.x);
   };
   pdl_trigger();
-  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x, 1);
+  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x, 0, 1);
   pdl_wait();
   if ((int)blockIdx.x < g.n_tiles) {
-    prefetch(blockIdx.x, 2);
-    if (fast) fetch_env(blockIdx.x, 0);
+    prefetch(blockIdx.x, 0, 2);
+    if (fast) fetch_env(blockIdx.x, 0, 0);
   }
 
   // In-kernel episode (MODE 0, host guarantees at most one tile per CTA and scheduled records for all
@@ -2169,9 +2184,13 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   // into its own staging slots, the next step's (static) record is fetched while this one computes, and the
   // running metrics travel through the staged record -- nothing is re-read from global memory.
   const int n_epi = (MODE == 0 && in.n_steps > 1) ? in.n_steps : 1;
+  for (int st = 0; st < n_stream; ++st)
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x)
   for (int epi = 0; epi < n_epi; ++epi, parity ^= 1) {
     const bool epi_more = MODE == 0 && epi + 1 < n_epi;
+    // the item after this one: the CTA's next tile of this step, or its first tile of the next step of the stream
+    int nt = tile + gridDim.x, nst = st;
+    if (nt >= g.n_tiles && st + 1 < n_stream) { nt = blockIdx.x; nst = st + 1; }
     const int r0 = tile * g.envs_per_tile;
     const int E = min(g.envs_per_tile, p.R - r0);
     const int slots = E * Ns;
@@ -2219,10 +2238,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     }
     // the thread holds its inputs in registers: its staging slots are free, the next tile's copies are
     // issued now and have the whole tile to land
-    {
-      const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) prefetch(nt, 3);
-    }
+    if (nt < g.n_tiles) prefetch(nt, nst, 3);
     if constexpr (MODE == 0) {
       if (epi_more && active && fast)   // house-update inputs of the next step of the episode (static record)
         cp_async8(s_os + threadIdx.x, &in.sched_rec[(size_t)(epi + 1) * p.R + r0 + e_loc].od_prev_f);
@@ -2319,8 +2335,7 @@ k_fused_tma(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     __syncthreads();
     // every warp is past the previous tile's phase 3: the other parity of s_stage is free again
     if (fast) {
-      const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) fetch_env(nt, parity ^ 1);
+      if (nt < g.n_tiles) fetch_env(nt, nst, parity ^ 1);
       if constexpr (MODE == 0) {
         if (epi_more && (int)threadIdx.x < E) {   // record of the next step; its metrics part is filled by env_stage_store
           const char *src = reinterpret_cast<const char *>(in.sched_rec + (size_t)(epi + 1) * p.R + r0 + threadIdx.x);

@@ -1,5 +1,6 @@
 """BatchedEnv / Philox / drop-in Environment on the GPU, against the NumPy oracle."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -482,6 +483,45 @@ def test_run_equals_repeated_steps(n, R, policy, base_mode, layout):
         assert torch.equal(a.state[k], b.state[k]), k
     with pytest.raises(Exception):   # injected noise is a per-step input: rejected for n_steps > 1
         _run_with_noise(b, R)
+
+
+@pytest.mark.parametrize("n,R,layout,rotate", [(1000, 640, "tarmac", True),      # one cluster per tile (k_fused_tma<1>), 2.2 tiles per CTA
+                                              (100, 6100, "tarmac", False),     # ten clusters per tile (generic instantiation)
+                                              (37, 16000, "tarmac", True)])     # padded rows, ragged last tile
+def test_tape_stream_equals_per_step_launches(n, R, layout, rotate):
+    """``drsim_run_tape`` on the staged fused kernel with at least two tiles per CTA runs the step loop INSIDE the
+    kernel (StepIn::stream_steps: no boundary between the steps of a schedule block).  Same bits as one launch per
+    step (``DRSIM_NO_STREAM=1``), over a schedule-block boundary, with a rotating and a linear tape."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+
+    prop = _prop(n, **{"power_grid_prop/signal_properties/mode": "sinusoidals"})
+    T = 70 if rotate else 9
+    planes = 3 if rotate else T
+    a = BatchedEnv(prop, R, policy="external", noise="philox", seed=5, obs_layout=layout)
+    a.reset()
+    info = a.sim.fused_info()
+    assert info["variant"] == "staged" and info["tiles"] >= 2 * info["grid"], info          # otherwise the stream is not taken and the test is vacuous
+    b = copy.deepcopy(a)
+    tape = (torch.rand((planes, R, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)) < 0.5).to(torch.uint8)
+    launches0 = a.sim.launch_count
+    a.run(T, tape, rotate=rotate)
+    torch.cuda.synchronize()
+    assert a.sim.launch_count - launches0 <= 2 * 3 + 2     # two schedule blocks (+ their two generator kernels each), not T launches
+    os.environ["DRSIM_NO_STREAM"] = "1"
+    try:
+        b.run(T, tape, rotate=rotate)
+    finally:
+        del os.environ["DRSIM_NO_STREAM"]
+    torch.cuda.synchronize()
+    for k in ("dt_air", "dt_mass", "sso", "flags", "reward", "obs", "signal", "power", "od_temp", "metrics"):
+        assert torch.equal(a.state[k], b.state[k]), k
+    # and the stream leaves the handle in a state ordinary steps continue from
+    a.step(tape[0]); b.step(tape[0])
+    torch.cuda.synchronize()
+    for k in ("dt_air", "sso", "flags", "reward", "obs", "metrics"):
+        assert torch.equal(a.state[k], b.state[k]), k
 
 
 def _run_with_noise(env, R):
