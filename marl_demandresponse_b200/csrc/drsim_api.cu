@@ -92,6 +92,7 @@ struct drsim_handle {
   // pinned + mapped snapshot for the dict API (drsim_snapshot)
   unsigned char *h_snap = nullptr, *h_snap_dev = nullptr;
   size_t snap_bytes = 0, snap_obs_off = 0;
+  int launch_grid = 0;                       // transient: grid of the next fused launch (tape stream), 0 = fused_grid
   unsigned long long *actor_dbg = nullptr;   // DRSIM_ACTOR_DBG: phase stamps of CTA 0 of the last k_actor3x launch
   unsigned long long *shard_dbg = nullptr;   // DRSIM_SHARD_DBG: per-CTA time stamps of the last k_shard launch
   int *h_peer_err = nullptr, *h_peer_err_dev = nullptr;   // mapped: set by a kernel whose exchange wait timed out
@@ -1047,28 +1048,30 @@ static void launch_tma(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
   const SimParams &p = h->p;
   const FusedGeom &g = h->geom;
+  const int grid = h->launch_grid ? h->launch_grid : h->fused_grid;
   const bool plain = p.own_dim == 10 && p.msg_dim == 4 && (p.obs_dim % 2) == 0 && p.obs_dim > 0;
   const bool common = plain && in.sched_od != nullptr && p.policy == DRSIM_POLICY_EXTERNAL &&
                       p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   const bool poll = in.act_poll_err != nullptr;   // copy-engine mode of drsim_step_host
   if (common && !g.need_msg && g.envs_per_tile == 1) {
-    if (poll) launch_pdl(k_fused_tma<1, true>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
-    else launch_pdl(k_fused_tma<1>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    if (poll) launch_pdl(k_fused_tma<1, true>, grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    else launch_pdl(k_fused_tma<1>, grid, kThreads, g.smem_bytes, s, pl, p, in, g);
   } else if (common && g.need_msg && g.envs_per_tile > 1) {
-    if (poll) launch_pdl(k_fused_tma<2, true>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
-    else launch_pdl(k_fused_tma<2>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    if (poll) launch_pdl(k_fused_tma<2, true>, grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    else launch_pdl(k_fused_tma<2>, grid, kThreads, g.smem_bytes, s, pl, p, in, g);
   } else {
-    if (poll) launch_pdl(k_fused_tma<0, true>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
-    else launch_pdl(k_fused_tma<0>, h->fused_grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    if (poll) launch_pdl(k_fused_tma<0, true>, grid, kThreads, g.smem_bytes, s, pl, p, in, g);
+    else launch_pdl(k_fused_tma<0>, grid, kThreads, g.smem_bytes, s, pl, p, in, g);
   }
 }
 
 static void launch_rows(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<float> pl = make_planes<float>(h);
+  const int grid = h->launch_grid ? h->launch_grid : h->fused_grid;
   if (h->geom.in_stride && in.act_poll_err)
-    launch_pdl(k_fused_rows<true, true>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
-  else if (h->geom.in_stride) launch_pdl(k_fused_rows<true>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
-  else launch_pdl(k_fused_rows<false>, h->fused_grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+    launch_pdl(k_fused_rows<true, true>, grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+  else if (h->geom.in_stride) launch_pdl(k_fused_rows<true>, grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
+  else launch_pdl(k_fused_rows<false>, grid, kThreads, h->geom.smem_bytes, s, pl, h->p, in, h->geom);
 }
 
 // steps the wide-row kernel cannot take (injected noise, on-device policies, common penalty modes)
@@ -1246,13 +1249,20 @@ extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_ste
     if (left == 0) return 0;
     n_steps = left;
   }
-  // Action tape on the staged fused kernel with at least two tiles per CTA: the step loop runs INSIDE the kernel
-  // (StepIn::stream_steps), one launch per block of scheduled records.  Nothing a CTA reads of step k + 1 comes from
-  // another CTA, so the steps of a block have no boundary between them (no launch ramp / tail, no grid-wide wait).
-  const bool taped = tape && n_steps > 1 && h->fused_ok && h->real_bytes == 4 && h->fused_direct && h->geom.use_tma &&
-                      !h->geom.use_rows && p.policy == DRSIM_POLICY_EXTERNAL && p.base_mode == DRSIM_BASE_CONSTANT &&
-                      h->geom.n_tiles >= 2 * h->fused_grid && !h->mirror_next && !h->act_poll_next && !h->obs_override &&
-                      !h->reward_override && !h->broken && !getenv("DRSIM_NO_STREAM");
+  // Action tape (or an on-device bang-bang policy) on a staged fused kernel with at least two tiles per CTA: the step
+  // loop runs INSIDE the kernel (StepIn::stream_steps), one launch per block of scheduled records.  Nothing a CTA
+  // reads of step k + 1 comes from another CTA, so the steps of a block have no boundary between them (no launch
+  // ramp / tail, no grid-wide wait).
+  // every CTA needs at least two tiles (its next step's first tile must not be the tile it is still updating): the
+  // stream runs on min(resident CTAs, tiles / 2) CTAs, and only when that costs at most a tenth of the resident grid
+  const int sgrid = h->fused_ok ? std::min(h->fused_grid, h->geom.n_tiles / 2) : 0;
+  const bool tma_path = h->fused_direct && h->geom.use_tma && !h->geom.use_rows;
+  const bool rows_path = h->geom.use_rows && h->geom.in_stride && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+  const bool policy_ok = tape ? p.policy == DRSIM_POLICY_EXTERNAL
+                              : (tma_path && p.policy != DRSIM_POLICY_EXTERNAL && p.policy != DRSIM_POLICY_GREEDY_MYOPIC);
+  const bool taped = n_steps > 1 && h->fused_ok && h->real_bytes == 4 && (tma_path || rows_path) && policy_ok &&
+                     p.base_mode == DRSIM_BASE_CONSTANT && sgrid * 10 >= h->fused_grid * 9 && !h->mirror_next &&
+                     !h->act_poll_next && !h->obs_override && !h->reward_override && !h->broken && !getenv("DRSIM_NO_STREAM");
   int first = 0;
   if (taped) {
     a.actions = tape;
@@ -1265,8 +1275,10 @@ extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_ste
       in.tape_planes = tape_planes;
       in.tape_first = first;
       in.tape_stride = action_stride;
-      if (k == 1) in.actions = tape + (size_t)(tape_planes > 0 ? first % tape_planes : first) * action_stride;
+      if (k == 1 && tape) in.actions = tape + (size_t)(tape_planes > 0 ? first % tape_planes : first) * action_stride;
+      h->launch_grid = sgrid;
       const int rc = launch_fused<float>(h, in, (cudaStream_t)stream);
+      h->launch_grid = 0;
       if (rc) return rc;
       h->step += k;
       first += k;

@@ -2526,10 +2526,11 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   int parity = 0;
 
   // schedule record + running metrics of tile t's clusters -> shared memory (threads e < E, cp.async)
-  auto fetch_env = [&](int t, int par) {
+  auto fetch_env = [&](int t, int st, int par) {
     const int tr0 = t * g.envs_per_tile;
     if ((int)threadIdx.x < min(g.envs_per_tile, p.R - tr0))
-      env_stage_fetch(s_rec_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec, pl.metrics, tr0 + threadIdx.x);
+      env_stage_fetch(s_rec_base + (size_t)par * g.envs_per_tile + threadIdx.x, in.sched_rec + (size_t)st * p.R, pl.metrics,
+                      tr0 + threadIdx.x);
   };
   // thread-private input staging (see k_fused_tma): the 16 bytes a thread consumes of each of the
   // eleven 32-bit planes, its flags / action words and its cluster's two fp32 scalars are copied into
@@ -2542,7 +2543,14 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
   const uint8_t *actions = in.actions ? in.actions : pl.actions;
   // (plain cp.async here: with a run-time plane stride, ptxas 12.9 encodes the L2::cache_hint form of
   // LDGSTS with a uniform-register shared offset that the B200 rejects as an illegal instruction)
-  auto prefetch = [&](int t, int part) {
+  // in-kernel step loop over an action tape (StepIn::stream_steps, see k_fused_tma; STAGED only)
+  const int n_stream = (STAGED && in.stream_steps > 1) ? in.stream_steps : 1;
+  auto step_actions = [&](int st) -> const uint8_t * {
+    if (n_stream == 1 || !in.actions) return actions;
+    const int j = in.tape_first + st;
+    return in.actions + (size_t)(in.tape_planes > 0 ? j % in.tape_planes : j) * in.tape_stride;
+  };
+  auto prefetch = [&](int t, int st, int part) {
     if constexpr (!STAGED) return;
     const int tr0 = t * g.envs_per_tile;
     const int tslots = min(g.envs_per_tile, p.R - tr0) * Ns;
@@ -2560,19 +2568,23 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       cp_async16(d + in_stride, pl.t_mass + o);
       cp_async16(d + 2 * in_stride, pl.sso + o);
       cp_async4(s_flags + threadIdx.x, pl.flags + o);
-      cp_async4(s_act + threadIdx.x, actions + o);
-      cp_async8(s_os + threadIdx.x, &in.sched_rec[tr0 + (int)fast_div((uint32_t)s0, p.fd_ns)].od_prev_f);
+      cp_async4(s_act + threadIdx.x, step_actions(st) + o);
+      cp_async8(s_os + threadIdx.x, &in.sched_rec[(size_t)st * p.R + tr0 + (int)fast_div((uint32_t)s0, p.fd_ns)].od_prev_f);
     }
   };
   pdl_trigger();
-  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x, 1);
+  if ((int)blockIdx.x < g.n_tiles) prefetch(blockIdx.x, 0, 1);
   pdl_wait();
   if ((int)blockIdx.x < g.n_tiles) {
-    prefetch(blockIdx.x, 2);
-    fetch_env(blockIdx.x, 0);
+    prefetch(blockIdx.x, 0, 2);
+    fetch_env(blockIdx.x, 0, 0);
   }
 
+  for (int st = 0; st < n_stream; ++st)
   for (int tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, parity ^= 1) {
+    // the item after this one: the CTA's next tile of this step, or its first tile of the next step of the stream
+    int nt = tile + gridDim.x, nst = st;
+    if (nt >= g.n_tiles && st + 1 < n_stream) { nt = blockIdx.x; nst = st + 1; }
     const int r0 = tile * g.envs_per_tile;
     const int E = min(g.envs_per_tile, p.R - r0);
     const int slots = E * Ns;
@@ -2616,10 +2628,8 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
       const float2 v = s_os[threadIdx.x];
       w.od = v.x; w.solar = v.y;
     }
-    {  // the thread holds its inputs in registers: the next tile's copies fly during this tile
-      const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) prefetch(nt, 3);
-    }
+    // the thread holds its inputs in registers: the next tile's copies fly during this tile
+    if (nt < g.n_tiles) prefetch(nt, nst, 3);
     if (active) {
       house4_compute_f32<true>(pl, p, w, base + s0, min(4, p.N - n0), h, red);
 #pragma unroll
@@ -2654,10 +2664,8 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
     }
     if (threadIdx.x < E) cp_async_wait_all();  // this tile's records (issued a whole tile ago) are in s_rec
     __syncthreads();
-    {  // every warp is past the previous tile: the other parity of s_rec is free again
-      const int nt = tile + gridDim.x;
-      if (nt < g.n_tiles) fetch_env(nt, parity ^ 1);
-    }
+    // every warp is past the previous tile: the other parity of s_rec is free again
+    if (nt < g.n_tiles) fetch_env(nt, nst, parity ^ 1);
 
     // ---- phase 2: fold the cluster power in (E threads, a few dozen instructions) ----------
     double a[kRed] = {0, 0, 0, 0, 0};

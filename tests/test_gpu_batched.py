@@ -485,10 +485,13 @@ def test_run_equals_repeated_steps(n, R, policy, base_mode, layout):
         _run_with_noise(b, R)
 
 
-@pytest.mark.parametrize("n,R,layout,rotate", [(1000, 640, "tarmac", True),      # one cluster per tile (k_fused_tma<1>), 2.2 tiles per CTA
-                                              (100, 6100, "tarmac", False),     # ten clusters per tile (generic instantiation)
-                                              (37, 16000, "tarmac", True)])     # padded rows, ragged last tile
-def test_tape_stream_equals_per_step_launches(n, R, layout, rotate):
+@pytest.mark.parametrize("n,R,layout,rotate,policy", [
+    (1000, 640, "tarmac", True, "external"),             # one cluster per tile (k_fused_tma<1>), 2.2 tiles per CTA
+    (100, 6100, "tarmac", False, "external"),            # ten clusters per tile (generic instantiation)
+    (37, 16000, "tarmac", True, "external"),             # padded rows, ragged last tile
+    (100, 4096, "hand_engineered", True, "external"),    # BASELINE config 3: wide rows (k_fused_rows), 586 tiles on 293 CTAs
+    (100, 6100, "tarmac", True, "deadband_bangbang")])   # on-device policy, no tape
+def test_tape_stream_equals_per_step_launches(n, R, layout, rotate, policy):
     """``drsim_run_tape`` on the staged fused kernel with at least two tiles per CTA runs the step loop INSIDE the
     kernel (StepIn::stream_steps: no boundary between the steps of a schedule block).  Same bits as one launch per
     step (``DRSIM_NO_STREAM=1``), over a schedule-block boundary, with a rotating and a linear tape."""
@@ -499,12 +502,14 @@ def test_tape_stream_equals_per_step_launches(n, R, layout, rotate):
     prop = _prop(n, **{"power_grid_prop/signal_properties/mode": "sinusoidals"})
     T = 70 if rotate else 9
     planes = 3 if rotate else T
-    a = BatchedEnv(prop, R, policy="external", noise="philox", seed=5, obs_layout=layout)
+    a = BatchedEnv(prop, R, policy=policy, noise="philox", seed=5, obs_layout=layout)
     a.reset()
     info = a.sim.fused_info()
-    assert info["variant"] == "staged" and info["tiles"] >= 2 * info["grid"], info          # otherwise the stream is not taken and the test is vacuous
+    assert info["variant"] in ("staged", "staged_rows") and (info["tiles"] // 2) * 10 >= info["grid"] * 9, info          # otherwise the stream is not taken and the test is vacuous
     b = copy.deepcopy(a)
     tape = (torch.rand((planes, R, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)) < 0.5).to(torch.uint8)
+    if policy != "external":
+        tape = None
     launches0 = a.sim.launch_count
     a.run(T, tape, rotate=rotate)
     torch.cuda.synchronize()
@@ -518,7 +523,7 @@ def test_tape_stream_equals_per_step_launches(n, R, layout, rotate):
     for k in ("dt_air", "dt_mass", "sso", "flags", "reward", "obs", "signal", "power", "od_temp", "metrics"):
         assert torch.equal(a.state[k], b.state[k]), k
     # and the stream leaves the handle in a state ordinary steps continue from
-    a.step(tape[0]); b.step(tape[0])
+    a.step(None if tape is None else tape[0]); b.step(None if tape is None else tape[0])
     torch.cuda.synchronize()
     for k in ("dt_air", "sso", "flags", "reward", "obs", "metrics"):
         assert torch.equal(a.state[k], b.state[k]), k
