@@ -342,8 +342,10 @@ def committed_traffic(workload: str) -> dict:
         t = d.get(workload)
         if not t:
             return {"traffic": None}
-        return {"traffic": t["dram_bytes_read"] + t["dram_bytes_write"], "traffic_read": t["dram_bytes_read"],
-                "traffic_write": t["dram_bytes_write"], "traffic_launches_averaged": t.get("launches"),
+        k = float(t.get("steps_per_launch", 1))   # a launch of the in-kernel step loop advances 64 steps: traffic is per STEP
+        return {"traffic": (t["dram_bytes_read"] + t["dram_bytes_write"]) / k, "traffic_read": t["dram_bytes_read"] / k,
+                "traffic_write": t["dram_bytes_write"] / k, "traffic_launches_averaged": t.get("launches"),
+                "traffic_per": "step" + (f" (launch total / {int(k)} steps)" if k > 1 else " (= launch)"),
                 "traffic_stale": d.get("source_hash") != source_hash()}
     except Exception:  # noqa: BLE001
         return {"traffic": None}
@@ -501,6 +503,16 @@ def run_gpu_arm(args, wl) -> None:
         sampler.start()   # nvidia-smi needs ~0.1 s to deliver its first sample: start it before the warm-up
     ms_step, launches, one_call = w.device_resident(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else {}
+    # the same drsim_run_tape call with the in-kernel step loop switched off: one launch per step (the definition of
+    # `value` before the loop existed), reported next to it under roofline.per_step_launch
+    streamed = one_call and launches * 2 < args.steps
+    ms_launch = launches_launch = None
+    if streamed:
+        os.environ["DRSIM_NO_STREAM"] = "1"
+        try:
+            ms_launch, launches_launch, _ = w.device_resident(min(args.steps, 2000), args.warmup)
+        finally:
+            del os.environ["DRSIM_NO_STREAM"]
 
     # ---- end to end through the host-buffer C-ABI entry: `e2e` (full result) and `e2e_summary` -------------
     acts_host = [a.contiguous().cpu().pin_memory() for a in w.acts]
@@ -615,6 +627,10 @@ def run_gpu_arm(args, wl) -> None:
         cfg = workload_config(wl, world, D, args.exchange, args.flush_l2)
         cfg["timed_region"] = (f"{args.steps} steps enqueued by one drsim_run_tape call (rotating 4-plane action tape)" if one_call
                                else f"{args.steps} Python -> C step calls")
+        if streamed:
+            cfg["timed_region"] += ("; the step loop runs inside the kernel (one launch per 64-step block of schedule records: a "
+                                    "CTA's inputs of step k+1 come only from itself, so the steps of a block have no boundary); "
+                                    "roofline.per_step_launch = the same call with one launch per step")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
@@ -628,8 +644,16 @@ def run_gpu_arm(args, wl) -> None:
                          **({"note": "latency-bound workload (one small cluster): the fraction is reported for completeness"}
                             if R * n_local < 100000 else {}),
                          "unit": "GB/s", "frac": achieved / peak, **committed_traffic(args.workload),
-                         "algorithmic_bytes_per_launch": R * n_local * bytes_hs,
+                         "algorithmic_bytes_per_step": R * n_local * bytes_hs,
+                         "steps_per_launch": 64 if streamed else 1,
+                         "algorithmic_bytes_per_launch": R * n_local * bytes_hs * (64 if streamed else 1),
                          "bytes_per_house_step": bytes_hs,
+                         **({"per_step_launch": {"ms_per_step": ms_launch, "value": w.total_houses / (ms_launch * 1e-3),
+                                                 "achieved": R * n_local * bytes_hs / (ms_launch * 1e-3) / 1e9,
+                                                 "frac": R * n_local * bytes_hs / (ms_launch * 1e-3) / 1e9 / peak,
+                                                 "gpu_launches": launches_launch, "steps": min(args.steps, 2000),
+                                                 **committed_traffic(args.workload + "_per_step_launch")}}
+                            if streamed else {}),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback 6650"},
             "clocks": clocks,
         }

@@ -43,6 +43,10 @@ def main():
                   "(profiles/tools/ncu_traffic.py)"}
     for arg in sys.argv[1:]:
         wl, path = arg.split("=", 1)
+        steps = 1
+        if ":" in path:            # wl=file.csv:64 -- every captured launch advances 64 steps (in-kernel step loop)
+            path, k = path.rsplit(":", 1)
+            steps = int(k)
         ls = parse(path)
         # the dominant kernel = the one with the largest total duration among the captured launches
         by = {}
@@ -50,7 +54,7 @@ def main():
             by.setdefault(d["kernel"], []).append(d)
         name, group = max(by.items(), key=lambda kv: sum(x.get("gpu__time_duration.sum", 0.0) for x in kv[1]))
         n = len(group)
-        out[wl] = {"kernel": name.split("(")[0], "launches": n,
+        out[wl] = {"kernel": name.split("(")[0], "launches": n, "steps_per_launch": steps,
                    "dram_bytes_read": sum(x["dram__bytes_read.sum"] for x in group) / n,
                    "dram_bytes_write": sum(x["dram__bytes_write.sum"] for x in group) / n,
                    "gpu_time_us_under_ncu": sum(x["gpu__time_duration.sum"] for x in group) / n,
