@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(kAct2Threads, 1) k_actor2(ActorArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kAct3Threads = 416;    // 8 producer warps + 4 consumer warps + the MMA warp (13 warps: 128 registers each)
 constexpr int kAct3MaxChunks = 5;    // 32-column chunks of the layer-2 operand (N1 <= 144)
-constexpr int kAct3PreChunks = 9;    // 16-byte K chunks in HALF an observation row (K1 <= 72)
+constexpr int kAct3PreChunks = 9;    // most 16-byte K chunks in HALF an observation row (K1 <= 72); the kernel is instantiated
+                                     // for 2 / 4 / 7 / 9 so that the unrolled row handling carries no predicated-off work
 
 DRSIM_D void pack_weights_split(unsigned char *dst_hi, unsigned char *dst_lo, const float *w, const float *b, int n_out, int n_in,
                                 int Np, int Kp, bool gen_one, int tid, int nthreads) {
@@ -487,6 +488,7 @@ DRSIM_D void tmem_wait_ld_dep(uint32_t r[16]) {
       a.dbg[(it * 3 + role) * 16 + (slot)] = (unsigned long long)clock64();                       \
   } while (0)
 
+template <int PRE>   // 16-byte K chunks per thread in the observation operand (>= K1 / 8)
 __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // mbarriers: 0 a1_ready (256) | 1 GEMM1 done | 2..6 a2_ready[chunk] (256) | 7, 8 GEMM2 done [slot] |
@@ -538,14 +540,14 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
   if (role == 0) {
     // ---------------------------------------------------------------- producers
     const int nch = a.K1 >> 2, c_lo = part ? nch / 2 : 0, c_hi = part ? nch : nch / 2;   // this thread's 16-byte K chunks
-    float pre[kAct3PreChunks * 4];
+    float pre[PRE * 4];
     auto fetch = [&](int tile) {
       const long long row = (long long)tile * kActRows + t;
       const bool live = row < a.rows;
       const float *g = a.obs + (size_t)(live ? row : 0) * a.D;
       if ((a.D & 1) == 0) {
 #pragma unroll
-        for (int j = 0; j < kAct3PreChunks * 2; ++j) {
+        for (int j = 0; j < PRE * 2; ++j) {
           const int k = c_lo * 4 + 2 * j;
           float2 v = make_float2(0.f, 0.f);
           if (live && k < c_hi * 4 && k < a.D) v = __ldg(reinterpret_cast<const float2 *>(g + k));
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < kAct3PreChunks * 4; ++j) {
+        for (int j = 0; j < PRE * 4; ++j) {
           const int k = c_lo * 4 + j;
           pre[j] = (live && k < c_hi * 4 && k < a.D) ? __ldg(g + k) : 0.f;
         }
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
       // layer-1 operand: [obs | 1 | 0 ...] as hi + lo, one 16-byte store per K chunk (consecutive rows are contiguous:
       // conflict-free).  The previous tile's GEMM1 has completed (bar1 was waited for below).
 #pragma unroll
-      for (int j = 0; j < kAct3PreChunks; ++j) {
+      for (int j = 0; j < PRE; ++j) {
         const int c = c_lo + j;
         if (c < c_hi) {
           float v[4], h[4], l[4];
@@ -593,14 +595,16 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
       tc_fence_after();
       ACT3_STAMP(3);
       uint32_t r[2][16];
-      if (part < ng) tmem_ld16_issue(R1 + lane_off + (uint32_t)(16 * part), r[0]);
+      const uint32_t src = R1 + lane_off;
+      if (part < ng) tmem_ld16_issue(src + (uint32_t)(16 * part), r[0]);
 #pragma unroll
       for (int k = 0; k < kAct3MaxChunks; ++k) {
         if (k < nchunk) {
           const int g = 2 * k + part;                    // granule g of chunk k belongs to column half g & 1
           if (g < ng) {
             tmem_wait_ld_dep(r[k & 1]);
-            if (k + 1 < nchunk && g + 2 < ng) tmem_ld16_issue(R1 + lane_off + (uint32_t)(16 * (g + 2)), r[(k + 1) & 1]);
+            if (k + 1 < nchunk && g + 2 < ng)            // the next granule flies under this one
+              tmem_ld16_issue(src + (uint32_t)(16 * (g + 2)), r[(k + 1) & 1]);
             uint32_t l[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -675,43 +679,55 @@ __global__ void __launch_bounds__(kAct3Threads, 1) k_actor3x(ActorArgs a) {
       mbar_wait_bounded(bar2 + s, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       ACT3_STAMP(1);
-      for (int g = 0; g < ng2; g += 2) {
-        uint32_t r[2][16];
-        const bool two = g + 1 < ng2;
-        tmem_ld16_issue(src + (uint32_t)(16 * g), r[0]);
-        if (two) tmem_ld16_issue(src + (uint32_t)(16 * g + 16), r[1]);
-        tmem_wait_ld_dep(r[0]);
-        if (two) tmem_wait_ld_dep(r[1]);
-        if (g + 2 >= ng2) {        // the slot's last read: GEMM2 of tile it + 2 may overwrite it
-          tc_fence_before();
-          mbar_arrive(r2_free + s);
-          ACT3_STAMP(2);
-        }
-        const float4 *wa = reinterpret_cast<const float4 *>(w3 + 16 * g), *wb = reinterpret_cast<const float4 *>(w3 + a.N2 + 16 * g);
+      // rounds of two 16-column granules; the next round's loads fly under this round's arithmetic, two accumulators
+      // per logit keep the FMA chains short
+      float acc2 = 0.f, acc3 = 0.f;
+      uint32_t r[2][2][16];
+      const int nrounds = (ng2 + 1) >> 1;
+      tmem_ld16_issue(src, r[0][0]);
+      if (1 < ng2) tmem_ld16_issue(src + 16u, r[0][1]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 u = wa[q], v = wb[q];
-          const float x0 = fmaxf(__uint_as_float(r[0][4 * q]), 0.f), x1 = fmaxf(__uint_as_float(r[0][4 * q + 1]), 0.f),
-                      x2 = fmaxf(__uint_as_float(r[0][4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(r[0][4 * q + 3]), 0.f);
-          acc0 = fmaf(x0, u.x, acc0); acc0 = fmaf(x1, u.y, acc0); acc0 = fmaf(x2, u.z, acc0); acc0 = fmaf(x3, u.w, acc0);
-          acc1 = fmaf(x0, v.x, acc1); acc1 = fmaf(x1, v.y, acc1); acc1 = fmaf(x2, v.z, acc1); acc1 = fmaf(x3, v.w, acc1);
-        }
-        if (two) {
+      for (int rd = 0; rd < (kAct3MaxChunks + 1); ++rd) {
+        if (rd < nrounds) {
+          const int g = 2 * rd;
+          const bool two = g + 1 < ng2;
+          tmem_wait_ld_dep(r[rd & 1][0]);
+          if (two) tmem_wait_ld_dep(r[rd & 1][1]);
+          if (rd + 1 < nrounds) {
+            tmem_ld16_issue(src + (uint32_t)(16 * g + 32), r[(rd + 1) & 1][0]);
+            if (g + 3 < ng2) tmem_ld16_issue(src + (uint32_t)(16 * g + 48), r[(rd + 1) & 1][1]);
+          } else {                   // the slot's last loads have completed: GEMM2 of tile it + 2 may overwrite it
+            tc_fence_before();
+            mbar_arrive(r2_free + s);
+            ACT3_STAMP(2);
+          }
+          const float4 *wa = reinterpret_cast<const float4 *>(w3 + 16 * g), *wb = reinterpret_cast<const float4 *>(w3 + a.N2 + 16 * g);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 u = wa[4 + q], v = wb[4 + q];
-            const float x0 = fmaxf(__uint_as_float(r[1][4 * q]), 0.f), x1 = fmaxf(__uint_as_float(r[1][4 * q + 1]), 0.f),
-                        x2 = fmaxf(__uint_as_float(r[1][4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(r[1][4 * q + 3]), 0.f);
-            acc0 = fmaf(x0, u.x, acc0); acc0 = fmaf(x1, u.y, acc0); acc0 = fmaf(x2, u.z, acc0); acc0 = fmaf(x3, u.w, acc0);
-            acc1 = fmaf(x0, v.x, acc1); acc1 = fmaf(x1, v.y, acc1); acc1 = fmaf(x2, v.z, acc1); acc1 = fmaf(x3, v.w, acc1);
+            const float4 u = wa[q], v = wb[q];
+            const float x0 = fmaxf(__uint_as_float(r[rd & 1][0][4 * q]), 0.f), x1 = fmaxf(__uint_as_float(r[rd & 1][0][4 * q + 1]), 0.f),
+                        x2 = fmaxf(__uint_as_float(r[rd & 1][0][4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(r[rd & 1][0][4 * q + 3]), 0.f);
+            acc0 = fmaf(x0, u.x, acc0); acc2 = fmaf(x1, u.y, acc2); acc0 = fmaf(x2, u.z, acc0); acc2 = fmaf(x3, u.w, acc2);
+            acc1 = fmaf(x0, v.x, acc1); acc3 = fmaf(x1, v.y, acc3); acc1 = fmaf(x2, v.z, acc1); acc3 = fmaf(x3, v.w, acc3);
+          }
+          if (two) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 u = wa[4 + q], v = wb[4 + q];
+              const float x0 = fmaxf(__uint_as_float(r[rd & 1][1][4 * q]), 0.f), x1 = fmaxf(__uint_as_float(r[rd & 1][1][4 * q + 1]), 0.f),
+                          x2 = fmaxf(__uint_as_float(r[rd & 1][1][4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(r[rd & 1][1][4 * q + 3]), 0.f);
+              acc0 = fmaf(x0, u.x, acc0); acc2 = fmaf(x1, u.y, acc2); acc0 = fmaf(x2, u.z, acc0); acc2 = fmaf(x3, u.w, acc2);
+              acc1 = fmaf(x0, v.x, acc1); acc3 = fmaf(x1, v.y, acc3); acc1 = fmaf(x2, v.z, acc1); acc3 = fmaf(x3, v.w, acc3);
+            }
           }
         }
       }
       {
-        const float l0 = acc0, l1 = acc1;
+        const float l0 = acc0 + acc2, l1 = acc1 + acc3;
         const long long row = (long long)tile * kActRows + t;
         if (row < a.rows) {
-          const long long rr = row / a.Ns;
+          // replica / house of the row: 32-bit division whenever the row index allows it (the 64-bit one is ~100 instructions)
+          const long long rr = a.rows < (1ll << 31) ? (long long)((uint32_t)row / (uint32_t)a.Ns) : row / a.Ns;
           const int n = (int)(row - rr * a.Ns);
           uint8_t act = 0;
           float p_draw = 0.f, p1 = 0.f;

@@ -1872,8 +1872,10 @@ static int policy_step_impl(drsim_t *h, const drsim_actor_net *net, uint64_t see
     }
     a.dbg = h->actor_dbg;
     k_actor_pack3x<<<40, 512, 0, (cudaStream_t)stream>>>(a, h->actor_image);
-    CU_TRY(cudaFuncSetAttribute(k_actor3x, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
-    launch_pdl(k_actor3x, std::min(tiles, h->sm_count), kAct3Threads, (size_t)a.smem_bytes, (cudaStream_t)stream, a);
+    const int pre = a.K1 / 8;                     // 16-byte K chunks per producer thread
+    auto kern = pre <= 2 ? k_actor3x<2> : pre <= 4 ? k_actor3x<4> : pre <= 7 ? k_actor3x<7> : k_actor3x<kAct3PreChunks>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes));
+    launch_pdl(kern, std::min(tiles, h->sm_count), kAct3Threads, (size_t)a.smem_bytes, (cudaStream_t)stream, a);
     h->launches++;
   } else {
     // one spare K column per layer carries the bias (constant-one column in A), one spare output row regenerates the one

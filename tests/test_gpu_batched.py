@@ -316,10 +316,14 @@ def _torch_actor(D, h1, h2, seed):
     return fc, forward
 
 
-@pytest.mark.parametrize("R,n,layout,h1,h2", [(300, 100, "hand_engineered", 100, 100), (7, 1000, "tarmac", 100, 100),
-                                              (33, 37, "hand_engineered", 64, 48), (5, 9, "tarmac", 111, 96),
-                                              (520, 100, "hand_engineered", 100, 100), (1100, 100, "tarmac", 32, 16)])
-def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
+@pytest.mark.parametrize("R,n,layout,h1,h2,nb_comm", [
+    (300, 100, "hand_engineered", 100, 100, 10), (7, 1000, "tarmac", 100, 100, 10), (33, 37, "hand_engineered", 64, 48, 10),
+    (5, 9, "tarmac", 111, 96, 10),                      # widest layers that fit the tensor memory (no spare columns)
+    (520, 100, "hand_engineered", 100, 100, 10),        # three tiles per CTA: every pipeline slot is recycled
+    (1100, 100, "tarmac", 32, 16, 10),                  # narrow layers: a single chunk, nothing through the spare columns
+    (40, 100, "hand_engineered", 100, 100, 3),          # D = 22: the 4-chunk instantiation of the row handling
+    (40, 100, "hand_engineered", 80, 100, 12)])         # D = 58: the 9-chunk instantiation; 16 in-place columns
+def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2, nb_comm):
     """the tcgen05 actor + categorical draw against a plain PyTorch fp32 forward of the same
     weights.  Probabilities: TF32 operands (10-bit mantissa, rounded to nearest), fp32 accumulation -> |dp| <= 5e-3
     on logits three times wider than the default initialisation gives.  The draw
@@ -331,7 +335,7 @@ def test_on_device_actor_matches_torch_fp32(R, n, layout, h1, h2):
     from marl_demandresponse_b200.batched import synthetic_state
     from oracle import philox
 
-    prop = _prop(n)
+    prop = _prop(n, **{"cluster_prop/agents_comm_prop/max_nb_agents_communication": nb_comm})
     env = BatchedEnv(prop, R, obs_layout=layout, noise="philox", seed=17, rep_offset=40)
     env.reset(synthetic_state(prop, R, seed=4, rep_offset=40))
     D = env.sim.D
