@@ -255,7 +255,12 @@ int drsim_run(drsim_t *h, const drsim_step_args *args, int n_steps, size_t actio
 /* The same with a ROTATING action tape of `tape_planes` planes: step k reads plane k % tape_planes
  * (tape_planes = 0: no wrap, drsim_run).  Also accepts a house-sharded handle (every step is then a
  * drsim_step_sharded: all ranks must run the same number of steps), so that a rollout of one cluster split
- * across GPUs is enqueued by one C call per rank instead of one host-language call per step. */
+ * across GPUs is enqueued by one C call per rank instead of one host-language call per step.
+ * On the staged fused kernels (fp32, replicas on one GPU, constant base power, at least two tiles per CTA) the
+ * steps of a block of schedule records run INSIDE one launch: a CTA's inputs of step k + 1 are its own outputs of
+ * step k plus the tape, so consecutive steps have no boundary between CTAs (bit-identical to
+ * one launch per step, which DRSIM_NO_STREAM=1 in the environment restores).  The action planes of the whole block
+ * must therefore stay untouched until the call's work on `stream` has completed -- as for any asynchronous call. */
 int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_steps, size_t action_stride, int tape_planes,
                    void *stream);
 
