@@ -645,8 +645,8 @@ def run_gpu_arm(args, wl) -> None:
                             if R * n_local < 100000 else {}),
                          "unit": "GB/s", "frac": achieved / peak, **committed_traffic(args.workload),
                          "algorithmic_bytes_per_step": R * n_local * bytes_hs,
-                         "steps_per_launch": 64 if streamed else 1,
-                         "algorithmic_bytes_per_launch": R * n_local * bytes_hs * (64 if streamed else 1),
+                         "steps_per_launch": min(64, args.steps) if streamed else 1,
+                         "algorithmic_bytes_per_launch": R * n_local * bytes_hs * (min(64, args.steps) if streamed else 1),
                          "bytes_per_house_step": bytes_hs,
                          **({"per_step_launch": {"ms_per_step": ms_launch, "value": w.total_houses / (ms_launch * 1e-3),
                                                  "achieved": R * n_local * bytes_hs / (ms_launch * 1e-3) / 1e9,
