@@ -489,13 +489,15 @@ def test_run_equals_repeated_steps(n, R, policy, base_mode, layout):
         _run_with_noise(b, R)
 
 
-@pytest.mark.parametrize("n,R,layout,rotate,policy", [
-    (1000, 640, "tarmac", True, "external"),             # one cluster per tile (k_fused_tma<1>), 2.2 tiles per CTA
-    (100, 6100, "tarmac", False, "external"),            # ten clusters per tile (generic instantiation)
-    (37, 16000, "tarmac", True, "external"),             # padded rows, ragged last tile
-    (100, 4096, "hand_engineered", True, "external"),    # BASELINE config 3: wide rows (k_fused_rows), 586 tiles on 293 CTAs
-    (100, 6100, "tarmac", True, "deadband_bangbang")])   # on-device policy, no tape
-def test_tape_stream_equals_per_step_launches(n, R, layout, rotate, policy):
+@pytest.mark.parametrize("n,R,layout,rotate,policy,nb_comm,tile_envs", [
+    (1000, 640, "tarmac", True, "external", 10, None),             # one cluster per tile (k_fused_tma<1>), 2.2 tiles per CTA
+    (1000, 2048, "tarmac", True, "external", 10, None),            # BASELINE config 4 at full size: 7 tiles per CTA
+    (100, 6100, "tarmac", False, "external", 10, None),            # ten clusters per tile (generic instantiation)
+    (37, 16000, "tarmac", True, "external", 10, None),             # padded rows, ragged last tile
+    (100, 4096, "hand_engineered", True, "external", 10, None),    # BASELINE config 3: wide rows (k_fused_rows), 586 tiles on 293 CTAs
+    (100, 1800, "hand_engineered", True, "external", 2, 3),        # messages in whole-tile rows (k_fused_tma<2>): 18 columns, 3 clusters per tile
+    (100, 6100, "tarmac", True, "deadband_bangbang", 10, None)])   # on-device policy, no tape
+def test_tape_stream_equals_per_step_launches(n, R, layout, rotate, policy, nb_comm, tile_envs, monkeypatch):
     """``drsim_run_tape`` on the staged fused kernel with at least two tiles per CTA runs the step loop INSIDE the
     kernel (StepIn::stream_steps: no boundary between the steps of a schedule block).  Same bits as one launch per
     step (``DRSIM_NO_STREAM=1``), over a schedule-block boundary, with a rotating and a linear tape."""
@@ -503,7 +505,10 @@ def test_tape_stream_equals_per_step_launches(n, R, layout, rotate, policy):
 
     from marl_demandresponse_b200 import BatchedEnv
 
-    prop = _prop(n, **{"power_grid_prop/signal_properties/mode": "sinusoidals"})
+    if tile_envs is not None:
+        monkeypatch.setenv("DRSIM_TILE_ENVS", str(tile_envs))
+    prop = _prop(n, **{"power_grid_prop/signal_properties/mode": "sinusoidals",
+                       "cluster_prop/agents_comm_prop/max_nb_agents_communication": nb_comm})
     T = 70 if rotate else 9
     planes = 3 if rotate else T
     a = BatchedEnv(prop, R, policy=policy, noise="philox", seed=5, obs_layout=layout)
