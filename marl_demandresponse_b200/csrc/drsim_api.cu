@@ -903,7 +903,7 @@ static int launch_house_phase(drsim_handle *h, const StepIn &in, cudaStream_t s)
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
+    launch_pdl(k_greedy<real>, p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s, pl, p, n2);
     h->launches++;
   }
   launch_pdl(k_house<real>, p.R * h->chunks, kThreads, 0, s, pl, p, in, h->chunks);
@@ -1002,7 +1002,7 @@ static int launch_shard(drsim_handle *h, StepIn in, cudaStream_t s) {
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
+    launch_pdl(k_greedy<real>, p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s, pl, p, n2);
     h->launches++;
   }
   if (needs_halo(p)) {   // the peers push their edge-house records into this rank's halo inbox (reduce_cluster)
@@ -1094,7 +1094,7 @@ static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
-    k_greedy<real><<<p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s>>>(pl, p, n2);
+    launch_pdl(k_greedy<real>, p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s, pl, p, n2);
     h->launches++;
   }
   // (greedy-myopic actions were just written into the action plane by k_greedy: external to the step kernel)

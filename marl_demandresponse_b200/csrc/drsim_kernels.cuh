@@ -2865,6 +2865,11 @@ __global__ void __launch_bounds__(1024) k_greedy(Planes<real> pl, SimParams p, i
   int *idx = reinterpret_cast<int *>(key + n_pow2);
   const int r = blockIdx.x;
   const size_t rb = (size_t)r * p.Ns;
+  // programmatic dependent launch on both sides: this grid becomes resident under the tail of the step before it, and
+  // the step kernel behind it sets itself up (static planes) while the sort runs -- it waits for this grid's completion
+  // before it reads the actions
+  pdl_wait();
+  pdl_trigger();
   if (n_pow2 <= (int)blockDim.x) {
     // one element per thread: compare-exchange distances below 32 go through warp shuffles (no shared
     // memory, no barrier), only the 15 of 55 stages with a distance >= 32 (n = 1024) cross warps
