@@ -1087,10 +1087,35 @@ static int launch_chunked_fallback(drsim_handle *h, const StepIn &in, cudaStream
   return launch_env_phase<real>(h, in, nullptr, 1, s);
 }
 
+// A handle whose clusters fit a warp (<= 32 plane slots) in a handful of replicas: the latency-oriented kernel k_small
+// (one house per lane) instead of the tile kernels (four houses per thread).  fp32, plain columns only.
+static bool small_handle(const drsim_handle *h) {
+  const SimParams &p = h->p;
+  if (getenv("DRSIM_NO_SMALL") || h->real_bytes != 4 || !h->fused_ok || p.Ns > 32 || p.N != p.n_global || p.R > 256) return false;
+  if (p.obs_dim == 0) return true;
+  if (p.own_dim != 10 || (p.obs_dim & 1)) return false;
+  const bool msgs = p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && p.nb_comm > 0;
+  return msgs ? (p.msg_dim == 4 && p.obs_dim == 10 + 4 * p.nb_comm) : p.obs_dim == 10;
+}
+
 template <typename real>
 static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
   const SimParams &p = h->p;
+  if constexpr (sizeof(real) == 4) {
+    if (small_handle(h) && in.sched_rec && in.advance && in.do_interp <= 0 && !in.act_poll_err && !pl.dur) {
+      if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && !in.actions) {
+        int n2 = 1;
+        while (n2 < p.N) n2 <<= 1;
+        launch_pdl(k_greedy<real>, p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s, pl, p, n2);
+        h->launches++;
+      }
+      launch_pdl(k_small, (p.R + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0, s, pl, p, in);
+      h->launches++;
+      CU_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
   if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && in.advance && !in.actions) {
     int n2 = 1;
     while (n2 < p.N) n2 <<= 1;
@@ -1231,9 +1256,11 @@ extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_ste
   // the kernel (k_fused_tma<0>, StepIn::n_steps), one launch per block of scheduled records -- a small
   // cluster then costs the in-kernel step latency instead of one dependent launch per step.
   const SimParams &p = h->p;
-  const bool episode = !tape && h->fused_ok && h->real_bytes == 4 && h->fused_direct && h->geom.use_tma && !h->geom.use_rows &&
+  const bool small = small_handle(h);   // k_small: steps in registers, any number of replicas per launch
+  const bool episode = !tape && h->fused_ok && h->real_bytes == 4 &&
+                       (small || (h->fused_direct && h->geom.use_tma && !h->geom.use_rows && h->geom.n_tiles <= h->fused_grid)) &&
                        p.policy != DRSIM_POLICY_EXTERNAL && p.policy != DRSIM_POLICY_GREEDY_MYOPIC &&
-                       p.base_mode == DRSIM_BASE_CONSTANT && h->geom.n_tiles <= h->fused_grid && !getenv("DRSIM_NO_EPISODE");
+                       p.base_mode == DRSIM_BASE_CONSTANT && !getenv("DRSIM_NO_EPISODE");
   if (episode) {
     int left = n_steps;
     while (left > 0) {
@@ -1260,8 +1287,10 @@ extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_ste
   const bool rows_path = h->geom.use_rows && h->geom.in_stride && p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
   const bool policy_ok = tape ? p.policy == DRSIM_POLICY_EXTERNAL
                               : (tma_path && p.policy != DRSIM_POLICY_EXTERNAL && p.policy != DRSIM_POLICY_GREEDY_MYOPIC);
-  const bool taped = n_steps > 1 && h->fused_ok && h->real_bytes == 4 && (tma_path || rows_path) && policy_ok &&
-                     p.base_mode == DRSIM_BASE_CONSTANT && sgrid * 10 >= h->fused_grid * 9 && !h->mirror_next &&
+  const bool taped = n_steps > 1 && h->fused_ok && h->real_bytes == 4 &&
+                     (small ? (tape && p.policy == DRSIM_POLICY_EXTERNAL)
+                            : ((tma_path || rows_path) && policy_ok && sgrid * 10 >= h->fused_grid * 9)) &&
+                     p.base_mode == DRSIM_BASE_CONSTANT && !h->mirror_next &&
                      !h->act_poll_next && !h->obs_override && !h->reward_override && !h->broken && !getenv("DRSIM_NO_STREAM");
   int first = 0;
   if (taped) {
@@ -1276,7 +1305,7 @@ extern "C" int drsim_run_tape(drsim_t *h, const drsim_step_args *args, int n_ste
       in.tape_first = first;
       in.tape_stride = action_stride;
       if (k == 1 && tape) in.actions = tape + (size_t)(tape_planes > 0 ? first % tape_planes : first) * action_stride;
-      h->launch_grid = sgrid;
+      h->launch_grid = small ? 0 : sgrid;
       const int rc = launch_fused<float>(h, in, (cudaStream_t)stream);
       h->launch_grid = 0;
       if (rc) return rc;

@@ -2753,6 +2753,147 @@ k_fused_rows(Planes<float> pl, SimParams p, StepIn in, FusedGeom g) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Small clusters, latency-oriented (BASELINE config 1: the default 10-house cluster).  The tile
+// kernels give every thread four houses, so a 10-house cluster runs on three threads and one step
+// is a ~2,000-instruction dependent chain (8 us).  Here a WARP owns a cluster of at most 32 houses,
+// one house per lane: the lock-out state machine and the thermal update of house4_compute_f32 per
+// lane, the five cluster sums by shuffle butterflies, the power fold-in / reward / row of every
+// house by its own lane, neighbour messages by shuffles instead of shared memory.  The state lives
+// in registers across the steps of one launch (StepIn::n_steps: on-device policy; StepIn::
+// stream_steps: action tape) and goes back to the planes after every step like everything else the
+// step produces.  Conditions (checked by the host): fp32, scheduled env path, plain columns.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallWarps = 4;   // clusters per CTA
+
+__global__ void __launch_bounds__(kSmallWarps * 32) k_small(Planes<float> pl, SimParams p, StepIn in) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = (int)blockIdx.x * kSmallWarps + warp;
+  pdl_trigger();
+  if (r >= p.R) return;
+  const int Ns = p.Ns, N = p.N, D = p.obs_dim, nbc = p.nb_comm;
+  const KC<float> kc(p);
+  const bool slot = lane < Ns, ok = lane < N;          // plane slot / real house
+  const size_t o = (size_t)r * Ns + (slot ? lane : 0);
+  const int policy = p.policy;
+  const bool ext = policy == DRSIM_POLICY_EXTERNAL || policy == DRSIM_POLICY_GREEDY_MYOPIC;
+  const bool individual = p.penalty_mode == DRSIM_PEN_INDIVIDUAL_L2;
+  const bool need_msg = p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && nbc > 0;
+  const int dt = p.dt, dur = p.lockout_duration;
+  const float half_db = p.hf.half_db;
+  // launch-invariant planes before the dependency wait, what the step before wrote after it
+  // (padding slots of the plane stride are stepped like houses with zero planes, exactly as the tile kernels do)
+  float tg = 0.f, cap = 0.f, c[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (slot) {
+    tg = __ldg(pl.target + o);
+    cap = __ldg(pl.cap + o);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c[k] = __ldg(pl.coef[k] + o);
+  }
+  pdl_wait();
+  float ta = 0.f, tm = 0.f;
+  int sso = 0;
+  uint32_t f = 0;
+  if (slot) { ta = pl.t_air[o]; tm = pl.t_mass[o]; sso = pl.sso[o]; f = pl.flags[o]; }
+  double m[DRSIM_N_METRICS];
+#pragma unroll
+  for (int q = 0; q < DRSIM_N_METRICS; ++q) m[q] = pl.metrics[(size_t)r * DRSIM_N_METRICS + q];
+  const int n_steps = max(1, max(in.n_steps, in.stream_steps));
+  const float pmax_n = cap * p.hf.inv_cop * p.hf.inv_nrs;
+  const float tg20 = tg - 20.f;
+
+  for (int k = 0; k < n_steps; ++k) {
+    const SchedRec *rec = in.sched_rec + (size_t)k * p.R + r;
+    const float od = __ldg(&rec->od_prev_f), solar = __ldg(&rec->solar_f);
+    // ---- house update: the expressions of house4_compute_f32 for one house ----
+    const bool on = f & 1u;
+    bool a = false;
+    if (ext) {
+      const uint8_t *acts = in.actions ? in.actions : pl.actions;
+      if (in.actions && in.stream_steps > 1) {
+        const int j = in.tape_first + k;
+        acts = in.actions + (size_t)(in.tape_planes > 0 ? j % in.tape_planes : j) * in.tape_stride;
+      }
+      a = slot && acts[o] != 0;
+    } else if (policy == DRSIM_POLICY_DEADBAND_BANGBANG) a = ta < -half_db ? false : (ta > half_db ? true : on);
+    else if (policy == DRSIM_POLICY_BANGBANG) a = ta > 0.f;
+    else if (policy == DRSIM_POLICY_ALWAYS_ON) a = true;
+    sso = sso + (on ? 0 : dt);
+    bool lock = !on && sso < dur;
+    const bool on_n = !lock && a;
+    sso = on_n ? 0 : sso;
+    lock = lock || (!on_n && sso + dt < dur);
+    f = (on_n ? 1u : 0u) | (lock ? 2u : 0u);
+    const float Qa = (on_n ? cap * p.hf.neg_inv_opl : 0.f) + solar;
+    const float odr = od - tg;
+    const float ia = fmaf(c[2], Qa, fmaf(c[1], odr - ta, c[0] * (tm - ta)));
+    const float im = fmaf(c[5], Qa, fmaf(c[4], odr - tm, c[3] * (ta - tm)));
+    ta = ta + ia;
+    tm = tm + im;
+    const float mk = ok ? 1.f : 0.f;
+    const float dd = fmaxf(fabsf(ta) - half_db, 0.f);
+    const float pen = dd * dd * mk;
+    float red[kRed] = {fmaf(on_n ? mk : 0.f, cap * p.hf.inv_cop, 0.f), fmaf(pen, p.hf.inv_n, 0.f), pen, mk * ta, (ta * mk) * ta};
+    // ---- the five cluster sums: every lane ends up with the totals ----
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      float t[kRed];
+#pragma unroll
+      for (int q = 0; q < kRed; ++q) t[q] = __shfl_xor_sync(0xffffffffu, red[q], s);
+      red_combine(red, t);
+    }
+    double rd[kRed];
+#pragma unroll
+    for (int q = 0; q < kRed; ++q) rd[q] = (double)red[q];
+    // ---- env values every house needs (the fold-in of the fused kernels) ----
+    EnvBroadcast<float> e;
+    e.signal_n = __ldg(&rec->signal_n); e.solar_n = __ldg(&rec->solar_n); e.od_n = __ldg(&rec->od_n);
+    e.power_n = (float)(rd[0] * p.inv_nrs);
+    e.rew_sig = (float)signal_penalty(p, rd[0], __ldg(&rec->signal_prev));
+    e.pen_common = (float)rd[1];
+    e.pen_max = (float)rd[2];
+    // ---- outputs of the step: state, reward, observation row ----
+    if (slot) {
+      pl.t_air[o] = ta; pl.t_mass[o] = tm; pl.sso[o] = sso; pl.flags[o] = (uint8_t)f;
+      pl.reward[o] = ok ? (individual ? reward_f32_individual(p, ta, e.rew_sig) : house_reward<float>(p, kc, ta, tg, e)) : 0.f;
+    }
+    const float sso_n = (float)fast_div((uint32_t)sso, p.fd_dur);                     // norm.py:40-43, :79-82
+    // this house's message record (building.py:102-139 through norm.py:31-60), read by its neighbours through shuffles
+    const float m0 = ok ? ta * 0.2f : 0.f, m1 = ok ? sso_n : 0.f, m2 = (ok && (f & 1u)) ? pmax_n : 0.f, m3 = ok ? pmax_n : 0.f;
+    if (D > 0) {
+      float2 *row = reinterpret_cast<float2 *>(pl.obs + o * D);
+      if (slot) {
+        row[0] = make_float2(ok ? (float)(f & 1u) : 0.f, ok ? (float)((f >> 1) & 1u) : 0.f);
+        row[1] = make_float2(ok ? sso_n : 0.f, ok ? 1.f : 0.f);
+        row[2] = ok ? make_float2(e.power_n, e.signal_n) : make_float2(0.f, 0.f);
+        row[3] = make_float2(ok ? p.hf.deadband : 0.f, ok ? (ta + tg20) * 0.2f : 0.f);
+        row[4] = make_float2(ok ? (tm + tg20) * 0.2f : 0.f, ok ? tg20 * 0.2f : 0.f);
+      }
+      if (need_msg) {
+        for (int q = 0; q < nbc; ++q) {      // (every lane takes part in the shuffles)
+          const int nb = ok ? neighbour_of(p, pl.comm_table, r, lane, q) : 0;
+          const float v0 = __shfl_sync(0xffffffffu, m0, nb), v1 = __shfl_sync(0xffffffffu, m1, nb),
+                      v2 = __shfl_sync(0xffffffffu, m2, nb), v3 = __shfl_sync(0xffffffffu, m3, nb);
+          if (slot) {
+            row[5 + 2 * q] = ok ? make_float2(v0, v1) : make_float2(0.f, 0.f);
+            row[6 + 2 * q] = ok ? make_float2(v2, v3) : make_float2(0.f, 0.f);
+          }
+        }
+      } else if (slot && !ok) {
+        for (int q = 5; q < D / 2; ++q) row[q] = make_float2(0.f, 0.f);
+      }
+    }
+    // ---- env planes + running metrics (one lane; the staged record of the fused kernels, built in registers) ----
+    if (lane == 0) {
+      EnvStage st;
+      st.rec = *rec;
+#pragma unroll
+      for (int q = 0; q < DRSIM_N_METRICS; ++q) st.m[q] = m[q];
+      env_stage_store<float>(pl, p, r, st, rd, in.host_env, m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Reset on the device: property noise + initial state from Philox streams keyed by
 // (global replica, global house, draw) and (global replica, draw); the update coefficients are
 // derived in fp64 right here.  One thread per house; thread n == 0 of a replica also writes the env

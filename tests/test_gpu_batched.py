@@ -37,7 +37,10 @@ def _oracle_run(prop, st, actions, od_noise, perlin):
 
 @pytest.mark.parametrize("n,R,layout,path", [(100, 24, "hand_engineered", "auto"), (1000, 6, "tarmac", "auto"),
                                              (1000, 3, "hand_engineered", "auto"), (2500, 2, "hand_engineered", "auto"),
-                                             (100, 24, "hand_engineered", "split"), (37, 9, "hand_engineered", "auto")])
+                                             (100, 24, "hand_engineered", "split"), (37, 9, "hand_engineered", "auto"),
+                                             # clusters that fit a warp: the one-house-per-lane kernel (k_small)
+                                             (10, 7, "hand_engineered", "auto"), (22, 5, "tarmac", "auto"),
+                                             (32, 3, "hand_engineered", "auto"), (9, 130, "hand_engineered", "auto")])
 def test_batched_env_philox_matches_oracle(n, R, layout, path):
     """Device Philox streams (od noise, perlin-like signal noise) == their NumPy restatement, and the
     whole batched step == the oracle driven by those values."""
@@ -536,6 +539,50 @@ def test_tape_stream_equals_per_step_launches(n, R, layout, rotate, policy, nb_c
     torch.cuda.synchronize()
     for k in ("dt_air", "sso", "flags", "reward", "obs", "metrics"):
         assert torch.equal(a.state[k], b.state[k]), k
+
+
+@pytest.mark.parametrize("n,R,layout,policy,nb_comm", [(10, 5, "hand_engineered", "external", 9), (10, 1, "hand_engineered", "deadband_bangbang", 9),
+                                                    (31, 200, "tarmac", "external", 10), (12, 9, "hand_engineered", "bangbang", 4),
+                                                    (5, 3, "none", "external", 2)])
+def test_small_cluster_kernel_matches_tile_kernels(n, R, layout, policy, nb_comm):
+    """Clusters of at most 32 houses in a handful of replicas step on ``k_small`` (one house per lane, the state in
+    registers across the steps of a launch).  Against the tile kernels (``DRSIM_NO_SMALL=1``): discrete state and env
+    scalars bit-exact, continuous values to fp32 rounding (the cluster sums are associated differently); the in-kernel
+    step loop (on-device policy / action tape) == one launch per step, bit for bit."""
+    import torch
+
+    from marl_demandresponse_b200 import BatchedEnv
+
+    prop = _prop(n, **{"power_grid_prop/signal_properties/mode": "sinusoidals", "cluster_prop/house_prop/deadband": 0.4,
+                       "cluster_prop/agents_comm_prop/max_nb_agents_communication": nb_comm})
+    T = 70
+    tape = None
+    if policy == "external":
+        tape = (torch.rand((T, R, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4)) < 0.5).to(torch.uint8)
+    a = BatchedEnv(prop, R, policy=policy, noise="philox", seed=9, obs_layout=layout)
+    a.reset()
+    b, c = copy.deepcopy(a), copy.deepcopy(a)
+    l0 = a.sim.launch_count
+    a.run(T, tape)                                       # k_small, steps inside the kernel
+    assert a.sim.launch_count - l0 <= 2 * 3
+    for t in range(T):                                   # k_small, one launch per step
+        b.step(None if tape is None else tape[t])
+    os.environ["DRSIM_NO_SMALL"] = "1"
+    try:
+        for t in range(T):                               # tile kernels
+            c.step(None if tape is None else tape[t])
+    finally:
+        del os.environ["DRSIM_NO_SMALL"]
+    torch.cuda.synchronize()
+    keys = [k for k in ("dt_air", "dt_mass", "sso", "flags", "reward", "obs", "signal", "power", "od_temp", "metrics")
+            if a.state[k] is not None]                   # (obs_layout "none": no observation plane)
+    for k in keys:
+        assert torch.equal(a.state[k], b.state[k]), k
+    for k in ("sso", "flags", "signal", "od_temp"):
+        assert torch.equal(a.state[k], c.state[k]), k
+    for k in ("dt_air", "dt_mass", "reward", "obs", "power", "metrics"):
+        if k in keys:
+            torch.testing.assert_close(a.state[k], c.state[k], rtol=3e-6, atol=3e-6)
 
 
 def _run_with_noise(env, R):
