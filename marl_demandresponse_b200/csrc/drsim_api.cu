@@ -92,6 +92,7 @@ struct drsim_handle {
   // pinned + mapped snapshot for the dict API (drsim_snapshot)
   unsigned char *h_snap = nullptr, *h_snap_dev = nullptr;
   size_t snap_bytes = 0, snap_obs_off = 0;
+  bool snap_next = false, snap_fused = false;   // transient: the next small-cluster step writes the host snapshot itself
   int launch_grid = 0;                       // transient: grid of the next fused launch (tape stream), 0 = fused_grid
   unsigned long long *actor_dbg = nullptr;   // DRSIM_ACTOR_DBG: phase stamps of CTA 0 of the last k_actor3x launch
   unsigned long long *shard_dbg = nullptr;   // DRSIM_SHARD_DBG: per-CTA time stamps of the last k_shard launch
@@ -1098,10 +1099,39 @@ static bool small_handle(const drsim_handle *h) {
   return msgs ? (p.msg_dim == 4 && p.obs_dim == 10 + 4 * p.nb_comm) : p.obs_dim == 10;
 }
 
+static int snap_targets(drsim_handle *h, SnapPtrs &o, unsigned char **obs_dev);
+
+// ... and the fp64 build (the drop-in Environment): k_small_gen<double>, any observation / message option
+static bool small64_handle(const drsim_handle *h) {
+  const SimParams &p = h->p;
+  return !getenv("DRSIM_NO_SMALL") && h->real_bytes == 8 && h->fused_ok && p.Ns <= 32 && p.N == p.n_global && p.R <= 256;
+}
+
 template <typename real>
 static int launch_fused(drsim_handle *h, const StepIn &in, cudaStream_t s) {
   const Planes<real> pl = make_planes<real>(h);
   const SimParams &p = h->p;
+  if constexpr (sizeof(real) == 8) {
+    if (small64_handle(h) && in.advance && in.do_interp <= 0 && !pl.dur) {
+      if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && !in.actions) {
+        int n2 = 1;
+        while (n2 < p.N) n2 <<= 1;
+        launch_pdl(k_greedy<real>, p.R, std::min(1024, std::max(32, n2)), (size_t)n2 * 24, s, pl, p, n2);
+        h->launches++;
+      }
+      SnapPtrs so{};
+      unsigned char *so_obs = nullptr;
+      if (h->snap_next) {
+        if (int rc = snap_targets(h, so, &so_obs)) return rc;
+        h->snap_fused = true;
+      }
+      launch_pdl(k_small_gen<double>, (p.R + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, 0, s, pl, p, in, so,
+                 reinterpret_cast<double *>(so_obs));
+      h->launches++;
+      CU_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
   if constexpr (sizeof(real) == 4) {
     if (small_handle(h) && in.sched_rec && in.advance && in.do_interp <= 0 && !in.act_poll_err && !pl.dur) {
       if (p.policy == DRSIM_POLICY_GREEDY_MYOPIC && !in.actions) {
@@ -1442,7 +1472,8 @@ static size_t snap_layout(const drsim_handle *h, size_t off[8]) {
 }
 
 // enqueues the snapshot kernel + the observation-row copy on `s`; the caller synchronises
-static int enqueue_snapshot(drsim_handle *h, cudaStream_t s) {
+// the mapped pinned snapshot buffer (allocated on first use) as the device sees it
+static int snap_targets(drsim_handle *h, SnapPtrs &o, unsigned char **obs_dev) {
   size_t off[8];
   const size_t bytes = snap_layout(h, off);
   if (bytes > ((size_t)512 << 20)) return fail(DRSIM_E_ARG, "drsim_snapshot: more than 512 MB -- use the tensor views for clusters this large");
@@ -1451,11 +1482,19 @@ static int enqueue_snapshot(drsim_handle *h, cudaStream_t s) {
     CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->h_snap_dev), h->h_snap, 0));
     h->snap_bytes = bytes;
   }
-  SnapPtrs o{};
   unsigned char *d = h->h_snap_dev;
   o.t_air = reinterpret_cast<double *>(d + off[0]); o.t_mass = reinterpret_cast<double *>(d + off[1]);
   o.reward = reinterpret_cast<double *>(d + off[2]); o.sso = reinterpret_cast<int32_t *>(d + off[3]);
   o.on = d + off[4]; o.lockout = d + off[5]; o.env = reinterpret_cast<double *>(d + off[6]);
+  if (obs_dev) *obs_dev = h->p.obs_dim ? d + off[7] : nullptr;
+  return 0;
+}
+
+static int enqueue_snapshot(drsim_handle *h, cudaStream_t s) {
+  size_t off[8];
+  snap_layout(h, off);
+  SnapPtrs o{};
+  if (int rc = snap_targets(h, o, nullptr)) return rc;
   const SimParams &p = h->p;
   const long long n = std::max<long long>((long long)p.R * p.N, p.R);
   if (h->real_bytes == 8) k_snapshot<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(make_planes<double>(h), p, o);
@@ -1588,9 +1627,12 @@ static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_n
   }
   h->mirror_next = mirror;
   h->act_poll_next = dma_poll;
+  h->snap_next = snap != nullptr;   // a small-cluster step (k_small_gen) writes the snapshot itself
+  h->snap_fused = false;
   int rc = run_step(h, &a, 1, di, s);
   h->mirror_next = nullptr;
   h->act_poll_next = false;
+  h->snap_next = false;
   if (rc) {
     if (dma_poll) {  // the kernel did not run: nothing consumed the copy, restore the poison
       cudaStreamSynchronize(h->copy_stream);
@@ -1613,7 +1655,7 @@ static int step_host_impl(drsim_t *h, const uint8_t *actions, const double *od_n
     else CU_TRY(cudaMemcpy2DAsync(obs_out, (size_t)p.N * row, h->slab + h->o_obs, (size_t)p.Ns * row, (size_t)p.N * row, p.R,
                                   cudaMemcpyDeviceToHost, s));
   }
-  if (snap) {
+  if (snap && !h->snap_fused) {
     if (int rc2 = enqueue_snapshot(h, s)) return rc2;
   }
   if (env_out && mirror) {

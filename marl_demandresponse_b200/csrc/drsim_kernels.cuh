@@ -2893,6 +2893,144 @@ __global__ void __launch_bounds__(kSmallWarps * 32) k_small(Planes<float> pl, Si
   }
 }
 
+// host snapshot of the dict API (drsim_snapshot): dense [R][N] arrays + [R][kSnapEnv] env scalars in mapped pinned memory
+struct SnapPtrs {
+  double *t_air, *t_mass, *reward;   // [R][N]
+  int32_t *sso;                      // [R][N]
+  uint8_t *on, *lockout;             // [R][N]
+  double *env;                       // [R][kSnapEnv]
+};
+constexpr int kSnapEnv = 8;   // od_temp, signal, power, solar, base_power, epoch, t_since_interp, max_power
+
+// The same mapping for the steps k_small does not take: the fp64 build (the drop-in `Environment` replays the
+// reference's kelvin formula in fp64 and injects its noise per step) with every observation / message option --
+// one house per lane through the helpers of house4_step (hvac.py:43-64, building.py:141-222), butterfly sums in
+// `real`, the scheduled or the inline env epilogue on lane 0 (environment.py:87-106), rows written by their own
+// lane with obs_own (utils/norm.py:71-218).  One step per launch.  A 10-house cluster took 35 us on the fp64
+// tile kernel (three active threads, a serial fp64 epilogue between two CTA barriers).
+// `snap` / `snap_obs` (optional, mapped pinned host memory): the host snapshot of drsim_step_host_snapshot is written
+// by the same lanes -- no second kernel and no D2H copy behind the step, one synchronisation for the whole call.
+template <typename real>
+__global__ void __launch_bounds__(kSmallWarps * 32) k_small_gen(Planes<real> pl, SimParams p, StepIn in, SnapPtrs snap, real *snap_obs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = (int)blockIdx.x * kSmallWarps + warp;
+  pdl_trigger();
+  if (r >= p.R) return;
+  constexpr int NC = NCoef<real>::n;
+  const int Ns = p.Ns, N = p.N, D = p.obs_dim, nbc = p.nb_comm;
+  const KC<real> kc(p);
+  const bool slot = lane < Ns, ok = lane < N;
+  const size_t rb = (size_t)r * Ns, o = rb + (slot ? lane : 0);
+  const bool ext = p.policy == DRSIM_POLICY_EXTERNAL || p.policy == DRSIM_POLICY_GREEDY_MYOPIC;
+  const bool need_msg = p.obs_layout == DRSIM_OBS_HAND_ENGINEERED && nbc > 0;
+  real tg = 0, cap = 0, c[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) c[k] = 0;
+  if (ok) {
+    tg = __ldg(pl.target + o);
+    cap = __ldg(pl.cap + o);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) c[k] = __ldg(pl.coef[k] + o);
+  }
+  pdl_wait();
+  EnvRegs er{};
+  if (lane == 0) er = env_load(pl, in, r);
+  const real od_prev = (real)pl.od_temp[r], solar = (real)pl.solar_next[r];
+  real ta = 0, tm = 0;
+  int sso = 0;
+  uint32_t f = 0;
+  real red[kRed] = {0, 0, 0, 0, 0};
+  if (ok) {   // one house of house4_step (padding slots are not stepped on this path)
+    ta = pl.t_air[o]; tm = pl.t_mass[o]; sso = pl.sso[o]; f = pl.flags[o];
+    const bool extv = ext && (in.actions ? in.actions : pl.actions)[o] != 0;
+    const bool a = Rep<real>::act(p.policy, ta, tg, kc.db, f & 1u, extv);
+    hvac_fsm(f, sso, a, p.dt, p.lockout_duration);
+    const real q = (f & 1u) ? hvac_heat(cap, kc.one_plus_latent, kc.neg_inv_opl) : (real)0;
+    thermal_step(ta, tm, c, Rep<real>::od_in(od_prev, tg), q + solar);
+    if (f & 1u) red[0] = qdiv(cap, kc.cop, kc.inv_cop);
+    const real pen = Rep<real>::pen(tg, kc.db, ta);
+    red[1] = qdiv(pen, kc.n_glob, kc.inv_n);
+    red[2] = pen;
+    const real dT = Rep<real>::dev(ta, tg);
+    red[3] = dT;
+    red[4] = dT * dT;
+    pl.t_air[o] = ta; pl.t_mass[o] = tm; pl.sso[o] = sso; pl.flags[o] = (uint8_t)f;
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    real t[kRed];
+#pragma unroll
+    for (int q = 0; q < kRed; ++q) t[q] = __shfl_xor_sync(0xffffffffu, red[q], s);
+    red_combine(red, t);
+  }
+  double a[kRed];
+#pragma unroll
+  for (int q = 0; q < kRed; ++q) a[q] = (double)red[q];
+  // env epilogue on lane 0, its broadcast values to every lane
+  EnvBroadcast<real> e{};
+  EnvFast ef{};
+  const bool fast = in.sched_od != nullptr;
+  if (lane == 0) e = fast ? env_fast_compute<real>(p, er, a, ef) : env_epilogue<real>(pl, p, in, r, er, a, 0.0);
+  e.power_n = __shfl_sync(0xffffffffu, e.power_n, 0); e.signal_n = __shfl_sync(0xffffffffu, e.signal_n, 0);
+  e.solar_n = __shfl_sync(0xffffffffu, e.solar_n, 0); e.od_n = __shfl_sync(0xffffffffu, e.od_n, 0);
+  e.rew_sig = __shfl_sync(0xffffffffu, e.rew_sig, 0); e.pen_common = __shfl_sync(0xffffffffu, e.pen_common, 0);
+  e.pen_max = __shfl_sync(0xffffffffu, e.pen_max, 0);
+  if (slot) pl.reward[o] = ok ? house_reward<real>(p, kc, ta, tg, e) : (real)0;
+  if (D > 0) {
+    const real sso_n = (real)fast_div((uint32_t)sso, p.fd_dur);                     // norm.py:40-43, :79-82
+    const real pmax_n = qdiv(qdiv(cap, kc.cop, kc.inv_cop), kc.nrs, kc.inv_nrs);
+    // this house's message record (building.py:102-139 through norm.py:31-60): its neighbours read it through shuffles
+    const real m0 = ok ? div5(Rep<real>::dev(ta, tg)) : (real)0, m1 = ok ? sso_n : (real)0,
+               m2 = (ok && (f & 1u)) ? pmax_n : (real)0, m3 = ok ? pmax_n : (real)0;
+    real *row = pl.obs + o * D;
+    int q = 0;
+    if (ok) {
+      real ratio[4] = {0, 0, 0, 0};
+      if (p.st_thermal)
+        for (int k = 0; k < 4; ++k) ratio[k] = pl.ratio[k][o];
+      q = obs_own<real>(row, p, f, sso_n, Rep<real>::minus20(ta, tg), Rep<real>::minus20(tm, tg), tg - (real)20, e, ratio, 3);
+    } else if (slot) {
+      for (int k = 0; k < D; ++k) row[k] = (real)0;
+    }
+    if (need_msg) {
+      for (int k = 0; k < nbc; ++k) {      // (every lane takes part in the shuffles)
+        const int nb = ok ? neighbour_of(p, pl.comm_table, r, lane, k) : 0;
+        const real v0 = __shfl_sync(0xffffffffu, m0, nb), v1 = __shfl_sync(0xffffffffu, m1, nb),
+                   v2 = __shfl_sync(0xffffffffu, m2, nb), v3 = __shfl_sync(0xffffffffu, m3, nb);
+        if (ok) {
+          row[q++] = v0; row[q++] = v1; row[q++] = v2; row[q++] = v3;
+          if (p.msg_thermal)
+            for (int t = 0; t < 4; ++t) row[q++] = (real)pl.ratio[t][rb + nb];
+          if (p.msg_hvac) { row[q++] = (real)p.cop; row[q++] = (real)p.latent; row[q++] = (real)p.dcap; }
+        }
+      }
+    }
+  }
+  if (lane == 0 && fast) env_fast_store<real>(pl, p, r, er, ef, a);   // env planes + running metrics, off the other lanes' path
+  if (snap.t_air) {   // the arrays of k_snapshot, from registers (fp32 planes hold deviations from the set-point)
+    if (ok) {
+      const size_t i = (size_t)r * N + lane;
+      const double shift = sizeof(real) == 4 ? (double)tg : 0.0;
+      snap.t_air[i] = (double)ta + shift;
+      snap.t_mass[i] = (double)tm + shift;
+      snap.reward[i] = (double)pl.reward[o];
+      snap.sso[i] = sso;
+      snap.on[i] = (uint8_t)(f & 1u);
+      snap.lockout[i] = (uint8_t)((f >> 1) & 1u);
+      if (snap_obs && D > 0) {
+        const real *src = pl.obs + o * D;
+        real *dst = snap_obs + i * D;
+        for (int k = 0; k < D; ++k) dst[k] = src[k];
+      }
+    }
+    if (lane == 0) {   // (the env planes were just written by this lane)
+      double *ev = snap.env + (size_t)r * kSnapEnv;
+      ev[0] = pl.od_temp[r]; ev[1] = pl.signal[r]; ev[2] = pl.power[r]; ev[3] = pl.solar_cur[r];
+      ev[4] = pl.base_power[r]; ev[5] = (double)pl.epoch[r]; ev[6] = (double)pl.t_since_interp[r]; ev[7] = pl.max_power[r];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Reset on the device: property noise + initial state from Philox streams keyed by
 // (global replica, global house, draw) and (global replica, draw); the update coefficients are
@@ -3275,13 +3413,6 @@ __global__ void __launch_bounds__(256) k_metrics_ref(Planes<real> pl, SimParams 
 // as fp64 (the fp32 build keeps deviations), rewards as fp64, seconds_since_off, the two flags, the env scalars.
 // The observation rows follow by one copy-engine transfer; the caller synchronises once.
 // ------------------------------------------------------------------------------------------
-struct SnapPtrs {
-  double *t_air, *t_mass, *reward;   // [R][N]
-  int32_t *sso;                      // [R][N]
-  uint8_t *on, *lockout;             // [R][N]
-  double *env;                       // [R][kSnapEnv]
-};
-constexpr int kSnapEnv = 8;   // od_temp, signal, power, solar, base_power, epoch, t_since_interp, max_power
 
 template <typename real>
 __global__ void k_snapshot(Planes<real> pl, SimParams p, SnapPtrs o) {
