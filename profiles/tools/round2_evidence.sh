@@ -1,5 +1,7 @@
 # run on the GPU box (1 GPU): the round-2 evidence set -> gpurun_out/
 set -x
+# the DRAM-traffic capture first: it stamps profiles/r2_traffic.json with the source hash the bench lines then report against
+bash profiles/tools/capture_traffic.sh > gpurun_out/capture_traffic.log 2>&1
 python bench.py > gpurun_out/r2_bench_c4_1gpu.json 2> gpurun_out/r2_bench_c4_1gpu.err
 # the driver's own command line (20 steps: ONE launch of the in-kernel step loop)
 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_bench_c4_1gpu_steps20.json 2> /dev/null
@@ -7,7 +9,6 @@ for wl in c3 c5 c2 c1; do
   python bench.py --workload $wl --no-c5 > gpurun_out/r2_bench_${wl}_1gpu.json 2> gpurun_out/r2_bench_${wl}_1gpu.err
 done
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null
-bash profiles/tools/capture_traffic.sh > gpurun_out/capture_traffic.log 2>&1
 python profiles/tools/time_dropin.py 10 100 1000 > gpurun_out/r2_dropin_times.txt 2>&1
 python profiles/tools/time_actor.py > gpurun_out/r2_actor_times.txt 2>&1
 python profiles/tools/actor_phases.py c4 > gpurun_out/r2_actor_phases_c4.txt 2>&1
