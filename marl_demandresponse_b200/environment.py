@@ -260,7 +260,7 @@ def norm_state_dict(obs_dicts: ObsDict, env_props: Any = None) -> List[np.ndarra
     v = getattr(obs_dicts, "vectors", None)
     if v is None:
         raise TypeError("norm_state_dict needs the ObsDict returned by marl_demandresponse_b200.Environment")
-    return [row for row in v]
+    return list(v)   # one row view per agent (a list, like the reference's)
 
 
 class Environment:
