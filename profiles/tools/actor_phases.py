@@ -27,9 +27,9 @@ buf = np.zeros((8, 3, 16), dtype=np.uint64)
 n = L.drsim_debug_actor_times(env.sim._h, buf.ctypes.data_as(C.c_void_p))
 assert n == buf.size, n
 t0 = int(buf[0][buf[0] > 0].min())
-names = {0: ["start", "a1 arrived", "fetch issued", "bar1 (in-place part) passed", "chunk0", "chunk1", "chunk2", "chunk3", "chunk4"],
+names = {0: ["start", "a1 arrived", "fetch issued", "bar1 passed", "chunk0", "chunk1", "chunk2", "chunk3", "chunk4"],
          1: ["wait bar2", "bar2 passed", "R2 drained", "tile done"],
-         2: ["a1 ready (next tile)", "GEMM1 first part issued (next tile)", "c0 ready", "c1 ready", "c2 ready", "c3 ready", "c4 ready", "GEMM2 committed"]}
+         2: ["a1 ready", "GEMM1 issued", "c0 ready", "c1 ready", "c2 ready", "c3 ready", "c4 ready", "GEMM2 committed"]}
 print(f"{which}: clock64 cycles since the first stamp of CTA 0 (producer warp 0 / consumer warp 8 / MMA warp)")
 for it in range(8):
     for role, rn in ((0, "prod"), (2, "mma "), (1, "cons")):
